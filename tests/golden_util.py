@@ -1,0 +1,65 @@
+"""Helpers shared by the parity tests: golden-case loading and error metrics."""
+import glob
+import json
+import os
+
+import numpy as np
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def case_names(pattern="*"):
+    out = []
+    for f in sorted(glob.glob(os.path.join(GOLDEN, pattern + ".npz"))):
+        nm = os.path.basename(f)[:-4]
+        if nm != "tables":
+            out.append(nm)
+    return out
+
+
+_tables = None
+
+
+def tables():
+    global _tables
+    if _tables is None:
+        _tables = dict(np.load(os.path.join(GOLDEN, "tables.npz")))
+    return _tables
+
+
+def load_case(name):
+    z = dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+    cfg = json.loads(str(z.pop("cfg")))
+    return cfg, z
+
+
+def table_key(N, K, J, L, phasing):
+    return "N%d_K%d_J%d_L%d_%s" % (N, K, J, L, phasing)
+
+
+def grid_only_inputs(seed, PK, M, n_reps, cdt):
+    """Same generator as tests/golden/make_golden.py:grid_only_inputs."""
+    rs = np.random.RandomState(seed + 1)
+    g = rs.standard_normal((PK, n_reps)) + 1j * rs.standard_normal((PK, n_reps))
+    ysamp = rs.standard_normal((M, n_reps)) + 1j * rs.standard_normal((M, n_reps))
+    return g.astype(cdt), ysamp.astype(cdt)
+
+
+def rel_l2(a, b):
+    a = np.asarray(a)
+    b = np.asarray(b)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    nb = np.linalg.norm(b.ravel())
+    return np.linalg.norm((a - b).ravel()) / (nb if nb > 0 else 1.0)
+
+
+# north_star tolerances: relative L2 <= 1e-5 (complex64), <= 1e-12 (complex128)
+TOL = {"single": 1e-5, "double": 1e-12}
+
+
+def ctor_kwargs(cfg):
+    return dict(Nd=tuple(cfg["Nd"]), Jd=tuple(cfg["Jd"]), Kd=tuple(cfg["Kd"]),
+                n_shift=tuple(cfg["n_shift"]), mode=cfg["mode"], Ld=cfg["Ld"],
+                precision=cfg["precision"], phasing=cfg["phasing"],
+                order=cfg["order"], ortho=cfg["ortho"],
+                adjoint_scalefactor=cfg["adjoint_scalefactor"])
