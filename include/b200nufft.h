@@ -1,0 +1,152 @@
+/*
+ * b200nufft.h -- C ABI of libb200nufft.so (sm_100a), the B200-native replacement for
+ * the native layer of mrrt.nufft's NUFFT hot path.
+ *
+ * Plain pointers and sizes only; no torch/cupy types.  Device arrays are exchanged by
+ * raw device pointer (obtained from a DLPack / __cuda_array_interface__ producer on the
+ * Python side).  Every entry point returns 0 on success or a B2N_E* code; the message
+ * is available from b2n_last_error() (thread-local).  All launches go to the
+ * cudaStream_t passed as `stream` (0 = legacy default stream).
+ *
+ * What each entry point replaces in the reference (paths under mrrt/nufft/):
+ *   b2n_plan_create / _destroy   NufftBase._init_gpu (_nufft.py:362-390): cuFFT plan +
+ *                                NVRTC RawKernel compilation (cuda/cupy.py:70-183) +
+ *                                launch config (_cupy.py:16-44).  Nothing is compiled
+ *                                at run time here.
+ *   b2n_plan_set_tables          upload of NufftBase.h (_nufft.py:880-935); values are
+ *                                computed on the host exactly as the reference does.
+ *   b2n_plan_set_points          tm = omega/gam (_nufft.py:338-342) + the new bin-sort
+ *                                step (no reference counterpart).
+ *   b2n_interp_fwd               _interp{1,2,3}_table_forward (_nufft_table.pyx:29,215,
+ *                                444) -> TYPE_interp{n}_table1_{real,complex}_forward
+ *                                (c/nufft_table.template.c:43,97,538,623,710,822) and
+ *                                the interp{n}_table*_per_GPUkernel RawKernels
+ *                                (cuda/jinja/table_{1,2,3}d_forward.jinja).
+ *   b2n_interp_adj               _interp{1,2,3}_table_adj (pyx:120,328,574) ->
+ *                                *_adj / *_adj_inner (template.c:144-531, 924-1202) and
+ *                                the *_per_adj_GPUkernel RawKernels
+ *                                (cuda/jinja/table_{1,2,3}d_adjoint.jinja).
+ *   b2n_nufft_fwd / b2n_nufft_adj  nufft_forward / nufft_adj (_nufft.py:1275-1397,
+ *                                1459-1578): sn scaling, zero-pad, cuFFT, phase_before,
+ *                                interpolation, phase_after / the mirror image.
+ *   b2n_plan_set_sparse, b2n_spmv_fwd / _adj
+ *                                _init_sparsemat's matrix (_nufft.py:751-877) held in
+ *                                fixed-width (ELL) form, `obj.p * xk` (:1384) and
+ *                                `obj.p.H * xk` (:1505) (scipy / cuSPARSE SpMV).
+ */
+#ifndef B200NUFFT_H
+#define B200NUFFT_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2N_OK 0
+#define B2N_EINVAL 1   /* bad argument (maps to ValueError) */
+#define B2N_ECUDA 2    /* CUDA runtime / cuFFT failure (maps to RuntimeError) */
+#define B2N_ESTATE 3   /* call sequence error, e.g. points not set (RuntimeError) */
+#define B2N_ENONFINITE 4 /* NaN/Inf sample coordinate (ValueError) */
+
+#define B2N_SINGLE 0   /* float / complex64 */
+#define B2N_DOUBLE 1   /* double / complex128 */
+
+#define B2N_COORD_TM 0     /* coordinates already in grid units (tm) */
+#define B2N_COORD_OMEGA 1  /* radians; tm = omega / (2*pi/K) in the precision dtype */
+
+typedef struct b2n_plan b2n_plan;
+
+int b2n_version(void);
+const char *b2n_last_error(void);
+
+/* ndim in 1..3; Nd, Kd, Jd: ndim ints; L: table oversampling (table length J*L+1);
+ * precision: B2N_SINGLE/B2N_DOUBLE; table_is_complex: 0 real table (phasing="real"),
+ * 1 complex table (phasing="complex"); device: CUDA device ordinal. */
+int b2n_plan_create(int ndim, const int *Nd, const int *Kd, const int *Jd, int L,
+                    int precision, int table_is_complex, int device, b2n_plan **out);
+int b2n_plan_destroy(b2n_plan *plan);
+
+/* integer options: "tile1","tile2","tile3" (bin shape in grid cells), "chunk"
+ * (max samples per work item), "force_generic" (1 = never use the tiled / sliding
+ * kernels), "use_tma" (0 = cooperative tile loads only).  Must precede set_points. */
+int b2n_plan_set_option(b2n_plan *plan, const char *name, long value);
+long b2n_plan_get_option(b2n_plan *plan, const char *name);
+
+/* h_host[d]: HOST pointer to Jd[d]*L+1 entries, real (or interleaved complex) in the
+ * precision dtype. */
+int b2n_plan_set_tables(b2n_plan *plan, const void *const *h_host);
+
+/* Host-side plan constants for the full transforms:
+ *  sn1d[d]      HOST double[Nd[d]]   per-axis deapodization factor (sn = product)
+ *  pb_angle[d]  HOST real[Kd[d]] in the precision dtype: per-axis phase_before angle
+ *               (2*pi/K*n_mid)*k, or NULL for a complex table (no phase_before)
+ *  fwd_scale    multiplies the gridded spectrum in the forward transform (1/sqrt(prod K)
+ *               if ortho else 1)
+ *  adj_scale    multiplies the UNNORMALISED inverse FFT in the adjoint
+ *               (adjoint_scalefactor, or adjoint_scalefactor/sqrt(prod K) if ortho) */
+int b2n_plan_set_scaling(b2n_plan *plan, const double *const *sn1d,
+                         const void *const *pb_angle, double fwd_scale,
+                         double adj_scale);
+
+/* coords_dev: DEVICE [M, ndim] column-major (axis d at offset d*M), precision dtype.
+ * Computes tm (if kind==B2N_COORD_OMEGA), window origins, bin ids, sort keys, the stable
+ * sort permutation and the sorted coordinate copy.  Synchronises `stream`. */
+int b2n_plan_set_points(b2n_plan *plan, const void *coords_dev, int64_t M, int kind,
+                        void *stream);
+
+/* Optional per-sample unit phasor multiplied into the forward output and (conjugated)
+ * into the adjoint input: phase_after (_nufft.py:717-724) or phase_shift (:898-903).
+ * phase_dev: DEVICE complex[M] in the precision dtype, acquisition order; NULL clears. */
+int b2n_plan_set_sample_phase(b2n_plan *plan, const void *phase_dev, void *stream);
+
+int64_t b2n_plan_num_points(b2n_plan *plan);
+int64_t b2n_plan_num_bins(b2n_plan *plan);
+/* copy-outs for the bit-exact tests; any pointer may be NULL.
+ * tm_dev real[M*ndim]; bin_ids_dev int32[M] (acquisition order); keys_dev int64[M]
+ * (acquisition order); perm_dev int32[M] (sorted position -> acquisition index). */
+int b2n_plan_get_points(b2n_plan *plan, void *tm_dev, int32_t *bin_ids_dev,
+                        int64_t *keys_dev, int32_t *perm_dev, void *stream);
+
+/* Interpolation only (the reference's grid_only switches).
+ * grid_dev: complex[prod(Kd) * nbatch], first axis fastest, batch slowest.
+ * samples_dev: complex[M * nbatch], acquisition order, batch slowest.
+ * apply_phase != 0 applies the sample phase set by b2n_plan_set_sample_phase. */
+int b2n_interp_fwd(b2n_plan *plan, const void *grid_dev, void *samples_dev, int nbatch,
+                   int apply_phase, void *stream);
+/* zeroes grid_dev first, like the reference (template.c:965-966, :1107-1108) */
+int b2n_interp_adj(b2n_plan *plan, const void *samples_dev, void *grid_dev, int nbatch,
+                   int apply_phase, void *stream);
+
+/* Full transforms.  image_dev: complex[prod(Nd) * nbatch] first axis fastest. */
+int b2n_nufft_fwd(b2n_plan *plan, const void *image_dev, void *samples_dev, int nbatch,
+                  void *stream);
+int b2n_nufft_adj(b2n_plan *plan, const void *samples_dev, void *image_dev, int nbatch,
+                  void *stream);
+
+/* Sparse mode.  coef[d]: DEVICE [Jd[d], M] (tap fastest) per-axis coefficient, double
+ * (real table) or interleaved complex double; kidx[d]: DEVICE int32 [Jd[d], M] wrapped
+ * grid index per tap.  The ELL matrix (prod(Jd) entries per row) is formed on the device
+ * as the reference forms it: products in double in axis order, conjugated, times the
+ * optional per-row phasor row_phase (DEVICE complex double[M] or NULL), then cast to the
+ * precision dtype (_nufft.py:812-858). */
+int b2n_plan_set_sparse(b2n_plan *plan, const void *const *coef, const int32_t *const *kidx,
+                        int64_t M, const void *row_phase, void *stream);
+int64_t b2n_plan_sparse_nnz(b2n_plan *plan);
+/* copy-out of the ELL arrays: vals (real or complex, precision dtype) [nnz], cols int32
+ * [nnz], row-major (row m holds entries m*prod(Jd) ..). */
+int b2n_plan_get_sparse(b2n_plan *plan, void *vals_dev, int32_t *cols_dev, void *stream);
+int b2n_spmv_fwd(b2n_plan *plan, const void *grid_dev, void *samples_dev, int nbatch,
+                 void *stream);
+int b2n_spmv_adj(b2n_plan *plan, const void *samples_dev, void *grid_dev, int nbatch,
+                 void *stream);
+
+/* bytes of device memory owned by the plan */
+int64_t b2n_plan_device_bytes(b2n_plan *plan);
+/* number of kernel launches (ours + cuFFT calls counted as 1) issued so far */
+int64_t b2n_plan_launch_count(b2n_plan *plan);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200NUFFT_H */

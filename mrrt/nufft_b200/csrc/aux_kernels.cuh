@@ -1,0 +1,295 @@
+// Plan-time preprocessing (tm, window origins, bin ids, sort keys), the fused
+// scale / zero-pad / phase / crop kernels around cuFFT, and the fixed-width (ELL)
+// sparse-mode kernels.
+#pragma once
+#include "common.cuh"
+
+namespace b2n {
+
+// ---------------------------------------------------------------------------------
+// trajectory preprocessing (new step; integer results are bit-exact vs
+// oracle/nufft_oracle.py:bin_sort)
+// ---------------------------------------------------------------------------------
+template <typename T> struct Gam { T g[3]; };
+
+template <typename T>
+__global__ void prep_points_kernel(Geom g, Gam<T> gam, int kind, const T* __restrict__ coords,
+                                   T* __restrict__ tm, uint64_t* __restrict__ keys,
+                                   int32_t* __restrict__ bin_ids, int32_t* __restrict__ iota,
+                                   int* __restrict__ nonfinite) {
+    const int64_t M = g.M;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < M;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t bin = 0, cell = 0;
+        int64_t bstride = 1, cstride = 1;
+        bool ok = true;
+#pragma unroll
+        for (int d = 0; d < kMaxDim; d++) {
+            if (d < g.ndim) {
+                T t = coords[(int64_t)d * M + i];
+                // tm = omega / gam in the precision dtype (_nufft.py:338-342)
+                if (kind == 1) t = div_rn(t, gam.g[d]);
+                ok = ok && is_finite(t);
+                tm[(int64_t)d * M + i] = t;
+                int kw = 0;
+                if (ok) kw = wrap_index(window_origin<T>(t, g.J[d]), g.K[d]);
+                bin += (int64_t)(kw / g.tile[d]) * bstride;
+                cell += (int64_t)(kw % g.tile[d]) * cstride;
+                bstride *= g.nbin[d];
+                cstride *= g.tile[d];
+            }
+        }
+        if (!ok) atomicExch(nonfinite, 1);
+        keys[i] = (uint64_t)(bin * cstride + cell);
+        bin_ids[i] = (int32_t)bin;
+        iota[i] = (int32_t)i;
+    }
+}
+
+template <typename T>
+__global__ void gather_points_kernel(int ndim, int64_t M, const int32_t* __restrict__ perm,
+                                     const T* __restrict__ tm, T* __restrict__ tm_s) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < M;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t m = perm[i];
+        for (int d = 0; d < ndim; d++) tm_s[(int64_t)d * M + i] = tm[(int64_t)d * M + m];
+    }
+}
+
+template <typename C>
+__global__ void gather_c_kernel(int64_t M, const int32_t* __restrict__ perm,
+                                const C* __restrict__ src, C* __restrict__ dst) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < M;
+         i += (int64_t)gridDim.x * blockDim.x)
+        dst[i] = src[perm[i]];
+}
+
+// first sorted position of every non-empty bin (bin_start pre-filled with -1)
+__global__ void bin_start_kernel(int64_t M, int cells_per_tile, const uint64_t* __restrict__ keys_s,
+                                 int32_t* __restrict__ bin_start) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < M;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = (int64_t)(keys_s[i] / (uint64_t)cells_per_tile);
+        if (i == 0 || (int64_t)(keys_s[i - 1] / (uint64_t)cells_per_tile) != b)
+            bin_start[b] = (int32_t)i;
+    }
+}
+
+__global__ void keys_to_i64_kernel(int64_t M, const uint64_t* __restrict__ k, int64_t* __restrict__ o) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < M;
+         i += (int64_t)gridDim.x * blockDim.x)
+        o[i] = (int64_t)k[i];
+}
+
+// ---------------------------------------------------------------------------------
+// fused kernels around the oversampled FFT
+// ---------------------------------------------------------------------------------
+struct AxisPtrs {
+    const double* sn[3];   // per-axis deapodization factors (double)
+    const void* pb[3];     // per-axis phase_before angle, precision dtype
+};
+
+// grid[k] = x[k] * sn[k] * fwd_scale inside the Nd corner, 0 elsewhere
+// (_nufft.py:1325-1331: `x * sn` then zero-padded FFT).  sn is the reference's dense
+// array re-formed on the fly: ((s1*s2)*s3) in double, then cast (:737-748).
+template <typename T>
+__global__ void pre_scale_pad_kernel(Geom g, AxisPtrs ax, T fwd_scale, int apply_scale,
+                                     const cplx_t<T>* __restrict__ image,
+                                     cplx_t<T>* __restrict__ grid, int nbatch) {
+    using C = cplx_t<T>;
+    const int64_t total = g.PK * nbatch;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = idx / g.PK;
+        int64_t r = idx - b * g.PK;
+        const int k1 = (int)(r % g.K[0]);
+        r /= g.K[0];
+        const int k2 = g.ndim > 1 ? (int)(r % g.K[1]) : 0;
+        const int k3 = g.ndim > 2 ? (int)(r / g.K[1]) : 0;
+        C v = make_c<T>(0, 0);
+        if (k1 < g.N[0] && (g.ndim < 2 || k2 < g.N[1]) && (g.ndim < 3 || k3 < g.N[2])) {
+            double s = ax.sn[0][k1];
+            int64_t n = k1;
+            if (g.ndim > 1) { s *= ax.sn[1][k2]; n += (int64_t)k2 * g.N[0]; }
+            if (g.ndim > 2) { s *= ax.sn[2][k3]; n += (int64_t)k3 * g.N[0] * g.N[1]; }
+            const T st = (T)s;
+            const C x = image[b * g.PN + n];
+            v = make_c<T>(x.x * st, x.y * st);
+            if (apply_scale) { v.x *= fwd_scale; v.y *= fwd_scale; }
+        }
+        grid[idx] = v;
+    }
+}
+
+__device__ __forceinline__ void sincos_t(float a, float* s, float* c) { sincosf(a, s, c); }
+__device__ __forceinline__ void sincos_t(double a, double* s, double* c) { sincos(a, s, c); }
+
+// grid[k] *= exp(+-i*((p1[k1]+p2[k2])+p3[k3])): phase_before with the angle summed in
+// the precision dtype in the reference's order (_nufft.py:703-715, :1370-1371, :1519-1520)
+template <typename T>
+__global__ void phase_before_kernel(Geom g, AxisPtrs ax, int conj, cplx_t<T>* __restrict__ grid,
+                                    int nbatch) {
+    using C = cplx_t<T>;
+    const int64_t total = g.PK * nbatch;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = idx % g.PK;
+        const int k1 = (int)(r % g.K[0]);
+        r /= g.K[0];
+        T ang = ((const T*)ax.pb[0])[k1];
+        if (g.ndim > 1) ang = ang + ((const T*)ax.pb[1])[(int)(r % g.K[1])];
+        if (g.ndim > 2) ang = ang + ((const T*)ax.pb[2])[(int)(r / g.K[1])];
+        T s, c;
+        sincos_t(ang, &s, &c);
+        if (conj) s = -s;
+        const C v = grid[idx];
+        grid[idx] = make_c<T>(v.x * c - v.y * s, v.x * s + v.y * c);
+    }
+}
+
+// image[n] = grid[n (corner)] * adj_scale * sn[n]   (_nufft.py:1560-1572)
+template <typename T>
+__global__ void post_crop_scale_kernel(Geom g, AxisPtrs ax, T adj_scale, int apply_scale,
+                                       const cplx_t<T>* __restrict__ grid,
+                                       cplx_t<T>* __restrict__ image, int nbatch) {
+    using C = cplx_t<T>;
+    const int64_t total = g.PN * nbatch;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = idx / g.PN;
+        int64_t r = idx - b * g.PN;
+        const int n1 = (int)(r % g.N[0]);
+        r /= g.N[0];
+        const int n2 = g.ndim > 1 ? (int)(r % g.N[1]) : 0;
+        const int n3 = g.ndim > 2 ? (int)(r / g.N[1]) : 0;
+        double s = ax.sn[0][n1];
+        int64_t k = n1;
+        if (g.ndim > 1) { s *= ax.sn[1][n2]; k += (int64_t)n2 * g.K[0]; }
+        if (g.ndim > 2) { s *= ax.sn[2][n3]; k += (int64_t)n3 * g.K[0] * g.K[1]; }
+        const T st = (T)s;
+        C v = grid[b * g.PK + k];
+        if (apply_scale) { v.x *= adj_scale; v.y *= adj_scale; }
+        image[idx] = make_c<T>(v.x * st, v.y * st);
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// sparse mode: fixed-width rows (exactly prod(Jd) entries per sample)
+// ---------------------------------------------------------------------------------
+struct SparseSrc {
+    const void* coef[3];      // [J_d, M] double or complex double, tap fastest
+    const int32_t* kidx[3];   // [J_d, M]
+};
+
+// values formed as the reference forms them (_nufft.py:812-858): products in double in
+// axis order, conjugate, optional row phase, cast to the matrix dtype
+template <typename T, bool CT>
+__global__ void build_ell_kernel(Geom g, SparseSrc src, const int32_t* __restrict__ perm,
+                                 const double2* __restrict__ row_phase, int nnzr,
+                                 typename WeightT<T, CT>::type* __restrict__ vals,
+                                 int32_t* __restrict__ cols) {
+    const int64_t total = g.M * nnzr;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total;
+         e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = e / nnzr;
+        int j = (int)(e - i * nnzr);
+        const int64_t m = perm[i];
+        int col = 0, kstride = 1;
+        double2 u = make_double2(1.0, 0.0);
+        for (int d = 0; d < g.ndim; d++) {
+            const int jd = j % g.J[d];
+            j /= g.J[d];
+            const int64_t a = m * g.J[d] + jd;
+            col += src.kidx[d][a] * kstride;
+            kstride *= g.K[d];
+            if (CT) {
+                const double2 c = ((const double2*)src.coef[d])[a];
+                u = d == 0 ? c : cmul(u, c);
+            } else {
+                const double c = ((const double*)src.coef[d])[a];
+                u.x = d == 0 ? c : u.x * c;
+            }
+        }
+        if constexpr (CT) {
+            u.y = -u.y;
+            if (row_phase != nullptr) u = cmul(u, row_phase[m]);
+            vals[e] = make_c<T>((T)u.x, (T)u.y);
+        } else {
+            vals[e] = (T)u.x;
+        }
+        cols[e] = col;
+    }
+}
+
+template <typename T, bool CT>
+__global__ void __launch_bounds__(256)
+spmv_fwd_kernel(Geom g, int nnzr, const typename WeightT<T, CT>::type* __restrict__ vals,
+                const int32_t* __restrict__ cols, const int32_t* __restrict__ perm,
+                const cplx_t<T>* __restrict__ grid, cplx_t<T>* __restrict__ out,
+                const cplx_t<T>* __restrict__ phase_s, int nbatch) {
+    using C = cplx_t<T>;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = warp; i < g.M; i += nwarp) {
+        const int64_t dst = perm[i];
+        for (int b = 0; b < nbatch; b++) {
+            const C* __restrict__ gb = grid + (int64_t)b * g.PK;
+            C acc = make_c<T>(0, 0);
+            for (int j = lane; j < nnzr; j += 32) {
+                const C p = w_mul(vals[i * nnzr + j], __ldg(gb + cols[i * nnzr + j]));
+                acc.x += p.x;
+                acc.y += p.y;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+                acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+            }
+            if (lane == 0) {
+                if (phase_s != nullptr) acc = cmul(acc, phase_s[i]);
+                out[(int64_t)b * g.M + dst] = acc;
+            }
+        }
+    }
+}
+
+template <typename T, bool CT>
+__global__ void __launch_bounds__(256)
+spmv_adj_kernel(Geom g, int nnzr, const typename WeightT<T, CT>::type* __restrict__ vals,
+                const int32_t* __restrict__ cols, const int32_t* __restrict__ perm,
+                const cplx_t<T>* __restrict__ samples, cplx_t<T>* __restrict__ grid,
+                const cplx_t<T>* __restrict__ phase_s, int nbatch) {
+    using C = cplx_t<T>;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = warp; i < g.M; i += nwarp) {
+        const int64_t srcm = perm[i];
+        for (int b = 0; b < nbatch; b++) {
+            C* __restrict__ gb = grid + (int64_t)b * g.PK;
+            C f = samples[(int64_t)b * g.M + srcm];
+            if (phase_s != nullptr) f = cmul_conj(f, phase_s[i]);
+            for (int j = lane; j < nnzr; j += 32)
+                atomic_add_c(gb + cols[i * nnzr + j], w_mul_conj(vals[i * nnzr + j], f));
+        }
+    }
+}
+
+// un-permute the ELL rows back to acquisition order for the copy-out used by tests
+template <typename V>
+__global__ void ell_unpermute_kernel(int64_t M, int nnzr, const int32_t* __restrict__ perm,
+                                     const V* __restrict__ vals_s, const int32_t* __restrict__ cols_s,
+                                     V* __restrict__ vals, int32_t* __restrict__ cols) {
+    const int64_t total = M * nnzr;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total;
+         e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = e / nnzr;
+        const int j = (int)(e - i * nnzr);
+        const int64_t m = perm[i];
+        if (vals != nullptr) vals[m * nnzr + j] = vals_s[e];
+        if (cols != nullptr) cols[m * nnzr + j] = cols_s[e];
+    }
+}
+
+}  // namespace b2n

@@ -1,0 +1,793 @@
+// libb200nufft.so -- C ABI (include/b200nufft.h) over hand-written sm_100a kernels.
+// Build: see mrrt/nufft_b200/build.py (nvcc -gencode arch=compute_100a,code=sm_100a).
+#include <cuda_runtime.h>
+#include <cufft.h>
+#include <cub/device/device_radix_sort.cuh>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../../include/b200nufft.h"
+#include "aux_kernels.cuh"
+#include "common.cuh"
+#include "dispatch.h"
+
+using namespace b2n;
+
+// ---------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CU(call)                                                                     \
+    do {                                                                             \
+        cudaError_t e_ = (call);                                                     \
+        if (e_ != cudaSuccess)                                                       \
+            return fail(B2N_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+#define FFT(call)                                                                    \
+    do {                                                                             \
+        cufftResult r_ = (call);                                                     \
+        if (r_ != CUFFT_SUCCESS)                                                     \
+            return fail(B2N_ECUDA, std::string(#call) + ": cufft error " + std::to_string((int)r_)); \
+    } while (0)
+
+// ---------------------------------------------------------------------------------
+// plan
+// ---------------------------------------------------------------------------------
+struct b2n_plan {
+    Geom g{};
+    int precision = 0;
+    int cplx_table = 0;
+    int device = 0;
+    int sm_count = 148;
+    // options
+    long opt_chunk = 2048;
+    long opt_force_generic = 0;
+    long opt_use_tma = 1;
+    long opt_sparse_mode = 0;
+    long opt_slide_pts = 256;
+    bool tile_user_set = false;
+    // tables
+    void* d_tab[3] = {nullptr, nullptr, nullptr};
+    bool tables_set = false;
+    bool tables_equal = false;   // all axes share one table
+    // scaling
+    double* d_sn[3] = {nullptr, nullptr, nullptr};
+    void* d_pb[3] = {nullptr, nullptr, nullptr};
+    bool scaling_set = false;
+    bool have_pb = false;
+    double fwd_scale = 1.0, adj_scale = 1.0;
+    // points
+    bool points_set = false;
+    void* d_tm = nullptr;        // [ndim][M] acquisition order
+    void* d_tm_s = nullptr;      // [ndim][M] sorted
+    uint64_t* d_keys = nullptr;  // acquisition order
+    int32_t* d_bin_ids = nullptr;
+    int32_t* d_perm = nullptr;
+    void* d_phase_s = nullptr;   // sorted sample phase or null
+    int64_t nbins = 0;
+    // work items of the tiled forward kernel: (bin, start, count, pad)
+    int4* d_items = nullptr;
+    int64_t n_items = 0;
+    // sparse
+    void* d_ell_vals = nullptr;
+    int32_t* d_ell_cols = nullptr;
+    int nnzr = 0;
+    bool sparse_set = false;
+    // fft
+    std::map<int, cufftHandle> fft_plans;
+    void* d_work = nullptr;
+    size_t work_bytes = 0;
+    int64_t dev_bytes = 0;
+    int64_t launches = 0;
+    int last_fwd_kernel = -1;   // 0 generic, 1 tiled
+    int last_adj_kernel = -1;   // 0 generic, 1 sliding window
+
+    size_t real_size() const { return precision == B2N_SINGLE ? 4 : 8; }
+    size_t cplx_size() const { return 2 * real_size(); }
+};
+
+static int dev_alloc(b2n_plan* p, void** ptr, size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    CU(cudaMalloc(ptr, bytes));
+    p->dev_bytes += (int64_t)bytes;
+    return B2N_OK;
+}
+static void dev_free(void* ptr) {
+    if (ptr) cudaFree(ptr);
+}
+
+static int grid_for(int64_t n, int block, int sm_count, int per_sm = 16) {
+    int64_t b = (n + block - 1) / block;
+    int64_t cap = (int64_t)sm_count * per_sm;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+extern "C" int b2n_version(void) { return 100; }
+extern "C" const char* b2n_last_error(void) { return g_err.c_str(); }
+
+static void default_tiles(b2n_plan* p) {
+    Geom& g = p->g;
+    if (!p->tile_user_set) {
+        if (g.ndim == 1) { g.tile[0] = 1024; }
+        if (g.ndim == 2) { g.tile[0] = 32; g.tile[1] = 32; }
+        if (g.ndim == 3) { g.tile[0] = 16; g.tile[1] = 16; g.tile[2] = 8; }
+        if (g.ndim == 3 && p->precision == B2N_DOUBLE) { g.tile[0] = 16; g.tile[1] = 8; g.tile[2] = 8; }
+    }
+    g.cells_per_tile = 1;
+    for (int d = 0; d < 3; d++) {
+        if (d >= g.ndim) g.tile[d] = 1;
+        if (g.tile[d] > g.K[d]) g.tile[d] = g.K[d];
+        if (g.tile[d] < 1) g.tile[d] = 1;
+        g.nbin[d] = (g.K[d] + g.tile[d] - 1) / g.tile[d];
+        g.cells_per_tile *= g.tile[d];
+    }
+}
+
+extern "C" int b2n_plan_create(int ndim, const int* Nd, const int* Kd, const int* Jd, int L,
+                               int precision, int table_is_complex, int device,
+                               b2n_plan** out) {
+    if (out == nullptr) return fail(B2N_EINVAL, "out is NULL");
+    if (ndim < 1 || ndim > 3) return fail(B2N_EINVAL, "dimensions > 3 not implemented");
+    if (precision != B2N_SINGLE && precision != B2N_DOUBLE)
+        return fail(B2N_EINVAL, "precision must be B2N_SINGLE or B2N_DOUBLE");
+    if (L < 1) return fail(B2N_EINVAL, "L must be >= 1");
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(B2N_EINVAL, "bad device ordinal");
+    CU(cudaSetDevice(device));
+    b2n_plan* p = new b2n_plan();
+    p->precision = precision;
+    p->cplx_table = table_is_complex ? 1 : 0;
+    p->device = device;
+    cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, device);
+    Geom& g = p->g;
+    g.ndim = ndim;
+    g.L = L;
+    g.PK = 1;
+    g.PN = 1;
+    for (int d = 0; d < 3; d++) {
+        g.N[d] = d < ndim ? Nd[d] : 1;
+        g.K[d] = d < ndim ? Kd[d] : 1;
+        g.J[d] = d < ndim ? Jd[d] : 1;
+        if (g.N[d] < 1 || g.K[d] < g.N[d] || g.J[d] < 1 || g.J[d] > kMaxJ) {
+            delete p;
+            return fail(B2N_EINVAL, "need 1 <= N <= K and 1 <= J <= 16 on every axis");
+        }
+        g.ncenter[d] = (g.J[d] * L) / 2;
+        g.tlen[d] = g.J[d] * L + 1;
+        g.PK *= g.K[d];
+        g.PN *= g.N[d];
+    }
+    if (g.PK >= ((int64_t)1 << 31)) {
+        delete p;
+        return fail(B2N_EINVAL, "prod(Kd) must be < 2^31");
+    }
+    default_tiles(p);
+    *out = p;
+    return B2N_OK;
+}
+
+static void free_points(b2n_plan* p) {
+    dev_free(p->d_tm); dev_free(p->d_tm_s); dev_free(p->d_keys); dev_free(p->d_bin_ids);
+    dev_free(p->d_perm); dev_free(p->d_phase_s); dev_free(p->d_items);
+    p->d_tm = p->d_tm_s = p->d_phase_s = nullptr;
+    p->d_keys = nullptr; p->d_bin_ids = nullptr; p->d_perm = nullptr; p->d_items = nullptr;
+    p->points_set = false;
+}
+
+extern "C" int b2n_plan_destroy(b2n_plan* p) {
+    if (p == nullptr) return B2N_OK;
+    cudaSetDevice(p->device);
+    for (auto& kv : p->fft_plans) cufftDestroy(kv.second);
+    free_points(p);
+    for (int d = 0; d < 3; d++) {
+        bool dup = false;
+        for (int e = 0; e < d; e++) dup = dup || (p->d_tab[e] == p->d_tab[d]);
+        if (!dup) dev_free(p->d_tab[d]);
+        dev_free(p->d_sn[d]);
+        dev_free(p->d_pb[d]);
+    }
+    dev_free(p->d_ell_vals);
+    dev_free(p->d_ell_cols);
+    dev_free(p->d_work);
+    delete p;
+    return B2N_OK;
+}
+
+extern "C" int b2n_plan_set_option(b2n_plan* p, const char* name, long value) {
+    if (p == nullptr || name == nullptr) return fail(B2N_EINVAL, "NULL argument");
+    std::string n(name);
+    if (n == "tile1" || n == "tile2" || n == "tile3") {
+        if (p->points_set) return fail(B2N_ESTATE, "tile options must precede set_points");
+        if (value < 1) return fail(B2N_EINVAL, "tile must be >= 1");
+        p->g.tile[n[4] - '1'] = (int)value;
+        p->tile_user_set = true;
+        default_tiles(p);
+    } else if (n == "chunk") {
+        if (value < 32) return fail(B2N_EINVAL, "chunk must be >= 32");
+        p->opt_chunk = value;
+    } else if (n == "force_generic") {
+        p->opt_force_generic = value;
+    } else if (n == "use_tma") {
+        p->opt_use_tma = value;
+    } else if (n == "sparse_mode") {
+        p->opt_sparse_mode = value;
+    } else if (n == "slide_pts") {
+        if (value < 32) return fail(B2N_EINVAL, "slide_pts must be >= 32");
+        p->opt_slide_pts = value;
+    } else {
+        return fail(B2N_EINVAL, "unknown option " + n);
+    }
+    return B2N_OK;
+}
+
+extern "C" long b2n_plan_get_option(b2n_plan* p, const char* name) {
+    if (p == nullptr || name == nullptr) return -1;
+    std::string n(name);
+    if (n == "tile1") return p->g.tile[0];
+    if (n == "tile2") return p->g.tile[1];
+    if (n == "tile3") return p->g.tile[2];
+    if (n == "chunk") return p->opt_chunk;
+    if (n == "force_generic") return p->opt_force_generic;
+    if (n == "use_tma") return p->opt_use_tma;
+    if (n == "sparse_mode") return p->opt_sparse_mode;
+    if (n == "slide_pts") return p->opt_slide_pts;
+    if (n == "n_items") return (long)p->n_items;
+    if (n == "last_fwd_kernel") return p->last_fwd_kernel;
+    if (n == "last_adj_kernel") return p->last_adj_kernel;
+    return -1;
+}
+
+extern "C" int b2n_plan_set_tables(b2n_plan* p, const void* const* h_host) {
+    if (p == nullptr || h_host == nullptr) return fail(B2N_EINVAL, "NULL argument");
+    CU(cudaSetDevice(p->device));
+    const Geom& g = p->g;
+    const size_t esz = p->cplx_table ? p->cplx_size() : p->real_size();
+    for (int d = 0; d < g.ndim; d++)
+        if (h_host[d] == nullptr) return fail(B2N_EINVAL, "h1 size problem");
+    // identical tables across axes are stored once (lets kernels keep a single copy
+    // in shared memory)
+    p->tables_equal = true;
+    for (int d = 1; d < g.ndim; d++)
+        if (g.tlen[d] != g.tlen[0] || memcmp(h_host[d], h_host[0], esz * g.tlen[0]) != 0)
+            p->tables_equal = false;
+    for (int d = 0; d < g.ndim; d++) {
+        if (d > 0 && p->tables_equal) {
+            p->d_tab[d] = p->d_tab[0];
+            continue;
+        }
+        if (p->d_tab[d] == nullptr) {
+            int rc = dev_alloc(p, &p->d_tab[d], esz * g.tlen[d]);
+            if (rc) return rc;
+        }
+        CU(cudaMemcpy(p->d_tab[d], h_host[d], esz * g.tlen[d], cudaMemcpyHostToDevice));
+    }
+    p->tables_set = true;
+    return B2N_OK;
+}
+
+extern "C" int b2n_plan_set_scaling(b2n_plan* p, const double* const* sn1d,
+                                    const void* const* pb_angle, double fwd_scale,
+                                    double adj_scale) {
+    if (p == nullptr || sn1d == nullptr) return fail(B2N_EINVAL, "NULL argument");
+    CU(cudaSetDevice(p->device));
+    const Geom& g = p->g;
+    for (int d = 0; d < g.ndim; d++) {
+        if (sn1d[d] == nullptr) return fail(B2N_EINVAL, "sn1d axis missing");
+        if (p->d_sn[d] == nullptr) {
+            int rc = dev_alloc(p, (void**)&p->d_sn[d], sizeof(double) * g.N[d]);
+            if (rc) return rc;
+        }
+        CU(cudaMemcpy(p->d_sn[d], sn1d[d], sizeof(double) * g.N[d], cudaMemcpyHostToDevice));
+    }
+    p->have_pb = pb_angle != nullptr;
+    if (p->have_pb) {
+        for (int d = 0; d < g.ndim; d++) {
+            if (pb_angle[d] == nullptr) return fail(B2N_EINVAL, "pb_angle axis missing");
+            if (p->d_pb[d] == nullptr) {
+                int rc = dev_alloc(p, &p->d_pb[d], p->real_size() * g.K[d]);
+                if (rc) return rc;
+            }
+            CU(cudaMemcpy(p->d_pb[d], pb_angle[d], p->real_size() * g.K[d], cudaMemcpyHostToDevice));
+        }
+    }
+    p->fwd_scale = fwd_scale;
+    p->adj_scale = adj_scale;
+    p->scaling_set = true;
+    return B2N_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// points: tm, keys, stable sort, sorted copies, work items
+// ---------------------------------------------------------------------------------
+template <typename T>
+static int set_points_t(b2n_plan* p, const void* coords, int64_t M, int kind, cudaStream_t st) {
+    Geom& g = p->g;
+    g.M = M;
+    int rc;
+    const size_t rs = sizeof(T);
+    if ((rc = dev_alloc(p, &p->d_tm, rs * M * g.ndim))) return rc;
+    if ((rc = dev_alloc(p, &p->d_tm_s, rs * M * g.ndim))) return rc;
+    if ((rc = dev_alloc(p, (void**)&p->d_keys, sizeof(uint64_t) * M))) return rc;
+    if ((rc = dev_alloc(p, (void**)&p->d_bin_ids, sizeof(int32_t) * M))) return rc;
+    if ((rc = dev_alloc(p, (void**)&p->d_perm, sizeof(int32_t) * M))) return rc;
+    p->nbins = (int64_t)g.nbin[0] * g.nbin[1] * g.nbin[2];
+    if (M == 0) {
+        p->n_items = 0;
+        p->points_set = true;
+        return B2N_OK;
+    }
+    uint64_t* keys_s = nullptr;
+    int32_t* iota = nullptr;
+    int* flag = nullptr;
+    int32_t* bin_start = nullptr;
+    void* tmp = nullptr;
+    CU(cudaMalloc(&keys_s, sizeof(uint64_t) * M));
+    CU(cudaMalloc(&iota, sizeof(int32_t) * M));
+    CU(cudaMalloc(&flag, sizeof(int)));
+    CU(cudaMemsetAsync(flag, 0, sizeof(int), st));
+    Gam<T> gam;
+    for (int d = 0; d < 3; d++) gam.g[d] = (T)(2.0 * M_PI / (double)g.K[d]);
+    prep_points_kernel<T><<<grid_for(M, 256, p->sm_count), 256, 0, st>>>(
+        g, gam, kind, (const T*)coords, (T*)p->d_tm, p->d_keys, p->d_bin_ids, iota, flag);
+    CU(cudaGetLastError());
+    // stable LSD radix sort over just the significant key bits
+    uint64_t maxkey = (uint64_t)p->nbins * (uint64_t)g.cells_per_tile;
+    int bits = 1;
+    while (bits < 64 && (maxkey >> bits) != 0) bits++;
+    size_t tmp_bytes = 0;
+    CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, p->d_keys, keys_s, iota, p->d_perm,
+                                       M, 0, bits, st));
+    CU(cudaMalloc(&tmp, tmp_bytes));
+    CU(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, p->d_keys, keys_s, iota, p->d_perm, M,
+                                       0, bits, st));
+    gather_points_kernel<T><<<grid_for(M, 256, p->sm_count), 256, 0, st>>>(
+        g.ndim, M, p->d_perm, (const T*)p->d_tm, (T*)p->d_tm_s);
+    CU(cudaGetLastError());
+    // bin boundaries -> host -> work items of at most opt_chunk samples
+    CU(cudaMalloc(&bin_start, sizeof(int32_t) * p->nbins));
+    CU(cudaMemsetAsync(bin_start, 0xff, sizeof(int32_t) * p->nbins, st));
+    bin_start_kernel<<<grid_for(M, 256, p->sm_count), 256, 0, st>>>(M, g.cells_per_tile, keys_s,
+                                                                    bin_start);
+    CU(cudaGetLastError());
+    std::vector<int32_t> hstart(p->nbins);
+    int hflag = 0;
+    CU(cudaMemcpyAsync(hstart.data(), bin_start, sizeof(int32_t) * p->nbins,
+                       cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&hflag, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    cudaFree(keys_s); cudaFree(iota); cudaFree(flag); cudaFree(bin_start); cudaFree(tmp);
+    if (hflag) {
+        free_points(p);
+        return fail(B2N_ENONFINITE, "omega contains NaN or Inf");
+    }
+    std::vector<int4> items;
+    int64_t next = M;
+    std::vector<int64_t> bend(p->nbins, 0);
+    for (int64_t b = p->nbins - 1; b >= 0; b--) {
+        if (hstart[b] >= 0) {
+            bend[b] = next;
+            next = hstart[b];
+        }
+    }
+    for (int64_t b = 0; b < p->nbins; b++) {
+        if (hstart[b] < 0) continue;
+        int64_t s = hstart[b], e = bend[b];
+        while (s < e) {
+            int64_t c = e - s < p->opt_chunk ? e - s : p->opt_chunk;
+            items.push_back(make_int4((int)b, (int)s, (int)c, 0));
+            s += c;
+        }
+    }
+    p->n_items = (int64_t)items.size();
+    if ((rc = dev_alloc(p, (void**)&p->d_items, sizeof(int4) * (items.size() + 1)))) return rc;
+    CU(cudaMemcpy(p->d_items, items.data(), sizeof(int4) * items.size(), cudaMemcpyHostToDevice));
+    p->launches += 4;
+    p->points_set = true;
+    return B2N_OK;
+}
+
+extern "C" int b2n_plan_set_points(b2n_plan* p, const void* coords_dev, int64_t M, int kind,
+                                   void* stream) {
+    if (p == nullptr) return fail(B2N_EINVAL, "NULL plan");
+    if (M < 0 || M >= ((int64_t)1 << 31)) return fail(B2N_EINVAL, "need 0 <= M < 2^31");
+    if (M > 0 && coords_dev == nullptr) return fail(B2N_EINVAL, "coords is NULL");
+    if (kind != B2N_COORD_TM && kind != B2N_COORD_OMEGA) return fail(B2N_EINVAL, "bad coordinate kind");
+    CU(cudaSetDevice(p->device));
+    free_points(p);
+    p->sparse_set = false;
+    if (p->precision == B2N_SINGLE) return set_points_t<float>(p, coords_dev, M, kind, (cudaStream_t)stream);
+    return set_points_t<double>(p, coords_dev, M, kind, (cudaStream_t)stream);
+}
+
+extern "C" int b2n_plan_set_sample_phase(b2n_plan* p, const void* phase_dev, void* stream) {
+    if (p == nullptr) return fail(B2N_EINVAL, "NULL plan");
+    if (!p->points_set) return fail(B2N_ESTATE, "set_points must precede set_sample_phase");
+    CU(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (phase_dev == nullptr) {
+        dev_free(p->d_phase_s);
+        p->d_phase_s = nullptr;
+        return B2N_OK;
+    }
+    const int64_t M = p->g.M;
+    if (p->d_phase_s == nullptr) {
+        int rc = dev_alloc(p, &p->d_phase_s, p->cplx_size() * M);
+        if (rc) return rc;
+    }
+    if (M > 0) {
+        if (p->precision == B2N_SINGLE)
+            gather_c_kernel<float2><<<grid_for(M, 256, p->sm_count), 256, 0, st>>>(
+                M, p->d_perm, (const float2*)phase_dev, (float2*)p->d_phase_s);
+        else
+            gather_c_kernel<double2><<<grid_for(M, 256, p->sm_count), 256, 0, st>>>(
+                M, p->d_perm, (const double2*)phase_dev, (double2*)p->d_phase_s);
+        CU(cudaGetLastError());
+        p->launches++;
+    }
+    return B2N_OK;
+}
+
+extern "C" int64_t b2n_plan_num_points(b2n_plan* p) { return p && p->points_set ? p->g.M : -1; }
+extern "C" int64_t b2n_plan_num_bins(b2n_plan* p) { return p ? (int64_t)p->g.nbin[0] * p->g.nbin[1] * p->g.nbin[2] : -1; }
+extern "C" int64_t b2n_plan_device_bytes(b2n_plan* p) { return p ? p->dev_bytes : -1; }
+extern "C" int64_t b2n_plan_launch_count(b2n_plan* p) { return p ? p->launches : -1; }
+
+extern "C" int b2n_plan_get_points(b2n_plan* p, void* tm_dev, int32_t* bin_ids_dev,
+                                   int64_t* keys_dev, int32_t* perm_dev, void* stream) {
+    if (p == nullptr) return fail(B2N_EINVAL, "NULL plan");
+    if (!p->points_set) return fail(B2N_ESTATE, "points not set");
+    CU(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t M = p->g.M;
+    if (M == 0) return B2N_OK;
+    if (tm_dev) CU(cudaMemcpyAsync(tm_dev, p->d_tm, p->real_size() * M * p->g.ndim, cudaMemcpyDeviceToDevice, st));
+    if (bin_ids_dev) CU(cudaMemcpyAsync(bin_ids_dev, p->d_bin_ids, sizeof(int32_t) * M, cudaMemcpyDeviceToDevice, st));
+    if (perm_dev) CU(cudaMemcpyAsync(perm_dev, p->d_perm, sizeof(int32_t) * M, cudaMemcpyDeviceToDevice, st));
+    if (keys_dev) {
+        keys_to_i64_kernel<<<grid_for(M, 256, p->sm_count), 256, 0, st>>>(M, p->d_keys, keys_dev);
+        CU(cudaGetLastError());
+    }
+    return B2N_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// interpolation dispatch
+// ---------------------------------------------------------------------------------
+static TablePtrs table_ptrs(const b2n_plan* p) {
+    return TablePtrs{{p->d_tab[0], p->d_tab[1], p->d_tab[2]}};
+}
+
+static int run_generic(b2n_plan* p, bool fwd, const void* in, void* out, int nbatch, bool phase,
+                       cudaStream_t st) {
+    const TablePtrs tabs = table_ptrs(p);
+    const void* ph = phase ? p->d_phase_s : nullptr;
+    if (p->precision == B2N_SINGLE)
+        return generic_launch_f32(p->g, p->cplx_table, tabs, p->d_tm_s, p->d_perm, fwd, in, out, ph,
+                                  nbatch, p->sm_count, st);
+    return generic_launch_f64(p->g, p->cplx_table, tabs, p->d_tm_s, p->d_perm, fwd, in, out, ph,
+                              nbatch, p->sm_count, st);
+}
+
+static int check_ready(b2n_plan* p, const void* a, const void* b, int nbatch) {
+    if (p == nullptr) return fail(B2N_EINVAL, "NULL plan");
+    if (!p->points_set) return fail(B2N_ESTATE, "points not set");
+    if (nbatch < 1) return fail(B2N_EINVAL, "nbatch must be >= 1");
+    if ((a == nullptr || b == nullptr) && p->g.M > 0) return fail(B2N_EINVAL, "NULL array");
+    return B2N_OK;
+}
+
+static int interp_fwd_impl(b2n_plan* p, const void* grid, void* samples, int nbatch, bool phase,
+                           cudaStream_t st) {
+    if (!p->tables_set) return fail(B2N_ESTATE, "tables not set");
+    if (p->g.M == 0) return B2N_OK;
+    bool done = false;
+    if (!p->opt_force_generic && !p->cplx_table) {
+        const void* ph = phase ? p->d_phase_s : nullptr;
+        int rc = p->precision == B2N_SINGLE
+                     ? tiled_fwd_f32(p->g, p->tables_equal, table_ptrs(p), p->d_tm_s, p->d_perm, p->d_items,
+                                     p->n_items, grid, samples, ph, nbatch, (int)p->opt_use_tma, st, &done)
+                     : tiled_fwd_f64(p->g, p->tables_equal, table_ptrs(p), p->d_tm_s, p->d_perm, p->d_items,
+                                     p->n_items, grid, samples, ph, nbatch, (int)p->opt_use_tma, st, &done);
+        if (rc != 0) return fail(B2N_ECUDA, "tiled forward launch failed: " + std::string(cudaGetErrorString((cudaError_t)rc)));
+    }
+    if (!done) {
+        int rc = run_generic(p, true, grid, samples, nbatch, phase, st);
+        if (rc != 0) return fail(B2N_ECUDA, "generic forward launch failed: " + std::string(cudaGetErrorString((cudaError_t)rc)));
+    }
+    p->last_fwd_kernel = done ? 1 : 0;
+    p->launches++;
+    return B2N_OK;
+}
+
+static int interp_adj_impl(b2n_plan* p, const void* samples, void* grid, int nbatch, bool phase,
+                           cudaStream_t st) {
+    if (!p->tables_set) return fail(B2N_ESTATE, "tables not set");
+    CU(cudaMemsetAsync(grid, 0, p->cplx_size() * p->g.PK * nbatch, st));
+    p->launches++;
+    if (p->g.M == 0) return B2N_OK;
+    bool done = false;
+    if (!p->opt_force_generic && !p->cplx_table) {
+        const void* ph = phase ? p->d_phase_s : nullptr;
+        int rc = p->precision == B2N_SINGLE
+                     ? slide_adj_f32(p->g, table_ptrs(p), p->d_tm_s, p->d_perm, samples, grid, ph, nbatch,
+                                     (int)p->opt_slide_pts, st, &done)
+                     : slide_adj_f64(p->g, table_ptrs(p), p->d_tm_s, p->d_perm, samples, grid, ph, nbatch,
+                                     (int)p->opt_slide_pts, st, &done);
+        if (rc != 0) return fail(B2N_ECUDA, "sliding adjoint launch failed: " + std::string(cudaGetErrorString((cudaError_t)rc)));
+    }
+    if (!done) {
+        int rc = run_generic(p, false, samples, grid, nbatch, phase, st);
+        if (rc != 0) return fail(B2N_ECUDA, "generic adjoint launch failed: " + std::string(cudaGetErrorString((cudaError_t)rc)));
+    }
+    p->last_adj_kernel = done ? 1 : 0;
+    p->launches++;
+    return B2N_OK;
+}
+
+extern "C" int b2n_interp_fwd(b2n_plan* p, const void* grid_dev, void* samples_dev, int nbatch,
+                              int apply_phase, void* stream) {
+    int rc = check_ready(p, grid_dev, samples_dev, nbatch);
+    if (rc) return rc;
+    CU(cudaSetDevice(p->device));
+    return interp_fwd_impl(p, grid_dev, samples_dev, nbatch, apply_phase && p->d_phase_s, (cudaStream_t)stream);
+}
+
+extern "C" int b2n_interp_adj(b2n_plan* p, const void* samples_dev, void* grid_dev, int nbatch,
+                              int apply_phase, void* stream) {
+    int rc = check_ready(p, samples_dev, grid_dev, nbatch);
+    if (rc) return rc;
+    if (grid_dev == nullptr) return fail(B2N_EINVAL, "NULL array");
+    CU(cudaSetDevice(p->device));
+    return interp_adj_impl(p, samples_dev, grid_dev, nbatch, apply_phase && p->d_phase_s, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------
+// sparse mode
+// ---------------------------------------------------------------------------------
+extern "C" int b2n_plan_set_sparse(b2n_plan* p, const void* const* coef,
+                                   const int32_t* const* kidx, int64_t M,
+                                   const void* row_phase, void* stream) {
+    if (p == nullptr || coef == nullptr || kidx == nullptr) return fail(B2N_EINVAL, "NULL argument");
+    if (!p->points_set) return fail(B2N_ESTATE, "set_points must precede set_sparse");
+    if (M != p->g.M) return fail(B2N_EINVAL, "M does not match set_points");
+    CU(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const Geom& g = p->g;
+    int nnzr = 1;
+    for (int d = 0; d < g.ndim; d++) nnzr *= g.J[d];
+    const int64_t nnz = M * nnzr;
+    const size_t vsz = p->cplx_table ? p->cplx_size() : p->real_size();
+    dev_free(p->d_ell_vals); dev_free(p->d_ell_cols);
+    p->d_ell_vals = nullptr; p->d_ell_cols = nullptr;
+    int rc;
+    if ((rc = dev_alloc(p, &p->d_ell_vals, vsz * nnz))) return rc;
+    if ((rc = dev_alloc(p, (void**)&p->d_ell_cols, sizeof(int32_t) * nnz))) return rc;
+    p->nnzr = nnzr;
+    if (nnz > 0) {
+        SparseSrc src{};
+        for (int d = 0; d < g.ndim; d++) { src.coef[d] = coef[d]; src.kidx[d] = kidx[d]; }
+        const int grid = grid_for(nnz, 256, p->sm_count);
+        const double2* rp = (const double2*)row_phase;
+        if (p->precision == B2N_SINGLE) {
+            if (p->cplx_table) build_ell_kernel<float, true><<<grid, 256, 0, st>>>(g, src, p->d_perm, rp, nnzr, (float2*)p->d_ell_vals, p->d_ell_cols);
+            else build_ell_kernel<float, false><<<grid, 256, 0, st>>>(g, src, p->d_perm, rp, nnzr, (float*)p->d_ell_vals, p->d_ell_cols);
+        } else {
+            if (p->cplx_table) build_ell_kernel<double, true><<<grid, 256, 0, st>>>(g, src, p->d_perm, rp, nnzr, (double2*)p->d_ell_vals, p->d_ell_cols);
+            else build_ell_kernel<double, false><<<grid, 256, 0, st>>>(g, src, p->d_perm, rp, nnzr, (double*)p->d_ell_vals, p->d_ell_cols);
+        }
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(st));
+        p->launches++;
+    }
+    p->sparse_set = true;
+    return B2N_OK;
+}
+
+extern "C" int64_t b2n_plan_sparse_nnz(b2n_plan* p) {
+    return p && p->sparse_set ? p->g.M * p->nnzr : -1;
+}
+
+extern "C" int b2n_plan_get_sparse(b2n_plan* p, void* vals_dev, int32_t* cols_dev, void* stream) {
+    if (p == nullptr) return fail(B2N_EINVAL, "NULL plan");
+    if (!p->sparse_set) return fail(B2N_ESTATE, "sparse matrix not set");
+    CU(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t nnz = p->g.M * p->nnzr;
+    if (nnz == 0) return B2N_OK;
+    const int grid = grid_for(nnz, 256, p->sm_count);
+    if (p->precision == B2N_SINGLE) {
+        if (p->cplx_table) ell_unpermute_kernel<float2><<<grid, 256, 0, st>>>(p->g.M, p->nnzr, p->d_perm, (const float2*)p->d_ell_vals, p->d_ell_cols, (float2*)vals_dev, cols_dev);
+        else ell_unpermute_kernel<float><<<grid, 256, 0, st>>>(p->g.M, p->nnzr, p->d_perm, (const float*)p->d_ell_vals, p->d_ell_cols, (float*)vals_dev, cols_dev);
+    } else {
+        if (p->cplx_table) ell_unpermute_kernel<double2><<<grid, 256, 0, st>>>(p->g.M, p->nnzr, p->d_perm, (const double2*)p->d_ell_vals, p->d_ell_cols, (double2*)vals_dev, cols_dev);
+        else ell_unpermute_kernel<double><<<grid, 256, 0, st>>>(p->g.M, p->nnzr, p->d_perm, (const double*)p->d_ell_vals, p->d_ell_cols, (double*)vals_dev, cols_dev);
+    }
+    CU(cudaGetLastError());
+    return B2N_OK;
+}
+
+template <typename T, bool CT>
+static void launch_spmv(b2n_plan* p, bool fwd, const void* in, void* out, int nbatch, bool phase,
+                        cudaStream_t st) {
+    using C = cplx_t<T>;
+    using W = typename WeightT<T, CT>::type;
+    const C* ph = phase ? (const C*)p->d_phase_s : nullptr;
+    const int grid = grid_for(p->g.M * 32, 256, p->sm_count, 16);
+    if (fwd)
+        spmv_fwd_kernel<T, CT><<<grid, 256, 0, st>>>(p->g, p->nnzr, (const W*)p->d_ell_vals, p->d_ell_cols, p->d_perm, (const C*)in, (C*)out, ph, nbatch);
+    else
+        spmv_adj_kernel<T, CT><<<grid, 256, 0, st>>>(p->g, p->nnzr, (const W*)p->d_ell_vals, p->d_ell_cols, p->d_perm, (const C*)in, (C*)out, ph, nbatch);
+}
+
+static int spmv_impl(b2n_plan* p, bool fwd, const void* in, void* out, int nbatch, bool phase,
+                     cudaStream_t st) {
+    if (!p->sparse_set) return fail(B2N_ESTATE, "sparse matrix not set");
+    if (!fwd) {
+        CU(cudaMemsetAsync(out, 0, p->cplx_size() * p->g.PK * nbatch, st));
+        p->launches++;
+    }
+    if (p->g.M == 0) return B2N_OK;
+    if (p->precision == B2N_SINGLE) {
+        if (p->cplx_table) launch_spmv<float, true>(p, fwd, in, out, nbatch, phase, st);
+        else launch_spmv<float, false>(p, fwd, in, out, nbatch, phase, st);
+    } else {
+        if (p->cplx_table) launch_spmv<double, true>(p, fwd, in, out, nbatch, phase, st);
+        else launch_spmv<double, false>(p, fwd, in, out, nbatch, phase, st);
+    }
+    CU(cudaGetLastError());
+    p->launches++;
+    return B2N_OK;
+}
+
+extern "C" int b2n_spmv_fwd(b2n_plan* p, const void* grid_dev, void* samples_dev, int nbatch,
+                            void* stream) {
+    int rc = check_ready(p, grid_dev, samples_dev, nbatch);
+    if (rc) return rc;
+    CU(cudaSetDevice(p->device));
+    return spmv_impl(p, true, grid_dev, samples_dev, nbatch, false, (cudaStream_t)stream);
+}
+
+extern "C" int b2n_spmv_adj(b2n_plan* p, const void* samples_dev, void* grid_dev, int nbatch,
+                            void* stream) {
+    int rc = check_ready(p, samples_dev, grid_dev, nbatch);
+    if (rc) return rc;
+    CU(cudaSetDevice(p->device));
+    return spmv_impl(p, false, samples_dev, grid_dev, nbatch, false, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------
+// full transforms: scale/pad -> cuFFT -> phase -> interpolate, and the mirror image
+// ---------------------------------------------------------------------------------
+static int get_fft(b2n_plan* p, int nbatch, cufftHandle* out) {
+    auto it = p->fft_plans.find(nbatch);
+    if (it != p->fft_plans.end()) {
+        *out = it->second;
+        return B2N_OK;
+    }
+    const Geom& g = p->g;
+    int n[3];
+    for (int d = 0; d < g.ndim; d++) n[d] = g.K[g.ndim - 1 - d];   // slowest axis first
+    cufftHandle h;
+    FFT(cufftCreate(&h));
+    size_t ws = 0;
+    FFT(cufftMakePlanMany(h, g.ndim, n, nullptr, 1, (int)g.PK, nullptr, 1, (int)g.PK,
+                          p->precision == B2N_SINGLE ? CUFFT_C2C : CUFFT_Z2Z, nbatch, &ws));
+    p->dev_bytes += (int64_t)ws;
+    p->fft_plans[nbatch] = h;
+    *out = h;
+    return B2N_OK;
+}
+
+static int ensure_work(b2n_plan* p, int nbatch) {
+    const size_t need = p->cplx_size() * (size_t)p->g.PK * nbatch;
+    if (need <= p->work_bytes) return B2N_OK;
+    if (p->d_work) {
+        cudaFree(p->d_work);
+        p->dev_bytes -= (int64_t)p->work_bytes;
+        p->d_work = nullptr;
+        p->work_bytes = 0;
+    }
+    int rc = dev_alloc(p, &p->d_work, need);
+    if (rc) return rc;
+    p->work_bytes = need;
+    return B2N_OK;
+}
+
+static AxisPtrs axis_ptrs(b2n_plan* p) {
+    AxisPtrs ax{};
+    for (int d = 0; d < 3; d++) { ax.sn[d] = p->d_sn[d]; ax.pb[d] = p->d_pb[d]; }
+    return ax;
+}
+
+template <typename T>
+static int nufft_fwd_t(b2n_plan* p, const void* image, void* samples, int nbatch, cudaStream_t st) {
+    using C = cplx_t<T>;
+    const Geom& g = p->g;
+    int rc;
+    if ((rc = ensure_work(p, nbatch))) return rc;
+    cufftHandle fft;
+    if ((rc = get_fft(p, nbatch, &fft))) return rc;
+    FFT(cufftSetStream(fft, st));
+    AxisPtrs ax = axis_ptrs(p);
+    C* work = (C*)p->d_work;
+    pre_scale_pad_kernel<T><<<grid_for(g.PK * nbatch, 256, p->sm_count, 32), 256, 0, st>>>(
+        g, ax, (T)p->fwd_scale, p->fwd_scale != 1.0, (const C*)image, work, nbatch);
+    CU(cudaGetLastError());
+    if (sizeof(T) == 4) FFT(cufftExecC2C(fft, (cufftComplex*)work, (cufftComplex*)work, CUFFT_FORWARD));
+    else FFT(cufftExecZ2Z(fft, (cufftDoubleComplex*)work, (cufftDoubleComplex*)work, CUFFT_FORWARD));
+    p->launches += 2;
+    if (p->have_pb) {
+        phase_before_kernel<T><<<grid_for(g.PK * nbatch, 256, p->sm_count, 32), 256, 0, st>>>(
+            g, ax, 0, work, nbatch);
+        CU(cudaGetLastError());
+        p->launches++;
+    }
+    if (p->opt_sparse_mode) return spmv_impl(p, true, work, samples, nbatch, p->d_phase_s != nullptr, st);
+    return interp_fwd_impl(p, work, samples, nbatch, p->d_phase_s != nullptr, st);
+}
+
+template <typename T>
+static int nufft_adj_t(b2n_plan* p, const void* samples, void* image, int nbatch, cudaStream_t st) {
+    using C = cplx_t<T>;
+    const Geom& g = p->g;
+    int rc;
+    if ((rc = ensure_work(p, nbatch))) return rc;
+    cufftHandle fft;
+    if ((rc = get_fft(p, nbatch, &fft))) return rc;
+    FFT(cufftSetStream(fft, st));
+    AxisPtrs ax = axis_ptrs(p);
+    C* work = (C*)p->d_work;
+    if (p->opt_sparse_mode) rc = spmv_impl(p, false, samples, work, nbatch, p->d_phase_s != nullptr, st);
+    else rc = interp_adj_impl(p, samples, work, nbatch, p->d_phase_s != nullptr, st);
+    if (rc) return rc;
+    if (p->have_pb) {
+        phase_before_kernel<T><<<grid_for(g.PK * nbatch, 256, p->sm_count, 32), 256, 0, st>>>(
+            g, ax, 1, work, nbatch);
+        CU(cudaGetLastError());
+        p->launches++;
+    }
+    if (sizeof(T) == 4) FFT(cufftExecC2C(fft, (cufftComplex*)work, (cufftComplex*)work, CUFFT_INVERSE));
+    else FFT(cufftExecZ2Z(fft, (cufftDoubleComplex*)work, (cufftDoubleComplex*)work, CUFFT_INVERSE));
+    post_crop_scale_kernel<T><<<grid_for(g.PN * nbatch, 256, p->sm_count, 32), 256, 0, st>>>(
+        g, ax, (T)p->adj_scale, p->adj_scale != 1.0, work, (C*)image, nbatch);
+    CU(cudaGetLastError());
+    p->launches += 2;
+    return B2N_OK;
+}
+
+extern "C" int b2n_nufft_fwd(b2n_plan* p, const void* image_dev, void* samples_dev, int nbatch,
+                             void* stream) {
+    int rc = check_ready(p, image_dev, samples_dev, nbatch);
+    if (rc) return rc;
+    if (image_dev == nullptr) return fail(B2N_EINVAL, "NULL array");
+    if (!p->scaling_set) return fail(B2N_ESTATE, "scaling not set");
+    CU(cudaSetDevice(p->device));
+    if (p->precision == B2N_SINGLE) return nufft_fwd_t<float>(p, image_dev, samples_dev, nbatch, (cudaStream_t)stream);
+    return nufft_fwd_t<double>(p, image_dev, samples_dev, nbatch, (cudaStream_t)stream);
+}
+
+extern "C" int b2n_nufft_adj(b2n_plan* p, const void* samples_dev, void* image_dev, int nbatch,
+                             void* stream) {
+    int rc = check_ready(p, samples_dev, image_dev, nbatch);
+    if (rc) return rc;
+    if (image_dev == nullptr) return fail(B2N_EINVAL, "NULL array");
+    if (!p->scaling_set) return fail(B2N_ESTATE, "scaling not set");
+    CU(cudaSetDevice(p->device));
+    if (p->precision == B2N_SINGLE) return nufft_adj_t<float>(p, samples_dev, image_dev, nbatch, (cudaStream_t)stream);
+    return nufft_adj_t<double>(p, samples_dev, image_dev, nbatch, (cudaStream_t)stream);
+}

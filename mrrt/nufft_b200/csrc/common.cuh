@@ -1,0 +1,116 @@
+// Shared device helpers for libb200nufft (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b2n {
+
+constexpr int kMaxJ = 16;   // largest supported kernel width per axis
+constexpr int kMaxDim = 3;
+
+template <typename T> struct Cplx;
+template <> struct Cplx<float> { using type = float2; };
+template <> struct Cplx<double> { using type = double2; };
+template <typename T> using cplx_t = typename Cplx<T>::type;
+
+template <typename T> __host__ __device__ inline cplx_t<T> make_c(T re, T im);
+template <> __host__ __device__ inline float2 make_c<float>(float re, float im) { return make_float2(re, im); }
+template <> __host__ __device__ inline double2 make_c<double>(double re, double im) { return make_double2(re, im); }
+
+// IEEE-correct division regardless of compile flags (tm must be bit-exact)
+__device__ __forceinline__ float div_rn(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ double div_rn(double a, double b) { return __ddiv_rn(a, b); }
+
+__device__ __forceinline__ bool is_finite(float a) { return isfinite(a); }
+__device__ __forceinline__ bool is_finite(double a) { return isfinite(a); }
+
+// window origin: koff = 1 + floor(t - J/2.) evaluated in double
+// (c/nufft_table.template.c:865-867; the promotion of a float t is exact)
+template <typename T> __device__ __forceinline__ int window_origin(T t, int J) {
+    return 1 + (int)floor((double)t - (double)J * 0.5);
+}
+
+__device__ __forceinline__ int wrap_index(int k, int K) {
+    int r = k % K;
+    return r < 0 ? r + K : r;
+}
+
+// Device-side description of the transform geometry (passed by value to kernels)
+struct Geom {
+    int ndim;
+    int N[3];
+    int K[3];
+    int J[3];
+    int L;
+    int ncenter[3];   // floor(J*L/2): centre of each table
+    int tlen[3];      // J*L+1
+    int tile[3];      // bin shape in grid cells
+    int nbin[3];      // bins per axis
+    int64_t PK;       // prod(K)
+    int64_t PN;       // prod(N)
+    int64_t M;        // samples
+    int cells_per_tile;
+};
+
+// One tap coefficient by linear interpolation of the centred table
+// (template.c:870-873): p=(t-k)*L in T, n=floor(p), alf=p-n,
+// coef=(1-alf)*h[n]+alf*h[n+1].  The n+1 read is clamped to the last entry: it can
+// only exceed the table when alf==0 (the reference reads one past the end there).
+template <typename T>
+__device__ __forceinline__ T tap_real(const T* __restrict__ h, int ncenter, int tlen, T t, int k, int L) {
+    const T p = (t - (T)k) * (T)L;
+    const T fl = floor(p);
+    const int n = (int)fl;
+    const T alf = p - fl;
+    const int i0 = ncenter + n;
+    const int i1 = min(i0 + 1, tlen - 1);
+    return ((T)1 - alf) * h[i0] + alf * h[i1];
+}
+
+template <typename T>
+__device__ __forceinline__ cplx_t<T> tap_cplx(const cplx_t<T>* __restrict__ h, int ncenter, int tlen, T t, int k, int L) {
+    const T p = (t - (T)k) * (T)L;
+    const T fl = floor(p);
+    const int n = (int)fl;
+    const T alf = p - fl;
+    const int i0 = ncenter + n;
+    const int i1 = min(i0 + 1, tlen - 1);
+    const cplx_t<T> a = h[i0], b = h[i1];
+    return make_c<T>(((T)1 - alf) * a.x + alf * b.x, ((T)1 - alf) * a.y + alf * b.y);
+}
+
+__device__ __forceinline__ void atomic_add_c(float2* p, float2 v) {
+    atomicAdd(p, v);   // REDG.E.ADD.F32x2 on sm_90+
+}
+__device__ __forceinline__ void atomic_add_c(double2* p, double2 v) {
+    atomicAdd(&p->x, v.x);
+    atomicAdd(&p->y, v.y);
+}
+
+template <typename C> __device__ __forceinline__ C cmul(C a, C b) {
+    C r;
+    r.x = a.x * b.x - a.y * b.y;
+    r.y = a.x * b.y + a.y * b.x;
+    return r;
+}
+template <typename C> __device__ __forceinline__ C cmul_conj(C a, C b) {   // a * conj(b)
+    C r;
+    r.x = a.x * b.x + a.y * b.y;
+    r.y = a.y * b.x - a.x * b.y;
+    return r;
+}
+
+// weight algebra: W is T (real table) or cplx_t<T> (complex table)
+template <typename T, bool CT> struct WeightT { using type = T; };
+template <typename T> struct WeightT<T, true> { using type = cplx_t<T>; };
+__device__ __forceinline__ float2 w_mul(float w, float2 v) { return make_float2(w * v.x, w * v.y); }
+__device__ __forceinline__ double2 w_mul(double w, double2 v) { return make_double2(w * v.x, w * v.y); }
+__device__ __forceinline__ float2 w_mul(float2 w, float2 v) { return cmul(w, v); }
+__device__ __forceinline__ double2 w_mul(double2 w, double2 v) { return cmul(w, v); }
+// conj(w) * v
+__device__ __forceinline__ float2 w_mul_conj(float w, float2 v) { return make_float2(w * v.x, w * v.y); }
+__device__ __forceinline__ double2 w_mul_conj(double w, double2 v) { return make_double2(w * v.x, w * v.y); }
+__device__ __forceinline__ float2 w_mul_conj(float2 w, float2 v) { return cmul_conj(v, w); }
+__device__ __forceinline__ double2 w_mul_conj(double2 w, double2 v) { return cmul_conj(v, w); }
+
+}  // namespace b2n

@@ -1,0 +1,30 @@
+// Host-side entry points of the per-precision kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace b2n {
+
+struct TablePtrs {
+    const void* h[3];
+};
+
+// each returns 0 or a cudaError_t
+#define B2N_DECLARE(SUF)                                                                          \
+    int generic_launch_##SUF(const Geom& g, int cplx_table, const TablePtrs& tabs, const void* tm_s, \
+                             const int32_t* perm, bool fwd, const void* in, void* out,           \
+                             const void* phase_s, int nbatch, int sm_count, cudaStream_t st);    \
+    int tiled_fwd_##SUF(const Geom& g, bool tables_equal, const TablePtrs& tabs, const void* tm_s, \
+                        const int32_t* perm, const int4* items, int64_t n_items, const void* grid, \
+                        void* out, const void* phase_s, int nbatch, int use_tma, cudaStream_t st, \
+                        bool* done);                                                             \
+    int slide_adj_##SUF(const Geom& g, const TablePtrs& tabs, const void* tm_s, const int32_t* perm, \
+                        const void* samples, void* grid, const void* phase_s, int nbatch,        \
+                        int pts_per_warp, cudaStream_t st, bool* done);
+B2N_DECLARE(f32)
+B2N_DECLARE(f64)
+#undef B2N_DECLARE
+
+}  // namespace b2n

@@ -1,0 +1,311 @@
+// Tiled forward interpolation (2-D / 3-D, real table, uniform compile-time J).
+//
+// One CTA = one work item = up to `chunk` bin-sorted samples of one bin.  The bin's
+// grid tile plus its J-1 halo is staged in shared memory -- by one TMA box load
+// (cp.async.bulk.tensor, mbarrier completion) when the box does not cross the periodic
+// boundary, by cooperative wrapped loads otherwise -- the Kaiser-Bessel lookup table is
+// staged next to it, and each thread then gathers its samples' J^d taps from shared
+// memory.  Samples inside a bin are sorted by cell (first axis fastest), so the lanes
+// of a warp read neighbouring or identical shared-memory words (broadcast).
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+#include "dispatch.h"
+
+namespace b2n {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    uint32_t spins = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (++spins > (1u << 26)) __trap();   // never hang the device on a bad descriptor
+    }
+}
+
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar,
+                                            int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar,
+                                            int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+
+struct TileShape {
+    int E1, E2, E3;   // tile + halo extents (cells)
+    int E1p;          // padded row pitch (cells)
+    int tile_bytes;   // E1p*E2*E3*sizeof(C) rounded up to 128
+};
+
+template <typename T, int NDIM, int J, bool TAB_SMEM>
+__global__ void __launch_bounds__(256)
+interp_fwd_tiled_kernel(const __grid_constant__ CUtensorMap tmap, Geom g, TileShape ts, int use_tma,
+                        const T* __restrict__ tab, const T* __restrict__ tm_s,
+                        const int32_t* __restrict__ perm, const int4* __restrict__ items,
+                        const cplx_t<T>* __restrict__ grid, cplx_t<T>* __restrict__ out,
+                        const cplx_t<T>* __restrict__ phase_s) {
+    using C = cplx_t<T>;
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t mbar;
+    C* tile = (C*)smem;
+    T* stab = (T*)(smem + ts.tile_bytes);
+    const int tid = threadIdx.x;
+    const int4 it = items[blockIdx.x];
+    const int b = blockIdx.y;
+    int bin = it.x;
+    const int o1 = (bin % g.nbin[0]) * g.tile[0];
+    bin /= g.nbin[0];
+    const int o2 = NDIM > 1 ? (bin % g.nbin[1]) * g.tile[1] : 0;
+    const int o3 = NDIM > 2 ? (bin / g.nbin[1]) * g.tile[2] : 0;
+    const bool interior = (o1 + ts.E1 <= g.K[0]) && (NDIM < 2 || o2 + ts.E2 <= g.K[1]) &&
+                          (NDIM < 3 || o3 + ts.E3 <= g.K[2]);
+    const bool tma = use_tma && interior;
+    if (tma) {
+        if (tid == 0) mbar_init(&mbar, 1);
+        __syncthreads();
+        if (tid == 0) {
+            mbar_expect_tx(&mbar, (uint32_t)(ts.E1p * ts.E2 * ts.E3 * (int)sizeof(C)));
+            if (NDIM == 2) tma_load_3d(tile, &tmap, &mbar, 2 * o1, o2, b);
+            else tma_load_4d(tile, &tmap, &mbar, 2 * o1, o2, o3, b);
+        }
+    } else {
+        const C* __restrict__ gb = grid + (int64_t)b * g.PK;
+        const int n = ts.E1 * ts.E2 * ts.E3;
+        for (int e = tid; e < n; e += blockDim.x) {
+            const int i1 = e % ts.E1;
+            const int r = e / ts.E1;
+            const int i2 = r % ts.E2;
+            const int i3 = r / ts.E2;
+            int k1 = o1 + i1; if (k1 >= g.K[0]) k1 -= g.K[0];
+            int k2 = o2 + i2; if (k2 >= g.K[1]) k2 -= g.K[1];
+            int k3 = o3 + i3; if (k3 >= g.K[2]) k3 -= g.K[2];
+            // K may be smaller than tile+halo on tiny grids
+            k1 %= g.K[0]; k2 %= g.K[1]; k3 %= g.K[2];
+            tile[(i3 * ts.E2 + i2) * ts.E1p + i1] = __ldg(gb + ((int64_t)k3 * g.K[1] + k2) * g.K[0] + k1);
+        }
+    }
+    if (TAB_SMEM) {
+        for (int e = tid; e < g.tlen[0]; e += blockDim.x) stab[e] = __ldg(tab + e);
+    }
+    __syncthreads();
+    if (tma) mbar_wait(&mbar, 0);
+    const T* __restrict__ h = TAB_SMEM ? stab : tab;
+    const int64_t M = g.M;
+    const int end = it.y + it.z;
+    for (int i = it.y + tid; i < end; i += blockDim.x) {
+        T w[NDIM][J];
+        int c[NDIM];
+#pragma unroll
+        for (int d = 0; d < NDIM; d++) {
+            const T t = tm_s[(int64_t)d * M + i];
+            const int koff = window_origin<T>(t, J);
+            const int od = d == 0 ? o1 : (d == 1 ? o2 : o3);
+            c[d] = wrap_index(koff, g.K[d]) - od;
+#pragma unroll
+            for (int j = 0; j < J; j++)
+                w[d][j] = tap_real<T>(h, g.ncenter[0], g.tlen[0], t, koff + j, g.L);
+        }
+        C s3 = make_c<T>(0, 0);
+#pragma unroll
+        for (int j3 = 0; j3 < (NDIM > 2 ? J : 1); j3++) {
+            C s2 = make_c<T>(0, 0);
+#pragma unroll
+            for (int j2 = 0; j2 < (NDIM > 1 ? J : 1); j2++) {
+                int row = c[0];
+                if (NDIM == 2) row += (c[1] + j2) * ts.E1p;
+                if (NDIM == 3) row += ((c[NDIM > 2 ? 2 : 0] + j3) * ts.E2 + (c[1] + j2)) * ts.E1p;
+                const C* __restrict__ pr = tile + row;
+                C s1 = make_c<T>(0, 0);
+#pragma unroll
+                for (int j1 = 0; j1 < J; j1++) {
+                    const C v = pr[j1];
+                    s1.x += w[0][j1] * v.x;
+                    s1.y += w[0][j1] * v.y;
+                }
+                s2.x += w[NDIM > 1 ? 1 : 0][j2] * s1.x;
+                s2.y += w[NDIM > 1 ? 1 : 0][j2] * s1.y;
+            }
+            if (NDIM > 2) {
+                s3.x += w[NDIM > 2 ? 2 : 0][j3] * s2.x;
+                s3.y += w[NDIM > 2 ? 2 : 0][j3] * s2.y;
+            } else {
+                s3 = s2;
+            }
+        }
+        if (phase_s != nullptr) s3 = cmul(s3, phase_s[i]);
+        out[(int64_t)b * M + perm[i]] = s3;
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// tensor map over the grid viewed as REAL elements: dims (2*K1, K2[, K3], nbatch)
+template <typename T, int NDIM>
+static bool make_grid_tmap(CUtensorMap* map, const Geom& g, const TileShape& ts, const void* grid,
+                           int nbatch) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (enc == nullptr) return false;
+    const size_t cs = 2 * sizeof(T);
+    if ((g.K[0] * cs) % 16 != 0 || ((uintptr_t)grid % 16) != 0) return false;
+    if ((ts.E1p * cs) % 16 != 0 || 2 * ts.E1p > 256 || ts.E2 > 256 || ts.E3 > 256) return false;
+    cuuint64_t dims[4];
+    cuuint64_t strides[3];
+    cuuint32_t box[4];
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    dims[0] = 2 * (cuuint64_t)g.K[0];
+    box[0] = 2 * ts.E1p;
+    dims[1] = g.K[1];
+    box[1] = ts.E2;
+    strides[0] = g.K[0] * cs;
+    if (NDIM == 2) {
+        dims[2] = nbatch;
+        box[2] = 1;
+        strides[1] = (cuuint64_t)g.PK * cs;
+    } else {
+        dims[2] = g.K[2];
+        box[2] = ts.E3;
+        strides[1] = (cuuint64_t)g.K[0] * g.K[1] * cs;
+        dims[3] = nbatch;
+        box[3] = 1;
+        strides[2] = (cuuint64_t)g.PK * cs;
+    }
+    CUresult r = enc(map, sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64,
+                     NDIM + 1, const_cast<void*>(grid), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+template <typename T, int NDIM, int J>
+static int launch_fwd_tiled(const Geom& g, const TablePtrs& tabs, const void* tm_s,
+                            const int32_t* perm, const int4* items, int64_t n_items,
+                            const void* grid, void* out, const void* phase_s, int nbatch,
+                            int use_tma, cudaStream_t st, bool* done) {
+    using C = cplx_t<T>;
+    *done = false;
+    TileShape ts;
+    ts.E1 = g.tile[0] + J - 1;
+    ts.E2 = NDIM > 1 ? g.tile[1] + J - 1 : 1;
+    ts.E3 = NDIM > 2 ? g.tile[2] + J - 1 : 1;
+    // TMA box rows must be a multiple of 16 bytes
+    const int align = 16 / (int)sizeof(C) > 1 ? 16 / (int)sizeof(C) : 1;
+    ts.E1p = (ts.E1 + align - 1) / align * align;
+    const size_t tb = (size_t)ts.E1p * ts.E2 * ts.E3 * sizeof(C);
+    ts.tile_bytes = (int)((tb + 127) / 128 * 128);
+    const size_t tab_bytes = (size_t)g.tlen[0] * sizeof(T);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int max_smem = 0;
+    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    bool tab_smem = true;
+    size_t smem = ts.tile_bytes + tab_bytes;
+    if (smem > (size_t)max_smem || smem > 100 * 1024) {
+        tab_smem = false;
+        smem = ts.tile_bytes;
+    }
+    if (smem > (size_t)max_smem) return 0;
+    CUtensorMap map;
+    memset(&map, 0, sizeof(map));
+    const bool tma_ok = use_tma && make_grid_tmap<T, NDIM>(&map, g, ts, grid, nbatch);
+    dim3 gridDim((unsigned)n_items, (unsigned)nbatch);
+    cudaError_t e;
+    if (tab_smem) {
+        auto k = interp_fwd_tiled_kernel<T, NDIM, J, true>;
+        e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        k<<<gridDim, 256, smem, st>>>(map, g, ts, tma_ok ? 1 : 0, (const T*)tabs.h[0], (const T*)tm_s,
+                                      perm, items, (const C*)grid, (C*)out, (const C*)phase_s);
+    } else {
+        auto k = interp_fwd_tiled_kernel<T, NDIM, J, false>;
+        e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        k<<<gridDim, 256, smem, st>>>(map, g, ts, tma_ok ? 1 : 0, (const T*)tabs.h[0], (const T*)tm_s,
+                                      perm, items, (const C*)grid, (C*)out, (const C*)phase_s);
+    }
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    *done = true;
+    return 0;
+}
+
+// returns 0 or a cudaError_t; *done tells whether the tiled kernel took the call
+template <typename T>
+static int tiled_fwd_t(const Geom& g, bool tables_equal, const TablePtrs& tabs, const void* tm_s,
+                       const int32_t* perm, const int4* items, int64_t n_items, const void* grid,
+                       void* out, const void* phase_s, int nbatch, int use_tma, cudaStream_t st,
+                       bool* done) {
+    *done = false;
+    if (g.ndim < 2 || !tables_equal || n_items == 0 || n_items > 0x7fffffff || nbatch > 65535)
+        return 0;
+    for (int d = 1; d < g.ndim; d++)
+        if (g.J[d] != g.J[0]) return 0;
+#define B2N_TILED(ND, JJ)                                                                      \
+    return launch_fwd_tiled<T, ND, JJ>(g, tabs, tm_s, perm, items, n_items, grid, out, phase_s, \
+                                       nbatch, use_tma, st, done)
+    if (g.ndim == 2) {
+        switch (g.J[0]) {
+            case 4: B2N_TILED(2, 4);
+            case 6: B2N_TILED(2, 6);
+            case 8: B2N_TILED(2, 8);
+            default: return 0;
+        }
+    }
+    switch (g.J[0]) {
+        case 4: B2N_TILED(3, 4);
+        case 6: B2N_TILED(3, 6);
+        case 8: B2N_TILED(3, 8);
+        default: return 0;
+    }
+#undef B2N_TILED
+}
+
+}  // namespace b2n

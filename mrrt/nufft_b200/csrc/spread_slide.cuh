@@ -1,0 +1,216 @@
+// Sliding-window adjoint gridding (3-D, real table, uniform compile-time J).
+//
+// Shared-memory float atomics are CAS loops on sm_100a (ATOMS.CAST.SPIN), so the
+// adjoint does not accumulate in shared memory at all.  Instead each warp walks a
+// contiguous run of the cell-sorted samples ONE SAMPLE AT A TIME and keeps the sample's
+// whole J x J x J window of partial sums in REGISTERS: lane <-> (j2, j3) row of the
+// window, J accumulators per row along the fastest axis.  Because consecutive samples
+// of the sorted order sit in the same or the next cell along axis 1, the window slides:
+// only the column that leaves the window is flushed to HBM/L2 (one vector RED per row,
+// REDG.E.ADD.F32x2), everything else stays in registers.  A cell therefore receives
+// J*J reductions in total instead of one per contributing sample and tap, and there are
+// no write conflicts inside a warp by construction.
+//
+// Arithmetic per sample follows c/nufft_table.template.c:1122-1163: v3 = coef3*f,
+// v2 = coef2*v3, ck += coef1*v2.
+#pragma once
+#include "common.cuh"
+#include "dispatch.h"
+
+namespace b2n {
+
+template <typename T, int J>
+__global__ void __launch_bounds__(128)
+spread_slide3d_kernel(Geom g, const T* __restrict__ h1, const T* __restrict__ h2,
+                      const T* __restrict__ h3, const T* __restrict__ tm_s,
+                      const int32_t* __restrict__ perm, const cplx_t<T>* __restrict__ samples,
+                      cplx_t<T>* __restrict__ grid, const cplx_t<T>* __restrict__ phase_s,
+                      int pts_per_warp) {
+    using C = cplx_t<T>;
+    constexpr int R = J * J;                 // rows of the window
+    constexpr int RPL = (R + 31) / 32;       // rows per lane
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t M = g.M;
+    const int64_t begin = warp * pts_per_warp;
+    if (begin >= M) return;
+    const int64_t end = begin + pts_per_warp < M ? begin + pts_per_warp : M;
+    const int b = blockIdx.y;
+    const C* __restrict__ sb = samples + (int64_t)b * M;
+    C* __restrict__ gb = grid + (int64_t)b * g.PK;
+    const int K1 = g.K[0], K2 = g.K[1], K3 = g.K[2];
+
+    // static role of this lane: its rows (j2, j3) and, for the cooperative weight
+    // evaluation, one (axis, tap) pair
+    int rj2[RPL], rj3[RPL];
+    bool rvalid[RPL];
+#pragma unroll
+    for (int s = 0; s < RPL; s++) {
+        const int r = lane + 32 * s;
+        rvalid[s] = r < R;
+        rj2[s] = (r % R) % J;
+        rj3[s] = (r % R) / J;
+    }
+    const int wax = lane / J;                // 0,1,2 for lanes < 3J
+    const int wj = lane - wax * J;
+    const T* __restrict__ wh = wax == 0 ? h1 : (wax == 1 ? h2 : h3);
+
+    C acc[RPL][J];
+    int rowbase[RPL];
+#pragma unroll
+    for (int s = 0; s < RPL; s++) {
+        rowbase[s] = 0;
+#pragma unroll
+        for (int j = 0; j < J; j++) acc[s][j] = make_c<T>(0, 0);
+    }
+    int W1 = 0, W2 = -1, W3 = -1;            // wrapped window origin; W2<0: no window yet
+
+    for (int64_t base = begin; base < end; base += 32) {
+        const int cnt = (int)(end - base < 32 ? end - base : 32);
+        // coalesced load of up to 32 samples; lanes then take turns
+        T lt1 = 0, lt2 = 0, lt3 = 0;
+        C lf = make_c<T>(0, 0);
+        if (lane < cnt) {
+            const int64_t i = base + lane;
+            lt1 = tm_s[i];
+            lt2 = tm_s[M + i];
+            lt3 = tm_s[2 * M + i];
+            lf = sb[perm[i]];
+            if (phase_s != nullptr) lf = cmul_conj(lf, phase_s[i]);
+        }
+        for (int q = 0; q < cnt; q++) {
+            const T t1 = __shfl_sync(FULL, lt1, q);
+            const T t2 = __shfl_sync(FULL, lt2, q);
+            const T t3 = __shfl_sync(FULL, lt3, q);
+            C f;
+            f.x = __shfl_sync(FULL, lf.x, q);
+            f.y = __shfl_sync(FULL, lf.y, q);
+            const int ko1 = window_origin<T>(t1, J);
+            const int ko2 = window_origin<T>(t2, J);
+            const int ko3 = window_origin<T>(t3, J);
+            // cooperative weights: lane (axis, tap) evaluates one table coefficient
+            T wl = 0;
+            if (lane < 3 * J) {
+                const T ta = wax == 0 ? t1 : (wax == 1 ? t2 : t3);
+                const int ka = (wax == 0 ? ko1 : (wax == 1 ? ko2 : ko3)) + wj;
+                wl = tap_real<T>(wh, g.ncenter[wax], g.tlen[wax], ta, ka, g.L);
+            }
+            const int kw1 = wrap_index(ko1, K1);
+            const int kw2 = wrap_index(ko2, K2);
+            const int kw3 = wrap_index(ko3, K3);
+            const int d = kw1 - W1;
+            if (kw2 != W2 || kw3 != W3 || d < 0 || d >= J) {
+                // new row of cells (or a jump): flush the whole window
+                if (W2 >= 0) {
+#pragma unroll
+                    for (int j = 0; j < J; j++) {
+                        int k1 = W1 + j;
+                        if (k1 >= K1) k1 -= K1;
+#pragma unroll
+                        for (int s = 0; s < RPL; s++) {
+                            const C a = acc[s][j];
+                            if (rvalid[s] && (a.x != (T)0 || a.y != (T)0))
+                                atomic_add_c(gb + rowbase[s] + k1, a);
+                            acc[s][j] = make_c<T>(0, 0);
+                        }
+                    }
+                }
+                W1 = kw1; W2 = kw2; W3 = kw3;
+#pragma unroll
+                for (int s = 0; s < RPL; s++) {
+                    int k2 = W2 + rj2[s]; if (k2 >= K2) k2 -= K2;
+                    int k3 = W3 + rj3[s]; if (k3 >= K3) k3 -= K3;
+                    rowbase[s] = (k3 * K2 + k2) * K1;
+                }
+            } else {
+                for (int sft = 0; sft < d; sft++) {
+                    // slide by one cell: retire column 0
+                    int k1 = W1; if (k1 >= K1) k1 -= K1;
+#pragma unroll
+                    for (int s = 0; s < RPL; s++) {
+                        const C a = acc[s][0];
+                        if (rvalid[s] && (a.x != (T)0 || a.y != (T)0))
+                            atomic_add_c(gb + rowbase[s] + k1, a);
+#pragma unroll
+                        for (int j = 0; j + 1 < J; j++) acc[s][j] = acc[s][j + 1];
+                        acc[s][J - 1] = make_c<T>(0, 0);
+                    }
+                    W1++;
+                }
+            }
+            // accumulate this sample into the register window
+            T w1[J];
+#pragma unroll
+            for (int j = 0; j < J; j++) w1[j] = __shfl_sync(FULL, wl, j);
+#pragma unroll
+            for (int s = 0; s < RPL; s++) {
+                const T w2 = __shfl_sync(FULL, wl, J + rj2[s]);
+                const T w3 = __shfl_sync(FULL, wl, 2 * J + rj3[s]);
+                if (rvalid[s]) {
+                    const T v3x = w3 * f.x, v3y = w3 * f.y;
+                    const T v2x = w2 * v3x, v2y = w2 * v3y;
+#pragma unroll
+                    for (int j = 0; j < J; j++) {
+                        acc[s][j].x += w1[j] * v2x;
+                        acc[s][j].y += w1[j] * v2y;
+                    }
+                }
+            }
+        }
+    }
+    if (W2 >= 0) {
+#pragma unroll
+        for (int j = 0; j < J; j++) {
+            int k1 = W1 + j;
+            if (k1 >= K1) k1 -= K1;
+#pragma unroll
+            for (int s = 0; s < RPL; s++) {
+                const C a = acc[s][j];
+                if (rvalid[s] && (a.x != (T)0 || a.y != (T)0)) atomic_add_c(gb + rowbase[s] + k1, a);
+            }
+        }
+    }
+}
+
+template <typename T, int J>
+static int launch_slide(const Geom& g, const TablePtrs& tabs, const void* tm_s, const int32_t* perm,
+                        const void* samples, void* grid, const void* phase_s, int nbatch,
+                        int pts_per_warp, cudaStream_t st, bool* done) {
+    using C = cplx_t<T>;
+    const int64_t nwarps = (g.M + pts_per_warp - 1) / pts_per_warp;
+    const int64_t nblocks = (nwarps + 3) / 4;
+    if (nblocks > 0x7fffffff || nbatch > 65535) return 0;
+    dim3 gd((unsigned)nblocks, (unsigned)nbatch);
+    spread_slide3d_kernel<T, J><<<gd, 128, 0, st>>>(
+        g, (const T*)tabs.h[0], (const T*)tabs.h[1], (const T*)tabs.h[2], (const T*)tm_s, perm,
+        (const C*)samples, (C*)grid, (const C*)phase_s, pts_per_warp);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    *done = true;
+    return 0;
+}
+
+template <typename T>
+static int slide_adj_t(const Geom& g, const TablePtrs& tabs, const void* tm_s, const int32_t* perm,
+                       const void* samples, void* grid, const void* phase_s, int nbatch,
+                       int pts_per_warp, cudaStream_t st, bool* done) {
+    *done = false;
+    if (g.ndim != 3) return 0;
+    if (g.J[1] != g.J[0] || g.J[2] != g.J[0]) return 0;
+    // the window must not wrap onto itself
+    if (g.K[0] < g.J[0] || g.K[1] < g.J[0] || g.K[2] < g.J[0]) return 0;
+#define B2N_SLIDE(JJ) \
+    return launch_slide<T, JJ>(g, tabs, tm_s, perm, samples, grid, phase_s, nbatch, pts_per_warp, st, done)
+    switch (g.J[0]) {
+        case 4: B2N_SLIDE(4);
+        case 5: B2N_SLIDE(5);
+        case 6: B2N_SLIDE(6);
+        case 7: B2N_SLIDE(7);
+        case 8: B2N_SLIDE(8);
+        default: return 0;
+    }
+#undef B2N_SLIDE
+}
+
+}  // namespace b2n

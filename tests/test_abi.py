@@ -1,0 +1,99 @@
+"""CPU checks of the drop-in boundary: the shared library loads, exports every symbol
+include/b200nufft.h declares, and the Python binding covers each of them.  No compute."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "b200nufft.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(b2n_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from mrrt.nufft_b200 import _lib
+
+    names = _declared()
+    assert len(names) >= 20
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n), n
+    assert sorted(_lib.SIGNATURES) == names
+    assert _lib.load().b2n_version() >= 100
+
+
+def test_plan_create_argument_errors_without_gpu():
+    """Argument validation happens before any CUDA work where possible."""
+    from mrrt.nufft_b200 import _lib
+
+    lib = _lib.load()
+    plan = ctypes.c_void_p()
+    a3 = lambda *v: (ctypes.c_int * 3)(*v)
+    rc = lib.b2n_plan_create(4, a3(8, 8, 8), a3(16, 16, 16), a3(6, 6, 6), 1024, 0, 0, 0,
+                             ctypes.byref(plan))
+    assert rc == _lib.B2N_EINVAL
+    assert b"dimensions > 3" in lib.b2n_last_error()
+    with pytest.raises(ValueError):
+        _lib.check(rc)
+
+
+def test_host_plan_math_matches_golden_tables():
+    """Lookup tables are bit-identical to the reference's (float32-accurate in every
+    precision), including odd N and complex phasing."""
+    from golden_util import tables
+    from mrrt.nufft_b200 import _plan_math as pm
+
+    for key, h in tables().items():
+        N, K, J, L, ph = key.split("_")
+        mine = pm.lookup_table(int(N[1:]), int(J[1:]), int(K[1:]), int(L[1:]), ph)
+        assert np.array_equal(mine, h), key
+
+
+def test_host_plan_math_matches_golden_scaling():
+    from golden_util import case_names, load_case
+    from mrrt.nufft_b200 import _plan_math as pm
+    from mrrt.nufft_b200._kernels import BeattyKernel
+
+    for name in case_names("d[123]_table_*_K32_J6") + case_names("d3_table_double_*") + \
+            case_names("d1_table_*") + case_names("d3_mid*"):
+        cfg, z = load_case(name)
+        Nd, Kd, Jd = cfg["Nd"], cfg["Kd"], cfg["Jd"]
+        alphas = [BeattyKernel.beatty_alpha(j, k, n) for j, k, n in zip(Jd, Kd, Nd)]
+        sn1d = pm.deapodization_1d(Nd, Kd, Jd, alphas, cfg["phasing"])
+        rdt, cdt = pm.real_cplx_dtypes(cfg["precision"])
+        assert np.array_equal(pm.dense_sn(sn1d, tuple(Nd)).astype(rdt), z["sn"]), name
+        if "phase_after" in z:
+            mids = pm.n_mid(Nd, cfg["phasing"])
+            pa = pm.phase_after(z["omega"], mids, cfg["n_shift"], rdt, cdt)
+            assert np.array_equal(pa, z["phase_after"]), name
+
+
+def test_no_cpu_fallback():
+    import torch
+    from mrrt.nufft_b200 import NufftBase
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError):
+        NufftBase(Nd=(16, 16), omega=np.zeros((4, 2)), Jd=6)
+
+
+def test_kernel_objects():
+    """tests/test_kernels.py:17-58 of the reference: support, positivity, validation."""
+    from mrrt.nufft_b200 import BeattyKernel, kaiser_bessel
+
+    k = BeattyKernel((6, 4), (64, 48), (128, 72))
+    for d, J in enumerate((6, 4)):
+        x = np.linspace(-J / 2, J / 2, 101)
+        y = k.kernels[d](x)
+        assert np.all(y[1:-1] > 0) and y[0] == 0 and y[-1] == 0
+        assert np.all(k.kernels[d](np.array([J / 2 + 0.1, -J])) == 0)
+    assert abs(kaiser_bessel(np.array([0.0]), 6, k.alpha[0])[0] - 1.0) < 1e-15
+    with pytest.raises(ValueError):
+        BeattyKernel((6, 6), (64,), (128, 128))

@@ -1,0 +1,256 @@
+"""Parity of the CUDA path (through the C ABI) against the golden vectors of the real
+reference and against the CPU oracle on seeded inputs.  Needs a B200."""
+import numpy as np
+import pytest
+
+from golden_util import (TOL, case_names, ctor_kwargs, grid_only_inputs, load_case,
+                         rel_l2, table_key, tables)
+
+pytestmark = pytest.mark.gpu
+
+
+def _op(cfg, omega, **extra):
+    from mrrt.nufft_b200 import NufftBase
+
+    return NufftBase(omega=omega, on_gpu=True, **ctor_kwargs(cfg), **extra)
+
+
+@pytest.mark.parametrize("variant", ["auto", "generic"])
+@pytest.mark.parametrize("name", case_names())
+def test_golden(name, variant):
+    """fft / adj / grid_only stages vs what the reference package produced."""
+    from mrrt.nufft_b200 import nufft_adj, nufft_forward
+
+    cfg, z = load_case(name)
+    tol = TOL[cfg["precision"]]
+    opts = {"force_generic": 1} if variant == "generic" else {}
+    A = _op(cfg, z["omega"], options=opts)
+    # plan arrays: bit-exact
+    assert np.array_equal(A.sn, z["sn"])
+    if "phase_after" in z:
+        assert np.array_equal(A.phase_after, z["phase_after"])
+    if cfg["mode"] == "table":
+        assert np.array_equal(A.tm.cpu().numpy(), z["tm"])
+        for d in range(A.ndim):
+            key = table_key(A.Nd[d], A.Kd[d], A.Jd[d], cfg["Ld"], cfg["phasing"])
+            assert np.array_equal(A.h[d], tables()[key].astype(A.h[d].dtype))
+    y = A.fft(z["x"])
+    assert isinstance(y, np.ndarray) and y.dtype == z["y"].dtype and y.shape == z["y"].shape
+    assert rel_l2(y, z["y"]) <= tol
+    xa = A.adj(z["y"])
+    assert xa.dtype == z["x_adj"].dtype and xa.shape == z["x_adj"].shape
+    assert rel_l2(xa, z["x_adj"]) <= tol
+    g, ysamp = grid_only_inputs(cfg["seed"], int(np.prod(A.Kd)), A.M, cfg["n_reps"],
+                                A._cplx_dtype)
+    out = nufft_forward(A, g, grid_only=True).cpu().numpy()
+    assert rel_l2(out, z["interp_out"]) <= tol
+    out = nufft_adj(A, ysamp, grid_only=True).cpu().numpy()
+    assert rel_l2(out, z["grid_out"]) <= tol
+    if variant == "auto" and cfg["mode"] == "table" and cfg["phasing"] == "real" and A.ndim == 3 \
+            and len(set(A.Jd)) == 1 and A.Jd[0] in (4, 6, 8):
+        assert A.option("last_fwd_kernel") == 1   # tiled TMA kernel really ran
+        assert A.option("last_adj_kernel") == 1   # sliding-window kernel really ran
+
+
+@pytest.mark.parametrize("name", ["d1_sparse_single_real", "d1_sparse_double_complex",
+                                  "adjshift_sparse_real", "adjshift_sparse_complex"])
+def test_sparse_matrix_entries(name):
+    """The device-built interpolation matrix equals the reference's `p`."""
+    cfg, z = load_case(name)
+    A = _op(cfg, z["omega"])
+    p = A.p
+    p.sort_indices()
+    assert np.array_equal(p.indptr, z["p_indptr"])
+    assert np.array_equal(p.indices, z["p_indices"])
+    if cfg["phasing"] == "real":
+        assert np.array_equal(p.data, z["p_data"])
+    else:
+        assert rel_l2(p.data, z["p_data"]) <= 1e-6
+
+
+@pytest.mark.parametrize("precision", ["single", "double"])
+@pytest.mark.parametrize("ndim", [1, 2, 3])
+def test_bin_sort_bit_exact(ndim, precision):
+    """bin ids, sort keys and the stable permutation vs the CPU restatement."""
+    from oracle import nufft_oracle as orc
+
+    rs = np.random.RandomState(10 + ndim)
+    Nd = (40, 36, 30)[:ndim]
+    Kd = (80, 54, 45)[:ndim]
+    M = 20000
+    om = (rs.rand(M, ndim) * 4 - 2) * np.pi          # outside [-pi, pi): wrap exercised
+    om[:50] = 0.0                                     # repeated centre samples
+    om[50:60] = np.pi
+    om[60:70] = -np.pi
+    from mrrt.nufft_b200 import NufftBase
+
+    A = NufftBase(Nd=Nd, omega=om, Jd=6, Kd=Kd, precision=precision)
+    O = orc.OracleNufft(Nd=Nd, omega=om, Jd=6, Kd=Kd, precision=precision)
+    assert np.array_equal(A.tm.cpu().numpy(), O.tm)
+    bins, keys, perm = A.bin_sort()
+    obins, okeys, operm = orc.bin_sort(O.tm, O.Jd, O.Kd, A.tile)
+    assert np.array_equal(bins.cpu().numpy(), obins)
+    assert np.array_equal(keys.cpu().numpy(), okeys)
+    assert np.array_equal(perm.cpu().numpy(), operm)
+
+
+def _radial3d(S, n):
+    s = np.arange(S)
+    z = 1 - (2 * s + 1) / S
+    phi = s * np.pi * (3 - np.sqrt(5))
+    rxy = np.sqrt(1 - z * z)
+    d = np.stack([rxy * np.cos(phi), rxy * np.sin(phi), z], 1)
+    r = 2 * np.pi * (np.arange(n) - n // 2) / n
+    return (d[:, None, :] * r[None, :, None]).reshape(-1, 3)
+
+
+@pytest.mark.parametrize("precision", ["single", "double"])
+@pytest.mark.parametrize("variant", ["auto", "generic", "no_tma"])
+def test_mid_3d_radial_vs_oracle(precision, variant):
+    """3-D radial, J=6, Kd=1.5N (BASELINE configs[4] scaled down) vs the live oracle."""
+    from oracle import nufft_oracle as orc
+    from mrrt.nufft_b200 import NufftBase, nufft_adj, nufft_forward
+
+    Nd, Kd = (32, 32, 32), (48, 48, 48)
+    rdt = np.float32 if precision == "single" else np.float64
+    om = _radial3d(700, 64).astype(rdt)
+    opts = {"generic": {"force_generic": 1}, "no_tma": {"use_tma": 0}, "auto": {}}[variant]
+    A = NufftBase(Nd=Nd, omega=om, Jd=6, Kd=Kd, precision=precision, options=opts)
+    eng = "reference" if orc.have_reference_engine() else "port"
+    O = orc.OracleNufft(Nd=Nd, omega=om, Jd=6, Kd=Kd, precision=precision, engine=eng)
+    rs = np.random.RandomState(0)
+    x = (rs.standard_normal(Nd) + 1j * rs.standard_normal(Nd)).astype(A._cplx_dtype)
+    tol = TOL[precision]
+    y, yo = A.fft(x), O.fft(x)
+    assert rel_l2(y, yo) <= tol
+    assert rel_l2(A.adj(yo), O.adj(yo)) <= tol
+    g, ys = grid_only_inputs(5, int(np.prod(Kd)), A.M, 2, A._cplx_dtype)
+    assert rel_l2(nufft_forward(A, g, grid_only=True).cpu().numpy(), O.fft(g, grid_only=True)) <= tol
+    assert rel_l2(nufft_adj(A, ys, grid_only=True).cpu().numpy(), O.adj(ys, grid_only=True)) <= tol
+    assert rel_l2(A.norm(x), O.norm(x)) <= 2 * tol
+
+
+@pytest.mark.parametrize("precision", ["single", "double"])
+def test_mid_2d_radial_vs_oracle(precision):
+    """2-D radial 128^2, Kd=2N, J=6 (BASELINE configs[0] scaled down), 3 coils."""
+    from oracle import nufft_oracle as orc
+    from mrrt.nufft_b200 import NufftBase
+
+    Nd, Kd = (128, 128), (256, 256)
+    S, n = 101, 256
+    ang = np.pi * np.arange(S) / S
+    r = 2 * np.pi * (np.arange(n) - n / 2) / n
+    rdt = np.float32 if precision == "single" else np.float64
+    om = np.stack([np.outer(np.cos(ang), r).ravel(), np.outer(np.sin(ang), r).ravel()], 1).astype(rdt)
+    A = NufftBase(Nd=Nd, omega=om, Jd=6, Kd=Kd, precision=precision)
+    eng = "reference" if orc.have_reference_engine() else "port"
+    O = orc.OracleNufft(Nd=Nd, omega=om, Jd=6, Kd=Kd, precision=precision, engine=eng)
+    rs = np.random.RandomState(0)
+    x = (rs.standard_normal(Nd + (3,)) + 1j * rs.standard_normal(Nd + (3,))).astype(A._cplx_dtype)
+    tol = TOL[precision]
+    yo = O.fft(x)
+    assert rel_l2(A.fft(x), yo) <= tol
+    assert rel_l2(A.adj(yo), O.adj(yo)) <= tol
+
+
+def test_sparse_mode_vs_oracle_sparse():
+    """Sparse mode is checked against the reference's SPARSE path (configs[1])."""
+    from oracle import nufft_oracle as orc
+    from mrrt.nufft_b200 import NufftBase
+
+    Nd, Kd = (64, 64), (128, 128)
+    rs = np.random.RandomState(1)
+    om = np.clip((np.pi / 3) * rs.standard_normal((20000, 2)), -np.pi, np.pi - 1e-6)
+    for mode in ("sparse", "table"):
+        A = NufftBase(Nd=Nd, omega=om, Jd=6, Kd=Kd, precision="double", mode=mode)
+        O = orc.OracleNufft(Nd=Nd, omega=om, Jd=6, Kd=Kd, precision="double", mode=mode)
+        x = rs.standard_normal(Nd) + 1j * rs.standard_normal(Nd)
+        yo = O.fft(x)
+        assert rel_l2(A.fft(x), yo) <= TOL["double"]
+        assert rel_l2(A.adj(yo), O.adj(yo)) <= TOL["double"]
+
+
+def test_adjointness_and_linearity_large():
+    """Size-independent properties at a size the oracle would need minutes for:
+    <A x, y> = <x, A^H y> and linearity, 3-D 128^3 / Kd 192^3 / J=6 / 2 M samples."""
+    import torch
+    from mrrt.nufft_b200 import NufftBase
+
+    Nd, Kd = (128, 128, 128), (192, 192, 192)
+    om = _radial3d(8000, 256).astype(np.float32)
+    A = NufftBase(Nd=Nd, omega=om, Jd=6, Kd=Kd, precision="single")
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn(Nd, dtype=torch.complex64, device="cuda", generator=g)
+    x2 = torch.randn(Nd, dtype=torch.complex64, device="cuda", generator=g)
+    y = torch.randn(A.M, dtype=torch.complex64, device="cuda", generator=g)
+    Ax = A.fft(x)
+    Ahy = A.adj(y)
+    lhs = torch.vdot(y.to(torch.complex128), Ax.to(torch.complex128))
+    rhs = torch.vdot(Ahy.to(torch.complex128).flatten(), x.to(torch.complex128).flatten())
+    assert abs(lhs - rhs) / abs(lhs) < 2e-5
+    lin = A.fft(x + 2 * x2) - (Ax + 2 * A.fft(x2))
+    assert float(torch.linalg.norm(lin) / torch.linalg.norm(Ax)) < 1e-5
+    # tiled/sliding kernels agree with the generic one-thread-per-sample kernels
+    B = NufftBase(Nd=Nd, omega=om, Jd=6, Kd=Kd, precision="single", options={"force_generic": 1})
+    assert float(torch.linalg.norm(B.fft(x) - Ax) / torch.linalg.norm(Ax)) < 1e-5
+    assert float(torch.linalg.norm(B.adj(y) - Ahy) / torch.linalg.norm(Ahy)) < 1e-5
+
+
+def test_array_kinds_and_dtypes():
+    """NumPy in -> NumPy out, torch in -> torch out; output dtype follows `precision`
+    whatever the input dtype (tests/test_nufft.py:376-388)."""
+    import torch
+    from mrrt.nufft_b200 import NufftBase
+
+    cfg, z = load_case("d1_table_single_real")
+    A = _op(cfg, z["omega"])
+    x = z["x"]
+    for xin in (x.astype(np.complex64), x.astype(np.complex128), x.real.astype(np.float32),
+                x.real.astype(np.float64)):
+        assert A.fft(xin).dtype == np.complex64
+    yt = A.fft(torch.from_numpy(x).cuda())
+    assert isinstance(yt, torch.Tensor) and yt.is_cuda and yt.dtype == torch.complex64
+    assert rel_l2(yt.cpu().numpy(), z["y"]) <= TOL["single"]
+    yc = A.fft(torch.from_numpy(x))
+    assert isinstance(yc, torch.Tensor) and not yc.is_cuda
+    A2 = NufftBase(Nd=cfg["Nd"], omega=z["omega"].astype(np.float64), Jd=6, Kd=cfg["Kd"],
+                   precision="auto")
+    assert A2._cplx_dtype == np.complex128
+    A3 = NufftBase(Nd=cfg["Nd"], omega=z["omega"].astype(np.float32), Jd=6, Kd=cfg["Kd"],
+                   precision="auto")
+    assert A3._cplx_dtype == np.complex64
+
+
+def test_errors_and_edges():
+    from mrrt.nufft_b200 import NufftBase
+
+    om = np.random.RandomState(0).rand(100, 2) * 2 * np.pi
+    with pytest.raises(ValueError):
+        NufftBase(Nd=(16, 16), omega=om, on_gpu=False)
+    with pytest.raises(ValueError):
+        NufftBase(Nd=(16, 16), omega=om[:, :1])
+    with pytest.raises(ValueError):
+        NufftBase(Nd=(16, 16), omega=om.astype(np.int32))
+    with pytest.raises(ValueError):
+        NufftBase(Nd=(16, 16), omega=om, mode="exact")
+    with pytest.raises(ValueError):
+        NufftBase(Nd=(16, 16), omega=om, mode="bogus")
+    bad = om.copy()
+    bad[3, 1] = np.nan
+    with pytest.raises(ValueError):
+        NufftBase(Nd=(16, 16), omega=bad)
+    A = NufftBase(Nd=(16, 16), omega=om, Jd=5)
+    with pytest.raises(ValueError):
+        A.fft(np.zeros((15, 16)))
+    with pytest.raises(ValueError):
+        A.adj(np.zeros(99))
+    # a single sample, and all samples in one cell (maximal collisions)
+    one = NufftBase(Nd=(16, 16), omega=om[:1], Jd=6)
+    assert one.fft(np.ones((16, 16))).shape == (1,)
+    same = np.zeros((5000, 3))
+    S = NufftBase(Nd=(8, 8, 8), omega=same, Jd=6, Kd=(16, 16, 16), precision="double")
+    from oracle import nufft_oracle as orc
+
+    O = orc.OracleNufft(Nd=(8, 8, 8), omega=same, Jd=6, Kd=(16, 16, 16), precision="double")
+    y = np.random.RandomState(1).standard_normal(5000) + 0j
+    assert rel_l2(S.adj(y), O.adj(y)) <= 1e-12
