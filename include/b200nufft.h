@@ -137,9 +137,9 @@ int64_t b2n_plan_sparse_nnz(b2n_plan *plan);
  * [nnz], row-major (row m holds entries m*prod(Jd) ..). */
 int b2n_plan_get_sparse(b2n_plan *plan, void *vals_dev, int32_t *cols_dev, void *stream);
 int b2n_spmv_fwd(b2n_plan *plan, const void *grid_dev, void *samples_dev, int nbatch,
-                 void *stream);
+                 int apply_phase, void *stream);
 int b2n_spmv_adj(b2n_plan *plan, const void *samples_dev, void *grid_dev, int nbatch,
-                 void *stream);
+                 int apply_phase, void *stream);
 
 /* bytes of device memory owned by the plan */
 int64_t b2n_plan_device_bytes(b2n_plan *plan);

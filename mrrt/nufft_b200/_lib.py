@@ -45,8 +45,8 @@ SIGNATURES = {
     "b2n_plan_set_sparse": (c_int, [c_vp, PP, PP, c_i64, c_vp, c_vp]),
     "b2n_plan_sparse_nnz": (c_i64, [c_vp]),
     "b2n_plan_get_sparse": (c_int, [c_vp, c_vp, c_vp, c_vp]),
-    "b2n_spmv_fwd": (c_int, [c_vp, c_vp, c_vp, c_int, c_vp]),
-    "b2n_spmv_adj": (c_int, [c_vp, c_vp, c_vp, c_int, c_vp]),
+    "b2n_spmv_fwd": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_vp]),
+    "b2n_spmv_adj": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_vp]),
     "b2n_plan_device_bytes": (c_i64, [c_vp]),
     "b2n_plan_launch_count": (c_i64, [c_vp]),
 }

@@ -494,7 +494,7 @@ def nufft_forward(obj, x, copy_x=True, grid_only=False, xp=None):
         stream = obj._stream()
         if grid_only:
             if obj.mode == "sparse":
-                rc = obj._lib.b2n_spmv_fwd(obj._plan, mem.data_ptr(), out.data_ptr(), n_reps, stream)
+                rc = obj._lib.b2n_spmv_fwd(obj._plan, mem.data_ptr(), out.data_ptr(), n_reps, 0, stream)
             else:
                 # phase_shift of complex phasing belongs to the interpolation stage
                 # (_nufft.py:1086-1095); phase_after does not
@@ -525,11 +525,12 @@ def nufft_adj(obj, xk, copy=True, return_psf=False, grid_only=False, xp=None):
         stream = obj._stream()
         if grid_only:
             out = torch.empty((n_reps, _prod(Kd)), dtype=mem.dtype, device=obj.device)
+            # the reference multiplies by conj(phase_after) BEFORE the gridding stage, so
+            # its grid_only adjoint includes it (_nufft.py:1495-1509), unlike grid_only forward
             if obj.mode == "sparse":
-                rc = obj._lib.b2n_spmv_adj(obj._plan, mem.data_ptr(), out.data_ptr(), n_reps, stream)
+                rc = obj._lib.b2n_spmv_adj(obj._plan, mem.data_ptr(), out.data_ptr(), n_reps, 1, stream)
             else:
-                rc = obj._lib.b2n_interp_adj(obj._plan, mem.data_ptr(), out.data_ptr(), n_reps,
-                                             1 if obj.phase_shift is not None else 0, stream)
+                rc = obj._lib.b2n_interp_adj(obj._plan, mem.data_ptr(), out.data_ptr(), n_reps, 1, stream)
             _lib.check(rc)
             return out.t()
         out = torch.empty((n_reps,) + tuple(reversed(Nd)), dtype=mem.dtype, device=obj.device)

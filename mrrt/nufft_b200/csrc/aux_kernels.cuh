@@ -56,6 +56,23 @@ __global__ void gather_points_kernel(int ndim, int64_t M, const int32_t* __restr
     }
 }
 
+// per sorted sample: unwrapped window origin ko = 1 + floor(t - J/2.) (double arithmetic,
+// template.c:865-867) and its periodic wrap kw, so the hot kernels do neither double
+// arithmetic nor integer division
+template <typename T>
+__global__ void point_windows_kernel(Geom g, const T* __restrict__ tm_s, int32_t* __restrict__ pt_ko,
+                                     int32_t* __restrict__ pt_kw) {
+    const int64_t M = g.M;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < M;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        for (int d = 0; d < g.ndim; d++) {
+            const int ko = window_origin<T>(tm_s[(int64_t)d * M + i], g.J[d]);
+            pt_ko[(int64_t)d * M + i] = ko;
+            pt_kw[(int64_t)d * M + i] = wrap_index(ko, g.K[d]);
+        }
+    }
+}
+
 template <typename C>
 __global__ void gather_c_kernel(int64_t M, const int32_t* __restrict__ perm,
                                 const C* __restrict__ src, C* __restrict__ dst) {

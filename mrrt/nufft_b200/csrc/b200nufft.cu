@@ -75,6 +75,8 @@ struct b2n_plan {
     uint64_t* d_keys = nullptr;  // acquisition order
     int32_t* d_bin_ids = nullptr;
     int32_t* d_perm = nullptr;
+    int32_t* d_pt_ko = nullptr;  // [ndim][M] sorted: unwrapped window origins
+    int32_t* d_pt_kw = nullptr;  // [ndim][M] sorted: wrapped window origins
     void* d_phase_s = nullptr;   // sorted sample phase or null
     int64_t nbins = 0;
     // work items of the tiled forward kernel: (bin, start, count, pad)
@@ -184,6 +186,8 @@ extern "C" int b2n_plan_create(int ndim, const int* Nd, const int* Kd, const int
 static void free_points(b2n_plan* p) {
     dev_free(p->d_tm); dev_free(p->d_tm_s); dev_free(p->d_keys); dev_free(p->d_bin_ids);
     dev_free(p->d_perm); dev_free(p->d_phase_s); dev_free(p->d_items);
+    dev_free(p->d_pt_ko); dev_free(p->d_pt_kw);
+    p->d_pt_ko = p->d_pt_kw = nullptr;
     p->d_tm = p->d_tm_s = p->d_phase_s = nullptr;
     p->d_keys = nullptr; p->d_bin_ids = nullptr; p->d_perm = nullptr; p->d_items = nullptr;
     p->points_set = false;
@@ -325,6 +329,8 @@ static int set_points_t(b2n_plan* p, const void* coords, int64_t M, int kind, cu
     if ((rc = dev_alloc(p, (void**)&p->d_keys, sizeof(uint64_t) * M))) return rc;
     if ((rc = dev_alloc(p, (void**)&p->d_bin_ids, sizeof(int32_t) * M))) return rc;
     if ((rc = dev_alloc(p, (void**)&p->d_perm, sizeof(int32_t) * M))) return rc;
+    if ((rc = dev_alloc(p, (void**)&p->d_pt_ko, sizeof(int32_t) * M * g.ndim))) return rc;
+    if ((rc = dev_alloc(p, (void**)&p->d_pt_kw, sizeof(int32_t) * M * g.ndim))) return rc;
     p->nbins = (int64_t)g.nbin[0] * g.nbin[1] * g.nbin[2];
     if (M == 0) {
         p->n_items = 0;
@@ -357,6 +363,9 @@ static int set_points_t(b2n_plan* p, const void* coords, int64_t M, int kind, cu
                                        0, bits, st));
     gather_points_kernel<T><<<grid_for(M, 256, p->sm_count), 256, 0, st>>>(
         g.ndim, M, p->d_perm, (const T*)p->d_tm, (T*)p->d_tm_s);
+    CU(cudaGetLastError());
+    point_windows_kernel<T><<<grid_for(M, 256, p->sm_count), 256, 0, st>>>(
+        g, (const T*)p->d_tm_s, p->d_pt_ko, p->d_pt_kw);
     CU(cudaGetLastError());
     // bin boundaries -> host -> work items of at most opt_chunk samples
     CU(cudaMalloc(&bin_start, sizeof(int32_t) * p->nbins));
@@ -499,9 +508,9 @@ static int interp_fwd_impl(b2n_plan* p, const void* grid, void* samples, int nba
     if (!p->opt_force_generic && !p->cplx_table) {
         const void* ph = phase ? p->d_phase_s : nullptr;
         int rc = p->precision == B2N_SINGLE
-                     ? tiled_fwd_f32(p->g, p->tables_equal, table_ptrs(p), p->d_tm_s, p->d_perm, p->d_items,
+                     ? tiled_fwd_f32(p->g, p->tables_equal, table_ptrs(p), p->d_tm_s, p->d_pt_ko, p->d_pt_kw, p->d_perm, p->d_items,
                                      p->n_items, grid, samples, ph, nbatch, (int)p->opt_use_tma, st, &done)
-                     : tiled_fwd_f64(p->g, p->tables_equal, table_ptrs(p), p->d_tm_s, p->d_perm, p->d_items,
+                     : tiled_fwd_f64(p->g, p->tables_equal, table_ptrs(p), p->d_tm_s, p->d_pt_ko, p->d_pt_kw, p->d_perm, p->d_items,
                                      p->n_items, grid, samples, ph, nbatch, (int)p->opt_use_tma, st, &done);
         if (rc != 0) return fail(B2N_ECUDA, "tiled forward launch failed: " + std::string(cudaGetErrorString((cudaError_t)rc)));
     }
@@ -524,9 +533,9 @@ static int interp_adj_impl(b2n_plan* p, const void* samples, void* grid, int nba
     if (!p->opt_force_generic && !p->cplx_table) {
         const void* ph = phase ? p->d_phase_s : nullptr;
         int rc = p->precision == B2N_SINGLE
-                     ? slide_adj_f32(p->g, table_ptrs(p), p->d_tm_s, p->d_perm, samples, grid, ph, nbatch,
+                     ? slide_adj_f32(p->g, table_ptrs(p), p->d_tm_s, p->d_pt_ko, p->d_pt_kw, p->d_perm, samples, grid, ph, nbatch,
                                      (int)p->opt_slide_pts, st, &done)
-                     : slide_adj_f64(p->g, table_ptrs(p), p->d_tm_s, p->d_perm, samples, grid, ph, nbatch,
+                     : slide_adj_f64(p->g, table_ptrs(p), p->d_tm_s, p->d_pt_ko, p->d_pt_kw, p->d_perm, samples, grid, ph, nbatch,
                                      (int)p->opt_slide_pts, st, &done);
         if (rc != 0) return fail(B2N_ECUDA, "sliding adjoint launch failed: " + std::string(cudaGetErrorString((cudaError_t)rc)));
     }
@@ -655,19 +664,22 @@ static int spmv_impl(b2n_plan* p, bool fwd, const void* in, void* out, int nbatc
 }
 
 extern "C" int b2n_spmv_fwd(b2n_plan* p, const void* grid_dev, void* samples_dev, int nbatch,
-                            void* stream) {
+                            int apply_phase, void* stream) {
     int rc = check_ready(p, grid_dev, samples_dev, nbatch);
     if (rc) return rc;
     CU(cudaSetDevice(p->device));
-    return spmv_impl(p, true, grid_dev, samples_dev, nbatch, false, (cudaStream_t)stream);
+    return spmv_impl(p, true, grid_dev, samples_dev, nbatch, apply_phase && p->d_phase_s,
+                     (cudaStream_t)stream);
 }
 
 extern "C" int b2n_spmv_adj(b2n_plan* p, const void* samples_dev, void* grid_dev, int nbatch,
-                            void* stream) {
+                            int apply_phase, void* stream) {
     int rc = check_ready(p, samples_dev, grid_dev, nbatch);
     if (rc) return rc;
+    if (grid_dev == nullptr) return fail(B2N_EINVAL, "NULL array");
     CU(cudaSetDevice(p->device));
-    return spmv_impl(p, false, samples_dev, grid_dev, nbatch, false, (cudaStream_t)stream);
+    return spmv_impl(p, false, samples_dev, grid_dev, nbatch, apply_phase && p->d_phase_s,
+                     (cudaStream_t)stream);
 }
 
 // ---------------------------------------------------------------------------------

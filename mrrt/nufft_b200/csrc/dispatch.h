@@ -17,10 +17,11 @@ struct TablePtrs {
                              const int32_t* perm, bool fwd, const void* in, void* out,           \
                              const void* phase_s, int nbatch, int sm_count, cudaStream_t st);    \
     int tiled_fwd_##SUF(const Geom& g, bool tables_equal, const TablePtrs& tabs, const void* tm_s, \
-                        const int32_t* perm, const int4* items, int64_t n_items, const void* grid, \
+                        const int32_t* pt_ko, const int32_t* pt_kw, const int32_t* perm, const int4* items, int64_t n_items, const void* grid, \
                         void* out, const void* phase_s, int nbatch, int use_tma, cudaStream_t st, \
                         bool* done);                                                             \
-    int slide_adj_##SUF(const Geom& g, const TablePtrs& tabs, const void* tm_s, const int32_t* perm, \
+    int slide_adj_##SUF(const Geom& g, const TablePtrs& tabs, const void* tm_s,                 \
+                        const int32_t* pt_ko, const int32_t* pt_kw, const int32_t* perm,        \
                         const void* samples, void* grid, const void* phase_s, int nbatch,        \
                         int pts_per_warp, cudaStream_t st, bool* done);
 B2N_DECLARE(f32)

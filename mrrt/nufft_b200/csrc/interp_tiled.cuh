@@ -73,6 +73,7 @@ template <typename T, int NDIM, int J, bool TAB_SMEM>
 __global__ void __launch_bounds__(256)
 interp_fwd_tiled_kernel(const __grid_constant__ CUtensorMap tmap, Geom g, TileShape ts, int use_tma,
                         const T* __restrict__ tab, const T* __restrict__ tm_s,
+                        const int32_t* __restrict__ pt_ko, const int32_t* __restrict__ pt_kw,
                         const int32_t* __restrict__ perm, const int4* __restrict__ items,
                         const cplx_t<T>* __restrict__ grid, cplx_t<T>* __restrict__ out,
                         const cplx_t<T>* __restrict__ phase_s) {
@@ -130,9 +131,9 @@ interp_fwd_tiled_kernel(const __grid_constant__ CUtensorMap tmap, Geom g, TileSh
 #pragma unroll
         for (int d = 0; d < NDIM; d++) {
             const T t = tm_s[(int64_t)d * M + i];
-            const int koff = window_origin<T>(t, J);
+            const int koff = pt_ko[(int64_t)d * M + i];      // 1 + floor(t - J/2.), plan time
             const int od = d == 0 ? o1 : (d == 1 ? o2 : o3);
-            c[d] = wrap_index(koff, g.K[d]) - od;
+            c[d] = pt_kw[(int64_t)d * M + i] - od;           // wrapped origin inside the tile
 #pragma unroll
             for (int j = 0; j < J; j++)
                 w[d][j] = tap_real<T>(h, g.ncenter[0], g.tlen[0], t, koff + j, g.L);
@@ -227,7 +228,7 @@ static bool make_grid_tmap(CUtensorMap* map, const Geom& g, const TileShape& ts,
 
 template <typename T, int NDIM, int J>
 static int launch_fwd_tiled(const Geom& g, const TablePtrs& tabs, const void* tm_s,
-                            const int32_t* perm, const int4* items, int64_t n_items,
+                            const int32_t* pt_ko, const int32_t* pt_kw, const int32_t* perm, const int4* items, int64_t n_items,
                             const void* grid, void* out, const void* phase_s, int nbatch,
                             int use_tma, cudaStream_t st, bool* done) {
     using C = cplx_t<T>;
@@ -263,13 +264,13 @@ static int launch_fwd_tiled(const Geom& g, const TablePtrs& tabs, const void* tm
         e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
         k<<<gridDim, 256, smem, st>>>(map, g, ts, tma_ok ? 1 : 0, (const T*)tabs.h[0], (const T*)tm_s,
-                                      perm, items, (const C*)grid, (C*)out, (const C*)phase_s);
+                                      pt_ko, pt_kw, perm, items, (const C*)grid, (C*)out, (const C*)phase_s);
     } else {
         auto k = interp_fwd_tiled_kernel<T, NDIM, J, false>;
         e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
         k<<<gridDim, 256, smem, st>>>(map, g, ts, tma_ok ? 1 : 0, (const T*)tabs.h[0], (const T*)tm_s,
-                                      perm, items, (const C*)grid, (C*)out, (const C*)phase_s);
+                                      pt_ko, pt_kw, perm, items, (const C*)grid, (C*)out, (const C*)phase_s);
     }
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
@@ -280,7 +281,7 @@ static int launch_fwd_tiled(const Geom& g, const TablePtrs& tabs, const void* tm
 // returns 0 or a cudaError_t; *done tells whether the tiled kernel took the call
 template <typename T>
 static int tiled_fwd_t(const Geom& g, bool tables_equal, const TablePtrs& tabs, const void* tm_s,
-                       const int32_t* perm, const int4* items, int64_t n_items, const void* grid,
+                       const int32_t* pt_ko, const int32_t* pt_kw, const int32_t* perm, const int4* items, int64_t n_items, const void* grid,
                        void* out, const void* phase_s, int nbatch, int use_tma, cudaStream_t st,
                        bool* done) {
     *done = false;
@@ -289,7 +290,7 @@ static int tiled_fwd_t(const Geom& g, bool tables_equal, const TablePtrs& tabs, 
     for (int d = 1; d < g.ndim; d++)
         if (g.J[d] != g.J[0]) return 0;
 #define B2N_TILED(ND, JJ)                                                                      \
-    return launch_fwd_tiled<T, ND, JJ>(g, tabs, tm_s, perm, items, n_items, grid, out, phase_s, \
+    return launch_fwd_tiled<T, ND, JJ>(g, tabs, tm_s, pt_ko, pt_kw, perm, items, n_items, grid, out, phase_s, \
                                        nbatch, use_tma, st, done)
     if (g.ndim == 2) {
         switch (g.J[0]) {

@@ -19,10 +19,24 @@
 
 namespace b2n {
 
+// staging record of one sample (16-byte aligned so that a lane-uniform read is a few
+// LDS.128 broadcasts instead of one shuffle per field)
+template <typename T> struct StagePt;
+template <> struct alignas(16) StagePt<float> {
+    float t[3]; float fx;
+    float fy; int ko[3];
+    int kw[3]; int pad;
+};
+template <> struct alignas(16) StagePt<double> {
+    double t[3]; double fx;
+    double fy; int ko[3]; int kw[3];
+};
+
 template <typename T, int J>
 __global__ void __launch_bounds__(128)
 spread_slide3d_kernel(Geom g, const T* __restrict__ h1, const T* __restrict__ h2,
                       const T* __restrict__ h3, const T* __restrict__ tm_s,
+                      const int32_t* __restrict__ pt_ko, const int32_t* __restrict__ pt_kw,
                       const int32_t* __restrict__ perm, const cplx_t<T>* __restrict__ samples,
                       cplx_t<T>* __restrict__ grid, const cplx_t<T>* __restrict__ phase_s,
                       int pts_per_warp) {
@@ -30,7 +44,9 @@ spread_slide3d_kernel(Geom g, const T* __restrict__ h1, const T* __restrict__ h2
     constexpr int R = J * J;                 // rows of the window
     constexpr int RPL = (R + 31) / 32;       // rows per lane
     constexpr unsigned FULL = 0xffffffffu;
+    __shared__ StagePt<T> stage[4][32];
     const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t M = g.M;
     const int64_t begin = warp * pts_per_warp;
@@ -52,9 +68,12 @@ spread_slide3d_kernel(Geom g, const T* __restrict__ h1, const T* __restrict__ h2
         rj2[s] = (r % R) % J;
         rj3[s] = (r % R) / J;
     }
-    const int wax = lane / J;                // 0,1,2 for lanes < 3J
+    const int wax = lane < J ? 0 : (lane < 2 * J ? 1 : 2);   // axis of this lane's tap
     const int wj = lane - wax * J;
+    const bool wactive = lane < 3 * J;
     const T* __restrict__ wh = wax == 0 ? h1 : (wax == 1 ? h2 : h3);
+    const int wnc = g.ncenter[wax], wtl = g.tlen[wax];
+    const T Lf = (T)g.L;
 
     C acc[RPL][J];
     int rowbase[RPL];
@@ -68,39 +87,39 @@ spread_slide3d_kernel(Geom g, const T* __restrict__ h1, const T* __restrict__ h2
 
     for (int64_t base = begin; base < end; base += 32) {
         const int cnt = (int)(end - base < 32 ? end - base : 32);
-        // coalesced load of up to 32 samples; lanes then take turns
-        T lt1 = 0, lt2 = 0, lt3 = 0;
-        C lf = make_c<T>(0, 0);
+        __syncwarp();
         if (lane < cnt) {
+            // coalesced loads of up to 32 samples into the staging records
             const int64_t i = base + lane;
-            lt1 = tm_s[i];
-            lt2 = tm_s[M + i];
-            lt3 = tm_s[2 * M + i];
-            lf = sb[perm[i]];
-            if (phase_s != nullptr) lf = cmul_conj(lf, phase_s[i]);
+            StagePt<T> p;
+            p.t[0] = tm_s[i]; p.t[1] = tm_s[M + i]; p.t[2] = tm_s[2 * M + i];
+            p.ko[0] = pt_ko[i]; p.ko[1] = pt_ko[M + i]; p.ko[2] = pt_ko[2 * M + i];
+            p.kw[0] = pt_kw[i]; p.kw[1] = pt_kw[M + i]; p.kw[2] = pt_kw[2 * M + i];
+            C f = sb[perm[i]];
+            if (phase_s != nullptr) f = cmul_conj(f, phase_s[i]);
+            p.fx = f.x; p.fy = f.y;
+            stage[wib][lane] = p;
         }
+        __syncwarp();
+        StagePt<T> cur = stage[wib][0];
         for (int q = 0; q < cnt; q++) {
-            const T t1 = __shfl_sync(FULL, lt1, q);
-            const T t2 = __shfl_sync(FULL, lt2, q);
-            const T t3 = __shfl_sync(FULL, lt3, q);
-            C f;
-            f.x = __shfl_sync(FULL, lf.x, q);
-            f.y = __shfl_sync(FULL, lf.y, q);
-            const int ko1 = window_origin<T>(t1, J);
-            const int ko2 = window_origin<T>(t2, J);
-            const int ko3 = window_origin<T>(t3, J);
+            StagePt<T> nxt = cur;
+            if (q + 1 < cnt) nxt = stage[wib][q + 1];   // prefetch the next record
             // cooperative weights: lane (axis, tap) evaluates one table coefficient
+            // (template.c:870-873)
             T wl = 0;
-            if (lane < 3 * J) {
-                const T ta = wax == 0 ? t1 : (wax == 1 ? t2 : t3);
-                const int ka = (wax == 0 ? ko1 : (wax == 1 ? ko2 : ko3)) + wj;
-                wl = tap_real<T>(wh, g.ncenter[wax], g.tlen[wax], ta, ka, g.L);
+            if (wactive) {
+                const T ta = wax == 0 ? cur.t[0] : (wax == 1 ? cur.t[1] : cur.t[2]);
+                const int ka = (wax == 0 ? cur.ko[0] : (wax == 1 ? cur.ko[1] : cur.ko[2])) + wj;
+                const T p = (ta - (T)ka) * Lf;
+                const T fl = floor(p);
+                const T alf = p - fl;
+                const int i0 = wnc + (int)fl;
+                const int i1 = min(i0 + 1, wtl - 1);
+                wl = ((T)1 - alf) * __ldg(wh + i0) + alf * __ldg(wh + i1);
             }
-            const int kw1 = wrap_index(ko1, K1);
-            const int kw2 = wrap_index(ko2, K2);
-            const int kw3 = wrap_index(ko3, K3);
-            const int d = kw1 - W1;
-            if (kw2 != W2 || kw3 != W3 || d < 0 || d >= J) {
+            const int d = cur.kw[0] - W1;
+            if (cur.kw[1] != W2 || cur.kw[2] != W3 || d < 0 || d >= J) {
                 // new row of cells (or a jump): flush the whole window
                 if (W2 >= 0) {
 #pragma unroll
@@ -109,14 +128,12 @@ spread_slide3d_kernel(Geom g, const T* __restrict__ h1, const T* __restrict__ h2
                         if (k1 >= K1) k1 -= K1;
 #pragma unroll
                         for (int s = 0; s < RPL; s++) {
-                            const C a = acc[s][j];
-                            if (rvalid[s] && (a.x != (T)0 || a.y != (T)0))
-                                atomic_add_c(gb + rowbase[s] + k1, a);
+                            if (rvalid[s]) atomic_add_c(gb + rowbase[s] + k1, acc[s][j]);
                             acc[s][j] = make_c<T>(0, 0);
                         }
                     }
                 }
-                W1 = kw1; W2 = kw2; W3 = kw3;
+                W1 = cur.kw[0]; W2 = cur.kw[1]; W3 = cur.kw[2];
 #pragma unroll
                 for (int s = 0; s < RPL; s++) {
                     int k2 = W2 + rj2[s]; if (k2 >= K2) k2 -= K2;
@@ -126,17 +143,14 @@ spread_slide3d_kernel(Geom g, const T* __restrict__ h1, const T* __restrict__ h2
             } else {
                 for (int sft = 0; sft < d; sft++) {
                     // slide by one cell: retire column 0
-                    int k1 = W1; if (k1 >= K1) k1 -= K1;
 #pragma unroll
                     for (int s = 0; s < RPL; s++) {
-                        const C a = acc[s][0];
-                        if (rvalid[s] && (a.x != (T)0 || a.y != (T)0))
-                            atomic_add_c(gb + rowbase[s] + k1, a);
+                        if (rvalid[s]) atomic_add_c(gb + rowbase[s] + W1, acc[s][0]);
 #pragma unroll
                         for (int j = 0; j + 1 < J; j++) acc[s][j] = acc[s][j + 1];
                         acc[s][J - 1] = make_c<T>(0, 0);
                     }
-                    W1++;
+                    W1++;   // < K1: the new origin cur.kw[0] is a wrapped index
                 }
             }
             // accumulate this sample into the register window
@@ -148,7 +162,7 @@ spread_slide3d_kernel(Geom g, const T* __restrict__ h1, const T* __restrict__ h2
                 const T w2 = __shfl_sync(FULL, wl, J + rj2[s]);
                 const T w3 = __shfl_sync(FULL, wl, 2 * J + rj3[s]);
                 if (rvalid[s]) {
-                    const T v3x = w3 * f.x, v3y = w3 * f.y;
+                    const T v3x = w3 * cur.fx, v3y = w3 * cur.fy;
                     const T v2x = w2 * v3x, v2y = w2 * v3y;
 #pragma unroll
                     for (int j = 0; j < J; j++) {
@@ -157,6 +171,7 @@ spread_slide3d_kernel(Geom g, const T* __restrict__ h1, const T* __restrict__ h2
                     }
                 }
             }
+            cur = nxt;
         }
     }
     if (W2 >= 0) {
@@ -165,16 +180,15 @@ spread_slide3d_kernel(Geom g, const T* __restrict__ h1, const T* __restrict__ h2
             int k1 = W1 + j;
             if (k1 >= K1) k1 -= K1;
 #pragma unroll
-            for (int s = 0; s < RPL; s++) {
-                const C a = acc[s][j];
-                if (rvalid[s] && (a.x != (T)0 || a.y != (T)0)) atomic_add_c(gb + rowbase[s] + k1, a);
-            }
+            for (int s = 0; s < RPL; s++)
+                if (rvalid[s]) atomic_add_c(gb + rowbase[s] + k1, acc[s][j]);
         }
     }
 }
 
 template <typename T, int J>
-static int launch_slide(const Geom& g, const TablePtrs& tabs, const void* tm_s, const int32_t* perm,
+static int launch_slide(const Geom& g, const TablePtrs& tabs, const void* tm_s,
+                        const int32_t* pt_ko, const int32_t* pt_kw, const int32_t* perm,
                         const void* samples, void* grid, const void* phase_s, int nbatch,
                         int pts_per_warp, cudaStream_t st, bool* done) {
     using C = cplx_t<T>;
@@ -183,7 +197,7 @@ static int launch_slide(const Geom& g, const TablePtrs& tabs, const void* tm_s, 
     if (nblocks > 0x7fffffff || nbatch > 65535) return 0;
     dim3 gd((unsigned)nblocks, (unsigned)nbatch);
     spread_slide3d_kernel<T, J><<<gd, 128, 0, st>>>(
-        g, (const T*)tabs.h[0], (const T*)tabs.h[1], (const T*)tabs.h[2], (const T*)tm_s, perm,
+        g, (const T*)tabs.h[0], (const T*)tabs.h[1], (const T*)tabs.h[2], (const T*)tm_s, pt_ko, pt_kw, perm,
         (const C*)samples, (C*)grid, (const C*)phase_s, pts_per_warp);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
@@ -192,7 +206,8 @@ static int launch_slide(const Geom& g, const TablePtrs& tabs, const void* tm_s, 
 }
 
 template <typename T>
-static int slide_adj_t(const Geom& g, const TablePtrs& tabs, const void* tm_s, const int32_t* perm,
+static int slide_adj_t(const Geom& g, const TablePtrs& tabs, const void* tm_s,
+                       const int32_t* pt_ko, const int32_t* pt_kw, const int32_t* perm,
                        const void* samples, void* grid, const void* phase_s, int nbatch,
                        int pts_per_warp, cudaStream_t st, bool* done) {
     *done = false;
@@ -201,7 +216,7 @@ static int slide_adj_t(const Geom& g, const TablePtrs& tabs, const void* tm_s, c
     // the window must not wrap onto itself
     if (g.K[0] < g.J[0] || g.K[1] < g.J[0] || g.K[2] < g.J[0]) return 0;
 #define B2N_SLIDE(JJ) \
-    return launch_slide<T, JJ>(g, tabs, tm_s, perm, samples, grid, phase_s, nbatch, pts_per_warp, st, done)
+    return launch_slide<T, JJ>(g, tabs, tm_s, pt_ko, pt_kw, perm, samples, grid, phase_s, nbatch, pts_per_warp, st, done)
     switch (g.J[0]) {
         case 4: B2N_SLIDE(4);
         case 5: B2N_SLIDE(5);
