@@ -68,7 +68,8 @@ int b2n_plan_create(int ndim, const int *Nd, const int *Kd, const int *Jd, int L
 int b2n_plan_destroy(b2n_plan *plan);
 
 /* integer options: "tile1","tile2","tile3" (bin shape in grid cells), "chunk"
- * (max samples per work item), "force_generic" (1 = never use the tiled / sliding
+ * (max samples per work item), "slide_pts" (samples per warp in the sliding-window
+ * adjoint), "profile", "force_generic" (1 = never use the tiled / sliding
  * kernels), "use_tma" (0 = cooperative tile loads only).  Must precede set_points. */
 int b2n_plan_set_option(b2n_plan *plan, const char *name, long value);
 long b2n_plan_get_option(b2n_plan *plan, const char *name);
@@ -143,8 +144,13 @@ int b2n_spmv_adj(b2n_plan *plan, const void *samples_dev, void *grid_dev, int nb
 
 /* bytes of device memory owned by the plan */
 int64_t b2n_plan_device_bytes(b2n_plan *plan);
-/* number of kernel launches (ours + cuFFT calls counted as 1) issued so far */
+/* number of OUR kernel launches issued so far (cuFFT executions and memsets are counted
+ * separately: option "lib_calls") */
 int64_t b2n_plan_launch_count(b2n_plan *plan);
+/* With option "profile"=1 every interpolation kernel launch is bracketed by CUDA events
+ * on the launching stream.  out[0..3] = {forward kernel total ms, launches, adjoint
+ * kernel total ms, launches} since the previous call; synchronises those events. */
+int b2n_plan_get_timing(b2n_plan *plan, double *out);
 
 #ifdef __cplusplus
 }

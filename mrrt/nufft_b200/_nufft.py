@@ -389,6 +389,16 @@ class NufftBase(object):
     def option(self, name):
         return int(self._lib.b2n_plan_get_option(self._plan, name.encode()))
 
+    def set_option(self, name, value):
+        _lib.check(self._lib.b2n_plan_set_option(self._plan, name.encode(), int(value)))
+
+    def kernel_timing(self):
+        """(fwd_ms_total, fwd_launches, adj_ms_total, adj_launches) of the interpolation
+        kernels since the last call; needs ``set_option("profile", 1)``."""
+        out = (ctypes.c_double * 4)()
+        _lib.check(self._lib.b2n_plan_get_timing(self._plan, out))
+        return tuple(out)
+
     @property
     def launch_count(self):
         return int(self._lib.b2n_plan_launch_count(self._plan))

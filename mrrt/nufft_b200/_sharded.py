@@ -1,0 +1,106 @@
+"""Multi-GPU use of the NUFFT operator: one process per GPU (``torch.distributed``).
+
+Two shardings, as the path allows:
+
+* ``CoilShardedNufft``   -- multi-coil / batched transforms.  Coils are independent
+  (the reference loops over them: _nufft.py:1069-1084, template.c:405-412), so each
+  rank owns ``n_coils / world`` coils with a replicated plan and NO communication.
+* ``SampleShardedNufft`` -- one very large problem.  The sample set is sharded; the
+  forward transform needs nothing from other ranks (each rank interpolates its samples
+  from its own copy of the oversampled spectrum); the adjoint produces a partial image
+  per rank and ONE all-reduce (sum) combines them.  By linearity of the inverse FFT the
+  cropped ``Nd`` image is reduced rather than the ``Kd`` grid (3.4x fewer bytes at
+  Kd = 1.5 Nd).
+
+``op_factory`` builds the per-rank operator (default: the CUDA ``NufftBase``); the CPU
+tests pass the oracle operator to exercise this host logic over gloo.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n, world, rank):
+    """Contiguous balanced split of ``range(n)``: the first ``n % world`` ranks get one
+    extra element."""
+    base, extra = divmod(int(n), int(world))
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def _default_factory():
+    from ._nufft import NufftBase
+
+    return NufftBase
+
+
+def _all_reduce_sum(x, group):
+    """In-place sum over ranks of a (possibly Fortran-ordered, complex) array."""
+    if isinstance(x, np.ndarray):
+        buf = np.ascontiguousarray(x.T)            # F-ordered result -> C-contiguous view
+        t = torch.view_as_real(torch.from_numpy(buf))
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        return buf.T
+    mem = x.permute(*reversed(range(x.dim())))      # the operator returns F-ordered views
+    if not mem.is_contiguous():
+        mem = mem.contiguous()
+    dist.all_reduce(torch.view_as_real(mem), op=dist.ReduceOp.SUM, group=group)
+    return mem.permute(*reversed(range(mem.dim())))
+
+
+class SampleShardedNufft(object):
+    """Sample-sharded operator: rank r holds samples ``[lo, hi)`` of ``omega``."""
+
+    def __init__(self, Nd, omega, group=None, op_factory=None, **kwargs):
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        omega = np.asarray(omega) if not isinstance(omega, torch.Tensor) else omega
+        if omega.ndim == 1:
+            omega = omega[:, None]
+        self.M_total = omega.shape[0]
+        self.lo, self.hi = shard_range(self.M_total, self.world, self.rank)
+        factory = op_factory or _default_factory()
+        self.op = factory(Nd=Nd, omega=omega[self.lo:self.hi], **kwargs)
+        self.M = self.hi - self.lo
+
+    def fft(self, x):
+        """Forward transform of the (replicated) image to this rank's samples."""
+        return self.op.fft(x)
+
+    def adj(self, k_local):
+        """Adjoint of this rank's samples, summed over ranks (one all-reduce)."""
+        x = self.op.adj(k_local)
+        if self.world > 1:
+            x = _all_reduce_sum(x, self.group)
+        return x
+
+    def norm(self, x):
+        return self.adj(self.fft(x))
+
+
+class CoilShardedNufft(object):
+    """Coil-sharded operator: rank r transforms coils ``[c0, c1)``; no communication."""
+
+    def __init__(self, Nd, omega, n_coils, group=None, op_factory=None, **kwargs):
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.n_coils = int(n_coils)
+        self.c0, self.c1 = shard_range(self.n_coils, self.world, self.rank)
+        factory = op_factory or _default_factory()
+        self.op = factory(Nd=Nd, omega=omega, **kwargs)
+
+    def local_coils(self, x, order="F"):
+        """Slice this rank's coils out of a full multi-coil array (coil axis last for
+        order "F", first for "C")."""
+        return x[..., self.c0:self.c1] if order == "F" else x[self.c0:self.c1]
+
+    def fft(self, x_local):
+        return self.op.fft(x_local)
+
+    def adj(self, k_local):
+        return self.op.adj(k_local)
+
+    def norm(self, x_local):
+        return self.op.adj(self.op.fft(x_local))

@@ -92,7 +92,10 @@ struct b2n_plan {
     void* d_work = nullptr;
     size_t work_bytes = 0;
     int64_t dev_bytes = 0;
-    int64_t launches = 0;
+    int64_t launches = 0;        // our own kernels
+    int64_t lib_calls = 0;       // cuFFT executions and memsets
+    long opt_profile = 0;        // record CUDA events around the interpolation kernels
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_fwd, ev_adj;
     int last_fwd_kernel = -1;   // 0 generic, 1 tiled
     int last_adj_kernel = -1;   // 0 generic, 1 sliding window
 
@@ -230,6 +233,8 @@ extern "C" int b2n_plan_set_option(b2n_plan* p, const char* name, long value) {
         p->opt_use_tma = value;
     } else if (n == "sparse_mode") {
         p->opt_sparse_mode = value;
+    } else if (n == "profile") {
+        p->opt_profile = value;
     } else if (n == "slide_pts") {
         if (value < 32) return fail(B2N_EINVAL, "slide_pts must be >= 32");
         p->opt_slide_pts = value;
@@ -250,6 +255,8 @@ extern "C" long b2n_plan_get_option(b2n_plan* p, const char* name) {
     if (n == "use_tma") return p->opt_use_tma;
     if (n == "sparse_mode") return p->opt_sparse_mode;
     if (n == "slide_pts") return p->opt_slide_pts;
+    if (n == "profile") return p->opt_profile;
+    if (n == "lib_calls") return (long)p->lib_calls;
     if (n == "n_items") return (long)p->n_items;
     if (n == "last_fwd_kernel") return p->last_fwd_kernel;
     if (n == "last_adj_kernel") return p->last_adj_kernel;
@@ -456,6 +463,29 @@ extern "C" int64_t b2n_plan_num_bins(b2n_plan* p) { return p ? (int64_t)p->g.nbi
 extern "C" int64_t b2n_plan_device_bytes(b2n_plan* p) { return p ? p->dev_bytes : -1; }
 extern "C" int64_t b2n_plan_launch_count(b2n_plan* p) { return p ? p->launches : -1; }
 
+// out[0..3] = {forward interpolation kernel: total ms, launches; adjoint: total ms, launches}
+// measured with CUDA events on the launching stream since the last call (option "profile")
+extern "C" int b2n_plan_get_timing(b2n_plan* p, double* out) {
+    if (p == nullptr || out == nullptr) return fail(B2N_EINVAL, "NULL argument");
+    CU(cudaSetDevice(p->device));
+    for (int k = 0; k < 2; k++) {
+        auto& v = k == 0 ? p->ev_fwd : p->ev_adj;
+        double tot = 0;
+        for (auto& e : v) {
+            float ms = 0;
+            CU(cudaEventSynchronize(e.second));
+            CU(cudaEventElapsedTime(&ms, e.first, e.second));
+            tot += ms;
+            cudaEventDestroy(e.first);
+            cudaEventDestroy(e.second);
+        }
+        out[2 * k] = tot;
+        out[2 * k + 1] = (double)v.size();
+        v.clear();
+    }
+    return B2N_OK;
+}
+
 extern "C" int b2n_plan_get_points(b2n_plan* p, void* tm_dev, int32_t* bin_ids_dev,
                                    int64_t* keys_dev, int32_t* perm_dev, void* stream) {
     if (p == nullptr) return fail(B2N_EINVAL, "NULL plan");
@@ -492,6 +522,19 @@ static int run_generic(b2n_plan* p, bool fwd, const void* in, void* out, int nba
                               nbatch, p->sm_count, st);
 }
 
+static void prof_begin(b2n_plan* p, bool fwd, cudaStream_t st) {
+    if (!p->opt_profile) return;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0, st);
+    (fwd ? p->ev_fwd : p->ev_adj).push_back({e0, e1});
+}
+static void prof_end(b2n_plan* p, bool fwd, cudaStream_t st) {
+    if (!p->opt_profile) return;
+    cudaEventRecord((fwd ? p->ev_fwd : p->ev_adj).back().second, st);
+}
+
 static int check_ready(b2n_plan* p, const void* a, const void* b, int nbatch) {
     if (p == nullptr) return fail(B2N_EINVAL, "NULL plan");
     if (!p->points_set) return fail(B2N_ESTATE, "points not set");
@@ -505,6 +548,7 @@ static int interp_fwd_impl(b2n_plan* p, const void* grid, void* samples, int nba
     if (!p->tables_set) return fail(B2N_ESTATE, "tables not set");
     if (p->g.M == 0) return B2N_OK;
     bool done = false;
+    prof_begin(p, true, st);
     if (!p->opt_force_generic && !p->cplx_table) {
         const void* ph = phase ? p->d_phase_s : nullptr;
         int rc = p->precision == B2N_SINGLE
@@ -518,6 +562,7 @@ static int interp_fwd_impl(b2n_plan* p, const void* grid, void* samples, int nba
         int rc = run_generic(p, true, grid, samples, nbatch, phase, st);
         if (rc != 0) return fail(B2N_ECUDA, "generic forward launch failed: " + std::string(cudaGetErrorString((cudaError_t)rc)));
     }
+    prof_end(p, true, st);
     p->last_fwd_kernel = done ? 1 : 0;
     p->launches++;
     return B2N_OK;
@@ -527,9 +572,10 @@ static int interp_adj_impl(b2n_plan* p, const void* samples, void* grid, int nba
                            cudaStream_t st) {
     if (!p->tables_set) return fail(B2N_ESTATE, "tables not set");
     CU(cudaMemsetAsync(grid, 0, p->cplx_size() * p->g.PK * nbatch, st));
-    p->launches++;
+    p->lib_calls++;
     if (p->g.M == 0) return B2N_OK;
     bool done = false;
+    prof_begin(p, false, st);
     if (!p->opt_force_generic && !p->cplx_table) {
         const void* ph = phase ? p->d_phase_s : nullptr;
         int rc = p->precision == B2N_SINGLE
@@ -543,6 +589,7 @@ static int interp_adj_impl(b2n_plan* p, const void* samples, void* grid, int nba
         int rc = run_generic(p, false, samples, grid, nbatch, phase, st);
         if (rc != 0) return fail(B2N_ECUDA, "generic adjoint launch failed: " + std::string(cudaGetErrorString((cudaError_t)rc)));
     }
+    prof_end(p, false, st);
     p->last_adj_kernel = done ? 1 : 0;
     p->launches++;
     return B2N_OK;
@@ -648,7 +695,7 @@ static int spmv_impl(b2n_plan* p, bool fwd, const void* in, void* out, int nbatc
     if (!p->sparse_set) return fail(B2N_ESTATE, "sparse matrix not set");
     if (!fwd) {
         CU(cudaMemsetAsync(out, 0, p->cplx_size() * p->g.PK * nbatch, st));
-        p->launches++;
+        p->lib_calls++;
     }
     if (p->g.M == 0) return B2N_OK;
     if (p->precision == B2N_SINGLE) {
@@ -742,7 +789,8 @@ static int nufft_fwd_t(b2n_plan* p, const void* image, void* samples, int nbatch
     CU(cudaGetLastError());
     if (sizeof(T) == 4) FFT(cufftExecC2C(fft, (cufftComplex*)work, (cufftComplex*)work, CUFFT_FORWARD));
     else FFT(cufftExecZ2Z(fft, (cufftDoubleComplex*)work, (cufftDoubleComplex*)work, CUFFT_FORWARD));
-    p->launches += 2;
+    p->launches += 1;
+    p->lib_calls += 1;
     if (p->have_pb) {
         phase_before_kernel<T><<<grid_for(g.PK * nbatch, 256, p->sm_count, 32), 256, 0, st>>>(
             g, ax, 0, work, nbatch);
@@ -778,7 +826,8 @@ static int nufft_adj_t(b2n_plan* p, const void* samples, void* image, int nbatch
     post_crop_scale_kernel<T><<<grid_for(g.PN * nbatch, 256, p->sm_count, 32), 256, 0, st>>>(
         g, ax, (T)p->adj_scale, p->adj_scale != 1.0, work, (C*)image, nbatch);
     CU(cudaGetLastError());
-    p->launches += 2;
+    p->launches += 1;
+    p->lib_calls += 1;
     return B2N_OK;
 }
 
