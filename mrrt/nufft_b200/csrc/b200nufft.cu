@@ -57,6 +57,7 @@ struct b2n_plan {
     long opt_use_tma = 1;
     long opt_sparse_mode = 0;
     long opt_slide_pts = 256;
+    long opt_adj_kernel = 2;     // 0 generic, 1 sliding window + global REDs, 2 tiled sliding window
     bool tile_user_set = false;
     // tables
     void* d_tab[3] = {nullptr, nullptr, nullptr};
@@ -97,7 +98,7 @@ struct b2n_plan {
     long opt_profile = 0;        // record CUDA events around the interpolation kernels
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_fwd, ev_adj;
     int last_fwd_kernel = -1;   // 0 generic, 1 tiled
-    int last_adj_kernel = -1;   // 0 generic, 1 sliding window
+    int last_adj_kernel = -1;   // 0 generic, 1 sliding window, 2 tiled sliding window
 
     size_t real_size() const { return precision == B2N_SINGLE ? 4 : 8; }
     size_t cplx_size() const { return 2 * real_size(); }
@@ -233,6 +234,8 @@ extern "C" int b2n_plan_set_option(b2n_plan* p, const char* name, long value) {
         p->opt_use_tma = value;
     } else if (n == "sparse_mode") {
         p->opt_sparse_mode = value;
+    } else if (n == "adj_kernel") {
+        p->opt_adj_kernel = value;
     } else if (n == "profile") {
         p->opt_profile = value;
     } else if (n == "slide_pts") {
@@ -256,6 +259,7 @@ extern "C" long b2n_plan_get_option(b2n_plan* p, const char* name) {
     if (n == "sparse_mode") return p->opt_sparse_mode;
     if (n == "slide_pts") return p->opt_slide_pts;
     if (n == "profile") return p->opt_profile;
+    if (n == "adj_kernel") return p->opt_adj_kernel;
     if (n == "lib_calls") return (long)p->lib_calls;
     if (n == "n_items") return (long)p->n_items;
     if (n == "last_fwd_kernel") return p->last_fwd_kernel;
@@ -576,7 +580,17 @@ static int interp_adj_impl(b2n_plan* p, const void* samples, void* grid, int nba
     if (p->g.M == 0) return B2N_OK;
     bool done = false;
     prof_begin(p, false, st);
-    if (!p->opt_force_generic && !p->cplx_table) {
+    if (!p->opt_force_generic && !p->cplx_table && p->opt_adj_kernel == 2) {
+        const void* ph = phase ? p->d_phase_s : nullptr;
+        int rc = p->precision == B2N_SINGLE
+                     ? tile_adj_f32(p->g, table_ptrs(p), p->d_tm_s, p->d_pt_ko, p->d_pt_kw, p->d_perm, p->d_items,
+                                    p->n_items, samples, grid, ph, nbatch, (int)p->opt_use_tma, st, &done)
+                     : tile_adj_f64(p->g, table_ptrs(p), p->d_tm_s, p->d_pt_ko, p->d_pt_kw, p->d_perm, p->d_items,
+                                    p->n_items, samples, grid, ph, nbatch, (int)p->opt_use_tma, st, &done);
+        if (rc != 0) return fail(B2N_ECUDA, "tiled adjoint launch failed: " + std::string(cudaGetErrorString((cudaError_t)rc)));
+        if (done) p->last_adj_kernel = 2;
+    }
+    if (!done && !p->opt_force_generic && !p->cplx_table && p->opt_adj_kernel >= 1) {
         const void* ph = phase ? p->d_phase_s : nullptr;
         int rc = p->precision == B2N_SINGLE
                      ? slide_adj_f32(p->g, table_ptrs(p), p->d_tm_s, p->d_pt_ko, p->d_pt_kw, p->d_perm, samples, grid, ph, nbatch,
@@ -584,13 +598,14 @@ static int interp_adj_impl(b2n_plan* p, const void* samples, void* grid, int nba
                      : slide_adj_f64(p->g, table_ptrs(p), p->d_tm_s, p->d_pt_ko, p->d_pt_kw, p->d_perm, samples, grid, ph, nbatch,
                                      (int)p->opt_slide_pts, st, &done);
         if (rc != 0) return fail(B2N_ECUDA, "sliding adjoint launch failed: " + std::string(cudaGetErrorString((cudaError_t)rc)));
+        if (done) p->last_adj_kernel = 1;
     }
     if (!done) {
         int rc = run_generic(p, false, samples, grid, nbatch, phase, st);
         if (rc != 0) return fail(B2N_ECUDA, "generic adjoint launch failed: " + std::string(cudaGetErrorString((cudaError_t)rc)));
     }
     prof_end(p, false, st);
-    p->last_adj_kernel = done ? 1 : 0;
+    if (!done) p->last_adj_kernel = 0;
     p->launches++;
     return B2N_OK;
 }

@@ -32,7 +32,7 @@ template <> struct alignas(16) StagePt<double> {
     double fy; int ko[3]; int kw[3];
 };
 
-template <typename T, int J>
+template <typename T, int J, bool TAB_SMEM>
 __global__ void __launch_bounds__(128)
 spread_slide3d_kernel(Geom g, const T* __restrict__ h1, const T* __restrict__ h2,
                       const T* __restrict__ h3, const T* __restrict__ tm_s,
@@ -45,10 +45,18 @@ spread_slide3d_kernel(Geom g, const T* __restrict__ h1, const T* __restrict__ h2
     constexpr int RPL = (R + 31) / 32;       // rows per lane
     constexpr unsigned FULL = 0xffffffffu;
     __shared__ StagePt<T> stage[4][32];
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t M = g.M;
+    if (TAB_SMEM) {
+        // all axes share one table (checked by the launcher): stage it in shared memory,
+        // a gather from L1 costs one tag cycle per distinct sector
+        T* stab = (T*)dyn_smem;
+        for (int e = threadIdx.x; e < g.tlen[0]; e += blockDim.x) stab[e] = __ldg(h1 + e);
+        __syncthreads();
+    }
     const int64_t begin = warp * pts_per_warp;
     if (begin >= M) return;
     const int64_t end = begin + pts_per_warp < M ? begin + pts_per_warp : M;
@@ -71,7 +79,7 @@ spread_slide3d_kernel(Geom g, const T* __restrict__ h1, const T* __restrict__ h2
     const int wax = lane < J ? 0 : (lane < 2 * J ? 1 : 2);   // axis of this lane's tap
     const int wj = lane - wax * J;
     const bool wactive = lane < 3 * J;
-    const T* __restrict__ wh = wax == 0 ? h1 : (wax == 1 ? h2 : h3);
+    const T* __restrict__ wh = TAB_SMEM ? (const T*)dyn_smem : (wax == 0 ? h1 : (wax == 1 ? h2 : h3));
     const int wnc = g.ncenter[wax], wtl = g.tlen[wax];
     const T Lf = (T)g.L;
 
@@ -116,7 +124,7 @@ spread_slide3d_kernel(Geom g, const T* __restrict__ h1, const T* __restrict__ h2
                 const T alf = p - fl;
                 const int i0 = wnc + (int)fl;
                 const int i1 = min(i0 + 1, wtl - 1);
-                wl = ((T)1 - alf) * __ldg(wh + i0) + alf * __ldg(wh + i1);
+                wl = ((T)1 - alf) * wh[i0] + alf * wh[i1];
             }
             const int d = cur.kw[0] - W1;
             if (cur.kw[1] != W2 || cur.kw[2] != W3 || d < 0 || d >= J) {
@@ -196,10 +204,23 @@ static int launch_slide(const Geom& g, const TablePtrs& tabs, const void* tm_s,
     const int64_t nblocks = (nwarps + 3) / 4;
     if (nblocks > 0x7fffffff || nbatch > 65535) return 0;
     dim3 gd((unsigned)nblocks, (unsigned)nbatch);
-    spread_slide3d_kernel<T, J><<<gd, 128, 0, st>>>(
-        g, (const T*)tabs.h[0], (const T*)tabs.h[1], (const T*)tabs.h[2], (const T*)tm_s, pt_ko, pt_kw, perm,
-        (const C*)samples, (C*)grid, (const C*)phase_s, pts_per_warp);
-    cudaError_t e = cudaGetLastError();
+    const bool tab_smem = tabs.h[0] == tabs.h[1] && tabs.h[1] == tabs.h[2] &&
+                          (size_t)g.tlen[0] * sizeof(T) <= 40 * 1024;
+    cudaError_t e;
+    if (tab_smem) {
+        const size_t smem = (size_t)g.tlen[0] * sizeof(T);
+        auto k = spread_slide3d_kernel<T, J, true>;
+        e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        k<<<gd, 128, smem, st>>>(g, (const T*)tabs.h[0], (const T*)tabs.h[1], (const T*)tabs.h[2],
+                                 (const T*)tm_s, pt_ko, pt_kw, perm, (const C*)samples, (C*)grid,
+                                 (const C*)phase_s, pts_per_warp);
+    } else {
+        spread_slide3d_kernel<T, J, false><<<gd, 128, 0, st>>>(
+            g, (const T*)tabs.h[0], (const T*)tabs.h[1], (const T*)tabs.h[2], (const T*)tm_s, pt_ko,
+            pt_kw, perm, (const C*)samples, (C*)grid, (const C*)phase_s, pts_per_warp);
+    }
+    e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
     *done = true;
     return 0;
