@@ -15,12 +15,12 @@ template <typename T> struct Gam { T g[3]; };
 template <typename T>
 __global__ void prep_points_kernel(Geom g, Gam<T> gam, int kind, const T* __restrict__ coords,
                                    T* __restrict__ tm, uint64_t* __restrict__ keys,
-                                   int32_t* __restrict__ bin_ids, int32_t* __restrict__ iota,
-                                   int* __restrict__ nonfinite) {
+                                   uint64_t* __restrict__ keys_b, int32_t* __restrict__ bin_ids,
+                                   int32_t* __restrict__ iota, int* __restrict__ nonfinite) {
     const int64_t M = g.M;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < M;
          i += (int64_t)gridDim.x * blockDim.x) {
-        int64_t bin = 0, cell = 0;
+        int64_t bin = 0, cell = 0, cell_b = 0;
         int64_t bstride = 1, cstride = 1;
         bool ok = true;
 #pragma unroll
@@ -35,12 +35,15 @@ __global__ void prep_points_kernel(Geom g, Gam<T> gam, int kind, const T* __rest
                 if (ok) kw = wrap_index(window_origin<T>(t, g.J[d]), g.K[d]);
                 bin += (int64_t)(kw / g.tile[d]) * bstride;
                 cell += (int64_t)(kw % g.tile[d]) * cstride;
+                // adjoint order: LAST axis fastest inside the bin
+                cell_b = cell_b * g.tile[d] + (kw % g.tile[d]);
                 bstride *= g.nbin[d];
                 cstride *= g.tile[d];
             }
         }
         if (!ok) atomicExch(nonfinite, 1);
         keys[i] = (uint64_t)(bin * cstride + cell);
+        if (keys_b != nullptr) keys_b[i] = (uint64_t)(bin * cstride + cell_b);
         bin_ids[i] = (int32_t)bin;
         iota[i] = (int32_t)i;
     }

@@ -57,7 +57,10 @@ struct b2n_plan {
     long opt_use_tma = 1;
     long opt_sparse_mode = 0;
     long opt_slide_pts = 256;
-    long opt_adj_kernel = 2;     // 0 generic, 1 sliding window + global REDs, 2 tiled sliding window
+    // 0 generic, 1 sliding window + global REDs, 2 tiled sliding window (smem tile),
+    // 3 register window with lane-parallel batch weights and the adjoint sort order
+    long opt_adj_kernel = 3;
+    long opt_order_b = 1;        // build the adjoint sort order (adj_kernel 3)
     bool tile_user_set = false;
     // tables
     void* d_tab[3] = {nullptr, nullptr, nullptr};
@@ -78,6 +81,13 @@ struct b2n_plan {
     int32_t* d_perm = nullptr;
     int32_t* d_pt_ko = nullptr;  // [ndim][M] sorted: unwrapped window origins
     int32_t* d_pt_kw = nullptr;  // [ndim][M] sorted: wrapped window origins
+    // second ("adjoint") sort order: same bins, cells ordered last-axis-fastest
+    bool have_b = false;
+    void* d_tm_sb = nullptr;
+    int32_t* d_perm_b = nullptr;
+    int32_t* d_pt_ko_b = nullptr;
+    int32_t* d_pt_kw_b = nullptr;
+    void* d_phase_sb = nullptr;
     void* d_phase_s = nullptr;   // sorted sample phase or null
     int64_t nbins = 0;
     // work items of the tiled forward kernel: (bin, start, count, pad)
@@ -192,6 +202,11 @@ static void free_points(b2n_plan* p) {
     dev_free(p->d_perm); dev_free(p->d_phase_s); dev_free(p->d_items);
     dev_free(p->d_pt_ko); dev_free(p->d_pt_kw);
     p->d_pt_ko = p->d_pt_kw = nullptr;
+    dev_free(p->d_tm_sb); dev_free(p->d_perm_b); dev_free(p->d_pt_ko_b); dev_free(p->d_pt_kw_b);
+    dev_free(p->d_phase_sb);
+    p->d_tm_sb = p->d_phase_sb = nullptr;
+    p->d_perm_b = p->d_pt_ko_b = p->d_pt_kw_b = nullptr;
+    p->have_b = false;
     p->d_tm = p->d_tm_s = p->d_phase_s = nullptr;
     p->d_keys = nullptr; p->d_bin_ids = nullptr; p->d_perm = nullptr; p->d_items = nullptr;
     p->points_set = false;
@@ -236,6 +251,9 @@ extern "C" int b2n_plan_set_option(b2n_plan* p, const char* name, long value) {
         p->opt_sparse_mode = value;
     } else if (n == "adj_kernel") {
         p->opt_adj_kernel = value;
+    } else if (n == "order_b") {
+        if (p->points_set) return fail(B2N_ESTATE, "order_b must precede set_points");
+        p->opt_order_b = value;
     } else if (n == "profile") {
         p->opt_profile = value;
     } else if (n == "slide_pts") {
@@ -348,6 +366,16 @@ static int set_points_t(b2n_plan* p, const void* coords, int64_t M, int kind, cu
         p->points_set = true;
         return B2N_OK;
     }
+    // the adjoint order is only used by the 3-D register-window kernel
+    const bool want_b = g.ndim == 3 && !p->cplx_table && p->opt_adj_kernel == 3 && p->opt_order_b;
+    uint64_t* keys_b = nullptr;
+    if (want_b) {
+        if ((rc = dev_alloc(p, &p->d_tm_sb, rs * M * g.ndim))) return rc;
+        if ((rc = dev_alloc(p, (void**)&p->d_perm_b, sizeof(int32_t) * M))) return rc;
+        if ((rc = dev_alloc(p, (void**)&p->d_pt_ko_b, sizeof(int32_t) * M * g.ndim))) return rc;
+        if ((rc = dev_alloc(p, (void**)&p->d_pt_kw_b, sizeof(int32_t) * M * g.ndim))) return rc;
+        CU(cudaMalloc(&keys_b, sizeof(uint64_t) * M));
+    }
     uint64_t* keys_s = nullptr;
     int32_t* iota = nullptr;
     int* flag = nullptr;
@@ -360,7 +388,7 @@ static int set_points_t(b2n_plan* p, const void* coords, int64_t M, int kind, cu
     Gam<T> gam;
     for (int d = 0; d < 3; d++) gam.g[d] = (T)(2.0 * M_PI / (double)g.K[d]);
     prep_points_kernel<T><<<grid_for(M, 256, p->sm_count), 256, 0, st>>>(
-        g, gam, kind, (const T*)coords, (T*)p->d_tm, p->d_keys, p->d_bin_ids, iota, flag);
+        g, gam, kind, (const T*)coords, (T*)p->d_tm, p->d_keys, keys_b, p->d_bin_ids, iota, flag);
     CU(cudaGetLastError());
     // stable LSD radix sort over just the significant key bits
     uint64_t maxkey = (uint64_t)p->nbins * (uint64_t)g.cells_per_tile;
@@ -378,6 +406,22 @@ static int set_points_t(b2n_plan* p, const void* coords, int64_t M, int kind, cu
     point_windows_kernel<T><<<grid_for(M, 256, p->sm_count), 256, 0, st>>>(
         g, (const T*)p->d_tm_s, p->d_pt_ko, p->d_pt_kw);
     CU(cudaGetLastError());
+    if (want_b) {
+        uint64_t* keys_bs = nullptr;
+        CU(cudaMalloc(&keys_bs, sizeof(uint64_t) * M));
+        CU(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys_b, keys_bs, iota, p->d_perm_b, M, 0,
+                                           bits, st));
+        gather_points_kernel<T><<<grid_for(M, 256, p->sm_count), 256, 0, st>>>(
+            g.ndim, M, p->d_perm_b, (const T*)p->d_tm, (T*)p->d_tm_sb);
+        CU(cudaGetLastError());
+        point_windows_kernel<T><<<grid_for(M, 256, p->sm_count), 256, 0, st>>>(
+            g, (const T*)p->d_tm_sb, p->d_pt_ko_b, p->d_pt_kw_b);
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(st));
+        cudaFree(keys_bs);
+        cudaFree(keys_b);
+        p->have_b = true;
+    }
     // bin boundaries -> host -> work items of at most opt_chunk samples
     CU(cudaMalloc(&bin_start, sizeof(int32_t) * p->nbins));
     CU(cudaMemsetAsync(bin_start, 0xff, sizeof(int32_t) * p->nbins, st));
@@ -441,7 +485,8 @@ extern "C" int b2n_plan_set_sample_phase(b2n_plan* p, const void* phase_dev, voi
     cudaStream_t st = (cudaStream_t)stream;
     if (phase_dev == nullptr) {
         dev_free(p->d_phase_s);
-        p->d_phase_s = nullptr;
+        dev_free(p->d_phase_sb);
+        p->d_phase_s = p->d_phase_sb = nullptr;
         return B2N_OK;
     }
     const int64_t M = p->g.M;
@@ -458,6 +503,19 @@ extern "C" int b2n_plan_set_sample_phase(b2n_plan* p, const void* phase_dev, voi
                 M, p->d_perm, (const double2*)phase_dev, (double2*)p->d_phase_s);
         CU(cudaGetLastError());
         p->launches++;
+        if (p->have_b) {
+            if (p->d_phase_sb == nullptr) {
+                int rc = dev_alloc(p, &p->d_phase_sb, p->cplx_size() * M);
+                if (rc) return rc;
+            }
+            if (p->precision == B2N_SINGLE)
+                gather_c_kernel<float2><<<grid_for(M, 256, p->sm_count), 256, 0, st>>>(
+                    M, p->d_perm_b, (const float2*)phase_dev, (float2*)p->d_phase_sb);
+            else
+                gather_c_kernel<double2><<<grid_for(M, 256, p->sm_count), 256, 0, st>>>(
+                    M, p->d_perm_b, (const double2*)phase_dev, (double2*)p->d_phase_sb);
+            CU(cudaGetLastError());
+        }
     }
     return B2N_OK;
 }
@@ -580,7 +638,24 @@ static int interp_adj_impl(b2n_plan* p, const void* samples, void* grid, int nba
     if (p->g.M == 0) return B2N_OK;
     bool done = false;
     prof_begin(p, false, st);
-    if (!p->opt_force_generic && !p->cplx_table && p->opt_adj_kernel == 2) {
+    if (!p->opt_force_generic && !p->cplx_table && p->opt_adj_kernel == 3) {
+        // register window, lane-parallel batch weights; adjoint sort order when built
+        const bool ob = p->have_b;
+        const void* ph = phase ? (ob ? p->d_phase_sb : p->d_phase_s) : nullptr;
+        const void* tms = ob ? p->d_tm_sb : p->d_tm_s;
+        const int32_t* ko = ob ? p->d_pt_ko_b : p->d_pt_ko;
+        const int32_t* kw = ob ? p->d_pt_kw_b : p->d_pt_kw;
+        const int32_t* pm = ob ? p->d_perm_b : p->d_perm;
+        const int slide_axis = ob ? 2 : 0;
+        int rc = p->precision == B2N_SINGLE
+                     ? window_adj_f32(p->g, table_ptrs(p), slide_axis, tms, ko, kw, pm, samples, grid, ph,
+                                      nbatch, (int)p->opt_slide_pts, st, &done)
+                     : window_adj_f64(p->g, table_ptrs(p), slide_axis, tms, ko, kw, pm, samples, grid, ph,
+                                      nbatch, (int)p->opt_slide_pts, st, &done);
+        if (rc != 0) return fail(B2N_ECUDA, "window adjoint launch failed: " + std::string(cudaGetErrorString((cudaError_t)rc)));
+        if (done) p->last_adj_kernel = 3;
+    }
+    if (!done && !p->opt_force_generic && !p->cplx_table && p->opt_adj_kernel == 2) {
         const void* ph = phase ? p->d_phase_s : nullptr;
         int rc = p->precision == B2N_SINGLE
                      ? tile_adj_f32(p->g, table_ptrs(p), p->d_tm_s, p->d_pt_ko, p->d_pt_kw, p->d_perm, p->d_items,

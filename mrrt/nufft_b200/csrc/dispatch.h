@@ -29,6 +29,14 @@ struct TablePtrs {
                        const int32_t* pt_kw, const int32_t* perm, const int4* items,             \
                        int64_t n_items, const void* samples, void* grid, const void* phase_s,    \
                        int nbatch, int use_tma, cudaStream_t st, bool* done);
+#define B2N_DECLARE3(SUF)                                                                        \
+    int window_adj_##SUF(const Geom& g, const TablePtrs& tabs, int slide_axis, const void* tm_s, \
+                         const int32_t* pt_ko, const int32_t* pt_kw, const int32_t* perm,        \
+                         const void* samples, void* grid, const void* phase_s, int nbatch,       \
+                         int pts_per_warp, cudaStream_t st, bool* done);
+B2N_DECLARE3(f32)
+B2N_DECLARE3(f64)
+#undef B2N_DECLARE3
 B2N_DECLARE2(f32)
 B2N_DECLARE2(f64)
 #undef B2N_DECLARE2

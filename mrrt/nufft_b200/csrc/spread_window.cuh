@@ -1,0 +1,276 @@
+// Register-window adjoint gridding, second generation (3-D, real table, uniform J).
+//
+// Each warp walks a contiguous run of cell-sorted samples and keeps the current sample's
+// J x J x J window of partial sums in registers: lane <-> one (b, c) position of the
+// window face, J accumulators along the SLIDE axis a.  Consecutive samples of the sorted
+// order sit in the same or the next cell along a, so the window slides and only the
+// retiring J x J face is sent to L2 (vector REDs).  Axis roles are a run-time
+// permutation: with the adjoint sort order (cells ordered axis-3-fastest inside a bin)
+// a = axis 3 and the lane face is (axis 1, axis 2), so that the lanes of one retiring
+// face write runs of J CONSECUTIVE grid cells -- 2-3 sectors per run instead of one
+// sector per lane (profiles/r01_notes.md: strided REDs were the L1TEX bottleneck).
+//
+// Per 32-sample batch the weights are evaluated LANE-PARALLEL (lane = sample: 3J table
+// taps each, table staged in shared memory) together with a window action code
+// (slide distance or "new window") and written to a per-warp staging record; the
+// per-sample loop then only does broadcast shared-memory reads and FMAs.
+//
+// Arithmetic per sample follows c/nufft_table.template.c:1122-1163:
+// v3 = coef3*f, v2 = coef2*v3, ck += coef1*v2 (the same products, grouped by axis role).
+#pragma once
+#include "common.cuh"
+#include "dispatch.h"
+
+namespace b2n {
+
+struct WindowAxes {
+    int ax[3];          // ax[0] = slide axis a, ax[1] = fast lane axis b, ax[2] = slow lane axis c
+    int K[3];           // grid size along (a, b, c)
+    int stride[3];      // grid stride (cells) along (a, b, c)
+};
+
+template <typename T, int J> struct WinRec {
+    static constexpr int kW = 3 * J + 2;                         // weights + fx, fy
+    static constexpr int kBytes = ((kW * (int)sizeof(T) + 15) / 16) * 16 + 16;
+};
+
+template <typename T, int J, bool TAB_SMEM>
+__global__ void __launch_bounds__(128)
+spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T* __restrict__ h2,
+                       const T* __restrict__ h3, const T* __restrict__ tm_s,
+                       const int32_t* __restrict__ pt_ko, const int32_t* __restrict__ pt_kw,
+                       const int32_t* __restrict__ perm, const cplx_t<T>* __restrict__ samples,
+                       cplx_t<T>* __restrict__ grid, const cplx_t<T>* __restrict__ phase_s,
+                       int pts_per_warp) {
+    using C = cplx_t<T>;
+    constexpr int R = J * J;
+    constexpr int RPL = (R + 31) / 32;
+    constexpr int RB = WinRec<T, J>::kBytes;
+    constexpr unsigned FULL = 0xffffffffu;
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    unsigned char* stage_all = dyn_smem;                          // [4 warps][32 records]
+    const T* stab = (const T*)(dyn_smem + 4 * 32 * RB);
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    unsigned char* stage = stage_all + wib * 32 * RB;
+    const int64_t M = g.M;
+    if (TAB_SMEM) {
+        T* st = (T*)(dyn_smem + 4 * 32 * RB);
+        for (int e = threadIdx.x; e < g.tlen[0]; e += blockDim.x) st[e] = __ldg(h1 + e);
+        __syncthreads();
+    }
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t begin = warp * pts_per_warp;
+    if (begin >= M) return;
+    const int64_t end = begin + pts_per_warp < M ? begin + pts_per_warp : M;
+    const int b = blockIdx.y;
+    const C* __restrict__ sb = samples + (int64_t)b * M;
+    C* __restrict__ gb = grid + (int64_t)b * g.PK;
+    const int aA = wa.ax[0], aB = wa.ax[1], aC = wa.ax[2];
+    const int KA = wa.K[0], KB = wa.K[1], KC = wa.K[2];
+    const int sA = wa.stride[0], sB = wa.stride[1], sC = wa.stride[2];
+    const T* __restrict__ tabA = TAB_SMEM ? stab : (aA == 0 ? h1 : (aA == 1 ? h2 : h3));
+    const T* __restrict__ tabB = TAB_SMEM ? stab : (aB == 0 ? h1 : (aB == 1 ? h2 : h3));
+    const T* __restrict__ tabC = TAB_SMEM ? stab : (aC == 0 ? h1 : (aC == 1 ? h2 : h3));
+    const T Lf = (T)g.L;
+
+    // this lane's positions on the window face: r = jb + J*jc
+    int rjb[RPL], rjc[RPL];
+    bool rvalid[RPL];
+#pragma unroll
+    for (int s = 0; s < RPL; s++) {
+        const int r = lane + 32 * s;
+        rvalid[s] = r < R;
+        rjb[s] = (r % R) % J;
+        rjc[s] = (r % R) / J;
+    }
+    C acc[RPL][J];
+    int facebase[RPL];      // grid offset of this lane's face position (axes b, c)
+#pragma unroll
+    for (int s = 0; s < RPL; s++) {
+        facebase[s] = 0;
+#pragma unroll
+        for (int j = 0; j < J; j++) acc[s][j] = make_c<T>(0, 0);
+    }
+    int WA = 0;             // wrapped window origin along the slide axis
+    bool have = false;
+    int pkA = -1 << 30, pkB = -1, pkC = -1;   // previous sample's wrapped origin
+
+    for (int64_t base = begin; base < end; base += 32) {
+        const int cnt = (int)(end - base < 32 ? end - base : 32);
+        __syncwarp();
+        // ---- batch phase: lane = sample
+        int kA = 0, kB = 0, kC = 0;
+        if (lane < cnt) {
+            const int64_t i = base + lane;
+            T* w = (T*)(stage + lane * RB);
+            int* ik = (int*)(stage + lane * RB + RB - 16);
+            const T tA = tm_s[(int64_t)aA * M + i], tB = tm_s[(int64_t)aB * M + i],
+                    tC = tm_s[(int64_t)aC * M + i];
+            const int oA = pt_ko[(int64_t)aA * M + i], oB = pt_ko[(int64_t)aB * M + i],
+                      oC = pt_ko[(int64_t)aC * M + i];
+            kA = pt_kw[(int64_t)aA * M + i];
+            kB = pt_kw[(int64_t)aB * M + i];
+            kC = pt_kw[(int64_t)aC * M + i];
+#pragma unroll
+            for (int j = 0; j < J; j++) {
+                w[j] = tap_real<T>(tabA, g.ncenter[aA], g.tlen[aA], tA, oA + j, g.L);
+                w[J + j] = tap_real<T>(tabB, g.ncenter[aB], g.tlen[aB], tB, oB + j, g.L);
+                w[2 * J + j] = tap_real<T>(tabC, g.ncenter[aC], g.tlen[aC], tC, oC + j, g.L);
+            }
+            C f = sb[perm[i]];
+            if (phase_s != nullptr) f = cmul_conj(f, phase_s[i]);
+            w[3 * J] = f.x;
+            w[3 * J + 1] = f.y;
+            ik[0] = kA; ik[1] = kB; ik[2] = kC;
+        }
+        // window action: slide distance along a, or -1 = new window
+        {
+            int qA = __shfl_up_sync(FULL, kA, 1), qB = __shfl_up_sync(FULL, kB, 1),
+                qC = __shfl_up_sync(FULL, kC, 1);
+            if (lane == 0) { qA = pkA; qB = pkB; qC = pkC; }
+            const int d = kA - qA;
+            const int act = (kB == qB && kC == qC && d >= 0 && d < J) ? d : -1;
+            if (lane < cnt) ((int*)(stage + lane * RB + RB - 16))[3] = act;
+            pkA = __shfl_sync(FULL, kA, cnt - 1);
+            pkB = __shfl_sync(FULL, kB, cnt - 1);
+            pkC = __shfl_sync(FULL, kC, cnt - 1);
+        }
+        (void)Lf;
+        __syncwarp();
+        // ---- sample loop: all lanes work on one sample
+        for (int q = 0; q < cnt; q++) {
+            const unsigned char* rec = stage + q * RB;
+            const int4 kk = *(const int4*)(rec + RB - 16);
+            if (kk.w < 0) {
+                if (have) {
+#pragma unroll
+                    for (int j = 0; j < J; j++) {
+                        int ka = WA + j;
+                        if (ka >= KA) ka -= KA;
+#pragma unroll
+                        for (int s = 0; s < RPL; s++) {
+                            if (rvalid[s]) atomic_add_c(gb + facebase[s] + ka * sA, acc[s][j]);
+                            acc[s][j] = make_c<T>(0, 0);
+                        }
+                    }
+                }
+                have = true;
+                WA = kk.x;
+#pragma unroll
+                for (int s = 0; s < RPL; s++) {
+                    int kb = kk.y + rjb[s]; if (kb >= KB) kb -= KB;
+                    int kc = kk.z + rjc[s]; if (kc >= KC) kc -= KC;
+                    facebase[s] = kb * sB + kc * sC;
+                }
+            } else {
+                for (int sft = 0; sft < kk.w; sft++) {
+#pragma unroll
+                    for (int s = 0; s < RPL; s++) {
+                        if (rvalid[s]) atomic_add_c(gb + facebase[s] + WA * sA, acc[s][0]);
+#pragma unroll
+                        for (int j = 0; j + 1 < J; j++) acc[s][j] = acc[s][j + 1];
+                        acc[s][J - 1] = make_c<T>(0, 0);
+                    }
+                    WA++;   // stays < KA: it ends at this sample's wrapped origin
+                }
+            }
+            const T* w = (const T*)rec;
+            T wA[J];
+#pragma unroll
+            for (int j = 0; j < J; j++) wA[j] = w[j];
+            const T fx = w[3 * J], fy = w[3 * J + 1];
+#pragma unroll
+            for (int s = 0; s < RPL; s++) {
+                if (rvalid[s]) {
+                    const T wb = w[J + rjb[s]];
+                    const T wc = w[2 * J + rjc[s]];
+                    // (coef_c * f) * coef_b, then * coef_a per cell
+                    const T v3x = wc * fx, v3y = wc * fy;
+                    const T v2x = wb * v3x, v2y = wb * v3y;
+#pragma unroll
+                    for (int j = 0; j < J; j++) {
+                        acc[s][j].x += wA[j] * v2x;
+                        acc[s][j].y += wA[j] * v2y;
+                    }
+                }
+            }
+        }
+    }
+    if (have) {
+#pragma unroll
+        for (int j = 0; j < J; j++) {
+            int ka = WA + j;
+            if (ka >= KA) ka -= KA;
+#pragma unroll
+            for (int s = 0; s < RPL; s++)
+                if (rvalid[s]) atomic_add_c(gb + facebase[s] + ka * sA, acc[s][j]);
+        }
+    }
+}
+
+template <typename T, int J>
+static int launch_window(const Geom& g, const TablePtrs& tabs, int slide_axis, const void* tm_s,
+                         const int32_t* pt_ko, const int32_t* pt_kw, const int32_t* perm,
+                         const void* samples, void* grid, const void* phase_s, int nbatch,
+                         int pts_per_warp, cudaStream_t st, bool* done) {
+    using C = cplx_t<T>;
+    const int64_t nwarps = (g.M + pts_per_warp - 1) / pts_per_warp;
+    const int64_t nblocks = (nwarps + 3) / 4;
+    if (nblocks > 0x7fffffff || nbatch > 65535) return 0;
+    WindowAxes wa;
+    if (slide_axis == 2) { wa.ax[0] = 2; wa.ax[1] = 0; wa.ax[2] = 1; }
+    else { wa.ax[0] = 0; wa.ax[1] = 1; wa.ax[2] = 2; }
+    const int strides[3] = {1, g.K[0], g.K[0] * g.K[1]};
+    for (int r = 0; r < 3; r++) { wa.K[r] = g.K[wa.ax[r]]; wa.stride[r] = strides[wa.ax[r]]; }
+    dim3 gd((unsigned)nblocks, (unsigned)nbatch);
+    const bool tab_smem = tabs.h[0] == tabs.h[1] && tabs.h[1] == tabs.h[2] &&
+                          (size_t)g.tlen[0] * sizeof(T) <= 56 * 1024;
+    const size_t stage_bytes = (size_t)4 * 32 * WinRec<T, J>::kBytes;
+    cudaError_t e;
+    if (tab_smem) {
+        const size_t smem = stage_bytes + (size_t)g.tlen[0] * sizeof(T);
+        auto k = spread_window3d_kernel<T, J, true>;
+        e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        k<<<gd, 128, smem, st>>>(g, wa, (const T*)tabs.h[0], (const T*)tabs.h[1], (const T*)tabs.h[2],
+                                 (const T*)tm_s, pt_ko, pt_kw, perm, (const C*)samples, (C*)grid,
+                                 (const C*)phase_s, pts_per_warp);
+    } else {
+        auto k = spread_window3d_kernel<T, J, false>;
+        e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes);
+        if (e != cudaSuccess) return (int)e;
+        k<<<gd, 128, stage_bytes, st>>>(g, wa, (const T*)tabs.h[0], (const T*)tabs.h[1],
+                                        (const T*)tabs.h[2], (const T*)tm_s, pt_ko, pt_kw, perm,
+                                        (const C*)samples, (C*)grid, (const C*)phase_s, pts_per_warp);
+    }
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    *done = true;
+    return 0;
+}
+
+template <typename T>
+static int window_adj_t(const Geom& g, const TablePtrs& tabs, int slide_axis, const void* tm_s,
+                        const int32_t* pt_ko, const int32_t* pt_kw, const int32_t* perm,
+                        const void* samples, void* grid, const void* phase_s, int nbatch,
+                        int pts_per_warp, cudaStream_t st, bool* done) {
+    *done = false;
+    if (g.ndim != 3) return 0;
+    if (g.J[1] != g.J[0] || g.J[2] != g.J[0]) return 0;
+    if (g.K[0] < g.J[0] || g.K[1] < g.J[0] || g.K[2] < g.J[0]) return 0;
+#define B2N_WIN(JJ)                                                                          \
+    return launch_window<T, JJ>(g, tabs, slide_axis, tm_s, pt_ko, pt_kw, perm, samples, grid, \
+                                phase_s, nbatch, pts_per_warp, st, done)
+    switch (g.J[0]) {
+        case 4: B2N_WIN(4);
+        case 5: B2N_WIN(5);
+        case 6: B2N_WIN(6);
+        case 7: B2N_WIN(7);
+        case 8: B2N_WIN(8);
+        default: return 0;
+    }
+#undef B2N_WIN
+}
+
+}  // namespace b2n

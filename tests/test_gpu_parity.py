@@ -49,7 +49,7 @@ def test_golden(name, variant):
     if variant == "auto" and cfg["mode"] == "table" and cfg["phasing"] == "real" and A.ndim == 3 \
             and len(set(A.Jd)) == 1 and A.Jd[0] in (4, 6, 8):
         assert A.option("last_fwd_kernel") == 1   # tiled TMA kernel really ran
-        assert A.option("last_adj_kernel") == 2   # tiled sliding-window kernel really ran
+        assert A.option("last_adj_kernel") == 3   # register-window kernel really ran
 
 
 @pytest.mark.parametrize("name", ["d1_sparse_single_real", "d1_sparse_double_complex",
@@ -105,7 +105,7 @@ def _radial3d(S, n):
 
 
 @pytest.mark.parametrize("precision", ["single", "double"])
-@pytest.mark.parametrize("variant", ["auto", "generic", "no_tma", "slide"])
+@pytest.mark.parametrize("variant", ["auto", "generic", "no_tma", "slide", "tile", "window_a"])
 def test_mid_3d_radial_vs_oracle(precision, variant):
     """3-D radial, J=6, Kd=1.5N (BASELINE configs[4] scaled down) vs the live oracle."""
     from oracle import nufft_oracle as orc
@@ -115,7 +115,8 @@ def test_mid_3d_radial_vs_oracle(precision, variant):
     rdt = np.float32 if precision == "single" else np.float64
     om = _radial3d(700, 64).astype(rdt)
     opts = {"generic": {"force_generic": 1}, "no_tma": {"use_tma": 0}, "auto": {},
-            "slide": {"adj_kernel": 1}}[variant]
+            "slide": {"adj_kernel": 1}, "tile": {"adj_kernel": 2},
+            "window_a": {"adj_kernel": 3, "order_b": 0}}[variant]
     A = NufftBase(Nd=Nd, omega=om, Jd=6, Kd=Kd, precision=precision, options=opts)
     eng = "reference" if orc.have_reference_engine() else "port"
     O = orc.OracleNufft(Nd=Nd, omega=om, Jd=6, Kd=Kd, precision=precision, engine=eng)
