@@ -72,7 +72,12 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
     const T* __restrict__ tabA = TAB_SMEM ? stab : (aA == 0 ? h1 : (aA == 1 ? h2 : h3));
     const T* __restrict__ tabB = TAB_SMEM ? stab : (aB == 0 ? h1 : (aB == 1 ? h2 : h3));
     const T* __restrict__ tabC = TAB_SMEM ? stab : (aC == 0 ? h1 : (aC == 1 ? h2 : h3));
-    const T Lf = (T)g.L;
+    const int ncA = aA == 0 ? g.ncenter[0] : (aA == 1 ? g.ncenter[1] : g.ncenter[2]);
+    const int ncB = aB == 0 ? g.ncenter[0] : (aB == 1 ? g.ncenter[1] : g.ncenter[2]);
+    const int ncC = aC == 0 ? g.ncenter[0] : (aC == 1 ? g.ncenter[1] : g.ncenter[2]);
+    const int tlA = aA == 0 ? g.tlen[0] : (aA == 1 ? g.tlen[1] : g.tlen[2]);
+    const int tlB = aB == 0 ? g.tlen[0] : (aB == 1 ? g.tlen[1] : g.tlen[2]);
+    const int tlC = aC == 0 ? g.tlen[0] : (aC == 1 ? g.tlen[1] : g.tlen[2]);
 
     // this lane's positions on the window face: r = jb + J*jc
     int rjb[RPL], rjc[RPL];
@@ -85,10 +90,10 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
         rjc[s] = (r % R) / J;
     }
     C acc[RPL][J];
-    int facebase[RPL];      // grid offset of this lane's face position (axes b, c)
+    C* faceptr[RPL];        // grid address of this lane's face position (axes b, c)
 #pragma unroll
     for (int s = 0; s < RPL; s++) {
-        facebase[s] = 0;
+        faceptr[s] = gb;
 #pragma unroll
         for (int j = 0; j < J; j++) acc[s][j] = make_c<T>(0, 0);
     }
@@ -114,9 +119,9 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
             kC = pt_kw[(int64_t)aC * M + i];
 #pragma unroll
             for (int j = 0; j < J; j++) {
-                w[j] = tap_real<T>(tabA, g.ncenter[aA], g.tlen[aA], tA, oA + j, g.L);
-                w[J + j] = tap_real<T>(tabB, g.ncenter[aB], g.tlen[aB], tB, oB + j, g.L);
-                w[2 * J + j] = tap_real<T>(tabC, g.ncenter[aC], g.tlen[aC], tC, oC + j, g.L);
+                w[j] = tap_real<T>(tabA, ncA, tlA, tA, oA + j, g.L);
+                w[J + j] = tap_real<T>(tabB, ncB, tlB, tB, oB + j, g.L);
+                w[2 * J + j] = tap_real<T>(tabC, ncC, tlC, tC, oC + j, g.L);
             }
             C f = sb[perm[i]];
             if (phase_s != nullptr) f = cmul_conj(f, phase_s[i]);
@@ -136,12 +141,26 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
             pkB = __shfl_sync(FULL, kB, cnt - 1);
             pkC = __shfl_sync(FULL, kC, cnt - 1);
         }
-        (void)Lf;
         __syncwarp();
         // ---- sample loop: all lanes work on one sample
+        int4 kk_next = *(const int4*)(stage + RB - 16);
         for (int q = 0; q < cnt; q++) {
             const unsigned char* rec = stage + q * RB;
-            const int4 kk = *(const int4*)(rec + RB - 16);
+            const int4 kk = kk_next;
+            if (q + 1 < cnt) kk_next = *(const int4*)(rec + RB + RB - 16);
+            // operands of this sample are fetched before the window update so that their
+            // shared-memory latency overlaps it
+            const T* w = (const T*)rec;
+            T wA[J];
+#pragma unroll
+            for (int j = 0; j < J; j++) wA[j] = w[j];
+            const T fx = w[3 * J], fy = w[3 * J + 1];
+            T wb[RPL], wc[RPL];
+#pragma unroll
+            for (int s = 0; s < RPL; s++) {
+                wb[s] = w[J + rjb[s]];
+                wc[s] = w[2 * J + rjc[s]];
+            }
             if (kk.w < 0) {
                 if (have) {
 #pragma unroll
@@ -150,7 +169,7 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
                         if (ka >= KA) ka -= KA;
 #pragma unroll
                         for (int s = 0; s < RPL; s++) {
-                            if (rvalid[s]) atomic_add_c(gb + facebase[s] + ka * sA, acc[s][j]);
+                            if (rvalid[s]) atomic_add_c(faceptr[s] + (int64_t)ka * sA, acc[s][j]);
                             acc[s][j] = make_c<T>(0, 0);
                         }
                     }
@@ -161,13 +180,14 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
                 for (int s = 0; s < RPL; s++) {
                     int kb = kk.y + rjb[s]; if (kb >= KB) kb -= KB;
                     int kc = kk.z + rjc[s]; if (kc >= KC) kc -= KC;
-                    facebase[s] = kb * sB + kc * sC;
+                    faceptr[s] = gb + ((int64_t)kb * sB + (int64_t)kc * sC);
                 }
             } else {
+#pragma unroll 1
                 for (int sft = 0; sft < kk.w; sft++) {
 #pragma unroll
                     for (int s = 0; s < RPL; s++) {
-                        if (rvalid[s]) atomic_add_c(gb + facebase[s] + WA * sA, acc[s][0]);
+                        if (rvalid[s]) atomic_add_c(faceptr[s] + (int64_t)WA * sA, acc[s][0]);
 #pragma unroll
                         for (int j = 0; j + 1 < J; j++) acc[s][j] = acc[s][j + 1];
                         acc[s][J - 1] = make_c<T>(0, 0);
@@ -175,19 +195,12 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
                     WA++;   // stays < KA: it ends at this sample's wrapped origin
                 }
             }
-            const T* w = (const T*)rec;
-            T wA[J];
-#pragma unroll
-            for (int j = 0; j < J; j++) wA[j] = w[j];
-            const T fx = w[3 * J], fy = w[3 * J + 1];
 #pragma unroll
             for (int s = 0; s < RPL; s++) {
                 if (rvalid[s]) {
-                    const T wb = w[J + rjb[s]];
-                    const T wc = w[2 * J + rjc[s]];
                     // (coef_c * f) * coef_b, then * coef_a per cell
-                    const T v3x = wc * fx, v3y = wc * fy;
-                    const T v2x = wb * v3x, v2y = wb * v3y;
+                    const T v3x = wc[s] * fx, v3y = wc[s] * fy;
+                    const T v2x = wb[s] * v3x, v2y = wb[s] * v3y;
 #pragma unroll
                     for (int j = 0; j < J; j++) {
                         acc[s][j].x += wA[j] * v2x;
@@ -204,7 +217,7 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
             if (ka >= KA) ka -= KA;
 #pragma unroll
             for (int s = 0; s < RPL; s++)
-                if (rvalid[s]) atomic_add_c(gb + facebase[s] + ka * sA, acc[s][j]);
+                if (rvalid[s]) atomic_add_c(faceptr[s] + (int64_t)ka * sA, acc[s][j]);
         }
     }
 }
