@@ -204,6 +204,28 @@ def test_adjointness_and_linearity_large():
     assert float(torch.linalg.norm(B.adj(y) - Ahy) / torch.linalg.norm(Ahy)) < 1e-5
 
 
+def test_bench_workload_subsample_vs_oracle():
+    """BASELINE configs[4] itself (3-D 256^3, Kd 384^3, J=6, complex64) on every 128th
+    spoke of the bench trajectory (M = 412k) against the reference's compiled C driven by
+    the oracle pipeline.  At this size the reference's own float32 rounding (phase_before
+    angles up to 2400 rad in float32, sequential float32 gridding) is what separates two
+    correct implementations; see DESIGN.md section 2."""
+    import bench
+    from oracle import nufft_oracle as orc
+    from mrrt.nufft_b200 import NufftBase
+
+    idx = np.arange(0, bench.SPOKES, 128)
+    om = np.concatenate([bench.radial3d(bench.SPOKES, bench.NREAD, int(s), int(s) + 1) for s in idx], 0)
+    A = NufftBase(Nd=bench.ND, omega=om, Jd=bench.JD, Kd=bench.KD, precision="single")
+    eng = "reference" if orc.have_reference_engine() else "port"
+    O = orc.OracleNufft(Nd=bench.ND, omega=om, Jd=bench.JD, Kd=bench.KD, precision="single",
+                        engine=eng)
+    x = bench.image()
+    yo = O.fft(x)
+    assert rel_l2(A.fft(x), yo) <= TOL["single"]
+    assert rel_l2(A.adj(yo), O.adj(yo)) <= TOL["single"]
+
+
 def test_array_kinds_and_dtypes():
     """NumPy in -> NumPy out, torch in -> torch out; output dtype follows `precision`
     whatever the input dtype (tests/test_nufft.py:376-388)."""
