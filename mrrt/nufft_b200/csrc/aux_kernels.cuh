@@ -112,32 +112,64 @@ struct AxisPtrs {
 // grid[k] = x[k] * sn[k] * fwd_scale inside the Nd corner, 0 elsewhere
 // (_nufft.py:1325-1331: `x * sn` then zero-padded FFT).  sn is the reference's dense
 // array re-formed on the fly: ((s1*s2)*s3) in double, then cast (:737-748).
-template <typename T>
+// One thread handles VEC consecutive cells of a grid row, so the row decode (integer
+// divisions) is amortised and the stores are 16-32 bytes wide.
+template <typename T, int VEC>
 __global__ void pre_scale_pad_kernel(Geom g, AxisPtrs ax, T fwd_scale, int apply_scale,
                                      const cplx_t<T>* __restrict__ image,
                                      cplx_t<T>* __restrict__ grid, int nbatch) {
     using C = cplx_t<T>;
-    const int64_t total = g.PK * nbatch;
+    const int cpr = (g.K[0] + VEC - 1) / VEC;               // chunks per row
+    const int64_t rows = (g.PK / g.K[0]) * nbatch;
+    const int64_t total = rows * cpr;
     for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
          idx += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t b = idx / g.PK;
-        int64_t r = idx - b * g.PK;
-        const int k1 = (int)(r % g.K[0]);
-        r /= g.K[0];
-        const int k2 = g.ndim > 1 ? (int)(r % g.K[1]) : 0;
-        const int k3 = g.ndim > 2 ? (int)(r / g.K[1]) : 0;
-        C v = make_c<T>(0, 0);
-        if (k1 < g.N[0] && (g.ndim < 2 || k2 < g.N[1]) && (g.ndim < 3 || k3 < g.N[2])) {
-            double s = ax.sn[0][k1];
-            int64_t n = k1;
-            if (g.ndim > 1) { s *= ax.sn[1][k2]; n += (int64_t)k2 * g.N[0]; }
-            if (g.ndim > 2) { s *= ax.sn[2][k3]; n += (int64_t)k3 * g.N[0] * g.N[1]; }
-            const T st = (T)s;
-            const C x = image[b * g.PN + n];
-            v = make_c<T>(x.x * st, x.y * st);
-            if (apply_scale) { v.x *= fwd_scale; v.y *= fwd_scale; }
+        const int64_t row = idx / cpr;
+        const int k1s = (int)(idx - row * cpr) * VEC;
+        const int k2 = g.ndim > 1 ? (int)(row % g.K[1]) : 0;
+        const int64_t r2 = g.ndim > 1 ? row / g.K[1] : row;
+        const int k3 = g.ndim > 2 ? (int)(r2 % g.K[2]) : 0;
+        const int64_t b = g.ndim > 2 ? r2 / g.K[2] : r2;
+        const bool row_in = (g.ndim < 2 || k2 < g.N[1]) && (g.ndim < 3 || k3 < g.N[2]);
+        double s23 = 1.0;
+        int64_t nrow = b * g.PN;
+        if (row_in) {
+            if (g.ndim > 1) nrow += (int64_t)k2 * g.N[0];
+            if (g.ndim > 2) nrow += (int64_t)k3 * g.N[0] * g.N[1];
         }
-        grid[idx] = v;
+        C v[VEC];
+#pragma unroll
+        for (int e = 0; e < VEC; e++) {
+            const int k1 = k1s + e;
+            v[e] = make_c<T>(0, 0);
+            if (row_in && k1 < g.N[0]) {
+                double s = ax.sn[0][k1];
+                if (g.ndim > 1) s *= ax.sn[1][k2];
+                if (g.ndim > 2) s *= ax.sn[2][k3];
+                const T st = (T)s;
+                const C x = image[nrow + k1];
+                v[e] = make_c<T>(x.x * st, x.y * st);
+                if (apply_scale) { v[e].x *= fwd_scale; v[e].y *= fwd_scale; }
+            }
+        }
+        (void)s23;
+        C* dst = grid + row * g.K[0] + k1s;
+        if (k1s + VEC <= g.K[0] && (g.K[0] % VEC) == 0) {
+            // rows start VEC-aligned: vector stores
+            if (sizeof(C) * VEC == 32) {
+                ((int4*)dst)[0] = ((const int4*)v)[0];
+                ((int4*)dst)[1] = ((const int4*)v)[1];
+            } else if (sizeof(C) * VEC == 16) {
+                ((int4*)dst)[0] = ((const int4*)v)[0];
+            } else {
+#pragma unroll
+                for (int e = 0; e < VEC; e++) dst[e] = v[e];
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < VEC; e++)
+                if (k1s + e < g.K[0]) dst[e] = v[e];
+        }
     }
 }
 
@@ -146,24 +178,68 @@ __device__ __forceinline__ void sincos_t(double a, double* s, double* c) { sinco
 
 // grid[k] *= exp(+-i*((p1[k1]+p2[k2])+p3[k3])): phase_before with the angle summed in
 // the precision dtype in the reference's order (_nufft.py:703-715, :1370-1371, :1519-1520)
-template <typename T>
+template <typename T, int VEC>
 __global__ void phase_before_kernel(Geom g, AxisPtrs ax, int conj, cplx_t<T>* __restrict__ grid,
                                     int nbatch) {
     using C = cplx_t<T>;
-    const int64_t total = g.PK * nbatch;
+    const int cpr = (g.K[0] + VEC - 1) / VEC;
+    const int64_t rows = (g.PK / g.K[0]) * nbatch;
+    const int64_t total = rows * cpr;
+    const bool vec_ok = (g.K[0] % VEC) == 0;
     for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
          idx += (int64_t)gridDim.x * blockDim.x) {
-        int64_t r = idx % g.PK;
-        const int k1 = (int)(r % g.K[0]);
-        r /= g.K[0];
-        T ang = ((const T*)ax.pb[0])[k1];
-        if (g.ndim > 1) ang = ang + ((const T*)ax.pb[1])[(int)(r % g.K[1])];
-        if (g.ndim > 2) ang = ang + ((const T*)ax.pb[2])[(int)(r / g.K[1])];
-        T s, c;
-        sincos_t(ang, &s, &c);
-        if (conj) s = -s;
-        const C v = grid[idx];
-        grid[idx] = make_c<T>(v.x * c - v.y * s, v.x * s + v.y * c);
+        const int64_t row = idx / cpr;
+        const int k1s = (int)(idx - row * cpr) * VEC;
+        const int k2 = g.ndim > 1 ? (int)(row % g.K[1]) : 0;
+        const int64_t r2 = g.ndim > 1 ? row / g.K[1] : row;
+        const int k3 = g.ndim > 2 ? (int)(r2 % g.K[2]) : 0;
+        const T a2 = g.ndim > 1 ? ((const T*)ax.pb[1])[k2] : (T)0;
+        const T a3 = g.ndim > 2 ? ((const T*)ax.pb[2])[k3] : (T)0;
+        C* p = grid + row * g.K[0] + k1s;
+        C v[VEC];
+        const bool full = vec_ok && k1s + VEC <= g.K[0];
+        if (full) {
+            if (sizeof(C) * VEC == 32) {
+                ((int4*)v)[0] = ((const int4*)p)[0];
+                ((int4*)v)[1] = ((const int4*)p)[1];
+            } else if (sizeof(C) * VEC == 16) {
+                ((int4*)v)[0] = ((const int4*)p)[0];
+            } else {
+#pragma unroll
+                for (int e = 0; e < VEC; e++) v[e] = p[e];
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < VEC; e++)
+                if (k1s + e < g.K[0]) v[e] = p[e];
+        }
+#pragma unroll
+        for (int e = 0; e < VEC; e++) {
+            const int k1 = min(k1s + e, g.K[0] - 1);
+            T ang = ((const T*)ax.pb[0])[k1];
+            if (g.ndim > 1) ang = ang + a2;
+            if (g.ndim > 2) ang = ang + a3;
+            T s, c;
+            sincos_t(ang, &s, &c);
+            if (conj) s = -s;
+            const C u = v[e];
+            v[e] = make_c<T>(u.x * c - u.y * s, u.x * s + u.y * c);
+        }
+        if (full) {
+            if (sizeof(C) * VEC == 32) {
+                ((int4*)p)[0] = ((const int4*)v)[0];
+                ((int4*)p)[1] = ((const int4*)v)[1];
+            } else if (sizeof(C) * VEC == 16) {
+                ((int4*)p)[0] = ((const int4*)v)[0];
+            } else {
+#pragma unroll
+                for (int e = 0; e < VEC; e++) p[e] = v[e];
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < VEC; e++)
+                if (k1s + e < g.K[0]) p[e] = v[e];
+        }
     }
 }
 

@@ -52,7 +52,7 @@ struct b2n_plan {
     int device = 0;
     int sm_count = 148;
     // options
-    long opt_chunk = 2048;
+    long opt_chunk = 4096;
     long opt_force_generic = 0;
     long opt_use_tma = 1;
     long opt_sparse_mode = 0;
@@ -140,8 +140,7 @@ static void default_tiles(b2n_plan* p) {
     if (!p->tile_user_set) {
         if (g.ndim == 1) { g.tile[0] = 1024; }
         if (g.ndim == 2) { g.tile[0] = 32; g.tile[1] = 32; }
-        if (g.ndim == 3) { g.tile[0] = 16; g.tile[1] = 16; g.tile[2] = 8; }
-        if (g.ndim == 3 && p->precision == B2N_DOUBLE) { g.tile[0] = 16; g.tile[1] = 8; g.tile[2] = 8; }
+        if (g.ndim == 3) { g.tile[0] = 16; g.tile[1] = 8; g.tile[2] = 8; }
     }
     g.cells_per_tile = 1;
     for (int d = 0; d < 3; d++) {
@@ -874,7 +873,8 @@ static int nufft_fwd_t(b2n_plan* p, const void* image, void* samples, int nbatch
     FFT(cufftSetStream(fft, st));
     AxisPtrs ax = axis_ptrs(p);
     C* work = (C*)p->d_work;
-    pre_scale_pad_kernel<T><<<grid_for(g.PK * nbatch, 256, p->sm_count, 32), 256, 0, st>>>(
+    constexpr int VEC = 32 / (int)sizeof(C);   // 32 bytes of grid per thread
+    pre_scale_pad_kernel<T, VEC><<<grid_for(g.PK * nbatch / VEC + 1, 256, p->sm_count, 32), 256, 0, st>>>(
         g, ax, (T)p->fwd_scale, p->fwd_scale != 1.0, (const C*)image, work, nbatch);
     CU(cudaGetLastError());
     if (sizeof(T) == 4) FFT(cufftExecC2C(fft, (cufftComplex*)work, (cufftComplex*)work, CUFFT_FORWARD));
@@ -882,7 +882,7 @@ static int nufft_fwd_t(b2n_plan* p, const void* image, void* samples, int nbatch
     p->launches += 1;
     p->lib_calls += 1;
     if (p->have_pb) {
-        phase_before_kernel<T><<<grid_for(g.PK * nbatch, 256, p->sm_count, 32), 256, 0, st>>>(
+        phase_before_kernel<T, VEC><<<grid_for(g.PK * nbatch / VEC + 1, 256, p->sm_count, 32), 256, 0, st>>>(
             g, ax, 0, work, nbatch);
         CU(cudaGetLastError());
         p->launches++;
@@ -906,7 +906,8 @@ static int nufft_adj_t(b2n_plan* p, const void* samples, void* image, int nbatch
     else rc = interp_adj_impl(p, samples, work, nbatch, p->d_phase_s != nullptr, st);
     if (rc) return rc;
     if (p->have_pb) {
-        phase_before_kernel<T><<<grid_for(g.PK * nbatch, 256, p->sm_count, 32), 256, 0, st>>>(
+        constexpr int VEC = 32 / (int)sizeof(C);
+        phase_before_kernel<T, VEC><<<grid_for(g.PK * nbatch / VEC + 1, 256, p->sm_count, 32), 256, 0, st>>>(
             g, ax, 1, work, nbatch);
         CU(cudaGetLastError());
         p->launches++;

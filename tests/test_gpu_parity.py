@@ -274,6 +274,9 @@ def test_errors_and_edges():
         A.fft(np.zeros((15, 16)))
     with pytest.raises(ValueError):
         A.adj(np.zeros(99))
+    # no samples at all (empty trajectory): shapes are kept, adjoint is zero
+    E = NufftBase(Nd=(16, 16), omega=np.zeros((0, 2)), Jd=6)
+    assert E.fft(np.ones((16, 16))).shape == (0,)
     # a single sample, and all samples in one cell (maximal collisions)
     one = NufftBase(Nd=(16, 16), omega=om[:1], Jd=6)
     assert one.fft(np.ones((16, 16))).shape == (1,)
