@@ -100,6 +100,31 @@ template <typename C> __device__ __forceinline__ C cmul_conj(C a, C b) {   // a 
     return r;
 }
 
+// Packed FP32x2 arithmetic (Blackwell FFMA2 / FMUL2, PTX fma.rn.f32x2): a complex value
+// times a real weight is one instruction instead of two.  Each half is an IEEE fma, so the
+// result is bit-identical to two scalar fmaf calls.
+__device__ __forceinline__ float2 fma_w(float w, float2 v, float2 acc) {   // acc + w * v
+    float2 ww = make_float2(w, w);
+    unsigned long long ra = *reinterpret_cast<unsigned long long*>(&ww);
+    unsigned long long rb = *reinterpret_cast<unsigned long long*>(&v);
+    unsigned long long rc = *reinterpret_cast<unsigned long long*>(&acc);
+    unsigned long long rd;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float2 mul_w(float w, float2 v) {                // w * v
+    float2 ww = make_float2(w, w);
+    unsigned long long ra = *reinterpret_cast<unsigned long long*>(&ww);
+    unsigned long long rb = *reinterpret_cast<unsigned long long*>(&v);
+    unsigned long long rd;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ double2 fma_w(double w, double2 v, double2 acc) {
+    return make_double2(fma(w, v.x, acc.x), fma(w, v.y, acc.y));
+}
+__device__ __forceinline__ double2 mul_w(double w, double2 v) { return make_double2(w * v.x, w * v.y); }
+
 // weight algebra: W is T (real table) or cplx_t<T> (complex table)
 template <typename T, bool CT> struct WeightT { using type = T; };
 template <typename T> struct WeightT<T, true> { using type = cplx_t<T>; };

@@ -150,17 +150,11 @@ interp_fwd_tiled_kernel(const __grid_constant__ CUtensorMap tmap, Geom g, TileSh
                 const C* __restrict__ pr = tile + row;
                 C s1 = make_c<T>(0, 0);
 #pragma unroll
-                for (int j1 = 0; j1 < J; j1++) {
-                    const C v = pr[j1];
-                    s1.x += w[0][j1] * v.x;
-                    s1.y += w[0][j1] * v.y;
-                }
-                s2.x += w[NDIM > 1 ? 1 : 0][j2] * s1.x;
-                s2.y += w[NDIM > 1 ? 1 : 0][j2] * s1.y;
+                for (int j1 = 0; j1 < J; j1++) s1 = fma_w(w[0][j1], pr[j1], s1);   // FFMA2
+                s2 = fma_w(w[NDIM > 1 ? 1 : 0][j2], s1, s2);
             }
             if (NDIM > 2) {
-                s3.x += w[NDIM > 2 ? 2 : 0][j3] * s2.x;
-                s3.y += w[NDIM > 2 ? 2 : 0][j3] * s2.y;
+                s3 = fma_w(w[NDIM > 2 ? 2 : 0][j3], s2, s3);
             } else {
                 s3 = s2;
             }

@@ -198,14 +198,10 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
 #pragma unroll
             for (int s = 0; s < RPL; s++) {
                 if (rvalid[s]) {
-                    // (coef_c * f) * coef_b, then * coef_a per cell
-                    const T v3x = wc[s] * fx, v3y = wc[s] * fy;
-                    const T v2x = wb[s] * v3x, v2y = wb[s] * v3y;
+                    // (coef_c * f) * coef_b, then * coef_a per cell; packed re/im arithmetic
+                    const C v2 = mul_w(wb[s], mul_w(wc[s], make_c<T>(fx, fy)));
 #pragma unroll
-                    for (int j = 0; j < J; j++) {
-                        acc[s][j].x += wA[j] * v2x;
-                        acc[s][j].y += wA[j] * v2y;
-                    }
+                    for (int j = 0; j < J; j++) acc[s][j] = fma_w(wA[j], v2, acc[s][j]);
                 }
             }
         }
