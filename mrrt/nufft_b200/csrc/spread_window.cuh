@@ -29,9 +29,18 @@ struct WindowAxes {
     int stride[3];      // grid stride (cells) along (a, b, c)
 };
 
+// Staging of one 32-sample batch: per sample a record of kW values (3J weights, fx, fy)
+// with an ODD pitch in elements, so that the 32 lanes' scalar stores (lane = sample)
+// fall in 32 different banks, plus a separate int4 (kA, kB, kC, action) per sample.
 template <typename T, int J> struct WinRec {
     static constexpr int kW = 3 * J + 2;                         // weights + fx, fy
-    static constexpr int kBytes = ((kW * (int)sizeof(T) + 15) / 16) * 16 + 16;
+    // odd pitch in units of sizeof(T): float records spread over all 32 banks, double
+    // records over all 16 bank pairs, and every element stays naturally aligned
+    static constexpr int kPitchElems = kW % 2 == 1 ? kW : kW + 1;
+    static constexpr int kPitch = kPitchElems * (int)sizeof(T);  // bytes between records
+    // per-warp staging: 32 records (padded to 16 bytes) + 32 action codes
+    static constexpr int kRecBytes = ((32 * kPitch + 15) / 16) * 16;
+    static constexpr int kBytes = kRecBytes + 32 * 16;           // per warp
 };
 
 template <typename T, int J, bool TAB_SMEM>
@@ -45,17 +54,18 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
     using C = cplx_t<T>;
     constexpr int R = J * J;
     constexpr int RPL = (R + 31) / 32;
-    constexpr int RB = WinRec<T, J>::kBytes;
+    constexpr int RB = WinRec<T, J>::kPitch;
+    constexpr int WB = WinRec<T, J>::kBytes;
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char dyn_smem[];
-    unsigned char* stage_all = dyn_smem;                          // [4 warps][32 records]
-    const T* stab = (const T*)(dyn_smem + 4 * 32 * RB);
+    const T* stab = (const T*)(dyn_smem + 4 * WB);
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
-    unsigned char* stage = stage_all + wib * 32 * RB;
+    unsigned char* stage = dyn_smem + wib * WB;                   // this warp's records
+    int4* actions = (int4*)(stage + WinRec<T, J>::kRecBytes);     // this warp's action codes
     const int64_t M = g.M;
     if (TAB_SMEM) {
-        T* st = (T*)(dyn_smem + 4 * 32 * RB);
+        T* st = (T*)(dyn_smem + 4 * WB);
         for (int e = threadIdx.x; e < g.tlen[0]; e += blockDim.x) st[e] = __ldg(h1 + e);
         __syncthreads();
     }
@@ -109,7 +119,6 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
         if (lane < cnt) {
             const int64_t i = base + lane;
             T* w = (T*)(stage + lane * RB);
-            int* ik = (int*)(stage + lane * RB + RB - 16);
             const T tA = tm_s[(int64_t)aA * M + i], tB = tm_s[(int64_t)aB * M + i],
                     tC = tm_s[(int64_t)aC * M + i];
             const int oA = pt_ko[(int64_t)aA * M + i], oB = pt_ko[(int64_t)aB * M + i],
@@ -127,7 +136,6 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
             if (phase_s != nullptr) f = cmul_conj(f, phase_s[i]);
             w[3 * J] = f.x;
             w[3 * J + 1] = f.y;
-            ik[0] = kA; ik[1] = kB; ik[2] = kC;
         }
         // window action: slide distance along a, or -1 = new window
         {
@@ -136,18 +144,18 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
             if (lane == 0) { qA = pkA; qB = pkB; qC = pkC; }
             const int d = kA - qA;
             const int act = (kB == qB && kC == qC && d >= 0 && d < J) ? d : -1;
-            if (lane < cnt) ((int*)(stage + lane * RB + RB - 16))[3] = act;
+            if (lane < cnt) actions[lane] = make_int4(kA, kB, kC, act);
             pkA = __shfl_sync(FULL, kA, cnt - 1);
             pkB = __shfl_sync(FULL, kB, cnt - 1);
             pkC = __shfl_sync(FULL, kC, cnt - 1);
         }
         __syncwarp();
         // ---- sample loop: all lanes work on one sample
-        int4 kk_next = *(const int4*)(stage + RB - 16);
+        int4 kk_next = actions[0];
         for (int q = 0; q < cnt; q++) {
             const unsigned char* rec = stage + q * RB;
             const int4 kk = kk_next;
-            if (q + 1 < cnt) kk_next = *(const int4*)(rec + RB + RB - 16);
+            if (q + 1 < cnt) kk_next = actions[q + 1];
             // operands of this sample are fetched before the window update so that their
             // shared-memory latency overlaps it
             const T* w = (const T*)rec;
@@ -235,7 +243,7 @@ static int launch_window(const Geom& g, const TablePtrs& tabs, int slide_axis, c
     dim3 gd((unsigned)nblocks, (unsigned)nbatch);
     const bool tab_smem = tabs.h[0] == tabs.h[1] && tabs.h[1] == tabs.h[2] &&
                           (size_t)g.tlen[0] * sizeof(T) <= 56 * 1024;
-    const size_t stage_bytes = (size_t)4 * 32 * WinRec<T, J>::kBytes;
+    const size_t stage_bytes = (size_t)4 * WinRec<T, J>::kBytes;
     cudaError_t e;
     if (tab_smem) {
         const size_t smem = stage_bytes + (size_t)g.tlen[0] * sizeof(T);
