@@ -76,6 +76,32 @@ __global__ void point_windows_kernel(Geom g, const T* __restrict__ tm_s, int32_t
     }
 }
 
+struct TabArgs {
+    const void* h[3];
+};
+
+// per sorted sample the 3J interpolation weights themselves (real tables): the table is
+// consulted once at plan time -- same expression as in the kernels, so the values are
+// bit-identical -- and the hot kernels stream the weights instead of gathering from the
+// table (a shared-memory gather costs several bank-conflict wavefronts per tap and the
+// forward kernel is shared-memory-bandwidth bound).  Layout [sum(J)][M], sample fastest.
+template <typename T>
+__global__ void point_weights_kernel(Geom g, TabArgs tabs, const T* __restrict__ tm_s,
+                                     const int32_t* __restrict__ pt_ko, T* __restrict__ wts) {
+    const int64_t M = g.M;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < M;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        int row = 0;
+        for (int d = 0; d < g.ndim; d++) {
+            const T t = tm_s[(int64_t)d * M + i];
+            const int ko = pt_ko[(int64_t)d * M + i];
+            for (int j = 0; j < g.J[d]; j++, row++)
+                wts[(int64_t)row * M + i] =
+                    tap_real<T>((const T*)tabs.h[d], g.ncenter[d], g.tlen[d], t, ko + j, g.L);
+        }
+    }
+}
+
 template <typename C>
 __global__ void gather_c_kernel(int64_t M, const int32_t* __restrict__ perm,
                                 const C* __restrict__ src, C* __restrict__ dst) {

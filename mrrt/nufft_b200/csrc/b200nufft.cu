@@ -88,6 +88,10 @@ struct b2n_plan {
     int32_t* d_pt_ko_b = nullptr;
     int32_t* d_pt_kw_b = nullptr;
     void* d_phase_sb = nullptr;
+    // plan-time interpolation weights [sum(J)][M] for each sort order (real tables)
+    void* d_wts = nullptr;
+    void* d_wts_b = nullptr;
+    long opt_precomp = 1;
     void* d_phase_s = nullptr;   // sorted sample phase or null
     int64_t nbins = 0;
     // work items of the tiled forward kernel: (bin, start, count, pad)
@@ -203,6 +207,8 @@ static void free_points(b2n_plan* p) {
     p->d_pt_ko = p->d_pt_kw = nullptr;
     dev_free(p->d_tm_sb); dev_free(p->d_perm_b); dev_free(p->d_pt_ko_b); dev_free(p->d_pt_kw_b);
     dev_free(p->d_phase_sb);
+    dev_free(p->d_wts); dev_free(p->d_wts_b);
+    p->d_wts = p->d_wts_b = nullptr;
     p->d_tm_sb = p->d_phase_sb = nullptr;
     p->d_perm_b = p->d_pt_ko_b = p->d_pt_kw_b = nullptr;
     p->have_b = false;
@@ -250,6 +256,9 @@ extern "C" int b2n_plan_set_option(b2n_plan* p, const char* name, long value) {
         p->opt_sparse_mode = value;
     } else if (n == "adj_kernel") {
         p->opt_adj_kernel = value;
+    } else if (n == "precomp_weights") {
+        if (p->points_set) return fail(B2N_ESTATE, "precomp_weights must precede set_points");
+        p->opt_precomp = value;
     } else if (n == "order_b") {
         if (p->points_set) return fail(B2N_ESTATE, "order_b must precede set_points");
         p->opt_order_b = value;
@@ -277,6 +286,7 @@ extern "C" long b2n_plan_get_option(b2n_plan* p, const char* name) {
     if (n == "slide_pts") return p->opt_slide_pts;
     if (n == "profile") return p->opt_profile;
     if (n == "adj_kernel") return p->opt_adj_kernel;
+    if (n == "precomp_weights") return p->d_wts != nullptr ? 1 : 0;
     if (n == "lib_calls") return (long)p->lib_calls;
     if (n == "n_items") return (long)p->n_items;
     if (n == "last_fwd_kernel") return p->last_fwd_kernel;
@@ -309,6 +319,8 @@ extern "C" int b2n_plan_set_tables(b2n_plan* p, const void* const* h_host) {
         CU(cudaMemcpy(p->d_tab[d], h_host[d], esz * g.tlen[d], cudaMemcpyHostToDevice));
     }
     p->tables_set = true;
+    dev_free(p->d_wts); dev_free(p->d_wts_b);
+    p->d_wts = p->d_wts_b = nullptr;
     return B2N_OK;
 }
 
@@ -583,6 +595,35 @@ static int run_generic(b2n_plan* p, bool fwd, const void* in, void* out, int nba
                               nbatch, p->sm_count, st);
 }
 
+// weights need both the points and the tables; built on first use
+template <typename T>
+static int build_weights_t(b2n_plan* p, cudaStream_t st) {
+    const Geom& g = p->g;
+    int rows = 0;
+    for (int d = 0; d < g.ndim; d++) rows += g.J[d];
+    TabArgs tabs{{p->d_tab[0], p->d_tab[1], p->d_tab[2]}};
+    int rc;
+    if ((rc = dev_alloc(p, &p->d_wts, sizeof(T) * (size_t)rows * g.M))) return rc;
+    point_weights_kernel<T><<<grid_for(g.M, 256, p->sm_count), 256, 0, st>>>(
+        g, tabs, (const T*)p->d_tm_s, p->d_pt_ko, (T*)p->d_wts);
+    CU(cudaGetLastError());
+    if (p->have_b) {
+        if ((rc = dev_alloc(p, &p->d_wts_b, sizeof(T) * (size_t)rows * g.M))) return rc;
+        point_weights_kernel<T><<<grid_for(g.M, 256, p->sm_count), 256, 0, st>>>(
+            g, tabs, (const T*)p->d_tm_sb, p->d_pt_ko_b, (T*)p->d_wts_b);
+        CU(cudaGetLastError());
+    }
+    p->launches += p->have_b ? 2 : 1;
+    return B2N_OK;
+}
+
+static int ensure_weights(b2n_plan* p, cudaStream_t st) {
+    if (!p->opt_precomp || p->cplx_table || p->g.ndim < 2 || p->d_wts != nullptr || p->g.M == 0)
+        return B2N_OK;
+    if (!p->tables_set || !p->points_set) return B2N_OK;
+    return p->precision == B2N_SINGLE ? build_weights_t<float>(p, st) : build_weights_t<double>(p, st);
+}
+
 static void prof_begin(b2n_plan* p, bool fwd, cudaStream_t st) {
     if (!p->opt_profile) return;
     cudaEvent_t e0, e1;
@@ -608,14 +649,18 @@ static int interp_fwd_impl(b2n_plan* p, const void* grid, void* samples, int nba
                            cudaStream_t st) {
     if (!p->tables_set) return fail(B2N_ESTATE, "tables not set");
     if (p->g.M == 0) return B2N_OK;
+    {
+        int rc = ensure_weights(p, st);
+        if (rc) return rc;
+    }
     bool done = false;
     prof_begin(p, true, st);
     if (!p->opt_force_generic && !p->cplx_table) {
         const void* ph = phase ? p->d_phase_s : nullptr;
         int rc = p->precision == B2N_SINGLE
-                     ? tiled_fwd_f32(p->g, p->tables_equal, table_ptrs(p), p->d_tm_s, p->d_pt_ko, p->d_pt_kw, p->d_perm, p->d_items,
+                     ? tiled_fwd_f32(p->g, p->tables_equal, table_ptrs(p), p->d_tm_s, p->d_wts, p->d_pt_ko, p->d_pt_kw, p->d_perm, p->d_items,
                                      p->n_items, grid, samples, ph, nbatch, (int)p->opt_use_tma, st, &done)
-                     : tiled_fwd_f64(p->g, p->tables_equal, table_ptrs(p), p->d_tm_s, p->d_pt_ko, p->d_pt_kw, p->d_perm, p->d_items,
+                     : tiled_fwd_f64(p->g, p->tables_equal, table_ptrs(p), p->d_tm_s, p->d_wts, p->d_pt_ko, p->d_pt_kw, p->d_perm, p->d_items,
                                      p->n_items, grid, samples, ph, nbatch, (int)p->opt_use_tma, st, &done);
         if (rc != 0) return fail(B2N_ECUDA, "tiled forward launch failed: " + std::string(cudaGetErrorString((cudaError_t)rc)));
     }
@@ -635,6 +680,10 @@ static int interp_adj_impl(b2n_plan* p, const void* samples, void* grid, int nba
     CU(cudaMemsetAsync(grid, 0, p->cplx_size() * p->g.PK * nbatch, st));
     p->lib_calls++;
     if (p->g.M == 0) return B2N_OK;
+    {
+        int rc = ensure_weights(p, st);
+        if (rc) return rc;
+    }
     bool done = false;
     prof_begin(p, false, st);
     if (!p->opt_force_generic && !p->cplx_table && p->opt_adj_kernel == 3) {
@@ -642,14 +691,15 @@ static int interp_adj_impl(b2n_plan* p, const void* samples, void* grid, int nba
         const bool ob = p->have_b;
         const void* ph = phase ? (ob ? p->d_phase_sb : p->d_phase_s) : nullptr;
         const void* tms = ob ? p->d_tm_sb : p->d_tm_s;
+        const void* wts = ob ? p->d_wts_b : p->d_wts;
         const int32_t* ko = ob ? p->d_pt_ko_b : p->d_pt_ko;
         const int32_t* kw = ob ? p->d_pt_kw_b : p->d_pt_kw;
         const int32_t* pm = ob ? p->d_perm_b : p->d_perm;
         const int slide_axis = ob ? 2 : 0;
         int rc = p->precision == B2N_SINGLE
-                     ? window_adj_f32(p->g, table_ptrs(p), slide_axis, tms, ko, kw, pm, samples, grid, ph,
+                     ? window_adj_f32(p->g, table_ptrs(p), slide_axis, tms, wts, ko, kw, pm, samples, grid, ph,
                                       nbatch, (int)p->opt_slide_pts, st, &done)
-                     : window_adj_f64(p->g, table_ptrs(p), slide_axis, tms, ko, kw, pm, samples, grid, ph,
+                     : window_adj_f64(p->g, table_ptrs(p), slide_axis, tms, wts, ko, kw, pm, samples, grid, ph,
                                       nbatch, (int)p->opt_slide_pts, st, &done);
         if (rc != 0) return fail(B2N_ECUDA, "window adjoint launch failed: " + std::string(cudaGetErrorString((cudaError_t)rc)));
         if (done) p->last_adj_kernel = 3;

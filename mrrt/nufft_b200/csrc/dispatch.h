@@ -17,7 +17,7 @@ struct TablePtrs {
                              const int32_t* perm, bool fwd, const void* in, void* out,           \
                              const void* phase_s, int nbatch, int sm_count, cudaStream_t st);    \
     int tiled_fwd_##SUF(const Geom& g, bool tables_equal, const TablePtrs& tabs, const void* tm_s, \
-                        const int32_t* pt_ko, const int32_t* pt_kw, const int32_t* perm, const int4* items, int64_t n_items, const void* grid, \
+                        const void* wts, const int32_t* pt_ko, const int32_t* pt_kw, const int32_t* perm, const int4* items, int64_t n_items, const void* grid, \
                         void* out, const void* phase_s, int nbatch, int use_tma, cudaStream_t st, \
                         bool* done);                                                             \
     int slide_adj_##SUF(const Geom& g, const TablePtrs& tabs, const void* tm_s,                 \
@@ -31,7 +31,7 @@ struct TablePtrs {
                        int nbatch, int use_tma, cudaStream_t st, bool* done);
 #define B2N_DECLARE3(SUF)                                                                        \
     int window_adj_##SUF(const Geom& g, const TablePtrs& tabs, int slide_axis, const void* tm_s, \
-                         const int32_t* pt_ko, const int32_t* pt_kw, const int32_t* perm,        \
+                         const void* wts, const int32_t* pt_ko, const int32_t* pt_kw, const int32_t* perm,        \
                          const void* samples, void* grid, const void* phase_s, int nbatch,       \
                          int pts_per_warp, cudaStream_t st, bool* done);
 B2N_DECLARE3(f32)

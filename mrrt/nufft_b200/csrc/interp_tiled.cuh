@@ -69,15 +69,18 @@ struct TileShape {
     int tile_bytes;   // E1p*E2*E3*sizeof(C) rounded up to 128
 };
 
-template <typename T, int NDIM, int J, bool TAB_SMEM>
+// TAB: 0 table in global memory, 1 table staged in shared memory, 2 plan-time weights
+template <typename T, int NDIM, int J, int TAB>
 __global__ void __launch_bounds__(256)
 interp_fwd_tiled_kernel(const __grid_constant__ CUtensorMap tmap, Geom g, TileShape ts, int use_tma,
-                        const T* __restrict__ tab, const T* __restrict__ tm_s,
+                        const T* __restrict__ tab, const T* __restrict__ wts,
+                        const T* __restrict__ tm_s,
                         const int32_t* __restrict__ pt_ko, const int32_t* __restrict__ pt_kw,
                         const int32_t* __restrict__ perm, const int4* __restrict__ items,
                         const cplx_t<T>* __restrict__ grid, cplx_t<T>* __restrict__ out,
                         const cplx_t<T>* __restrict__ phase_s) {
     using C = cplx_t<T>;
+    constexpr bool TAB_SMEM = TAB == 1;
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t mbar;
     C* tile = (C*)smem;
@@ -130,13 +133,18 @@ interp_fwd_tiled_kernel(const __grid_constant__ CUtensorMap tmap, Geom g, TileSh
         int c[NDIM];
 #pragma unroll
         for (int d = 0; d < NDIM; d++) {
-            const T t = tm_s[(int64_t)d * M + i];
-            const int koff = pt_ko[(int64_t)d * M + i];      // 1 + floor(t - J/2.), plan time
             const int od = d == 0 ? o1 : (d == 1 ? o2 : o3);
             c[d] = pt_kw[(int64_t)d * M + i] - od;           // wrapped origin inside the tile
+            if (TAB == 2) {
 #pragma unroll
-            for (int j = 0; j < J; j++)
-                w[d][j] = tap_real<T>(h, g.ncenter[0], g.tlen[0], t, koff + j, g.L);
+                for (int j = 0; j < J; j++) w[d][j] = wts[(int64_t)(d * J + j) * M + i];
+            } else {
+                const T t = tm_s[(int64_t)d * M + i];
+                const int koff = pt_ko[(int64_t)d * M + i];  // 1 + floor(t - J/2.), plan time
+#pragma unroll
+                for (int j = 0; j < J; j++)
+                    w[d][j] = tap_real<T>(h, g.ncenter[0], g.tlen[0], t, koff + j, g.L);
+            }
         }
         C s3 = make_c<T>(0, 0);
 #pragma unroll
@@ -222,7 +230,7 @@ static bool make_grid_tmap(CUtensorMap* map, const Geom& g, const TileShape& ts,
 
 template <typename T, int NDIM, int J>
 static int launch_fwd_tiled(const Geom& g, const TablePtrs& tabs, const void* tm_s,
-                            const int32_t* pt_ko, const int32_t* pt_kw, const int32_t* perm, const int4* items, int64_t n_items,
+                            const void* wts, const int32_t* pt_ko, const int32_t* pt_kw, const int32_t* perm, const int4* items, int64_t n_items,
                             const void* grid, void* out, const void* phase_s, int nbatch,
                             int use_tma, cudaStream_t st, bool* done) {
     using C = cplx_t<T>;
@@ -241,8 +249,8 @@ static int launch_fwd_tiled(const Geom& g, const TablePtrs& tabs, const void* tm
     cudaGetDevice(&dev);
     int max_smem = 0;
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    bool tab_smem = true;
-    size_t smem = ts.tile_bytes + tab_bytes;
+    bool tab_smem = wts == nullptr;
+    size_t smem = ts.tile_bytes + (tab_smem ? tab_bytes : 0);
     if (smem > (size_t)max_smem || smem > 100 * 1024) {
         tab_smem = false;
         smem = ts.tile_bytes;
@@ -253,19 +261,19 @@ static int launch_fwd_tiled(const Geom& g, const TablePtrs& tabs, const void* tm
     const bool tma_ok = use_tma && make_grid_tmap<T, NDIM>(&map, g, ts, grid, nbatch);
     dim3 gridDim((unsigned)n_items, (unsigned)nbatch);
     cudaError_t e;
-    if (tab_smem) {
-        auto k = interp_fwd_tiled_kernel<T, NDIM, J, true>;
-        e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        k<<<gridDim, 256, smem, st>>>(map, g, ts, tma_ok ? 1 : 0, (const T*)tabs.h[0], (const T*)tm_s,
-                                      pt_ko, pt_kw, perm, items, (const C*)grid, (C*)out, (const C*)phase_s);
-    } else {
-        auto k = interp_fwd_tiled_kernel<T, NDIM, J, false>;
-        e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        k<<<gridDim, 256, smem, st>>>(map, g, ts, tma_ok ? 1 : 0, (const T*)tabs.h[0], (const T*)tm_s,
-                                      pt_ko, pt_kw, perm, items, (const C*)grid, (C*)out, (const C*)phase_s);
+#define B2N_LAUNCH_FWD(TABV)                                                                       \
+    {                                                                                              \
+        auto k = interp_fwd_tiled_kernel<T, NDIM, J, TABV>;                                        \
+        e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
+        if (e != cudaSuccess) return (int)e;                                                       \
+        k<<<gridDim, 256, smem, st>>>(map, g, ts, tma_ok ? 1 : 0, (const T*)tabs.h[0],             \
+                                      (const T*)wts, (const T*)tm_s, pt_ko, pt_kw, perm, items,    \
+                                      (const C*)grid, (C*)out, (const C*)phase_s);                 \
     }
+    if (wts != nullptr) B2N_LAUNCH_FWD(2)
+    else if (tab_smem) B2N_LAUNCH_FWD(1)
+    else B2N_LAUNCH_FWD(0)
+#undef B2N_LAUNCH_FWD
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
     *done = true;
@@ -275,16 +283,17 @@ static int launch_fwd_tiled(const Geom& g, const TablePtrs& tabs, const void* tm
 // returns 0 or a cudaError_t; *done tells whether the tiled kernel took the call
 template <typename T>
 static int tiled_fwd_t(const Geom& g, bool tables_equal, const TablePtrs& tabs, const void* tm_s,
-                       const int32_t* pt_ko, const int32_t* pt_kw, const int32_t* perm, const int4* items, int64_t n_items, const void* grid,
+                       const void* wts, const int32_t* pt_ko, const int32_t* pt_kw, const int32_t* perm, const int4* items, int64_t n_items, const void* grid,
                        void* out, const void* phase_s, int nbatch, int use_tma, cudaStream_t st,
                        bool* done) {
     *done = false;
-    if (g.ndim < 2 || !tables_equal || n_items == 0 || n_items > 0x7fffffff || nbatch > 65535)
+    if (g.ndim < 2 || (!tables_equal && wts == nullptr) || n_items == 0 || n_items > 0x7fffffff ||
+        nbatch > 65535)
         return 0;
     for (int d = 1; d < g.ndim; d++)
         if (g.J[d] != g.J[0]) return 0;
 #define B2N_TILED(ND, JJ)                                                                      \
-    return launch_fwd_tiled<T, ND, JJ>(g, tabs, tm_s, pt_ko, pt_kw, perm, items, n_items, grid, out, phase_s, \
+    return launch_fwd_tiled<T, ND, JJ>(g, tabs, tm_s, wts, pt_ko, pt_kw, perm, items, n_items, grid, out, phase_s, \
                                        nbatch, use_tma, st, done)
     if (g.ndim == 2) {
         switch (g.J[0]) {

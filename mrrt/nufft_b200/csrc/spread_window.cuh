@@ -43,10 +43,12 @@ template <typename T, int J> struct WinRec {
     static constexpr int kBytes = kRecBytes + 32 * 16;           // per warp
 };
 
-template <typename T, int J, bool TAB_SMEM>
+// TAB: 0 table in global memory, 1 table staged in shared memory, 2 plan-time weights
+template <typename T, int J, int TAB>
 __global__ void __launch_bounds__(128)
 spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T* __restrict__ h2,
                        const T* __restrict__ h3, const T* __restrict__ tm_s,
+                       const T* __restrict__ wts,
                        const int32_t* __restrict__ pt_ko, const int32_t* __restrict__ pt_kw,
                        const int32_t* __restrict__ perm, const cplx_t<T>* __restrict__ samples,
                        cplx_t<T>* __restrict__ grid, const cplx_t<T>* __restrict__ phase_s,
@@ -64,6 +66,7 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
     unsigned char* stage = dyn_smem + wib * WB;                   // this warp's records
     int4* actions = (int4*)(stage + WinRec<T, J>::kRecBytes);     // this warp's action codes
     const int64_t M = g.M;
+    constexpr bool TAB_SMEM = TAB == 1;
     if (TAB_SMEM) {
         T* st = (T*)(dyn_smem + 4 * WB);
         for (int e = threadIdx.x; e < g.tlen[0]; e += blockDim.x) st[e] = __ldg(h1 + e);
@@ -119,18 +122,27 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
         if (lane < cnt) {
             const int64_t i = base + lane;
             T* w = (T*)(stage + lane * RB);
-            const T tA = tm_s[(int64_t)aA * M + i], tB = tm_s[(int64_t)aB * M + i],
-                    tC = tm_s[(int64_t)aC * M + i];
-            const int oA = pt_ko[(int64_t)aA * M + i], oB = pt_ko[(int64_t)aB * M + i],
-                      oC = pt_ko[(int64_t)aC * M + i];
             kA = pt_kw[(int64_t)aA * M + i];
             kB = pt_kw[(int64_t)aB * M + i];
             kC = pt_kw[(int64_t)aC * M + i];
+            if (TAB == 2) {
 #pragma unroll
-            for (int j = 0; j < J; j++) {
-                w[j] = tap_real<T>(tabA, ncA, tlA, tA, oA + j, g.L);
-                w[J + j] = tap_real<T>(tabB, ncB, tlB, tB, oB + j, g.L);
-                w[2 * J + j] = tap_real<T>(tabC, ncC, tlC, tC, oC + j, g.L);
+                for (int j = 0; j < J; j++) {
+                    w[j] = wts[(int64_t)(aA * J + j) * M + i];
+                    w[J + j] = wts[(int64_t)(aB * J + j) * M + i];
+                    w[2 * J + j] = wts[(int64_t)(aC * J + j) * M + i];
+                }
+            } else {
+                const T tA = tm_s[(int64_t)aA * M + i], tB = tm_s[(int64_t)aB * M + i],
+                        tC = tm_s[(int64_t)aC * M + i];
+                const int oA = pt_ko[(int64_t)aA * M + i], oB = pt_ko[(int64_t)aB * M + i],
+                          oC = pt_ko[(int64_t)aC * M + i];
+#pragma unroll
+                for (int j = 0; j < J; j++) {
+                    w[j] = tap_real<T>(tabA, ncA, tlA, tA, oA + j, g.L);
+                    w[J + j] = tap_real<T>(tabB, ncB, tlB, tB, oB + j, g.L);
+                    w[2 * J + j] = tap_real<T>(tabC, ncC, tlC, tC, oC + j, g.L);
+                }
             }
             C f = sb[perm[i]];
             if (phase_s != nullptr) f = cmul_conj(f, phase_s[i]);
@@ -228,7 +240,7 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
 
 template <typename T, int J>
 static int launch_window(const Geom& g, const TablePtrs& tabs, int slide_axis, const void* tm_s,
-                         const int32_t* pt_ko, const int32_t* pt_kw, const int32_t* perm,
+                         const void* wts, const int32_t* pt_ko, const int32_t* pt_kw, const int32_t* perm,
                          const void* samples, void* grid, const void* phase_s, int nbatch,
                          int pts_per_warp, cudaStream_t st, bool* done) {
     using C = cplx_t<T>;
@@ -245,22 +257,20 @@ static int launch_window(const Geom& g, const TablePtrs& tabs, int slide_axis, c
                           (size_t)g.tlen[0] * sizeof(T) <= 56 * 1024;
     const size_t stage_bytes = (size_t)4 * WinRec<T, J>::kBytes;
     cudaError_t e;
-    if (tab_smem) {
-        const size_t smem = stage_bytes + (size_t)g.tlen[0] * sizeof(T);
-        auto k = spread_window3d_kernel<T, J, true>;
-        e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        k<<<gd, 128, smem, st>>>(g, wa, (const T*)tabs.h[0], (const T*)tabs.h[1], (const T*)tabs.h[2],
-                                 (const T*)tm_s, pt_ko, pt_kw, perm, (const C*)samples, (C*)grid,
-                                 (const C*)phase_s, pts_per_warp);
-    } else {
-        auto k = spread_window3d_kernel<T, J, false>;
-        e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes);
-        if (e != cudaSuccess) return (int)e;
-        k<<<gd, 128, stage_bytes, st>>>(g, wa, (const T*)tabs.h[0], (const T*)tabs.h[1],
-                                        (const T*)tabs.h[2], (const T*)tm_s, pt_ko, pt_kw, perm,
-                                        (const C*)samples, (C*)grid, (const C*)phase_s, pts_per_warp);
+#define B2N_LAUNCH_WIN(TABV, SMEM)                                                                 \
+    {                                                                                              \
+        auto k = spread_window3d_kernel<T, J, TABV>;                                               \
+        e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM));     \
+        if (e != cudaSuccess) return (int)e;                                                       \
+        k<<<gd, 128, (SMEM), st>>>(g, wa, (const T*)tabs.h[0], (const T*)tabs.h[1],                \
+                                   (const T*)tabs.h[2], (const T*)tm_s, (const T*)wts, pt_ko, pt_kw, \
+                                   perm, (const C*)samples, (C*)grid, (const C*)phase_s,           \
+                                   pts_per_warp);                                                  \
     }
+    if (wts != nullptr) B2N_LAUNCH_WIN(2, stage_bytes)
+    else if (tab_smem) B2N_LAUNCH_WIN(1, stage_bytes + (size_t)g.tlen[0] * sizeof(T))
+    else B2N_LAUNCH_WIN(0, stage_bytes)
+#undef B2N_LAUNCH_WIN
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
     *done = true;
@@ -269,7 +279,7 @@ static int launch_window(const Geom& g, const TablePtrs& tabs, int slide_axis, c
 
 template <typename T>
 static int window_adj_t(const Geom& g, const TablePtrs& tabs, int slide_axis, const void* tm_s,
-                        const int32_t* pt_ko, const int32_t* pt_kw, const int32_t* perm,
+                        const void* wts, const int32_t* pt_ko, const int32_t* pt_kw, const int32_t* perm,
                         const void* samples, void* grid, const void* phase_s, int nbatch,
                         int pts_per_warp, cudaStream_t st, bool* done) {
     *done = false;
@@ -277,7 +287,7 @@ static int window_adj_t(const Geom& g, const TablePtrs& tabs, int slide_axis, co
     if (g.J[1] != g.J[0] || g.J[2] != g.J[0]) return 0;
     if (g.K[0] < g.J[0] || g.K[1] < g.J[0] || g.K[2] < g.J[0]) return 0;
 #define B2N_WIN(JJ)                                                                          \
-    return launch_window<T, JJ>(g, tabs, slide_axis, tm_s, pt_ko, pt_kw, perm, samples, grid, \
+    return launch_window<T, JJ>(g, tabs, slide_axis, tm_s, wts, pt_ko, pt_kw, perm, samples, grid, \
                                 phase_s, nbatch, pts_per_warp, st, done)
     switch (g.J[0]) {
         case 4: B2N_WIN(4);

@@ -2,10 +2,10 @@
 #include "spread_window.cuh"
 namespace b2n {
 int window_adj_f64(const Geom& g, const TablePtrs& tabs, int slide_axis, const void* tm_s,
-                   const int32_t* pt_ko, const int32_t* pt_kw, const int32_t* perm,
+                   const void* wts, const int32_t* pt_ko, const int32_t* pt_kw, const int32_t* perm,
                    const void* samples, void* grid, const void* phase_s, int nbatch,
                    int pts_per_warp, cudaStream_t st, bool* done) {
-    return window_adj_t<double>(g, tabs, slide_axis, tm_s, pt_ko, pt_kw, perm, samples, grid, phase_s,
-                            nbatch, pts_per_warp, st, done);
+    return window_adj_t<double>(g, tabs, slide_axis, tm_s, wts, pt_ko, pt_kw, perm, samples, grid,
+                            phase_s, nbatch, pts_per_warp, st, done);
 }
 }  // namespace b2n
