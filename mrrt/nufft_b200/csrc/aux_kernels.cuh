@@ -20,8 +20,8 @@ __global__ void prep_points_kernel(Geom g, Gam<T> gam, int kind, const T* __rest
     const int64_t M = g.M;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < M;
          i += (int64_t)gridDim.x * blockDim.x) {
-        int64_t bin = 0, cell = 0, cell_b = 0;
-        int64_t bstride = 1, cstride = 1;
+        int64_t bin = 0, cell = 0, bin_b = 0, cell_b = 0;
+        int64_t bstride = 1, cstride = 1, bstride_b = 1, cstride_b = 1;
         bool ok = true;
 #pragma unroll
         for (int d = 0; d < kMaxDim; d++) {
@@ -35,15 +35,18 @@ __global__ void prep_points_kernel(Geom g, Gam<T> gam, int kind, const T* __rest
                 if (ok) kw = wrap_index(window_origin<T>(t, g.J[d]), g.K[d]);
                 bin += (int64_t)(kw / g.tile[d]) * bstride;
                 cell += (int64_t)(kw % g.tile[d]) * cstride;
-                // adjoint order: LAST axis fastest inside the bin
-                cell_b = cell_b * g.tile[d] + (kw % g.tile[d]);
+                // adjoint order: its own (longer) bins, LAST axis fastest inside the bin
+                bin_b += (int64_t)(kw / g.tile_b[d]) * bstride_b;
+                cell_b = cell_b * g.tile_b[d] + (kw % g.tile_b[d]);
+                bstride_b *= g.nbin_b[d];
+                cstride_b *= g.tile_b[d];
                 bstride *= g.nbin[d];
                 cstride *= g.tile[d];
             }
         }
         if (!ok) atomicExch(nonfinite, 1);
         keys[i] = (uint64_t)(bin * cstride + cell);
-        if (keys_b != nullptr) keys_b[i] = (uint64_t)(bin * cstride + cell_b);
+        if (keys_b != nullptr) keys_b[i] = (uint64_t)(bin_b * cstride_b + cell_b);
         bin_ids[i] = (int32_t)bin;
         iota[i] = (int32_t)i;
     }

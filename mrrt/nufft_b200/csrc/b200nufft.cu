@@ -62,6 +62,7 @@ struct b2n_plan {
     long opt_adj_kernel = 3;
     long opt_order_b = 1;        // build the adjoint sort order (adj_kernel 3)
     bool tile_user_set = false;
+    bool tile_b_user_set = false;
     // tables
     void* d_tab[3] = {nullptr, nullptr, nullptr};
     bool tables_set = false;
@@ -145,6 +146,15 @@ static void default_tiles(b2n_plan* p) {
         if (g.ndim == 1) { g.tile[0] = 1024; }
         if (g.ndim == 2) { g.tile[0] = 32; g.tile[1] = 32; }
         if (g.ndim == 3) { g.tile[0] = 16; g.tile[1] = 8; g.tile[2] = 8; }
+    }
+    if (!p->tile_b_user_set) {
+        g.tile_b[0] = 16; g.tile_b[1] = 16; g.tile_b[2] = 64;
+    }
+    for (int d = 0; d < 3; d++) {
+        if (d >= g.ndim) g.tile_b[d] = 1;
+        if (g.tile_b[d] > g.K[d]) g.tile_b[d] = g.K[d];
+        if (g.tile_b[d] < 1) g.tile_b[d] = 1;
+        g.nbin_b[d] = (g.K[d] + g.tile_b[d] - 1) / g.tile_b[d];
     }
     g.cells_per_tile = 1;
     for (int d = 0; d < 3; d++) {
@@ -244,6 +254,12 @@ extern "C" int b2n_plan_set_option(b2n_plan* p, const char* name, long value) {
         if (value < 1) return fail(B2N_EINVAL, "tile must be >= 1");
         p->g.tile[n[4] - '1'] = (int)value;
         p->tile_user_set = true;
+        default_tiles(p);
+    } else if (n == "tileb1" || n == "tileb2" || n == "tileb3") {
+        if (p->points_set) return fail(B2N_ESTATE, "tile options must precede set_points");
+        if (value < 1) return fail(B2N_EINVAL, "tile must be >= 1");
+        p->g.tile_b[n[5] - '1'] = (int)value;
+        p->tile_b_user_set = true;
         default_tiles(p);
     } else if (n == "chunk") {
         if (value < 32) return fail(B2N_EINVAL, "chunk must be >= 32");
@@ -403,6 +419,11 @@ static int set_points_t(b2n_plan* p, const void* coords, int64_t M, int kind, cu
     CU(cudaGetLastError());
     // stable LSD radix sort over just the significant key bits
     uint64_t maxkey = (uint64_t)p->nbins * (uint64_t)g.cells_per_tile;
+    {
+        uint64_t mb = 1;
+        for (int d = 0; d < 3; d++) mb *= (uint64_t)g.nbin_b[d] * (uint64_t)g.tile_b[d];
+        if (mb > maxkey) maxkey = mb;
+    }
     int bits = 1;
     while (bits < 64 && (maxkey >> bits) != 0) bits++;
     size_t tmp_bytes = 0;

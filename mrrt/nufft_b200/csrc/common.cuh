@@ -46,6 +46,8 @@ struct Geom {
     int tlen[3];      // J*L+1
     int tile[3];      // bin shape in grid cells
     int nbin[3];      // bins per axis
+    int tile_b[3];    // bin shape of the adjoint sort order (long along the last axis)
+    int nbin_b[3];
     int64_t PK;       // prod(K)
     int64_t PN;       // prod(N)
     int64_t M;        // samples
