@@ -61,6 +61,7 @@ struct b2n_plan {
     // 3 register window with lane-parallel batch weights and the adjoint sort order
     long opt_adj_kernel = 3;
     long opt_order_b = 1;        // build the adjoint sort order (adj_kernel 3)
+    long opt_win_lanes = 16;     // lanes per sample in the register-window adjoint (16 or 32)
     bool tile_user_set = false;
     bool tile_b_user_set = false;
     // tables
@@ -275,6 +276,9 @@ extern "C" int b2n_plan_set_option(b2n_plan* p, const char* name, long value) {
     } else if (n == "precomp_weights") {
         if (p->points_set) return fail(B2N_ESTATE, "precomp_weights must precede set_points");
         p->opt_precomp = value;
+    } else if (n == "win_lanes") {
+        if (value != 16 && value != 32) return fail(B2N_EINVAL, "win_lanes must be 16 or 32");
+        p->opt_win_lanes = value;
     } else if (n == "order_b") {
         if (p->points_set) return fail(B2N_ESTATE, "order_b must precede set_points");
         p->opt_order_b = value;
@@ -717,11 +721,12 @@ static int interp_adj_impl(b2n_plan* p, const void* samples, void* grid, int nba
         const int32_t* kw = ob ? p->d_pt_kw_b : p->d_pt_kw;
         const int32_t* pm = ob ? p->d_perm_b : p->d_perm;
         const int slide_axis = ob ? 2 : 0;
+        const int wpts = (int)(p->opt_win_lanes == 32 ? -p->opt_slide_pts : p->opt_slide_pts);
         int rc = p->precision == B2N_SINGLE
                      ? window_adj_f32(p->g, table_ptrs(p), slide_axis, tms, wts, ko, kw, pm, samples, grid, ph,
-                                      nbatch, (int)p->opt_slide_pts, st, &done)
+                                      nbatch, wpts, st, &done)
                      : window_adj_f64(p->g, table_ptrs(p), slide_axis, tms, wts, ko, kw, pm, samples, grid, ph,
-                                      nbatch, (int)p->opt_slide_pts, st, &done);
+                                      nbatch, wpts, st, &done);
         if (rc != 0) return fail(B2N_ECUDA, "window adjoint launch failed: " + std::string(cudaGetErrorString((cudaError_t)rc)));
         if (done) p->last_adj_kernel = 3;
     }

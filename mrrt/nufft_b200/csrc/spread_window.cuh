@@ -43,8 +43,12 @@ template <typename T, int J> struct WinRec {
     static constexpr int kBytes = kRecBytes + 32 * 16;           // per warp
 };
 
-// TAB: 0 table in global memory, 1 table staged in shared memory, 2 plan-time weights
-template <typename T, int J, int TAB>
+// TAB: 0 table in global memory, 1 table staged in shared memory, 2 plan-time weights.
+// G:   lanes per sample (32 or 16).  With G = 16 every half-warp walks its OWN run of
+//      samples with its own register window: the per-sample instructions (operand loads,
+//      packed FMAs, loop control) are issued once for two samples, and the J*J = 36 face
+//      positions fill 16 lanes x 3 slots at 75 % instead of 32 lanes x 2 slots at 56 %.
+template <typename T, int J, int TAB, int G>
 __global__ void __launch_bounds__(128)
 spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T* __restrict__ h2,
                        const T* __restrict__ h3, const T* __restrict__ tm_s,
@@ -55,7 +59,8 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
                        int pts_per_warp) {
     using C = cplx_t<T>;
     constexpr int R = J * J;
-    constexpr int RPL = (R + 31) / 32;
+    constexpr int RPL = (R + G - 1) / G;
+    constexpr int NG = 32 / G;                                    // sample groups per warp
     constexpr int RB = WinRec<T, J>::kPitch;
     constexpr int WB = WinRec<T, J>::kBytes;
     constexpr unsigned FULL = 0xffffffffu;
@@ -73,9 +78,13 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
         __syncthreads();
     }
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    const int64_t begin = warp * pts_per_warp;
-    if (begin >= M) return;
-    const int64_t end = begin + pts_per_warp < M ? begin + pts_per_warp : M;
+    if (warp * pts_per_warp >= M) return;
+    // this lane group's contiguous run of samples
+    const int grp = lane / G;
+    const int lg = lane - grp * G;
+    const int per_group = pts_per_warp / NG;
+    const int64_t begin = warp * pts_per_warp + (int64_t)grp * per_group;
+    const int64_t end = begin + per_group < M ? begin + per_group : (begin < M ? M : begin);
     const int b = blockIdx.y;
     const C* __restrict__ sb = samples + (int64_t)b * M;
     C* __restrict__ gb = grid + (int64_t)b * g.PK;
@@ -97,7 +106,7 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
     bool rvalid[RPL];
 #pragma unroll
     for (int s = 0; s < RPL; s++) {
-        const int r = lane + 32 * s;
+        const int r = lg + G * s;
         rvalid[s] = r < R;
         rjb[s] = (r % R) % J;
         rjc[s] = (r % R) / J;
@@ -106,7 +115,7 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
     C* faceptr[RPL];        // grid address of this lane's face position (axes b, c)
 #pragma unroll
     for (int s = 0; s < RPL; s++) {
-        faceptr[s] = gb;
+        faceptr[s] = gb;   // (overwritten by the first window)
 #pragma unroll
         for (int j = 0; j < J; j++) acc[s][j] = make_c<T>(0, 0);
     }
@@ -114,13 +123,15 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
     bool have = false;
     int pkA = -1 << 30, pkB = -1, pkC = -1;   // previous sample's wrapped origin
 
-    for (int64_t base = begin; base < end; base += 32) {
-        const int cnt = (int)(end - base < 32 ? end - base : 32);
+    for (int it = 0; it < per_group; it += G) {
+        // (uniform trip count for the whole warp; groups past their end idle)
+        const int64_t base = begin + it;
+        const int cnt = (int)(base >= end ? 0 : (end - base < G ? end - base : G));
         __syncwarp();
-        // ---- batch phase: lane = sample
+        // ---- batch phase: lane = sample (record index = lane)
         int kA = 0, kB = 0, kC = 0;
-        if (lane < cnt) {
-            const int64_t i = base + lane;
+        if (lg < cnt) {
+            const int64_t i = base + lg;
             T* w = (T*)(stage + lane * RB);
             kA = pt_kw[(int64_t)aA * M + i];
             kB = pt_kw[(int64_t)aB * M + i];
@@ -151,23 +162,24 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
         }
         // window action: slide distance along a, or -1 = new window
         {
-            int qA = __shfl_up_sync(FULL, kA, 1), qB = __shfl_up_sync(FULL, kB, 1),
-                qC = __shfl_up_sync(FULL, kC, 1);
-            if (lane == 0) { qA = pkA; qB = pkB; qC = pkC; }
+            int qA = __shfl_up_sync(FULL, kA, 1, G), qB = __shfl_up_sync(FULL, kB, 1, G),
+                qC = __shfl_up_sync(FULL, kC, 1, G);
+            if (lg == 0) { qA = pkA; qB = pkB; qC = pkC; }
             const int d = kA - qA;
             const int act = (kB == qB && kC == qC && d >= 0 && d < J) ? d : -1;
-            if (lane < cnt) actions[lane] = make_int4(kA, kB, kC, act);
-            pkA = __shfl_sync(FULL, kA, cnt - 1);
-            pkB = __shfl_sync(FULL, kB, cnt - 1);
-            pkC = __shfl_sync(FULL, kC, cnt - 1);
+            if (lg < cnt) actions[lane] = make_int4(kA, kB, kC, act);
+            const int last = cnt > 0 ? cnt - 1 : 0;
+            const int nA = __shfl_sync(FULL, kA, last, G), nB = __shfl_sync(FULL, kB, last, G),
+                      nC = __shfl_sync(FULL, kC, last, G);
+            if (cnt > 0) { pkA = nA; pkB = nB; pkC = nC; }
         }
         __syncwarp();
         // ---- sample loop: all lanes work on one sample
-        int4 kk_next = actions[0];
+        int4 kk_next = actions[grp * G];
         for (int q = 0; q < cnt; q++) {
-            const unsigned char* rec = stage + q * RB;
+            const unsigned char* rec = stage + (grp * G + q) * RB;
             const int4 kk = kk_next;
-            if (q + 1 < cnt) kk_next = actions[q + 1];
+            if (q + 1 < cnt) kk_next = actions[grp * G + q + 1];
             // operands of this sample are fetched before the window update so that their
             // shared-memory latency overlaps it
             const T* w = (const T*)rec;
@@ -243,6 +255,10 @@ static int launch_window(const Geom& g, const TablePtrs& tabs, int slide_axis, c
                          const void* wts, const int32_t* pt_ko, const int32_t* pt_kw, const int32_t* perm,
                          const void* samples, void* grid, const void* phase_s, int nbatch,
                          int pts_per_warp, cudaStream_t st, bool* done) {
+    // negative pts_per_warp selects 32 lanes per sample (one window per warp)
+    const int lanes_per_sample = pts_per_warp < 0 ? 32 : 16;
+    if (pts_per_warp < 0) pts_per_warp = -pts_per_warp;
+    pts_per_warp = (pts_per_warp + 31) / 32 * 32;
     using C = cplx_t<T>;
     const int64_t nwarps = (g.M + pts_per_warp - 1) / pts_per_warp;
     const int64_t nblocks = (nwarps + 3) / 4;
@@ -258,8 +274,16 @@ static int launch_window(const Geom& g, const TablePtrs& tabs, int slide_axis, c
     const size_t stage_bytes = (size_t)4 * WinRec<T, J>::kBytes;
     cudaError_t e;
 #define B2N_LAUNCH_WIN(TABV, SMEM)                                                                 \
-    {                                                                                              \
-        auto k = spread_window3d_kernel<T, J, TABV>;                                               \
+    if (lanes_per_sample == 16) {                                                                  \
+        auto k = spread_window3d_kernel<T, J, TABV, 16>;                                           \
+        e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM));     \
+        if (e != cudaSuccess) return (int)e;                                                       \
+        k<<<gd, 128, (SMEM), st>>>(g, wa, (const T*)tabs.h[0], (const T*)tabs.h[1],                \
+                                   (const T*)tabs.h[2], (const T*)tm_s, (const T*)wts, pt_ko, pt_kw, \
+                                   perm, (const C*)samples, (C*)grid, (const C*)phase_s,           \
+                                   pts_per_warp);                                                  \
+    } else {                                                                                       \
+        auto k = spread_window3d_kernel<T, J, TABV, 32>;                                           \
         e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM));     \
         if (e != cudaSuccess) return (int)e;                                                       \
         k<<<gd, 128, (SMEM), st>>>(g, wa, (const T*)tabs.h[0], (const T*)tabs.h[1],                \
