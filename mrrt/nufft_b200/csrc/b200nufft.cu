@@ -61,6 +61,7 @@ struct b2n_plan {
     // 3 register window with lane-parallel batch weights and the adjoint sort order
     long opt_adj_kernel = 3;
     long opt_order_b = 1;        // build the adjoint sort order (adj_kernel 3)
+    long opt_fwd_pitch = 0;      // shared-memory row pitch of the forward tile (0 = automatic)
     long opt_win_lanes = 16;     // lanes per sample in the register-window adjoint (16 or 32)
     bool tile_user_set = false;
     bool tile_b_user_set = false;
@@ -276,8 +277,11 @@ extern "C" int b2n_plan_set_option(b2n_plan* p, const char* name, long value) {
     } else if (n == "precomp_weights") {
         if (p->points_set) return fail(B2N_ESTATE, "precomp_weights must precede set_points");
         p->opt_precomp = value;
+    } else if (n == "fwd_pitch") {
+        if (value < 0 || value > 127) return fail(B2N_EINVAL, "fwd_pitch must be in 0..127");
+        p->opt_fwd_pitch = value;
     } else if (n == "win_lanes") {
-        if (value != 16 && value != 32) return fail(B2N_EINVAL, "win_lanes must be 16 or 32");
+        if (value != 8 && value != 16 && value != 32) return fail(B2N_EINVAL, "win_lanes must be 8, 16 or 32");
         p->opt_win_lanes = value;
     } else if (n == "order_b") {
         if (p->points_set) return fail(B2N_ESTATE, "order_b must precede set_points");
@@ -682,11 +686,12 @@ static int interp_fwd_impl(b2n_plan* p, const void* grid, void* samples, int nba
     prof_begin(p, true, st);
     if (!p->opt_force_generic && !p->cplx_table) {
         const void* ph = phase ? p->d_phase_s : nullptr;
+        const int fwd_flags = (int)((p->opt_use_tma ? 1 : 0) | (p->opt_fwd_pitch << 8));
         int rc = p->precision == B2N_SINGLE
                      ? tiled_fwd_f32(p->g, p->tables_equal, table_ptrs(p), p->d_tm_s, p->d_wts, p->d_pt_ko, p->d_pt_kw, p->d_perm, p->d_items,
-                                     p->n_items, grid, samples, ph, nbatch, (int)p->opt_use_tma, st, &done)
+                                     p->n_items, grid, samples, ph, nbatch, fwd_flags, st, &done)
                      : tiled_fwd_f64(p->g, p->tables_equal, table_ptrs(p), p->d_tm_s, p->d_wts, p->d_pt_ko, p->d_pt_kw, p->d_perm, p->d_items,
-                                     p->n_items, grid, samples, ph, nbatch, (int)p->opt_use_tma, st, &done);
+                                     p->n_items, grid, samples, ph, nbatch, fwd_flags, st, &done);
         if (rc != 0) return fail(B2N_ECUDA, "tiled forward launch failed: " + std::string(cudaGetErrorString((cudaError_t)rc)));
     }
     if (!done) {
@@ -721,7 +726,8 @@ static int interp_adj_impl(b2n_plan* p, const void* samples, void* grid, int nba
         const int32_t* kw = ob ? p->d_pt_kw_b : p->d_pt_kw;
         const int32_t* pm = ob ? p->d_perm_b : p->d_perm;
         const int slide_axis = ob ? 2 : 0;
-        const int wpts = (int)(p->opt_win_lanes == 32 ? -p->opt_slide_pts : p->opt_slide_pts);
+        const int wpts = (int)(p->opt_win_lanes == 32 ? -p->opt_slide_pts
+                               : (p->opt_win_lanes == 8 ? p->opt_slide_pts + (1 << 20) : p->opt_slide_pts));
         int rc = p->precision == B2N_SINGLE
                      ? window_adj_f32(p->g, table_ptrs(p), slide_axis, tms, wts, ko, kw, pm, samples, grid, ph,
                                       nbatch, wpts, st, &done)

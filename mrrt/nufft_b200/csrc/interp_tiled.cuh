@@ -235,13 +235,22 @@ static int launch_fwd_tiled(const Geom& g, const TablePtrs& tabs, const void* tm
                             int use_tma, cudaStream_t st, bool* done) {
     using C = cplx_t<T>;
     *done = false;
+    // use_tma carries the requested row pitch in its upper bits (0 = automatic)
+    const int fwd_pitch = use_tma >> 8;
+    use_tma &= 0xff;
     TileShape ts;
     ts.E1 = g.tile[0] + J - 1;
     ts.E2 = NDIM > 1 ? g.tile[1] + J - 1 : 1;
     ts.E3 = NDIM > 2 ? g.tile[2] + J - 1 : 1;
-    // TMA box rows must be a multiple of 16 bytes
+    // TMA box rows must be a multiple of 16 bytes.  A row pitch of a whole number of
+    // 128-byte bank rows makes the bank depend on the axis-1 position only, which is what
+    // the cell-sorted (axis 1 fastest) lanes of a warp differ in: measured/simulated
+    // bank-conflict wavefronts drop from +31 % (pitch 22) to +18 % (pitch 32) on the
+    // bench trajectory (profiles/r01_notes.md).
     const int align = 16 / (int)sizeof(C) > 1 ? 16 / (int)sizeof(C) : 1;
     ts.E1p = (ts.E1 + align - 1) / align * align;
+    if (fwd_pitch > 0 && fwd_pitch >= ts.E1 && fwd_pitch % align == 0) ts.E1p = fwd_pitch;
+    else if (fwd_pitch == 0 && sizeof(C) == 8 && ts.E1 <= 32 && ts.E1 > 16) ts.E1p = 32;
     const size_t tb = (size_t)ts.E1p * ts.E2 * ts.E3 * sizeof(C);
     ts.tile_bytes = (int)((tb + 127) / 128 * 128);
     const size_t tab_bytes = (size_t)g.tlen[0] * sizeof(T);

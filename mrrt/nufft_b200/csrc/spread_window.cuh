@@ -256,8 +256,10 @@ static int launch_window(const Geom& g, const TablePtrs& tabs, int slide_axis, c
                          const void* samples, void* grid, const void* phase_s, int nbatch,
                          int pts_per_warp, cudaStream_t st, bool* done) {
     // negative pts_per_warp selects 32 lanes per sample (one window per warp)
-    const int lanes_per_sample = pts_per_warp < 0 ? 32 : 16;
-    if (pts_per_warp < 0) pts_per_warp = -pts_per_warp;
+    // pts_per_warp encodes the lane-group width: < 0 -> 32 lanes, >= 2^20 -> 8 lanes
+    int lanes_per_sample = 16;
+    if (pts_per_warp < 0) { lanes_per_sample = 32; pts_per_warp = -pts_per_warp; }
+    if (pts_per_warp >= (1 << 20)) { lanes_per_sample = 8; pts_per_warp -= (1 << 20); }
     pts_per_warp = (pts_per_warp + 31) / 32 * 32;
     using C = cplx_t<T>;
     const int64_t nwarps = (g.M + pts_per_warp - 1) / pts_per_warp;
@@ -274,7 +276,15 @@ static int launch_window(const Geom& g, const TablePtrs& tabs, int slide_axis, c
     const size_t stage_bytes = (size_t)4 * WinRec<T, J>::kBytes;
     cudaError_t e;
 #define B2N_LAUNCH_WIN(TABV, SMEM)                                                                 \
-    if (lanes_per_sample == 16) {                                                                  \
+    if (lanes_per_sample == 8) {                                                                   \
+        auto k = spread_window3d_kernel<T, J, TABV, 8>;                                            \
+        e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM));     \
+        if (e != cudaSuccess) return (int)e;                                                       \
+        k<<<gd, 128, (SMEM), st>>>(g, wa, (const T*)tabs.h[0], (const T*)tabs.h[1],                \
+                                   (const T*)tabs.h[2], (const T*)tm_s, (const T*)wts, pt_ko, pt_kw, \
+                                   perm, (const C*)samples, (C*)grid, (const C*)phase_s,           \
+                                   pts_per_warp);                                                  \
+    } else if (lanes_per_sample == 16) {                                                           \
         auto k = spread_window3d_kernel<T, J, TABV, 16>;                                           \
         e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM));     \
         if (e != cudaSuccess) return (int)e;                                                       \
