@@ -219,7 +219,7 @@ def run_gpu_arm(args):
     om_local = radial3d(SPOKES, NREAD, s_lo, s_hi)
     t0 = time.perf_counter()
     A = NufftBase(Nd=ND, omega=om_local, Jd=JD, Kd=KD, precision="single", mode="table",
-                  on_gpu=True, device=dev)
+                  on_gpu=True, device=dev, host_chunks=args.host_chunks)
     torch.cuda.synchronize()
     t_plan = time.perf_counter() - t0
     M_local = A.M
@@ -383,6 +383,8 @@ def main():
     ap.add_argument("--cpu-frac", type=int, default=256,
                     help="CPU legs use 1/frac of the spokes")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--host-chunks", type=int, default=4,
+                    help="sample ranges pipelined against host<->device copies in the e2e leg")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

@@ -119,6 +119,16 @@ int b2n_interp_fwd(b2n_plan *plan, const void *grid_dev, void *samples_dev, int 
 int b2n_interp_adj(b2n_plan *plan, const void *samples_dev, void *grid_dev, int nbatch,
                    int apply_phase, void *stream);
 
+/* The two halves of a full transform, for callers that pipeline host transfers of sample
+ * chunks against the interpolation (several plans over disjoint sample ranges sharing one
+ * grid): image -> oversampled spectrum (x*sn, zero-pad, FFT, phase_before) into grid_dev,
+ * and gridded spectrum -> image (conj phase_before, inverse FFT, crop, scale; grid_dev is
+ * overwritten).  b2n_interp_adj accepts apply_phase | 2 to ACCUMULATE into grid_dev
+ * instead of zeroing it first. */
+int b2n_grid_fwd(b2n_plan *plan, const void *image_dev, void *grid_dev, int nbatch,
+                 void *stream);
+int b2n_grid_adj(b2n_plan *plan, void *grid_dev, void *image_dev, int nbatch, void *stream);
+
 /* Full transforms.  image_dev: complex[prod(Nd) * nbatch] first axis fastest. */
 int b2n_nufft_fwd(b2n_plan *plan, const void *image_dev, void *samples_dev, int nbatch,
                   void *stream);

@@ -126,13 +126,26 @@ class NufftBase(object):
         Must be True: this operator has no CPU path.
     device : int or torch.device, optional
         CUDA device (default: the current one).
+    options : dict, optional
+        Integer plan options of the C ABI (``b2n_plan_set_option``).
+    host_chunks : int, optional
+        For HOST inputs (NumPy arrays / CPU tensors) in table mode: split the samples into
+        this many contiguous ranges, each with its own plan, and pipeline the host<->device
+        copies of one range against the interpolation of another (two CUDA streams).
+        Results are identical; 1 disables it.
     """
 
     def __init__(self, Nd, omega, Jd=4, Kd=None, precision="single", mode="table",
                  Ld=1024, ortho=False, n_shift=None, phasing="real",
                  adjoint_scalefactor=1.0, preplan_cufft=True, order="F", verbose=False,
-                 on_gpu=True, device=None, options=None):
+                 on_gpu=True, device=None, options=None, host_chunks=1):
         self.verbose = verbose
+        self.host_chunks = max(1, int(host_chunks))
+        self._children = None
+        self._ctor_kwargs = dict(Jd=Jd, Kd=Kd, precision=precision, mode=mode, Ld=Ld, ortho=ortho,
+                                 n_shift=n_shift, phasing=phasing,
+                                 adjoint_scalefactor=adjoint_scalefactor, order=order,
+                                 device=device, options=options)
         if on_gpu not in (True, False):
             raise ValueError("on_gpu must be True or False")
         if not on_gpu:
@@ -197,6 +210,7 @@ class NufftBase(object):
         self._real_dtype, self._cplx_dtype = pm.real_cplx_dtypes(precision)
         rdt, cdt = self._real_dtype, self._cplx_dtype
         self.M = omega_np.shape[0]
+        self._omega_host = omega_np if self.host_chunks > 1 else None
         if n_shift is None:
             self.n_shift = (0.0,) * self.ndim
         else:
@@ -427,6 +441,111 @@ class NufftBase(object):
             x = x.permute(*((x.dim() - 1,) + tuple(range(x.dim() - 1))))
         return x
 
+    # ------------------------------------------------------------------ host pipeline
+    def _pipelined(self, kind):
+        return (self.host_chunks > 1 and self.mode == "table" and self.M >= self.host_chunks
+                and (kind.kind == "numpy" or kind.host))
+
+    def _ensure_children(self):
+        """Sub-operators over contiguous sample ranges (built on first host call)."""
+        if self._children is None:
+            from ._sharded import shard_range
+
+            kw = dict(self._ctor_kwargs)
+            kw["device"] = self.device
+            self._children = []
+            for k in range(self.host_chunks):
+                lo, hi = shard_range(self.M, self.host_chunks, k)
+                self._children.append((lo, hi, NufftBase(self.Nd, self._omega_host[lo:hi], **kw)))
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        return self._children
+
+    def _host_tensor(self, x):
+        t = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.asarray(x))
+        cdt = _TORCH_C[self._cplx_dtype]
+        return t if t.dtype == cdt else t.to(cdt)
+
+    def _fft_host(self, x, kind):
+        """fft for a HOST array: H2D image, one spectrum, then per sample range the
+        interpolation on the compute stream while the previous range's samples travel
+        back on the copy stream."""
+        xt = self._host_tensor(x)
+        if self.order == "C":
+            xt = self._swap_reps(xt, self.nargin1)
+        if xt.numel() == 0 or xt.numel() % self.nargin1 != 0:
+            print("Input signal has the wrong size.")
+            raise ValueError("cannot reshape array of size {} into shape {}".format(
+                xt.numel(), tuple(self.Nd) + (-1,)))
+        n_reps = xt.numel() // self.nargin1
+        children = self._ensure_children()
+        cdt = _TORCH_C[self._cplx_dtype]
+        with torch.cuda.device(self.device):
+            main = torch.cuda.current_stream(self.device)
+            mem_h = _f_order_memory(xt, self.Nd).reshape(n_reps, self.nargin1)
+            mem = mem_h.to(self.device, non_blocking=True)
+            grid = torch.empty((n_reps, _prod(self.Kd)), dtype=cdt, device=self.device)
+            _lib.check(self._lib.b2n_grid_fwd(self._plan, mem.data_ptr(), grid.data_ptr(), n_reps,
+                                              self._stream()))
+            out_h = torch.empty((n_reps, self.M), dtype=cdt, pin_memory=True)
+            keep = []
+            for lo, hi, ch in children:
+                out_k = torch.empty((n_reps, hi - lo), dtype=cdt, device=self.device)
+                _lib.check(self._lib.b2n_interp_fwd(ch._plan, grid.data_ptr(), out_k.data_ptr(),
+                                                    n_reps, 1, self._stream()))
+                ev = torch.cuda.Event()
+                ev.record(main)
+                with torch.cuda.stream(self._copy_stream):
+                    self._copy_stream.wait_event(ev)
+                    out_h[:, lo:hi].copy_(out_k, non_blocking=True)
+                keep.append(out_k)
+            self._copy_stream.synchronize()
+        out = out_h.t()
+        if n_reps == 1:
+            out = out[..., 0]
+        if self.order == "C":
+            out = self._unswap_reps(out, self.nargout1)
+        return out.numpy() if kind.kind == "numpy" else out
+
+    def _adj_host(self, k, kind):
+        """adj for a HOST array: sample ranges are copied in on the copy stream while the
+        previous range is gridded (accumulating into one grid) on the compute stream."""
+        kt = self._host_tensor(k)
+        if self.order == "C":
+            kt = self._swap_reps(kt, self.nargout1)
+        if self.M == 0 or kt.numel() == 0 or kt.numel() % self.M != 0:
+            raise ValueError("invalid size")
+        n_reps = kt.numel() // self.M
+        children = self._ensure_children()
+        cdt = _TORCH_C[self._cplx_dtype]
+        with torch.cuda.device(self.device):
+            main = torch.cuda.current_stream(self.device)
+            mem_h = _f_order_memory(kt, (self.M,)).reshape(n_reps, self.M)
+            grid = torch.empty((n_reps, _prod(self.Kd)), dtype=cdt, device=self.device)
+            keep = []
+            for idx, (lo, hi, ch) in enumerate(children):
+                buf = torch.empty((n_reps, hi - lo), dtype=cdt, device=self.device)
+                ev = torch.cuda.Event()
+                with torch.cuda.stream(self._copy_stream):
+                    buf.copy_(mem_h[:, lo:hi], non_blocking=True)
+                    ev.record(self._copy_stream)
+                main.wait_event(ev)
+                # bit 0: apply the sample phase, bit 1: accumulate into the grid
+                _lib.check(self._lib.b2n_interp_adj(ch._plan, buf.data_ptr(), grid.data_ptr(), n_reps,
+                                                    1 | (2 if idx > 0 else 0), self._stream()))
+                keep.append(buf)
+            out = torch.empty((n_reps,) + tuple(reversed(self.Nd)), dtype=cdt, device=self.device)
+            _lib.check(self._lib.b2n_grid_adj(self._plan, grid.data_ptr(), out.data_ptr(), n_reps,
+                                              self._stream()))
+            out_h = torch.empty(out.shape, dtype=cdt, pin_memory=True)
+            out_h.copy_(out, non_blocking=False)
+            self._copy_stream.synchronize()
+        x = out_h.permute(*reversed(range(out_h.dim())))
+        if n_reps == 1:
+            x = x[..., 0]
+        if self.order == "C":
+            x = self._unswap_reps(x, self.nargin1)
+        return x.numpy() if kind.kind == "numpy" else x
+
     def fft(self, x):
         """Forward NUFFT (uniform spatial -> non-uniform frequency).
 
@@ -435,6 +554,8 @@ class NufftBase(object):
         Reference: _nufft.py:425-452.
         """
         kind = _ArrayKind(x)
+        if self._pipelined(kind):
+            return self._fft_host(x, kind)
         xt = kind.to_torch(x, self.device)
         if self.order == "C":
             xt = self._swap_reps(xt, self.nargin1)
@@ -447,6 +568,8 @@ class NufftBase(object):
         """Adjoint NUFFT (non-uniform frequency -> uniform spatial).
         Reference: _nufft.py:454-482."""
         kind = _ArrayKind(k)
+        if self._pipelined(kind):
+            return self._adj_host(k, kind)
         kt = kind.to_torch(k, self.device)
         if self.order == "C":
             kt = self._swap_reps(kt, self.nargout1)

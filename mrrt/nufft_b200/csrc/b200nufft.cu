@@ -705,10 +705,12 @@ static int interp_fwd_impl(b2n_plan* p, const void* grid, void* samples, int nba
 }
 
 static int interp_adj_impl(b2n_plan* p, const void* samples, void* grid, int nbatch, bool phase,
-                           cudaStream_t st) {
+                           cudaStream_t st, bool accumulate = false) {
     if (!p->tables_set) return fail(B2N_ESTATE, "tables not set");
-    CU(cudaMemsetAsync(grid, 0, p->cplx_size() * p->g.PK * nbatch, st));
-    p->lib_calls++;
+    if (!accumulate) {
+        CU(cudaMemsetAsync(grid, 0, p->cplx_size() * p->g.PK * nbatch, st));
+        p->lib_calls++;
+    }
     if (p->g.M == 0) return B2N_OK;
     {
         int rc = ensure_weights(p, st);
@@ -780,7 +782,8 @@ extern "C" int b2n_interp_adj(b2n_plan* p, const void* samples_dev, void* grid_d
     if (rc) return rc;
     if (grid_dev == nullptr) return fail(B2N_EINVAL, "NULL array");
     CU(cudaSetDevice(p->device));
-    return interp_adj_impl(p, samples_dev, grid_dev, nbatch, apply_phase && p->d_phase_s, (cudaStream_t)stream);
+    return interp_adj_impl(p, samples_dev, grid_dev, nbatch, (apply_phase & 1) && p->d_phase_s,
+                           (cudaStream_t)stream, (apply_phase & 2) != 0);
 }
 
 // ---------------------------------------------------------------------------------
@@ -944,17 +947,17 @@ static AxisPtrs axis_ptrs(b2n_plan* p) {
     return ax;
 }
 
+// image -> oversampled spectrum on the Kd grid (scale, zero-pad, FFT, phase_before)
 template <typename T>
-static int nufft_fwd_t(b2n_plan* p, const void* image, void* samples, int nbatch, cudaStream_t st) {
+static int grid_fwd_t(b2n_plan* p, const void* image, void* grid, int nbatch, cudaStream_t st) {
     using C = cplx_t<T>;
     const Geom& g = p->g;
     int rc;
-    if ((rc = ensure_work(p, nbatch))) return rc;
     cufftHandle fft;
     if ((rc = get_fft(p, nbatch, &fft))) return rc;
     FFT(cufftSetStream(fft, st));
     AxisPtrs ax = axis_ptrs(p);
-    C* work = (C*)p->d_work;
+    C* work = (C*)grid;
     constexpr int VEC = 32 / (int)sizeof(C);   // 32 bytes of grid per thread
     pre_scale_pad_kernel<T, VEC><<<grid_for(g.PK * nbatch / VEC + 1, 256, p->sm_count, 32), 256, 0, st>>>(
         g, ax, (T)p->fwd_scale, p->fwd_scale != 1.0, (const C*)image, work, nbatch);
@@ -969,24 +972,20 @@ static int nufft_fwd_t(b2n_plan* p, const void* image, void* samples, int nbatch
         CU(cudaGetLastError());
         p->launches++;
     }
-    if (p->opt_sparse_mode) return spmv_impl(p, true, work, samples, nbatch, p->d_phase_s != nullptr, st);
-    return interp_fwd_impl(p, work, samples, nbatch, p->d_phase_s != nullptr, st);
+    return B2N_OK;
 }
 
+// gridded spectrum -> image (conj phase_before, inverse FFT, crop, scale); grid is overwritten
 template <typename T>
-static int nufft_adj_t(b2n_plan* p, const void* samples, void* image, int nbatch, cudaStream_t st) {
+static int grid_adj_t(b2n_plan* p, void* grid, void* image, int nbatch, cudaStream_t st) {
     using C = cplx_t<T>;
     const Geom& g = p->g;
     int rc;
-    if ((rc = ensure_work(p, nbatch))) return rc;
     cufftHandle fft;
     if ((rc = get_fft(p, nbatch, &fft))) return rc;
     FFT(cufftSetStream(fft, st));
     AxisPtrs ax = axis_ptrs(p);
-    C* work = (C*)p->d_work;
-    if (p->opt_sparse_mode) rc = spmv_impl(p, false, samples, work, nbatch, p->d_phase_s != nullptr, st);
-    else rc = interp_adj_impl(p, samples, work, nbatch, p->d_phase_s != nullptr, st);
-    if (rc) return rc;
+    C* work = (C*)grid;
     if (p->have_pb) {
         constexpr int VEC = 32 / (int)sizeof(C);
         phase_before_kernel<T, VEC><<<grid_for(g.PK * nbatch / VEC + 1, 256, p->sm_count, 32), 256, 0, st>>>(
@@ -1004,6 +1003,51 @@ static int nufft_adj_t(b2n_plan* p, const void* samples, void* image, int nbatch
     return B2N_OK;
 }
 
+static int grid_fwd(b2n_plan* p, const void* image, void* grid, int nbatch, cudaStream_t st) {
+    return p->precision == B2N_SINGLE ? grid_fwd_t<float>(p, image, grid, nbatch, st)
+                                      : grid_fwd_t<double>(p, image, grid, nbatch, st);
+}
+static int grid_adj(b2n_plan* p, void* grid, void* image, int nbatch, cudaStream_t st) {
+    return p->precision == B2N_SINGLE ? grid_adj_t<float>(p, grid, image, nbatch, st)
+                                      : grid_adj_t<double>(p, grid, image, nbatch, st);
+}
+
+extern "C" int b2n_grid_fwd(b2n_plan* p, const void* image_dev, void* grid_dev, int nbatch,
+                            void* stream) {
+    if (p == nullptr) return fail(B2N_EINVAL, "NULL plan");
+    if (nbatch < 1) return fail(B2N_EINVAL, "nbatch must be >= 1");
+    if (image_dev == nullptr || grid_dev == nullptr) return fail(B2N_EINVAL, "NULL array");
+    if (!p->scaling_set) return fail(B2N_ESTATE, "scaling not set");
+    CU(cudaSetDevice(p->device));
+    return grid_fwd(p, image_dev, grid_dev, nbatch, (cudaStream_t)stream);
+}
+
+extern "C" int b2n_grid_adj(b2n_plan* p, void* grid_dev, void* image_dev, int nbatch, void* stream) {
+    if (p == nullptr) return fail(B2N_EINVAL, "NULL plan");
+    if (nbatch < 1) return fail(B2N_EINVAL, "nbatch must be >= 1");
+    if (image_dev == nullptr || grid_dev == nullptr) return fail(B2N_EINVAL, "NULL array");
+    if (!p->scaling_set) return fail(B2N_ESTATE, "scaling not set");
+    CU(cudaSetDevice(p->device));
+    return grid_adj(p, grid_dev, image_dev, nbatch, (cudaStream_t)stream);
+}
+
+static int nufft_fwd_impl(b2n_plan* p, const void* image, void* samples, int nbatch, cudaStream_t st) {
+    int rc;
+    if ((rc = ensure_work(p, nbatch))) return rc;
+    if ((rc = grid_fwd(p, image, p->d_work, nbatch, st))) return rc;
+    if (p->opt_sparse_mode) return spmv_impl(p, true, p->d_work, samples, nbatch, p->d_phase_s != nullptr, st);
+    return interp_fwd_impl(p, p->d_work, samples, nbatch, p->d_phase_s != nullptr, st);
+}
+
+static int nufft_adj_impl(b2n_plan* p, const void* samples, void* image, int nbatch, cudaStream_t st) {
+    int rc;
+    if ((rc = ensure_work(p, nbatch))) return rc;
+    if (p->opt_sparse_mode) rc = spmv_impl(p, false, samples, p->d_work, nbatch, p->d_phase_s != nullptr, st);
+    else rc = interp_adj_impl(p, samples, p->d_work, nbatch, p->d_phase_s != nullptr, st);
+    if (rc) return rc;
+    return grid_adj(p, p->d_work, image, nbatch, st);
+}
+
 extern "C" int b2n_nufft_fwd(b2n_plan* p, const void* image_dev, void* samples_dev, int nbatch,
                              void* stream) {
     int rc = check_ready(p, image_dev, samples_dev, nbatch);
@@ -1011,8 +1055,7 @@ extern "C" int b2n_nufft_fwd(b2n_plan* p, const void* image_dev, void* samples_d
     if (image_dev == nullptr) return fail(B2N_EINVAL, "NULL array");
     if (!p->scaling_set) return fail(B2N_ESTATE, "scaling not set");
     CU(cudaSetDevice(p->device));
-    if (p->precision == B2N_SINGLE) return nufft_fwd_t<float>(p, image_dev, samples_dev, nbatch, (cudaStream_t)stream);
-    return nufft_fwd_t<double>(p, image_dev, samples_dev, nbatch, (cudaStream_t)stream);
+    return nufft_fwd_impl(p, image_dev, samples_dev, nbatch, (cudaStream_t)stream);
 }
 
 extern "C" int b2n_nufft_adj(b2n_plan* p, const void* samples_dev, void* image_dev, int nbatch,
@@ -1022,6 +1065,5 @@ extern "C" int b2n_nufft_adj(b2n_plan* p, const void* samples_dev, void* image_d
     if (image_dev == nullptr) return fail(B2N_EINVAL, "NULL array");
     if (!p->scaling_set) return fail(B2N_ESTATE, "scaling not set");
     CU(cudaSetDevice(p->device));
-    if (p->precision == B2N_SINGLE) return nufft_adj_t<float>(p, samples_dev, image_dev, nbatch, (cudaStream_t)stream);
-    return nufft_adj_t<double>(p, samples_dev, image_dev, nbatch, (cudaStream_t)stream);
+    return nufft_adj_impl(p, samples_dev, image_dev, nbatch, (cudaStream_t)stream);
 }

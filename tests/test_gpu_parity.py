@@ -228,6 +228,29 @@ def test_bench_workload_subsample_vs_oracle():
     assert rel_l2(A.adj(yo), O.adj(yo)) <= TOL["single"]
 
 
+@pytest.mark.parametrize("name", ["d2_radial_table_single_real", "d3_table_single_real",
+                                  "d2_table_single_real_C2", "d3_mid_table_double_real_J4",
+                                  "d1_table_double_complex"])
+def test_host_pipeline_matches_golden(name):
+    """host_chunks > 1 (sample ranges pipelined against host<->device copies) gives the
+    same results as the single-plan path, for NumPy and pinned CPU tensors."""
+    import torch
+
+    cfg, z = load_case(name)
+    tol = TOL[cfg["precision"]]
+    A = _op(cfg, z["omega"], host_chunks=3)
+    y = A.fft(z["x"])
+    assert isinstance(y, np.ndarray) and y.shape == z["y"].shape and y.dtype == z["y"].dtype
+    assert rel_l2(y, z["y"]) <= tol
+    xa = A.adj(z["y"])
+    assert xa.shape == z["x_adj"].shape
+    assert rel_l2(xa, z["x_adj"]) <= tol
+    xt = torch.from_numpy(np.asfortranarray(z["x"]).astype(A._cplx_dtype)).pin_memory()
+    yt = A.fft(xt)
+    assert isinstance(yt, torch.Tensor) and not yt.is_cuda
+    assert rel_l2(yt.numpy(), z["y"]) <= tol
+
+
 def test_array_kinds_and_dtypes():
     """NumPy in -> NumPy out, torch in -> torch out; output dtype follows `precision`
     whatever the input dtype (tests/test_nufft.py:376-388)."""
