@@ -383,7 +383,7 @@ def main():
     ap.add_argument("--cpu-frac", type=int, default=256,
                     help="CPU legs use 1/frac of the spokes")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--host-chunks", type=int, default=4,
+    ap.add_argument("--host-chunks", type=int, default=8,
                     help="sample ranges pipelined against host<->device copies in the e2e leg")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
