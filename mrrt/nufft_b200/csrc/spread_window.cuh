@@ -48,7 +48,11 @@ template <typename T, int J> struct WinRec {
 //      samples with its own register window: the per-sample instructions (operand loads,
 //      packed FMAs, loop control) are issued once for two samples, and the J*J = 36 face
 //      positions fill 16 lanes x 3 slots at 75 % instead of 32 lanes x 2 slots at 56 %.
-template <typename T, int J, int TAB, int G>
+// RING: false = the J accumulators of a lane run along the slide axis and are shifted when
+//       the window slides; true = the slide axis is laid out ACROSS LANES (lane <-> (column,
+//       jb), registers <-> jc): sliding only advances a phase counter, the lanes that hold
+//       the retiring column flush it, nothing moves.
+template <typename T, int J, int TAB, int G, bool RING>
 __global__ void __launch_bounds__(128)
 spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T* __restrict__ h2,
                        const T* __restrict__ h3, const T* __restrict__ tm_s,
@@ -120,6 +124,14 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
         for (int j = 0; j < J; j++) acc[s][j] = make_c<T>(0, 0);
     }
     int WA = 0;             // wrapped window origin along the slide axis
+    int ph = 0;             // RING: physical column that holds logical column 0
+    int jlog[RPL];          // RING: logical column of each lane slot
+    int offC[J];            // RING: grid offsets of the J register positions (axis c)
+#pragma unroll
+    for (int s = 0; s < RPL; s++) jlog[s] = rjc[s];
+#pragma unroll
+    for (int j = 0; j < J; j++) offC[j] = 0;
+    (void)ph;
     bool have = false;
     int pkA = -1 << 30, pkB = -1, pkC = -1;   // previous sample's wrapped origin
 
@@ -174,8 +186,92 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
             if (cnt > 0) { pkA = nA; pkB = nB; pkC = nC; }
         }
         __syncwarp();
-        // ---- sample loop: all lanes work on one sample
+        // ---- sample loop: all lanes of a group work on one sample
         int4 kk_next = actions[grp * G];
+        if constexpr (RING) {
+            for (int q = 0; q < cnt; q++) {
+                const unsigned char* rec = stage + (grp * G + q) * RB;
+                const int4 kk = kk_next;
+                if (q + 1 < cnt) kk_next = actions[grp * G + q + 1];
+                const T* w = (const T*)rec;
+                // operands first (their latency overlaps the window update).  The logical
+                // column of this lane AFTER the update is known from the action code.
+                T wC[J];
+#pragma unroll
+                for (int j = 0; j < J; j++) wC[j] = w[2 * J + j];
+                const C f = make_c<T>(w[3 * J], w[3 * J + 1]);
+                int jl[RPL];
+                T wab[RPL];
+#pragma unroll
+                for (int s = 0; s < RPL; s++) {
+                    int t = jlog[s] - kk.w;
+                    if (t < 0) t += J;
+                    jl[s] = kk.w < 0 ? rjc[s] : t;      // rjc = physical column id of the slot
+                    wab[s] = w[jl[s]] * w[J + rjb[s]];
+                }
+                if (kk.w != 0) {
+                    if (kk.w < 0) {
+                        if (have) {
+                            // retire every column
+#pragma unroll
+                            for (int s = 0; s < RPL; s++) {
+                                if (rvalid[s]) {
+                                    int ka = WA + jlog[s];
+                                    if (ka >= KA) ka -= KA;
+                                    C* pcol = faceptr[s] + (int64_t)ka * sA;
+#pragma unroll
+                                    for (int j = 0; j < J; j++) atomic_add_c(pcol + offC[j], acc[s][j]);
+                                }
+#pragma unroll
+                                for (int j = 0; j < J; j++) acc[s][j] = make_c<T>(0, 0);
+                            }
+                        }
+                        have = true;
+                        WA = kk.x;
+                        ph = 0;
+#pragma unroll
+                        for (int s = 0; s < RPL; s++) {
+                            int kb = kk.y + rjb[s]; if (kb >= KB) kb -= KB;
+                            faceptr[s] = gb + (int64_t)kb * sB;
+                        }
+#pragma unroll
+                        for (int j = 0; j < J; j++) {
+                            int kc = kk.z + j; if (kc >= KC) kc -= KC;
+                            offC[j] = kc * sC;
+                        }
+                    } else {
+#pragma unroll 1
+                        for (int sft = 0; sft < kk.w; sft++) {
+                            // retire the column that holds logical position 0
+                            const int64_t offA = (int64_t)WA * sA;
+#pragma unroll
+                            for (int s = 0; s < RPL; s++) {
+                                if (rvalid[s] && rjc[s] == ph) {
+                                    C* pcol = faceptr[s] + offA;
+#pragma unroll
+                                    for (int j = 0; j < J; j++) {
+                                        atomic_add_c(pcol + offC[j], acc[s][j]);
+                                        acc[s][j] = make_c<T>(0, 0);
+                                    }
+                                }
+                            }
+                            ph = ph + 1 == J ? 0 : ph + 1;
+                            WA++;   // stays < KA: it ends at this sample's wrapped origin
+                        }
+                    }
+                }
+#pragma unroll
+                for (int s = 0; s < RPL; s++) {
+                    jlog[s] = jl[s];
+                    if (rvalid[s]) {
+                        const C v = mul_w(wab[s], f);
+#pragma unroll
+                        for (int j = 0; j < J; j++) acc[s][j] = fma_w(wC[j], v, acc[s][j]);
+                    }
+                }
+            }
+            continue;
+        }
         for (int q = 0; q < cnt; q++) {
             const unsigned char* rec = stage + (grp * G + q) * RB;
             const int4 kk = kk_next;
@@ -238,6 +334,21 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
             }
         }
     }
+    if constexpr (RING) {
+        if (have) {
+#pragma unroll
+            for (int s = 0; s < RPL; s++) {
+                if (rvalid[s]) {
+                    int ka = WA + jlog[s];
+                    if (ka >= KA) ka -= KA;
+                    C* pcol = faceptr[s] + (int64_t)ka * sA;
+#pragma unroll
+                    for (int j = 0; j < J; j++) atomic_add_c(pcol + offC[j], acc[s][j]);
+                }
+            }
+        }
+        return;
+    }
     if (have) {
 #pragma unroll
         for (int j = 0; j < J; j++) {
@@ -260,6 +371,9 @@ static int launch_window(const Geom& g, const TablePtrs& tabs, int slide_axis, c
     int lanes_per_sample = 16;
     if (pts_per_warp < 0) { lanes_per_sample = 32; pts_per_warp = -pts_per_warp; }
     if (pts_per_warp >= (1 << 20)) { lanes_per_sample = 8; pts_per_warp -= (1 << 20); }
+    // slide_axis carries the RING flag in bit 8
+    const bool ring = (slide_axis & 256) != 0;
+    slide_axis &= 255;
     pts_per_warp = (pts_per_warp + 31) / 32 * 32;
     using C = cplx_t<T>;
     const int64_t nwarps = (g.M + pts_per_warp - 1) / pts_per_warp;
@@ -277,7 +391,15 @@ static int launch_window(const Geom& g, const TablePtrs& tabs, int slide_axis, c
     cudaError_t e;
 #define B2N_LAUNCH_WIN(TABV, SMEM)                                                                 \
     if (lanes_per_sample == 8) {                                                                   \
-        auto k = spread_window3d_kernel<T, J, TABV, 8>;                                            \
+        auto k = spread_window3d_kernel<T, J, TABV, 8, false>;                                            \
+        e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM));     \
+        if (e != cudaSuccess) return (int)e;                                                       \
+        k<<<gd, 128, (SMEM), st>>>(g, wa, (const T*)tabs.h[0], (const T*)tabs.h[1],                \
+                                   (const T*)tabs.h[2], (const T*)tm_s, (const T*)wts, pt_ko, pt_kw, \
+                                   perm, (const C*)samples, (C*)grid, (const C*)phase_s,           \
+                                   pts_per_warp);                                                  \
+    } else if (lanes_per_sample == 16 && ring) {                                                   \
+        auto k = spread_window3d_kernel<T, J, TABV, 16, true>;                                     \
         e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM));     \
         if (e != cudaSuccess) return (int)e;                                                       \
         k<<<gd, 128, (SMEM), st>>>(g, wa, (const T*)tabs.h[0], (const T*)tabs.h[1],                \
@@ -285,7 +407,7 @@ static int launch_window(const Geom& g, const TablePtrs& tabs, int slide_axis, c
                                    perm, (const C*)samples, (C*)grid, (const C*)phase_s,           \
                                    pts_per_warp);                                                  \
     } else if (lanes_per_sample == 16) {                                                           \
-        auto k = spread_window3d_kernel<T, J, TABV, 16>;                                           \
+        auto k = spread_window3d_kernel<T, J, TABV, 16, false>;                                           \
         e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM));     \
         if (e != cudaSuccess) return (int)e;                                                       \
         k<<<gd, 128, (SMEM), st>>>(g, wa, (const T*)tabs.h[0], (const T*)tabs.h[1],                \
@@ -293,7 +415,7 @@ static int launch_window(const Geom& g, const TablePtrs& tabs, int slide_axis, c
                                    perm, (const C*)samples, (C*)grid, (const C*)phase_s,           \
                                    pts_per_warp);                                                  \
     } else {                                                                                       \
-        auto k = spread_window3d_kernel<T, J, TABV, 32>;                                           \
+        auto k = spread_window3d_kernel<T, J, TABV, 32, false>;                                           \
         e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM));     \
         if (e != cudaSuccess) return (int)e;                                                       \
         k<<<gd, 128, (SMEM), st>>>(g, wa, (const T*)tabs.h[0], (const T*)tabs.h[1],                \
