@@ -374,6 +374,65 @@ def run_gpu_arm(args):
         dist.destroy_process_group()
 
 
+def run_coil_arm(args):
+    """BASELINE configs[3]: 2-D 320^2, 32-coil radial batch (503 spokes x 640 samples,
+    Kd = 480^2, J = 6, complex64); coils sharded over the ranks, NO communication.
+    Strong scaling of the 32-coil batch; value = 2 * M * 32 / step time."""
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from mrrt.nufft_b200 import CoilShardedNufft
+
+    S, n, ncoil = 503, 640, 32
+    ang = np.pi * np.arange(S) / S
+    r = 2 * np.pi * (np.arange(n) - n / 2) / n
+    om = np.stack([np.outer(np.cos(ang), r).ravel(), np.outer(np.sin(ang), r).ravel()], 1).astype(np.float32)
+    A = CoilShardedNufft((320, 320), om, n_coils=ncoil, Jd=6, Kd=(480, 480), precision="single",
+                         device=dev)
+    nloc = A.c1 - A.c0
+    g = torch.Generator(device=dev).manual_seed(rank)
+    x = torch.randn((nloc, 320, 320), dtype=torch.complex64, device=dev, generator=g).permute(2, 1, 0)
+
+    def step():
+        return A.adj(A.fft(x))
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    if rank == 0:
+        print(json.dumps({
+            "metric": "non-uniform pts/s fwd+adj, 2D 320^2 32-coil batch", "unit": UNIT,
+            "value": 2.0 * om.shape[0] * ncoil / (ms_step / 1000.0), "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "2D 320^2 radial 503x640 (M=321920), Kd=480^2, Jd=6, complex64, "
+                                   "32 coils sharded over %d ranks (no communication)" % world}}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -383,6 +442,9 @@ def main():
     ap.add_argument("--cpu-frac", type=int, default=256,
                     help="CPU legs use 1/frac of the spokes")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--workload", default="c5", choices=["c5", "coils"],
+                    help="c5 = BASELINE configs[4] (the contract bench, default); coils = "
+                         "configs[3], the 32-coil 2-D batch sharded by coil")
     ap.add_argument("--host-chunks", type=int, default=8,
                     help="sample ranges pipelined against host<->device copies in the e2e leg")
     args = ap.parse_args()
@@ -390,6 +452,8 @@ def main():
         args.warmup = 3
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.workload == "coils":
+        run_coil_arm(args)
     else:
         run_gpu_arm(args)
 

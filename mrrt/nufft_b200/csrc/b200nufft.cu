@@ -132,6 +132,21 @@ static void dev_free(void* ptr) {
     if (ptr) cudaFree(ptr);
 }
 
+// plan-time scratch buffers: freed on every exit path
+struct Scratch {
+    std::vector<void*> ptrs;
+    ~Scratch() {
+        for (void* q : ptrs) cudaFree(q);
+    }
+    template <typename P> cudaError_t alloc(P** out, size_t bytes) {
+        void* q = nullptr;
+        cudaError_t e = cudaMalloc(&q, bytes ? bytes : 16);
+        if (e == cudaSuccess) ptrs.push_back(q);
+        *out = (P*)q;
+        return e;
+    }
+};
+
 static int grid_for(int64_t n, int block, int sm_count, int per_sm = 16) {
     int64_t b = (n + block - 1) / block;
     int64_t cap = (int64_t)sm_count * per_sm;
@@ -404,6 +419,7 @@ static int set_points_t(b2n_plan* p, const void* coords, int64_t M, int kind, cu
         p->points_set = true;
         return B2N_OK;
     }
+    Scratch scratch;
     // the adjoint order is only used by the 3-D register-window kernel
     const bool want_b = g.ndim == 3 && !p->cplx_table && p->opt_adj_kernel == 3 && p->opt_order_b;
     uint64_t* keys_b = nullptr;
@@ -412,16 +428,16 @@ static int set_points_t(b2n_plan* p, const void* coords, int64_t M, int kind, cu
         if ((rc = dev_alloc(p, (void**)&p->d_perm_b, sizeof(int32_t) * M))) return rc;
         if ((rc = dev_alloc(p, (void**)&p->d_pt_ko_b, sizeof(int32_t) * M * g.ndim))) return rc;
         if ((rc = dev_alloc(p, (void**)&p->d_pt_kw_b, sizeof(int32_t) * M * g.ndim))) return rc;
-        CU(cudaMalloc(&keys_b, sizeof(uint64_t) * M));
+        CU(scratch.alloc(&keys_b, sizeof(uint64_t) * M));
     }
     uint64_t* keys_s = nullptr;
     int32_t* iota = nullptr;
     int* flag = nullptr;
     int32_t* bin_start = nullptr;
     void* tmp = nullptr;
-    CU(cudaMalloc(&keys_s, sizeof(uint64_t) * M));
-    CU(cudaMalloc(&iota, sizeof(int32_t) * M));
-    CU(cudaMalloc(&flag, sizeof(int)));
+    CU(scratch.alloc(&keys_s, sizeof(uint64_t) * M));
+    CU(scratch.alloc(&iota, sizeof(int32_t) * M));
+    CU(scratch.alloc(&flag, sizeof(int)));
     CU(cudaMemsetAsync(flag, 0, sizeof(int), st));
     Gam<T> gam;
     for (int d = 0; d < 3; d++) gam.g[d] = (T)(2.0 * M_PI / (double)g.K[d]);
@@ -440,7 +456,7 @@ static int set_points_t(b2n_plan* p, const void* coords, int64_t M, int kind, cu
     size_t tmp_bytes = 0;
     CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, p->d_keys, keys_s, iota, p->d_perm,
                                        M, 0, bits, st));
-    CU(cudaMalloc(&tmp, tmp_bytes));
+    CU(scratch.alloc(&tmp, tmp_bytes));
     CU(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, p->d_keys, keys_s, iota, p->d_perm, M,
                                        0, bits, st));
     gather_points_kernel<T><<<grid_for(M, 256, p->sm_count), 256, 0, st>>>(
@@ -451,7 +467,7 @@ static int set_points_t(b2n_plan* p, const void* coords, int64_t M, int kind, cu
     CU(cudaGetLastError());
     if (want_b) {
         uint64_t* keys_bs = nullptr;
-        CU(cudaMalloc(&keys_bs, sizeof(uint64_t) * M));
+        CU(scratch.alloc(&keys_bs, sizeof(uint64_t) * M));
         CU(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys_b, keys_bs, iota, p->d_perm_b, M, 0,
                                            bits, st));
         gather_points_kernel<T><<<grid_for(M, 256, p->sm_count), 256, 0, st>>>(
@@ -461,12 +477,10 @@ static int set_points_t(b2n_plan* p, const void* coords, int64_t M, int kind, cu
             g, (const T*)p->d_tm_sb, p->d_pt_ko_b, p->d_pt_kw_b);
         CU(cudaGetLastError());
         CU(cudaStreamSynchronize(st));
-        cudaFree(keys_bs);
-        cudaFree(keys_b);
         p->have_b = true;
     }
     // bin boundaries -> host -> work items of at most opt_chunk samples
-    CU(cudaMalloc(&bin_start, sizeof(int32_t) * p->nbins));
+    CU(scratch.alloc(&bin_start, sizeof(int32_t) * p->nbins));
     CU(cudaMemsetAsync(bin_start, 0xff, sizeof(int32_t) * p->nbins, st));
     bin_start_kernel<<<grid_for(M, 256, p->sm_count), 256, 0, st>>>(M, g.cells_per_tile, keys_s,
                                                                     bin_start);
@@ -477,7 +491,6 @@ static int set_points_t(b2n_plan* p, const void* coords, int64_t M, int kind, cu
                        cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(&hflag, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    cudaFree(keys_s); cudaFree(iota); cudaFree(flag); cudaFree(bin_start); cudaFree(tmp);
     if (hflag) {
         free_points(p);
         return fail(B2N_ENONFINITE, "omega contains NaN or Inf");
