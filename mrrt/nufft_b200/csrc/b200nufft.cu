@@ -116,7 +116,7 @@ struct b2n_plan {
     long opt_profile = 0;        // record CUDA events around the interpolation kernels
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_fwd, ev_adj;
     int last_fwd_kernel = -1;   // 0 generic, 1 tiled
-    int last_adj_kernel = -1;   // 0 generic, 1 sliding window, 2 tiled sliding window
+    int last_adj_kernel = -1;   // 0 generic, 1 sliding window, 2 tiled, 3 register window, 4 2-D multi-coil window
 
     size_t real_size() const { return precision == B2N_SINGLE ? 4 : 8; }
     size_t cplx_size() const { return 2 * real_size(); }
@@ -734,7 +734,18 @@ static int interp_adj_impl(b2n_plan* p, const void* samples, void* grid, int nba
     }
     bool done = false;
     prof_begin(p, false, st);
-    if (!p->opt_force_generic && !p->cplx_table && p->opt_adj_kernel == 3) {
+    if (!p->opt_force_generic && !p->cplx_table && p->opt_adj_kernel >= 1 && p->g.ndim == 2) {
+        // 2-D multi-coil batches: register windows with the coil index as a window axis
+        const void* ph = phase ? p->d_phase_s : nullptr;
+        int rc = p->precision == B2N_SINGLE
+                     ? window2d_adj_f32(p->g, table_ptrs(p), p->d_tm_s, p->d_wts, p->d_pt_ko, p->d_pt_kw,
+                                        p->d_perm, samples, grid, ph, nbatch, (int)p->opt_slide_pts, st, &done)
+                     : window2d_adj_f64(p->g, table_ptrs(p), p->d_tm_s, p->d_wts, p->d_pt_ko, p->d_pt_kw,
+                                        p->d_perm, samples, grid, ph, nbatch, (int)p->opt_slide_pts, st, &done);
+        if (rc != 0) return fail(B2N_ECUDA, "2-D window adjoint launch failed: " + std::string(cudaGetErrorString((cudaError_t)rc)));
+        if (done) p->last_adj_kernel = 4;
+    }
+    if (!done && !p->opt_force_generic && !p->cplx_table && p->opt_adj_kernel == 3) {
         // register window, lane-parallel batch weights; adjoint sort order when built
         const bool ob = p->have_b;
         const void* ph = phase ? (ob ? p->d_phase_sb : p->d_phase_s) : nullptr;

@@ -34,6 +34,14 @@ struct TablePtrs {
                          const void* wts, const int32_t* pt_ko, const int32_t* pt_kw, const int32_t* perm,        \
                          const void* samples, void* grid, const void* phase_s, int nbatch,       \
                          int pts_per_warp, cudaStream_t st, bool* done);
+#define B2N_DECLARE4(SUF)                                                                        \
+    int window2d_adj_##SUF(const Geom& g, const TablePtrs& tabs, const void* tm_s, const void* wts, \
+                           const int32_t* pt_ko, const int32_t* pt_kw, const int32_t* perm,      \
+                           const void* samples, void* grid, const void* phase_s, int nbatch,     \
+                           int pts_per_warp, cudaStream_t st, bool* done);
+B2N_DECLARE4(f32)
+B2N_DECLARE4(f64)
+#undef B2N_DECLARE4
 B2N_DECLARE3(f32)
 B2N_DECLARE3(f64)
 #undef B2N_DECLARE3

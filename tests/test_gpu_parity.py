@@ -163,6 +163,32 @@ def test_mid_2d_radial_vs_oracle(precision):
     assert rel_l2(A.adj(yo), O.adj(yo)) <= tol
 
 
+@pytest.mark.parametrize("precision", ["single", "double"])
+@pytest.mark.parametrize("ncoil", [5, 12, 32, 37])
+def test_2d_multicoil_vs_oracle(precision, ncoil):
+    """2-D multi-coil batches (BASELINE configs[3] scaled down): the coil-as-window-axis
+    adjoint kernel and the batched forward, every coil against the oracle."""
+    from oracle import nufft_oracle as orc
+    from mrrt.nufft_b200 import NufftBase
+
+    Nd, Kd = (64, 64), (96, 96)
+    S, n = 41, 128
+    ang = np.pi * np.arange(S) / S
+    r = 2 * np.pi * (np.arange(n) - n / 2) / n
+    rdt = np.float32 if precision == "single" else np.float64
+    om = np.stack([np.outer(np.cos(ang), r).ravel(), np.outer(np.sin(ang), r).ravel()], 1).astype(rdt)
+    A = NufftBase(Nd=Nd, omega=om, Jd=6, Kd=Kd, precision=precision)
+    O = orc.OracleNufft(Nd=Nd, omega=om, Jd=6, Kd=Kd, precision=precision)
+    rs = np.random.RandomState(ncoil)
+    x = (rs.standard_normal(Nd + (ncoil,)) + 1j * rs.standard_normal(Nd + (ncoil,))).astype(A._cplx_dtype)
+    tol = TOL[precision]
+    yo = O.fft(x)
+    assert rel_l2(A.fft(x), yo) <= tol
+    xa = A.adj(yo)
+    assert A.option("last_adj_kernel") == 4
+    assert rel_l2(xa, O.adj(yo)) <= tol
+
+
 def test_sparse_mode_vs_oracle_sparse():
     """Sparse mode is checked against the reference's SPARSE path (configs[1])."""
     from oracle import nufft_oracle as orc
