@@ -108,6 +108,9 @@ struct b2n_plan {
     bool sparse_set = false;
     // fft
     std::map<int, cufftHandle> fft_plans;
+    bool fft_pruned_ready = false;
+    cufftHandle fft_2d = 0, fft_1d = 0;
+    long opt_pruned_fft = 1;
     void* d_work = nullptr;
     size_t work_bytes = 0;
     int64_t dev_bytes = 0;
@@ -249,6 +252,7 @@ extern "C" int b2n_plan_destroy(b2n_plan* p) {
     if (p == nullptr) return B2N_OK;
     cudaSetDevice(p->device);
     for (auto& kv : p->fft_plans) cufftDestroy(kv.second);
+    if (p->fft_pruned_ready) { cufftDestroy(p->fft_2d); cufftDestroy(p->fft_1d); }
     free_points(p);
     for (int d = 0; d < 3; d++) {
         bool dup = false;
@@ -296,6 +300,8 @@ extern "C" int b2n_plan_set_option(b2n_plan* p, const char* name, long value) {
     } else if (n == "fwd_pitch") {
         if (value < 0 || value > 127) return fail(B2N_EINVAL, "fwd_pitch must be in 0..127");
         p->opt_fwd_pitch = value;
+    } else if (n == "pruned_fft") {
+        p->opt_pruned_fft = value;
     } else if (n == "win_ring") {
         p->opt_win_ring = value;
     } else if (n == "win_lanes") {
@@ -953,6 +959,74 @@ static int get_fft(b2n_plan* p, int nbatch, cufftHandle* out) {
     return B2N_OK;
 }
 
+// Pruned oversampled FFT (3-D, one volume): the zero-padded input is non-zero only in the
+// planes k3 < N3 and the adjoint output is cropped to them, so the two in-plane passes run
+// on N3 of the K3 planes only (a batched 2-D plan over contiguous planes) and the pass
+// along axis 3 is a strided batched 1-D plan.  Same transform, fewer bytes moved.
+static bool pruned_ok(const b2n_plan* p, int nbatch) {
+    return p->opt_pruned_fft && p->g.ndim == 3 && nbatch == 1 && p->g.N[2] < p->g.K[2];
+}
+
+static int get_pruned_fft(b2n_plan* p, cufftHandle* plan2d, cufftHandle* plan1d) {
+    if (p->fft_pruned_ready) {
+        *plan2d = p->fft_2d;
+        *plan1d = p->fft_1d;
+        return B2N_OK;
+    }
+    const Geom& g = p->g;
+    const cufftType type = p->precision == B2N_SINGLE ? CUFFT_C2C : CUFFT_Z2Z;
+    size_t ws = 0;
+    int n2[2] = {g.K[1], g.K[0]};
+    FFT(cufftCreate(&p->fft_2d));
+    FFT(cufftMakePlanMany(p->fft_2d, 2, n2, nullptr, 1, g.K[0] * g.K[1], nullptr, 1, g.K[0] * g.K[1],
+                          type, g.N[2], &ws));
+    p->dev_bytes += (int64_t)ws;
+    int n1[1] = {g.K[2]};
+    int embed[1] = {g.K[2]};
+    FFT(cufftCreate(&p->fft_1d));
+    FFT(cufftMakePlanMany(p->fft_1d, 1, n1, embed, g.K[0] * g.K[1], 1, embed, g.K[0] * g.K[1], 1,
+                          type, g.K[0] * g.K[1], &ws));
+    p->dev_bytes += (int64_t)ws;
+    p->fft_pruned_ready = true;
+    *plan2d = p->fft_2d;
+    *plan1d = p->fft_1d;
+    return B2N_OK;
+}
+
+template <typename T>
+static int exec_fft(cufftHandle h, void* data, int dir) {
+    if (sizeof(T) == 4) FFT(cufftExecC2C(h, (cufftComplex*)data, (cufftComplex*)data, dir));
+    else FFT(cufftExecZ2Z(h, (cufftDoubleComplex*)data, (cufftDoubleComplex*)data, dir));
+    return B2N_OK;
+}
+
+// forward: in-plane passes on the non-zero planes, then axis 3; inverse: the reverse
+template <typename T>
+static int run_fft(b2n_plan* p, void* data, int nbatch, int dir, cudaStream_t st) {
+    int rc;
+    if (pruned_ok(p, nbatch)) {
+        cufftHandle h2, h1;
+        if ((rc = get_pruned_fft(p, &h2, &h1))) return rc;
+        FFT(cufftSetStream(h2, st));
+        FFT(cufftSetStream(h1, st));
+        if (dir == CUFFT_FORWARD) {
+            if ((rc = exec_fft<T>(h2, data, dir))) return rc;
+            if ((rc = exec_fft<T>(h1, data, dir))) return rc;
+        } else {
+            if ((rc = exec_fft<T>(h1, data, dir))) return rc;
+            if ((rc = exec_fft<T>(h2, data, dir))) return rc;
+        }
+        p->lib_calls += 2;
+        return B2N_OK;
+    }
+    cufftHandle fft;
+    if ((rc = get_fft(p, nbatch, &fft))) return rc;
+    FFT(cufftSetStream(fft, st));
+    if ((rc = exec_fft<T>(fft, data, dir))) return rc;
+    p->lib_calls += 1;
+    return B2N_OK;
+}
+
 static int ensure_work(b2n_plan* p, int nbatch) {
     const size_t need = p->cplx_size() * (size_t)p->g.PK * nbatch;
     if (need <= p->work_bytes) return B2N_OK;
@@ -980,19 +1054,14 @@ static int grid_fwd_t(b2n_plan* p, const void* image, void* grid, int nbatch, cu
     using C = cplx_t<T>;
     const Geom& g = p->g;
     int rc;
-    cufftHandle fft;
-    if ((rc = get_fft(p, nbatch, &fft))) return rc;
-    FFT(cufftSetStream(fft, st));
     AxisPtrs ax = axis_ptrs(p);
     C* work = (C*)grid;
     constexpr int VEC = 32 / (int)sizeof(C);   // 32 bytes of grid per thread
     pre_scale_pad_kernel<T, VEC><<<grid_for(g.PK * nbatch / VEC + 1, 256, p->sm_count, 32), 256, 0, st>>>(
         g, ax, (T)p->fwd_scale, p->fwd_scale != 1.0, (const C*)image, work, nbatch);
     CU(cudaGetLastError());
-    if (sizeof(T) == 4) FFT(cufftExecC2C(fft, (cufftComplex*)work, (cufftComplex*)work, CUFFT_FORWARD));
-    else FFT(cufftExecZ2Z(fft, (cufftDoubleComplex*)work, (cufftDoubleComplex*)work, CUFFT_FORWARD));
+    if ((rc = run_fft<T>(p, work, nbatch, CUFFT_FORWARD, st))) return rc;
     p->launches += 1;
-    p->lib_calls += 1;
     if (p->have_pb) {
         phase_before_kernel<T, VEC><<<grid_for(g.PK * nbatch / VEC + 1, 256, p->sm_count, 32), 256, 0, st>>>(
             g, ax, 0, work, nbatch);
@@ -1008,9 +1077,6 @@ static int grid_adj_t(b2n_plan* p, void* grid, void* image, int nbatch, cudaStre
     using C = cplx_t<T>;
     const Geom& g = p->g;
     int rc;
-    cufftHandle fft;
-    if ((rc = get_fft(p, nbatch, &fft))) return rc;
-    FFT(cufftSetStream(fft, st));
     AxisPtrs ax = axis_ptrs(p);
     C* work = (C*)grid;
     if (p->have_pb) {
@@ -1020,13 +1086,11 @@ static int grid_adj_t(b2n_plan* p, void* grid, void* image, int nbatch, cudaStre
         CU(cudaGetLastError());
         p->launches++;
     }
-    if (sizeof(T) == 4) FFT(cufftExecC2C(fft, (cufftComplex*)work, (cufftComplex*)work, CUFFT_INVERSE));
-    else FFT(cufftExecZ2Z(fft, (cufftDoubleComplex*)work, (cufftDoubleComplex*)work, CUFFT_INVERSE));
+    if ((rc = run_fft<T>(p, work, nbatch, CUFFT_INVERSE, st))) return rc;
     post_crop_scale_kernel<T><<<grid_for(g.PN * nbatch, 256, p->sm_count, 32), 256, 0, st>>>(
         g, ax, (T)p->adj_scale, p->adj_scale != 1.0, work, (C*)image, nbatch);
     CU(cudaGetLastError());
     p->launches += 1;
-    p->lib_calls += 1;
     return B2N_OK;
 }
 
