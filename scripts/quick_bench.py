@@ -35,15 +35,16 @@ def timeit(f, n=5, warm=2):
     return float(np.median(ts))
 
 
-def run(name, Nd, Kd, om, J, opts):
+def run(name, Nd, Kd, om, J, opts, precision="single"):
     t0 = time.time()
-    A = NufftBase(Nd=Nd, omega=om, Jd=J, Kd=Kd, precision="single", options=opts)
+    A = NufftBase(Nd=Nd, omega=om, Jd=J, Kd=Kd, precision=precision, options=opts)
     torch.cuda.synchronize()
     tplan = time.time() - t0
     PK = int(np.prod(Kd))
-    g = torch.randn(PK, dtype=torch.complex64, device="cuda")
-    y = torch.randn(A.M, dtype=torch.complex64, device="cuda")
-    x = torch.randn(tuple(reversed(Nd)), dtype=torch.complex64, device="cuda").permute(2, 1, 0)
+    cdt = torch.complex64 if precision == "single" else torch.complex128
+    g = torch.randn(PK, dtype=cdt, device="cuda")
+    y = torch.randn(A.M, dtype=cdt, device="cuda")
+    x = torch.randn(tuple(reversed(Nd)), dtype=cdt, device="cuda").permute(2, 1, 0)
     t_if = timeit(lambda: nufft_forward(A, g, grid_only=True))
     t_ia = timeit(lambda: nufft_adj(A, y, grid_only=True))
     t_f = timeit(lambda: A.fft(x))
