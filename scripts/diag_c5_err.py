@@ -7,7 +7,7 @@ from oracle import nufft_oracle as orc
 from golden_util import rel_l2
 from mrrt.nufft_b200 import NufftBase
 
-idx = np.arange(0, bench.SPOKES, 128)
+idx = np.arange(0, bench.SPOKES, int(sys.argv[1]) if len(sys.argv) > 1 else 128)
 om = np.concatenate([bench.radial3d(bench.SPOKES, bench.NREAD, int(s), int(s) + 1) for s in idx], 0)
 A = NufftBase(Nd=bench.ND, omega=om, Jd=bench.JD, Kd=bench.KD, precision="single")
 O = orc.OracleNufft(Nd=bench.ND, omega=om, Jd=bench.JD, Kd=bench.KD, precision="single", engine="reference")
