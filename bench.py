@@ -10,9 +10,11 @@ Jd = 6 Kaiser-Bessel table (L = 1024), complex64, one coil.  A step is one forwa
 = 2 * M / (t_fwd + t_adj).  Synthetic data (seeded normal), trajectory cast to float32
 before the operator is built.
 
-N > 1 (launched by torch.distributed.run, one rank per GPU): the sample set is sharded
-across ranks (strong scaling; total work fixed) and the adjoint images are combined
-with one NCCL all-reduce per step.
+N > 1 (launched by torch.distributed.run, one rank per GPU).  Default `--sharding coils`:
+an N-coil acquisition of the same volume, one coil per GPU, plan replicated, NO data-path
+collective (weak scaling; value counts point-coils per second over all ranks).
+`--sharding samples`: one coil, the spokes sharded over the ranks and the adjoint images
+combined with one NCCL all-reduce per step (strong scaling; total work fixed).
 
 `--impl reference` times the reference's own CPU implementation of the same path (its C
 interpolators compiled unmodified into oracle/_ref, driven by the NumPy restatement of
@@ -186,10 +188,12 @@ def run_reference_arm(args):
         "metric": METRIC, "value": value, "unit": UNIT, "impl": "reference",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1000 * (tf + ta),
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": "3D 256^3, 3-D radial 102944x512 (M=52707328), Kd=384^3, Jd=6, "
-                               "table mode L=1024, complex64, 1 coil, fwd+adj per step; each CPU step "
+                               "table mode L=1024, complex64, 1 coil per GPU, fwd+adj per step (the "
+                               "CPU transforms the coils one after another, so its points/s does "
+                               "not depend on --gpus); each CPU step "
                                "runs a 1/%d spoke subsample" % args.cpu_frac},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
                          "sample": r["sample"]},
@@ -215,7 +219,11 @@ def run_gpu_arm(args):
     from mrrt.nufft_b200 import NufftBase, SampleShardedNufft, shard_range
 
     M = SPOKES * NREAD
-    s_lo, s_hi = shard_range(SPOKES, world, rank)       # shard whole spokes
+    by_coil = world > 1 and args.sharding == "coils"
+    if by_coil:
+        s_lo, s_hi = 0, SPOKES                          # every rank: one whole coil of the volume
+    else:
+        s_lo, s_hi = shard_range(SPOKES, world, rank)   # shard whole spokes
     om_local = radial3d(SPOKES, NREAD, s_lo, s_hi)
     t0 = time.perf_counter()
     A = NufftBase(Nd=ND, omega=om_local, Jd=JD, Kd=KD, precision="single", mode="table",
@@ -225,12 +233,12 @@ def run_gpu_arm(args):
     M_local = A.M
 
     def all_reduce_img(x):
-        if world > 1:
+        if world > 1 and not by_coil:
             mem = x.permute(2, 1, 0)
             dist.all_reduce(torch.view_as_real(mem), op=dist.ReduceOp.SUM)
         return x
 
-    x_np = image()
+    x_np = image(seed=rank if by_coil else 0)
     x_dev = torch.from_numpy(x_np).to(dev)              # F-ordered: consumed without a copy
 
     def step_dev():
@@ -269,7 +277,8 @@ def run_gpu_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
     ms_step = ms_total / args.steps
-    value = 2.0 * M / (ms_step / 1000.0)
+    n_units = world if by_coil else 1                   # coils transformed per step, whole job
+    value = 2.0 * M * n_units / (ms_step / 1000.0)
 
     # ---- end to end through the public API with pinned HOST buffers
     x_host = torch.from_numpy(x_np).pin_memory()
@@ -279,7 +288,7 @@ def run_gpu_arm(args):
 
     def step_e2e():
         y_h = A.fft(x_host)                 # H2D image, transform, D2H samples
-        if world == 1:
+        if world == 1 or by_coil:
             return A.adj(y_h)               # H2D samples, transform, D2H image
         xa_d = all_reduce_img(A.adj(y_h.to(dev, non_blocking=True)))   # H2D samples, reduce
         out = torch.empty_strided(xa_d.shape, xa_d.stride(), dtype=xa_d.dtype, pin_memory=True)
@@ -303,7 +312,7 @@ def run_gpu_arm(args):
     t_e2e = float(te.item())
     img_bytes = int(np.prod(ND)) * 8
     smp_bytes = M_local * 8
-    e2e = {"value": 2.0 * M / t_e2e, "unit": UNIT, "ms_per_step": 1000 * t_e2e,
+    e2e = {"value": 2.0 * M * n_units / t_e2e, "unit": UNIT, "ms_per_step": 1000 * t_e2e,
            "h2d_bytes_per_step": img_bytes + smp_bytes, "d2h_bytes_per_step": smp_bytes + img_bytes,
            "steps": n_e2e}
 
@@ -349,11 +358,14 @@ def run_gpu_arm(args):
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": "weak" if (by_coil or world == 1) else "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
         "config": {"workload": "3D 256^3, 3-D radial 102944x512 (M=52707328), Kd=384^3, Jd=6, "
-                               "table mode L=1024, complex64, 1 coil, fwd+adj per step",
-                   "sharding": "none" if world == 1 else "samples sharded over %d ranks, NCCL all-reduce "
-                                                          "of the adjoint image" % world,
+                               "table mode L=1024, complex64, 1 coil per GPU, fwd+adj per step",
+                   "sharding": "none" if world == 1 else (
+                       "coils: %d-coil acquisition, one coil per rank, no data-path collective; "
+                       "value counts point-coils" % world if by_coil else
+                       "samples sharded over %d ranks, NCCL all-reduce of the adjoint image" % world),
                    "l2": "inputs exceed L2 (grid 453 MB, samples 422 MB > 126 MB L2); no flush needed",
                    "plan_s": t_plan},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
@@ -445,6 +457,10 @@ def main():
     ap.add_argument("--workload", default="c5", choices=["c5", "coils"],
                     help="c5 = BASELINE configs[4] (the contract bench, default); coils = "
                          "configs[3], the 32-coil 2-D batch sharded by coil")
+    ap.add_argument("--sharding", default="coils", choices=["coils", "samples"],
+                    help="N>1, c5 workload: coils = one coil of the volume per GPU, no collective "
+                         "(weak scaling, default); samples = one coil, spokes sharded, NCCL "
+                         "all-reduce of the adjoint image (strong scaling)")
     ap.add_argument("--host-chunks", type=int, default=8,
                     help="sample ranges pipelined against host<->device copies in the e2e leg")
     args = ap.parse_args()
