@@ -645,7 +645,12 @@ def nufft_forward(obj, x, copy_x=True, grid_only=False, xp=None):
 
 
 def nufft_adj(obj, xk, copy=True, return_psf=False, grid_only=False, xp=None):
-    """Adjoint NUFFT driver (reference: _nufft.py:1459-1578)."""
+    """Adjoint NUFFT driver (reference: _nufft.py:1459-1578).
+
+    ``grid_only`` returns the gridded samples ``(prod(Kd), reps)`` (conj(phase_after)
+    applied first, as upstream).  ``return_psf`` (upstream "EXPERIMENTAL",
+    _nufft.py:1495,1517-1518) grids WITHOUT conj(phase_after) and returns the first
+    repetition with shape ``Kd``."""
     Nd, Kd = obj.Nd, obj.Kd
     if not isinstance(xk, torch.Tensor):
         xk = _ArrayKind(xk).to_torch(xk, obj.device)
@@ -656,16 +661,25 @@ def nufft_adj(obj, xk, copy=True, return_psf=False, grid_only=False, xp=None):
     mem = _f_order_memory(xk, (obj.M,)).reshape(n_reps, obj.M)
     with torch.cuda.device(obj.device):
         stream = obj._stream()
-        if grid_only:
+        if grid_only or return_psf:
+            if return_psf and not grid_only:
+                mem, n_reps = mem[:1], 1            # only the first repetition is returned
             out = torch.empty((n_reps, _prod(Kd)), dtype=mem.dtype, device=obj.device)
             # the reference multiplies by conj(phase_after) BEFORE the gridding stage, so
-            # its grid_only adjoint includes it (_nufft.py:1495-1509), unlike grid_only forward
+            # its grid_only adjoint includes it (_nufft.py:1495-1509), unlike grid_only forward;
+            # return_psf skips it, but the phase_shift of complex phasing belongs to the
+            # table interpolator itself (_nufft.py:1141-1150) and stays
             if obj.mode == "sparse":
-                rc = obj._lib.b2n_spmv_adj(obj._plan, mem.data_ptr(), out.data_ptr(), n_reps, 1, stream)
+                rc = obj._lib.b2n_spmv_adj(obj._plan, mem.data_ptr(), out.data_ptr(), n_reps,
+                                           0 if return_psf else 1, stream)
             else:
-                rc = obj._lib.b2n_interp_adj(obj._plan, mem.data_ptr(), out.data_ptr(), n_reps, 1, stream)
+                ph = (1 if obj.phase_shift is not None else 0) if return_psf else 1
+                rc = obj._lib.b2n_interp_adj(obj._plan, mem.data_ptr(), out.data_ptr(), n_reps,
+                                             ph, stream)
             _lib.check(rc)
-            return out.t()
+            if grid_only:
+                return out.t()
+            return out[0].reshape(tuple(reversed(Kd))).permute(*reversed(range(len(Kd))))
         out = torch.empty((n_reps,) + tuple(reversed(Nd)), dtype=mem.dtype, device=obj.device)
         rc = obj._lib.b2n_nufft_adj(obj._plan, mem.data_ptr(), out.data_ptr(), n_reps, stream)
     _lib.check(rc)

@@ -542,8 +542,9 @@ class OracleNufft(object):
             out = self._unswap(out, self.M)
         return out
 
-    def adj(self, xk, grid_only=False):
-        """_nufft.py:454-482 and :1459-1578."""
+    def adj(self, xk, grid_only=False, return_psf=False):
+        """_nufft.py:454-482 and :1459-1578.  ``return_psf`` (:1495,:1517-1518): no
+        conj(phase_after), gridded first repetition returned with shape Kd."""
         xk = np.asarray(xk)
         if self.order == "C" and not grid_only:
             xk = self._swap(xk, self.M)
@@ -553,7 +554,7 @@ class OracleNufft(object):
         xk = np.asfortranarray(xk).astype(self._cplx_dtype)
         xk = np.reshape(xk, (self.M, -1), order="F").copy(order="A")
         n_reps = xk.shape[-1]
-        if self.phase_after is not None:
+        if self.phase_after is not None and not return_psf:
             xk *= self.phase_after.conj()[:, np.newaxis]
         xk_all = self.interp_adj(xk)
         if grid_only:
@@ -561,6 +562,8 @@ class OracleNufft(object):
         if xk_all.ndim == 1:
             xk_all = xk_all[:, None]
         xk_all = xk_all.reshape(Kd + (n_reps,), order="F")
+        if return_psf:
+            return xk_all[..., 0]
         if self.phase_before is not None:
             xk_all = xk_all * self.phase_before.conj()[..., np.newaxis]
         x = np.fft.ifftn(xk_all, s=Kd, axes=tuple(range(xk_all.ndim - 1)))

@@ -33,6 +33,19 @@ def load_case(name):
     return cfg, z
 
 
+def psf_cases():
+    """Outputs of the reference's nufft_adj(..., return_psf=True) for a subset of the
+    cases (tests/golden/make_golden_psf.py)."""
+    return dict(np.load(os.path.join(GOLDEN, "extra", "psf.npz")))
+
+
+PSF_CASES = ["d1_table_single_real", "d1_table_double_complex", "d1_sparse_single_real",
+             "d2_table_single_real_K33_J7", "d2_table_double_complex_K32_J6",
+             "d2_sparse_double_real_K33_J6", "d3_table_single_real", "d3_table_double_complex",
+             "d3_sparse_single_complex", "adjshift_table_real", "adjshift_table_complex",
+             "adjshift_sparse_complex", "d3_mid_table_single_real_J546"]
+
+
 def table_key(N, K, J, L, phasing):
     return "N%d_K%d_J%d_L%d_%s" % (N, K, J, L, phasing)
 

@@ -3,8 +3,8 @@ reference and against the CPU oracle on seeded inputs.  Needs a B200."""
 import numpy as np
 import pytest
 
-from golden_util import (TOL, case_names, ctor_kwargs, grid_only_inputs, load_case,
-                         rel_l2, table_key, tables)
+from golden_util import (PSF_CASES, TOL, case_names, ctor_kwargs, grid_only_inputs, load_case,
+                         psf_cases, rel_l2, table_key, tables)
 
 pytestmark = pytest.mark.gpu
 
@@ -50,6 +50,21 @@ def test_golden(name, variant):
             and len(set(A.Jd)) == 1 and A.Jd[0] in (4, 6, 8):
         assert A.option("last_fwd_kernel") == 1   # tiled TMA kernel really ran
         assert A.option("last_adj_kernel") == 3   # register-window kernel really ran
+
+
+@pytest.mark.parametrize("name", PSF_CASES)
+def test_return_psf_golden(name):
+    """nufft_adj(..., return_psf=True) vs the reference's output (_nufft.py:1495,1517)."""
+    from mrrt.nufft_b200 import nufft_adj
+
+    cfg, z = load_case(name)
+    want = psf_cases()[name]
+    A = _op(cfg, z["omega"])
+    _, ysamp = grid_only_inputs(cfg["seed"], int(np.prod(A.Kd)), A.M, cfg["n_reps"],
+                                A._cplx_dtype)
+    got = nufft_adj(A, ysamp, return_psf=True).cpu().numpy()
+    assert got.shape == want.shape and got.dtype == want.dtype
+    assert rel_l2(got, want) <= TOL[cfg["precision"]]
 
 
 @pytest.mark.parametrize("name", ["d1_sparse_single_real", "d1_sparse_double_complex",

@@ -4,8 +4,8 @@ CPU only."""
 import numpy as np
 import pytest
 
-from golden_util import (TOL, case_names, ctor_kwargs, grid_only_inputs, load_case,
-                         rel_l2, table_key, tables)
+from golden_util import (PSF_CASES, TOL, case_names, ctor_kwargs, grid_only_inputs, load_case,
+                         psf_cases, rel_l2, table_key, tables)
 from oracle import nufft_oracle as orc
 
 ENGINES = ["port"] + (["reference"] if orc.have_reference_engine() else [])
@@ -43,6 +43,19 @@ def test_oracle_matches_golden(name):
                                     cfg["n_reps"], A._cplx_dtype)
         assert rel_l2(A.fft(g, grid_only=True), z["interp_out"]) <= tol
         assert rel_l2(A.adj(ysamp, grid_only=True), z["grid_out"]) <= tol
+
+
+@pytest.mark.parametrize("name", PSF_CASES)
+def test_oracle_return_psf_matches_golden(name):
+    """adj(..., return_psf=True): no conj(phase_after), first repetition, shape Kd."""
+    cfg, z = load_case(name)
+    want = psf_cases()[name]
+    A = orc.OracleNufft(omega=z["omega"], **ctor_kwargs(cfg))
+    _, ysamp = grid_only_inputs(cfg["seed"], int(np.prod(A.Kd)), A.M, cfg["n_reps"],
+                                A._cplx_dtype)
+    got = A.adj(ysamp, return_psf=True)
+    assert got.shape == want.shape and got.dtype == want.dtype
+    assert rel_l2(got, want) <= ORACLE_TOL[cfg["precision"]]
 
 
 @pytest.mark.skipif(not orc.have_reference_engine(), reason="oracle/_ref not built")
