@@ -63,7 +63,9 @@ struct b2n_plan {
     long opt_order_b = 1;        // build the adjoint sort order (adj_kernel 3)
     long opt_fwd_pitch = 0;      // shared-memory row pitch of the forward tile (0 = automatic)
     long opt_win_lanes = 16;
-    long opt_win_ring = 0;       // 1: slide axis across lanes (no register shifts; measured slower)     // lanes per sample in the register-window adjoint (16 or 32)
+    // register-window adjoint: 0 register shifts, 1 lane ring, 2 fixed ring with rotated
+    // weights, 3 last shift of a slide fused into the FMAs (default; fastest measured)
+    long opt_win_ring = 3;
     bool tile_user_set = false;
     bool tile_b_user_set = false;
     // tables
@@ -303,6 +305,7 @@ extern "C" int b2n_plan_set_option(b2n_plan* p, const char* name, long value) {
     } else if (n == "pruned_fft") {
         p->opt_pruned_fft = value;
     } else if (n == "win_ring") {
+        if (value < 0 || value > 3) return fail(B2N_EINVAL, "win_ring must be in 0..3");
         p->opt_win_ring = value;
     } else if (n == "win_lanes") {
         if (value != 8 && value != 16 && value != 32) return fail(B2N_EINVAL, "win_lanes must be 8, 16 or 32");
@@ -760,7 +763,8 @@ static int interp_adj_impl(b2n_plan* p, const void* samples, void* grid, int nba
         const int32_t* ko = ob ? p->d_pt_ko_b : p->d_pt_ko;
         const int32_t* kw = ob ? p->d_pt_kw_b : p->d_pt_kw;
         const int32_t* pm = ob ? p->d_perm_b : p->d_perm;
-        const int slide_axis = (ob ? 2 : 0) | (p->opt_win_ring ? 256 : 0);
+        const int slide_axis = (ob ? 2 : 0) | (p->opt_win_ring == 1 ? 256 : 0) | (p->opt_win_ring == 2 ? 512 : 0) |
+                               (p->opt_win_ring == 3 ? 1024 : 0);
         const int wpts = (int)(p->opt_win_lanes == 32 ? -p->opt_slide_pts
                                : (p->opt_win_lanes == 8 ? p->opt_slide_pts + (1 << 20) : p->opt_slide_pts));
         int rc = p->precision == B2N_SINGLE

@@ -48,11 +48,21 @@ template <typename T, int J> struct WinRec {
 //      samples with its own register window: the per-sample instructions (operand loads,
 //      packed FMAs, loop control) are issued once for two samples, and the J*J = 36 face
 //      positions fill 16 lanes x 3 slots at 75 % instead of 32 lanes x 2 slots at 56 %.
-// RING: false = the J accumulators of a lane run along the slide axis and are shifted when
-//       the window slides; true = the slide axis is laid out ACROSS LANES (lane <-> (column,
+// RING: 0 = the J accumulators of a lane run along the slide axis and are shifted when
+//       the window slides; 1 = the slide axis is laid out ACROSS LANES (lane <-> (column,
 //       jb), registers <-> jc): sliding only advances a phase counter, the lanes that hold
-//       the retiring column flush it, nothing moves.
-template <typename T, int J, int TAB, int G, bool RING>
+//       the retiring column flush it, nothing moves; 2 = fixed register ring: accumulator
+//       r of a lane always holds the cell with (cell mod J) == r along the slide axis, the
+//       batch phase stores each sample's slide-axis weights in that rotated order, and a
+//       slide only flushes and clears the retiring register (no register shifts).
+// ring slot of the cell j cells past a window whose origin sits in slot m (= origin mod J)
+template <int J>
+__device__ __forceinline__ int rot_slot(int m, int j) {
+    const int r = m + j;
+    return r >= J ? r - J : r;
+}
+
+template <typename T, int J, int TAB, int G, int RING>
 __global__ void __launch_bounds__(128)
 spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T* __restrict__ h2,
                        const T* __restrict__ h3, const T* __restrict__ tm_s,
@@ -123,7 +133,10 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
 #pragma unroll
         for (int j = 0; j < J; j++) acc[s][j] = make_c<T>(0, 0);
     }
+    constexpr bool ROT = RING == 2;
+    constexpr bool FUSE = RING == 3;  // shift by one fused into the FMAs of the sliding sample
     int WA = 0;             // wrapped window origin along the slide axis
+    int mA = 0;             // ROT: WA mod J = ring slot that holds the window's first cell
     int ph = 0;             // RING: physical column that holds logical column 0
     int jlog[RPL];          // RING: logical column of each lane slot
     int offC[J];            // RING: grid offsets of the J register positions (axis c)
@@ -148,10 +161,12 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
             kA = pt_kw[(int64_t)aA * M + i];
             kB = pt_kw[(int64_t)aB * M + i];
             kC = pt_kw[(int64_t)aC * M + i];
+            // ROT: the slide-axis weight of cell kA + j goes to ring slot (kA + j) mod J
+            const int mrot = ROT ? kA % J : 0;
             if (TAB == 2) {
 #pragma unroll
                 for (int j = 0; j < J; j++) {
-                    w[j] = wts[(int64_t)(aA * J + j) * M + i];
+                    w[rot_slot<J>(mrot, j)] = wts[(int64_t)(aA * J + j) * M + i];
                     w[J + j] = wts[(int64_t)(aB * J + j) * M + i];
                     w[2 * J + j] = wts[(int64_t)(aC * J + j) * M + i];
                 }
@@ -162,7 +177,7 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
                           oC = pt_ko[(int64_t)aC * M + i];
 #pragma unroll
                 for (int j = 0; j < J; j++) {
-                    w[j] = tap_real<T>(tabA, ncA, tlA, tA, oA + j, g.L);
+                    w[rot_slot<J>(mrot, j)] = tap_real<T>(tabA, ncA, tlA, tA, oA + j, g.L);
                     w[J + j] = tap_real<T>(tabB, ncB, tlB, tB, oB + j, g.L);
                     w[2 * J + j] = tap_real<T>(tabC, ncC, tlC, tC, oC + j, g.L);
                 }
@@ -188,7 +203,7 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
         __syncwarp();
         // ---- sample loop: all lanes of a group work on one sample
         int4 kk_next = actions[grp * G];
-        if constexpr (RING) {
+        if constexpr (RING == 1) {
             for (int q = 0; q < cnt; q++) {
                 const unsigned char* rec = stage + (grp * G + q) * RB;
                 const int4 kk = kk_next;
@@ -293,7 +308,10 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
                 if (have) {
 #pragma unroll
                     for (int j = 0; j < J; j++) {
-                        int ka = WA + j;
+                        // ROT: register j is ring slot j = cell WA + ((j - mA) mod J)
+                        int jl = j;
+                        if (ROT) { jl = j - mA; if (jl < 0) jl += J; }
+                        int ka = WA + jl;
                         if (ka >= KA) ka -= KA;
 #pragma unroll
                         for (int s = 0; s < RPL; s++) {
@@ -304,6 +322,7 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
                 }
                 have = true;
                 WA = kk.x;
+                if (ROT) mA = WA % J;
 #pragma unroll
                 for (int s = 0; s < RPL; s++) {
                     int kb = kk.y + rjb[s]; if (kb >= KB) kb -= KB;
@@ -312,15 +331,54 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
                 }
             } else {
 #pragma unroll 1
-                for (int sft = 0; sft < kk.w; sft++) {
+                for (int sft = 0; sft < (FUSE ? kk.w - 1 : kk.w); sft++) {
+                    if constexpr (ROT) {
+                        // fixed ring: retire the slot of cell WA; nothing moves (the weights
+                        // were rotated into ring order by the batch phase)
+                        const int64_t offA = (int64_t)WA * sA;
 #pragma unroll
-                    for (int s = 0; s < RPL; s++) {
-                        if (rvalid[s]) atomic_add_c(faceptr[s] + (int64_t)WA * sA, acc[s][0]);
+                        for (int r = 0; r < J; r++) {
+                            if (mA == r) {
 #pragma unroll
-                        for (int j = 0; j + 1 < J; j++) acc[s][j] = acc[s][j + 1];
-                        acc[s][J - 1] = make_c<T>(0, 0);
+                                for (int s = 0; s < RPL; s++) {
+                                    if (rvalid[s]) atomic_add_c(faceptr[s] + offA, acc[s][r]);
+                                    acc[s][r] = make_c<T>(0, 0);
+                                }
+                            }
+                        }
+                        mA = mA + 1 == J ? 0 : mA + 1;
+                    } else {
+#pragma unroll
+                        for (int s = 0; s < RPL; s++) {
+                            if (rvalid[s]) atomic_add_c(faceptr[s] + (int64_t)WA * sA, acc[s][0]);
+#pragma unroll
+                            for (int j = 0; j + 1 < J; j++) acc[s][j] = acc[s][j + 1];
+                            acc[s][J - 1] = make_c<T>(0, 0);
+                        }
                     }
                     WA++;   // stays < KA: it ends at this sample's wrapped origin
+                }
+                if constexpr (FUSE) {
+                    if (kk.w > 0) {
+                        // last cell of the slide: flush register 0 and let the FMAs themselves
+                        // do the shift (destination j, addend j + 1) -- no register moves.
+                        // (Fusing slides by 2..J-1 cells the same way was measured: 124
+                        // registers and 5.25 ms instead of 4.79 ms: more divergence between the two
+                        // half-warps and one CTA per SM fewer.)
+#pragma unroll
+                        for (int s = 0; s < RPL; s++) {
+                            if (rvalid[s]) {
+                                atomic_add_c(faceptr[s] + (int64_t)WA * sA, acc[s][0]);
+                                const C v2 = mul_w(wb[s], mul_w(wc[s], make_c<T>(fx, fy)));
+#pragma unroll
+                                for (int j = 0; j + 1 < J; j++)
+                                    acc[s][j] = fma_w(wA[j], v2, acc[s][j + 1]);
+                                acc[s][J - 1] = fma_w(wA[J - 1], v2, make_c<T>(0, 0));
+                            }
+                        }
+                        WA++;
+                        continue;
+                    }
                 }
             }
 #pragma unroll
@@ -334,7 +392,7 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
             }
         }
     }
-    if constexpr (RING) {
+    if constexpr (RING == 1) {
         if (have) {
 #pragma unroll
             for (int s = 0; s < RPL; s++) {
@@ -352,7 +410,9 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
     if (have) {
 #pragma unroll
         for (int j = 0; j < J; j++) {
-            int ka = WA + j;
+            int jl = j;
+            if (ROT) { jl = j - mA; if (jl < 0) jl += J; }
+            int ka = WA + jl;
             if (ka >= KA) ka -= KA;
 #pragma unroll
             for (int s = 0; s < RPL; s++)
@@ -373,6 +433,8 @@ static int launch_window(const Geom& g, const TablePtrs& tabs, int slide_axis, c
     if (pts_per_warp >= (1 << 20)) { lanes_per_sample = 8; pts_per_warp -= (1 << 20); }
     // slide_axis carries the RING flag in bit 8
     const bool ring = (slide_axis & 256) != 0;
+    const bool rot = (slide_axis & 512) != 0;     // bit 9: fixed ring with rotated weights
+    const bool fuse = (slide_axis & 1024) != 0;   // bit 10: last shift fused into the FMAs
     slide_axis &= 255;
     pts_per_warp = (pts_per_warp + 31) / 32 * 32;
     using C = cplx_t<T>;
@@ -391,7 +453,23 @@ static int launch_window(const Geom& g, const TablePtrs& tabs, int slide_axis, c
     cudaError_t e;
 #define B2N_LAUNCH_WIN(TABV, SMEM)                                                                 \
     if (lanes_per_sample == 8) {                                                                   \
-        auto k = spread_window3d_kernel<T, J, TABV, 8, false>;                                            \
+        auto k = spread_window3d_kernel<T, J, TABV, 8, 0>;                                            \
+        e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM));     \
+        if (e != cudaSuccess) return (int)e;                                                       \
+        k<<<gd, 128, (SMEM), st>>>(g, wa, (const T*)tabs.h[0], (const T*)tabs.h[1],                \
+                                   (const T*)tabs.h[2], (const T*)tm_s, (const T*)wts, pt_ko, pt_kw, \
+                                   perm, (const C*)samples, (C*)grid, (const C*)phase_s,           \
+                                   pts_per_warp);                                                  \
+    } else if (lanes_per_sample == 16 && fuse) {                                                   \
+        auto k = spread_window3d_kernel<T, J, TABV, 16, 3>;                                        \
+        e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM));     \
+        if (e != cudaSuccess) return (int)e;                                                       \
+        k<<<gd, 128, (SMEM), st>>>(g, wa, (const T*)tabs.h[0], (const T*)tabs.h[1],                \
+                                   (const T*)tabs.h[2], (const T*)tm_s, (const T*)wts, pt_ko, pt_kw, \
+                                   perm, (const C*)samples, (C*)grid, (const C*)phase_s,           \
+                                   pts_per_warp);                                                  \
+    } else if (lanes_per_sample == 16 && rot) {                                                    \
+        auto k = spread_window3d_kernel<T, J, TABV, 16, 2>;                                        \
         e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM));     \
         if (e != cudaSuccess) return (int)e;                                                       \
         k<<<gd, 128, (SMEM), st>>>(g, wa, (const T*)tabs.h[0], (const T*)tabs.h[1],                \
@@ -399,7 +477,7 @@ static int launch_window(const Geom& g, const TablePtrs& tabs, int slide_axis, c
                                    perm, (const C*)samples, (C*)grid, (const C*)phase_s,           \
                                    pts_per_warp);                                                  \
     } else if (lanes_per_sample == 16 && ring) {                                                   \
-        auto k = spread_window3d_kernel<T, J, TABV, 16, true>;                                     \
+        auto k = spread_window3d_kernel<T, J, TABV, 16, 1>;                                        \
         e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM));     \
         if (e != cudaSuccess) return (int)e;                                                       \
         k<<<gd, 128, (SMEM), st>>>(g, wa, (const T*)tabs.h[0], (const T*)tabs.h[1],                \
@@ -407,7 +485,7 @@ static int launch_window(const Geom& g, const TablePtrs& tabs, int slide_axis, c
                                    perm, (const C*)samples, (C*)grid, (const C*)phase_s,           \
                                    pts_per_warp);                                                  \
     } else if (lanes_per_sample == 16) {                                                           \
-        auto k = spread_window3d_kernel<T, J, TABV, 16, false>;                                           \
+        auto k = spread_window3d_kernel<T, J, TABV, 16, 0>;                                           \
         e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM));     \
         if (e != cudaSuccess) return (int)e;                                                       \
         k<<<gd, 128, (SMEM), st>>>(g, wa, (const T*)tabs.h[0], (const T*)tabs.h[1],                \
@@ -415,7 +493,7 @@ static int launch_window(const Geom& g, const TablePtrs& tabs, int slide_axis, c
                                    perm, (const C*)samples, (C*)grid, (const C*)phase_s,           \
                                    pts_per_warp);                                                  \
     } else {                                                                                       \
-        auto k = spread_window3d_kernel<T, J, TABV, 32, false>;                                           \
+        auto k = spread_window3d_kernel<T, J, TABV, 32, 0>;                                           \
         e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM));     \
         if (e != cudaSuccess) return (int)e;                                                       \
         k<<<gd, 128, (SMEM), st>>>(g, wa, (const T*)tabs.h[0], (const T*)tabs.h[1],                \

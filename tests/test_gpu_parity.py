@@ -121,7 +121,7 @@ def _radial3d(S, n):
 
 @pytest.mark.parametrize("precision", ["single", "double"])
 @pytest.mark.parametrize("variant", ["auto", "generic", "no_tma", "slide", "tile", "window_a",
-                                     "window_32", "table_in_kernel", "window_ring"])
+                                     "window_32", "table_in_kernel", "window_ring", "window_rot", "window_fuse", "window_shift"])
 def test_mid_3d_radial_vs_oracle(precision, variant):
     """3-D radial, J=6, Kd=1.5N (BASELINE configs[4] scaled down) vs the live oracle."""
     from oracle import nufft_oracle as orc
@@ -133,7 +133,9 @@ def test_mid_3d_radial_vs_oracle(precision, variant):
     opts = {"generic": {"force_generic": 1}, "no_tma": {"use_tma": 0}, "auto": {},
             "slide": {"adj_kernel": 1}, "tile": {"adj_kernel": 2},
             "window_a": {"adj_kernel": 3, "order_b": 0}, "window_32": {"win_lanes": 32},
-            "table_in_kernel": {"precomp_weights": 0}, "window_ring": {"win_ring": 1}}[variant]
+            "table_in_kernel": {"precomp_weights": 0}, "window_ring": {"win_ring": 1},
+            "window_rot": {"win_ring": 2}, "window_fuse": {"win_ring": 3},
+            "window_shift": {"win_ring": 0}}[variant]
     A = NufftBase(Nd=Nd, omega=om, Jd=6, Kd=Kd, precision=precision, options=opts)
     eng = "reference" if orc.have_reference_engine() else "port"
     O = orc.OracleNufft(Nd=Nd, omega=om, Jd=6, Kd=Kd, precision=precision, engine=eng)
