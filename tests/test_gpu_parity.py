@@ -357,3 +357,67 @@ def test_errors_and_edges():
     O = orc.OracleNufft(Nd=(8, 8, 8), omega=same, Jd=6, Kd=(16, 16, 16), precision="double")
     y = np.random.RandomState(1).standard_normal(5000) + 0j
     assert rel_l2(S.adj(y), O.adj(y)) <= 1e-12
+
+
+@pytest.mark.parametrize("precision", ["single", "double"])
+@pytest.mark.parametrize("case", ["J_gt_K", "far_omega", "on_grid", "small_odd_K_3d", "K_eq_J_3d"])
+def test_wraparound_edges_vs_oracle(case, precision):
+    """Periodic-wrap corner cases of the table interpolators (template.c kmod logic):
+    windows wider than the grid, coordinates many periods away, samples exactly on grid
+    points and on the +-pi seam, grids smaller than a bin tile."""
+    from oracle import nufft_oracle as orc
+    from mrrt.nufft_b200 import NufftBase
+
+    rs = np.random.RandomState(11)
+    rdt = np.float32 if precision == "single" else np.float64
+    if case == "J_gt_K":
+        Nd, Kd, Jd = (4, 3), (5, 4), (6, 5)
+        om = (rs.rand(300, 2) * 2 - 1) * np.pi
+    elif case == "far_omega":
+        Nd, Kd, Jd = (16, 12), (32, 24), 6
+        om = (rs.rand(500, 2) * 2 - 1) * np.pi + 2 * np.pi * rs.randint(-3, 4, (500, 2))
+    elif case == "on_grid":
+        Nd, Kd, Jd = (16, 16), (32, 32), 6
+        k = rs.randint(-16, 17, (400, 2))
+        om = 2 * np.pi * k / 32.0
+        om[:4] = [[np.pi, -np.pi], [-np.pi, np.pi], [0, 0], [np.pi, np.pi]]
+    elif case == "small_odd_K_3d":
+        Nd, Kd, Jd = (6, 7, 5), (13, 11, 9), 6
+        om = (rs.rand(2000, 3) * 2 - 1) * np.pi
+    else:
+        Nd, Kd, Jd = (4, 4, 4), (6, 6, 6), 6
+        om = (rs.rand(1500, 3) * 2 - 1) * np.pi
+    om = om.astype(rdt)
+    # J > K: the reference's table builder raises IndexError there, its sparse mode works
+    # (duplicate columns are summed, _nufft.py:854-873) -- so that case is checked in sparse mode
+    mode = "sparse" if case == "J_gt_K" else "table"
+    A = NufftBase(Nd=Nd, omega=om, Jd=Jd, Kd=Kd, precision=precision, mode=mode)
+    eng = "reference" if orc.have_reference_engine() else "port"
+    O = orc.OracleNufft(Nd=Nd, omega=om, Jd=Jd, Kd=Kd, precision=precision, engine=eng, mode=mode)
+    if mode == "table":
+        assert np.array_equal(A.tm.cpu().numpy(), O.tm)
+    x = (rs.standard_normal(Nd) + 1j * rs.standard_normal(Nd)).astype(A._cplx_dtype)
+    y = (rs.standard_normal(A.M) + 1j * rs.standard_normal(A.M)).astype(A._cplx_dtype)
+    tol = TOL[precision]
+    assert rel_l2(A.fft(x), O.fft(x)) <= tol
+    assert rel_l2(A.adj(y), O.adj(y)) <= tol
+
+
+def test_many_repetitions():
+    """More repetitions than a CUDA grid's y extent (65535): the batch is split, not dropped."""
+    from oracle import nufft_oracle as orc
+    from mrrt.nufft_b200 import NufftBase
+
+    rs = np.random.RandomState(5)
+    om = (rs.rand(7, 1) * 2 - 1) * np.pi
+    A = NufftBase(Nd=(8,), omega=om, Jd=4, Kd=(16,), precision="single")
+    O = orc.OracleNufft(Nd=(8,), omega=om, Jd=4, Kd=(16,), precision="single")
+    reps = 66000
+    x = (rs.standard_normal((8, reps)) + 1j * rs.standard_normal((8, reps))).astype(np.complex64)
+    y = A.fft(x)
+    assert y.shape == (7, reps)
+    sel = [0, 1, 65534, 65535, 65536, reps - 1]
+    assert rel_l2(y[:, sel], O.fft(x[:, sel])) <= 1e-5
+    xa = A.adj(y)
+    assert xa.shape == (8, reps)
+    assert rel_l2(xa[:, sel], O.adj(y[:, sel])) <= 1e-5
