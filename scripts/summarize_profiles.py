@@ -38,6 +38,10 @@ want = [
     "lts__throughput.avg.pct_of_peak_sustained_elapsed",
     "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
     "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+    "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed",
+    "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_elapsed",
+    "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_elapsed",
+    "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_elapsed",
     "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
     "l1tex__t_sectors_pipe_lsu_mem_global_op_red.sum", "lts__t_requests_srcunit_tex_op_red.sum",
