@@ -124,6 +124,137 @@ __global__ void bin_start_kernel(int64_t M, int cells_per_tile, const uint64_t* 
     }
 }
 
+// ---- forward "slots": one or two consecutive sorted samples that sit in the SAME cell.
+// A thread of the tiled forward kernel then reads every tap of the shared window once for
+// both samples.  Pairs are formed greedily inside each run of equal sort keys (positions
+// 0|1, 2|3, ... of the run).
+// head[i] = i where a run of equal keys starts, else 0 (max-scanned into the run start)
+__global__ void slot_heads_kernel(int64_t M, const uint64_t* __restrict__ keys_s,
+                                  int32_t* __restrict__ head) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < M;
+         i += (int64_t)gridDim.x * blockDim.x)
+        head[i] = (i == 0 || keys_s[i] != keys_s[i - 1]) ? (int32_t)i : 0;
+}
+// isslot[i] = 1 when sample i opens a slot (even position inside its run)
+__global__ void slot_flags_kernel(int64_t M, const int32_t* __restrict__ runstart,
+                                  int32_t* __restrict__ isslot) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < M;
+         i += (int64_t)gridDim.x * blockDim.x)
+        isslot[i] = (((int32_t)i - runstart[i]) & 1) == 0 ? 1 : 0;
+}
+// slots[slotidx[i]] = (i << 1) | has_partner
+__global__ void slot_write_kernel(int64_t M, const uint64_t* __restrict__ keys_s,
+                                  const int32_t* __restrict__ isslot,
+                                  const int32_t* __restrict__ slotidx, uint32_t* __restrict__ slots) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < M;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        if (isslot[i]) {
+            const uint32_t pair = (i + 1 < M && keys_s[i + 1] == keys_s[i]) ? 1u : 0u;
+            slots[slotidx[i]] = ((uint32_t)i << 1) | pair;
+        }
+    }
+}
+// ---- column-interleaved slot order inside a bin.  The forward tile has a row pitch of whole
+// bank rows, so the bank of a tap depends on the axis-1 position ("column") of the window
+// only; a half-warp is conflict-free when its 16 lanes sit in 16 different columns.  Slots
+// are therefore reordered inside their bin by (rank within column, column).
+// key = bin * T0 + column
+__global__ void slot_colkey_kernel(int64_t ns, int cells_per_tile, int T0,
+                                   const uint64_t* __restrict__ keys_s,
+                                   const uint32_t* __restrict__ slots, uint64_t* __restrict__ key) {
+    for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < ns;
+         s += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t k = keys_s[slots[s] >> 1];
+        const uint64_t bin = k / (uint64_t)cells_per_tile;
+        const uint64_t col = (k % (uint64_t)cells_per_tile) % (uint64_t)T0;
+        key[s] = bin * (uint64_t)T0 + col;
+    }
+}
+// head[s] = s where a (bin, column) group starts in the column-sorted slot list, else 0
+__global__ void slot_grouphead_kernel(int64_t ns, const uint64_t* __restrict__ key,
+                                      int32_t* __restrict__ head) {
+    for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < ns;
+         s += (int64_t)gridDim.x * blockDim.x)
+        head[s] = (s == 0 || key[s] != key[s - 1]) ? (int32_t)s : 0;
+}
+// final key = (bin << 40) | (rank << 8) | column
+__global__ void slot_rankkey_kernel(int64_t ns, int T0, const uint64_t* __restrict__ key,
+                                    const int32_t* __restrict__ groupstart,
+                                    uint64_t* __restrict__ key_out) {
+    for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < ns;
+         s += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t bin = key[s] / (uint64_t)T0, col = key[s] % (uint64_t)T0;
+        const uint64_t rank = (uint64_t)((int32_t)s - groupstart[s]);
+        key_out[s] = (bin << 40) | (rank << 8) | col;
+    }
+}
+
+// ---- slot-ordered copies of what the forward kernel reads per slot
+__global__ void slot_pack_kernel(int64_t ns, int ndim, int64_t M, const uint32_t* __restrict__ slots,
+                                 const int32_t* __restrict__ pt_kw, const int32_t* __restrict__ perm,
+                                 int32_t* __restrict__ slot_kw, int32_t* __restrict__ slot_perm) {
+    for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < ns;
+         s += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t u = slots[s];
+        const int64_t i = u >> 1;
+        for (int d = 0; d < ndim; d++) slot_kw[(int64_t)d * ns + s] = pt_kw[(int64_t)d * M + i];
+        slot_perm[s] = perm[i];
+        slot_perm[ns + s] = (u & 1u) ? perm[i + 1] : -1;
+    }
+}
+template <typename C>
+__global__ void slot_phase_kernel(int64_t ns, const uint32_t* __restrict__ slots,
+                                  const int32_t* __restrict__ perm, const C* __restrict__ phase,
+                                  C* __restrict__ phase2) {
+    for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < ns;
+         s += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t u = slots[s];
+        const int64_t i = u >> 1;
+        phase2[2 * s] = phase[perm[i]];
+        C z;
+        z.x = 0;
+        z.y = 0;
+        phase2[2 * s + 1] = (u & 1u) ? phase[perm[i + 1]] : z;
+    }
+}
+// (weight, partner's weight or 0) per slot, same expression as point_weights_kernel
+template <typename T>
+__global__ void slot_weights_kernel(Geom g, TabArgs tabs, int64_t ns, const uint32_t* __restrict__ slots,
+                                    const T* __restrict__ tm_s, const int32_t* __restrict__ pt_ko,
+                                    typename Cplx<T>::type* __restrict__ wts2) {
+    const int64_t M = g.M;
+    for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < ns;
+         s += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t u = slots[s];
+        const int64_t i = u >> 1;
+        const bool pair = (u & 1u) != 0;
+        int row = 0;
+        for (int d = 0; d < g.ndim; d++) {
+            const T t = tm_s[(int64_t)d * M + i];
+            const T tq = tm_s[(int64_t)d * M + (pair ? i + 1 : i)];
+            const int ko = pt_ko[(int64_t)d * M + i];
+            // same wrapped cell, but the partner may sit whole periods away: its own origin
+            const int koq = pt_ko[(int64_t)d * M + (pair ? i + 1 : i)];
+            for (int j = 0; j < g.J[d]; j++, row++) {
+                typename Cplx<T>::type ww;
+                ww.x = tap_real<T>((const T*)tabs.h[d], g.ncenter[d], g.tlen[d], t, ko + j, g.L);
+                ww.y = pair ? tap_real<T>((const T*)tabs.h[d], g.ncenter[d], g.tlen[d], tq, koq + j, g.L)
+                            : (T)0;
+                wts2[(int64_t)row * ns + s] = ww;
+            }
+        }
+    }
+}
+
+// slot index of the first sample of every non-empty bin (bin starts always open a slot)
+__global__ void bin_slot_start_kernel(int64_t nbins, const int32_t* __restrict__ bin_start,
+                                      const int32_t* __restrict__ slotidx,
+                                      int32_t* __restrict__ bin_slot_start) {
+    for (int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; b < nbins;
+         b += (int64_t)gridDim.x * blockDim.x)
+        bin_slot_start[b] = bin_start[b] >= 0 ? slotidx[bin_start[b]] : -1;
+}
+
 __global__ void keys_to_i64_kernel(int64_t M, const uint64_t* __restrict__ k, int64_t* __restrict__ o) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < M;
          i += (int64_t)gridDim.x * blockDim.x)

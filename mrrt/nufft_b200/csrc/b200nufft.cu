@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cufft.h>
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include <cmath>
 #include <cstdio>
@@ -63,6 +64,8 @@ struct b2n_plan {
     long opt_order_b = 1;        // build the adjoint sort order (adj_kernel 3)
     long opt_fwd_pitch = 0;      // shared-memory row pitch of the forward tile (0 = automatic)
     long opt_win_lanes = 16;
+    long opt_fwd_pair = 1;       // tiled forward: same-cell sample pairs share one window pass
+    long opt_fwd_interleave = 1; // ... and the slots of a bin are ordered column-interleaved
     // register-window adjoint: 0 register shifts, 1 lane ring, 2 fixed ring with rotated
     // weights, 3 last shift of a slide fused into the FMAs (default; fastest measured)
     long opt_win_ring = 3;
@@ -103,6 +106,15 @@ struct b2n_plan {
     // work items of the tiled forward kernel: (bin, start, count, pad)
     int4* d_items = nullptr;
     int64_t n_items = 0;
+    // forward slots (pairs of same-cell samples) and the work items over them
+    uint32_t* d_slots = nullptr;
+    int32_t* d_slot_kw = nullptr;     // slot-ordered copies read by the packed forward kernel
+    int32_t* d_slot_perm = nullptr;
+    void* d_wts_f = nullptr;
+    void* d_phase_f = nullptr;
+    int4* d_items_f = nullptr;
+    int64_t n_items_f = 0;
+    int64_t n_slots = 0;
     // sparse
     void* d_ell_vals = nullptr;
     int32_t* d_ell_cols = nullptr;
@@ -236,12 +248,16 @@ extern "C" int b2n_plan_create(int ndim, const int* Nd, const int* Kd, const int
 static void free_points(b2n_plan* p) {
     dev_free(p->d_tm); dev_free(p->d_tm_s); dev_free(p->d_keys); dev_free(p->d_bin_ids);
     dev_free(p->d_perm); dev_free(p->d_phase_s); dev_free(p->d_items);
+    dev_free(p->d_slots); dev_free(p->d_items_f);
+    dev_free(p->d_slot_kw); dev_free(p->d_slot_perm); dev_free(p->d_wts_f); dev_free(p->d_phase_f);
+    p->d_slots = nullptr; p->d_items_f = nullptr; p->n_items_f = 0; p->n_slots = 0;
+    p->d_slot_kw = p->d_slot_perm = nullptr; p->d_wts_f = p->d_phase_f = nullptr;
     dev_free(p->d_pt_ko); dev_free(p->d_pt_kw);
     p->d_pt_ko = p->d_pt_kw = nullptr;
     dev_free(p->d_tm_sb); dev_free(p->d_perm_b); dev_free(p->d_pt_ko_b); dev_free(p->d_pt_kw_b);
     dev_free(p->d_phase_sb);
-    dev_free(p->d_wts); dev_free(p->d_wts_b);
-    p->d_wts = p->d_wts_b = nullptr;
+    dev_free(p->d_wts); dev_free(p->d_wts_b); dev_free(p->d_wts_f);
+    p->d_wts = p->d_wts_b = p->d_wts_f = nullptr;
     p->d_tm_sb = p->d_phase_sb = nullptr;
     p->d_perm_b = p->d_pt_ko_b = p->d_pt_kw_b = nullptr;
     p->have_b = false;
@@ -304,6 +320,10 @@ extern "C" int b2n_plan_set_option(b2n_plan* p, const char* name, long value) {
         p->opt_fwd_pitch = value;
     } else if (n == "pruned_fft") {
         p->opt_pruned_fft = value;
+    } else if (n == "fwd_pair") {
+        p->opt_fwd_pair = value;
+    } else if (n == "fwd_interleave") {
+        p->opt_fwd_interleave = value;
     } else if (n == "win_ring") {
         if (value < 0 || value > 3) return fail(B2N_EINVAL, "win_ring must be in 0..3");
         p->opt_win_ring = value;
@@ -337,9 +357,12 @@ extern "C" long b2n_plan_get_option(b2n_plan* p, const char* name) {
     if (n == "slide_pts") return p->opt_slide_pts;
     if (n == "profile") return p->opt_profile;
     if (n == "adj_kernel") return p->opt_adj_kernel;
-    if (n == "precomp_weights") return p->d_wts != nullptr ? 1 : 0;
+    if (n == "precomp_weights") return (p->d_wts != nullptr || p->d_wts_f != nullptr) ? 1 : 0;
     if (n == "lib_calls") return (long)p->lib_calls;
     if (n == "n_items") return (long)p->n_items;
+    if (n == "n_slots") return (long)p->n_slots;
+    if (n == "fwd_pair") return (long)p->opt_fwd_pair;
+    if (n == "fwd_interleave") return (long)p->opt_fwd_interleave;
     if (n == "last_fwd_kernel") return p->last_fwd_kernel;
     if (n == "last_adj_kernel") return p->last_adj_kernel;
     return -1;
@@ -370,8 +393,8 @@ extern "C" int b2n_plan_set_tables(b2n_plan* p, const void* const* h_host) {
         CU(cudaMemcpy(p->d_tab[d], h_host[d], esz * g.tlen[d], cudaMemcpyHostToDevice));
     }
     p->tables_set = true;
-    dev_free(p->d_wts); dev_free(p->d_wts_b);
-    p->d_wts = p->d_wts_b = nullptr;
+    dev_free(p->d_wts); dev_free(p->d_wts_b); dev_free(p->d_wts_f);
+    p->d_wts = p->d_wts_b = p->d_wts_f = nullptr;
     return B2N_OK;
 }
 
@@ -525,6 +548,96 @@ static int set_points_t(b2n_plan* p, const void* coords, int64_t M, int kind, cu
     p->n_items = (int64_t)items.size();
     if ((rc = dev_alloc(p, (void**)&p->d_items, sizeof(int4) * (items.size() + 1)))) return rc;
     CU(cudaMemcpy(p->d_items, items.data(), sizeof(int4) * items.size(), cudaMemcpyHostToDevice));
+    // forward slots: same-cell sample pairs share one pass over the window (tiled forward)
+    if (p->opt_fwd_pair && g.ndim >= 2 && !p->cplx_table) {
+        int32_t *head = nullptr, *isslot = nullptr, *slotidx = nullptr, *bss = nullptr;
+        CU(scratch.alloc(&head, sizeof(int32_t) * M));
+        CU(scratch.alloc(&isslot, sizeof(int32_t) * M));
+        CU(scratch.alloc(&slotidx, sizeof(int32_t) * M));
+        CU(scratch.alloc(&bss, sizeof(int32_t) * p->nbins));
+        slot_heads_kernel<<<grid_for(M, 256, p->sm_count), 256, 0, st>>>(M, keys_s, head);
+        CU(cudaGetLastError());
+        size_t sb1 = 0, sb2 = 0;
+        CU(cub::DeviceScan::InclusiveScan(nullptr, sb1, head, head, cub::Max(), (int)M, st));
+        CU(cub::DeviceScan::ExclusiveSum(nullptr, sb2, isslot, slotidx, (int)M, st));
+        void* stmp = nullptr;
+        CU(scratch.alloc(&stmp, sb1 > sb2 ? sb1 : sb2));
+        CU(cub::DeviceScan::InclusiveScan(stmp, sb1, head, head, cub::Max(), (int)M, st));
+        slot_flags_kernel<<<grid_for(M, 256, p->sm_count), 256, 0, st>>>(M, head, isslot);
+        CU(cudaGetLastError());
+        CU(cub::DeviceScan::ExclusiveSum(stmp, sb2, isslot, slotidx, (int)M, st));
+        int32_t last_idx = 0, last_flag = 0;
+        CU(cudaMemcpyAsync(&last_idx, slotidx + (M - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(&last_flag, isslot + (M - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        bin_slot_start_kernel<<<grid_for(p->nbins, 256, p->sm_count), 256, 0, st>>>(
+            p->nbins, bin_start, slotidx, bss);
+        CU(cudaGetLastError());
+        std::vector<int32_t> hss(p->nbins);
+        CU(cudaMemcpyAsync(hss.data(), bss, sizeof(int32_t) * p->nbins, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        p->n_slots = (int64_t)last_idx + last_flag;
+        if ((rc = dev_alloc(p, (void**)&p->d_slots, sizeof(uint32_t) * (p->n_slots + 1)))) return rc;
+        slot_write_kernel<<<grid_for(M, 256, p->sm_count), 256, 0, st>>>(M, keys_s, isslot, slotidx,
+                                                                         p->d_slots);
+        CU(cudaGetLastError());
+        if (p->opt_fwd_interleave && g.tile[0] <= 256 && p->nbins < ((int64_t)1 << 23)) {
+            // reorder the slots of every bin by (rank within column, column): two stable sorts
+            const int64_t ns = p->n_slots;
+            uint64_t *k1 = nullptr, *k1s = nullptr;
+            uint32_t* sl2 = nullptr;
+            CU(scratch.alloc(&k1, sizeof(uint64_t) * ns));
+            CU(scratch.alloc(&k1s, sizeof(uint64_t) * ns));
+            CU(scratch.alloc(&sl2, sizeof(uint32_t) * ns));
+            slot_colkey_kernel<<<grid_for(ns, 256, p->sm_count), 256, 0, st>>>(
+                ns, g.cells_per_tile, g.tile[0], keys_s, p->d_slots, k1);
+            CU(cudaGetLastError());
+            int b1 = 1;
+            while (b1 < 64 && (((uint64_t)p->nbins * (uint64_t)g.tile[0]) >> b1) != 0) b1++;
+            size_t tb = 0;
+            CU(cub::DeviceRadixSort::SortPairs(nullptr, tb, k1, k1s, p->d_slots, sl2, ns, 0, 64, st));
+            void* t2 = nullptr;
+            CU(scratch.alloc(&t2, tb));
+            CU(cub::DeviceRadixSort::SortPairs(t2, tb, k1, k1s, p->d_slots, sl2, ns, 0, b1, st));
+            // rank inside the (bin, column) group (head / isslot buffers are free again)
+            slot_grouphead_kernel<<<grid_for(ns, 256, p->sm_count), 256, 0, st>>>(ns, k1s, head);
+            CU(cudaGetLastError());
+            CU(cub::DeviceScan::InclusiveScan(stmp, sb1, head, head, cub::Max(), (int)ns, st));
+            slot_rankkey_kernel<<<grid_for(ns, 256, p->sm_count), 256, 0, st>>>(ns, g.tile[0], k1s, head, k1);
+            CU(cudaGetLastError());
+            int b2 = 40;
+            while (b2 < 64 && (((uint64_t)p->nbins << 40) >> b2) != 0) b2++;
+            CU(cub::DeviceRadixSort::SortPairs(t2, tb, k1, k1s, sl2, p->d_slots, ns, 0, b2, st));
+            p->launches += 6;
+        }
+        if ((rc = dev_alloc(p, (void**)&p->d_slot_kw, sizeof(int32_t) * p->n_slots * g.ndim))) return rc;
+        if ((rc = dev_alloc(p, (void**)&p->d_slot_perm, sizeof(int32_t) * p->n_slots * 2))) return rc;
+        slot_pack_kernel<<<grid_for(p->n_slots, 256, p->sm_count), 256, 0, st>>>(
+            p->n_slots, g.ndim, M, p->d_slots, p->d_pt_kw, p->d_perm, p->d_slot_kw, p->d_slot_perm);
+        CU(cudaGetLastError());
+        std::vector<int4> fitems;
+        int64_t nexts = p->n_slots;
+        std::vector<int64_t> send(p->nbins, 0);
+        for (int64_t b = p->nbins - 1; b >= 0; b--) {
+            if (hss[b] >= 0) {
+                send[b] = nexts;
+                nexts = hss[b];
+            }
+        }
+        for (int64_t b = 0; b < p->nbins; b++) {
+            if (hss[b] < 0) continue;
+            int64_t s0 = hss[b], e0 = send[b];
+            while (s0 < e0) {
+                int64_t c = e0 - s0 < p->opt_chunk ? e0 - s0 : p->opt_chunk;
+                fitems.push_back(make_int4((int)b, (int)s0, (int)c, 0));
+                s0 += c;
+            }
+        }
+        p->n_items_f = (int64_t)fitems.size();
+        if ((rc = dev_alloc(p, (void**)&p->d_items_f, sizeof(int4) * (fitems.size() + 1)))) return rc;
+        CU(cudaMemcpy(p->d_items_f, fitems.data(), sizeof(int4) * fitems.size(), cudaMemcpyHostToDevice));
+        CU(cudaStreamSynchronize(st));
+        p->launches += 5;
+    }
     p->launches += 4;
     p->points_set = true;
     return B2N_OK;
@@ -551,7 +664,8 @@ extern "C" int b2n_plan_set_sample_phase(b2n_plan* p, const void* phase_dev, voi
     if (phase_dev == nullptr) {
         dev_free(p->d_phase_s);
         dev_free(p->d_phase_sb);
-        p->d_phase_s = p->d_phase_sb = nullptr;
+        dev_free(p->d_phase_f);
+        p->d_phase_s = p->d_phase_sb = p->d_phase_f = nullptr;
         return B2N_OK;
     }
     const int64_t M = p->g.M;
@@ -568,6 +682,20 @@ extern "C" int b2n_plan_set_sample_phase(b2n_plan* p, const void* phase_dev, voi
                 M, p->d_perm, (const double2*)phase_dev, (double2*)p->d_phase_s);
         CU(cudaGetLastError());
         p->launches++;
+        if (p->d_slots != nullptr && p->n_slots > 0) {
+            if (p->d_phase_f == nullptr) {
+                int rc = dev_alloc(p, &p->d_phase_f, 2 * p->cplx_size() * p->n_slots);
+                if (rc) return rc;
+            }
+            if (p->precision == B2N_SINGLE)
+                slot_phase_kernel<float2><<<grid_for(p->n_slots, 256, p->sm_count), 256, 0, st>>>(
+                    p->n_slots, p->d_slots, p->d_perm, (const float2*)phase_dev, (float2*)p->d_phase_f);
+            else
+                slot_phase_kernel<double2><<<grid_for(p->n_slots, 256, p->sm_count), 256, 0, st>>>(
+                    p->n_slots, p->d_slots, p->d_perm, (const double2*)phase_dev, (double2*)p->d_phase_f);
+            CU(cudaGetLastError());
+            p->launches++;
+        }
         if (p->have_b) {
             if (p->d_phase_sb == nullptr) {
                 int rc = dev_alloc(p, &p->d_phase_sb, p->cplx_size() * M);
@@ -657,10 +785,24 @@ static int build_weights_t(b2n_plan* p, cudaStream_t st) {
     for (int d = 0; d < g.ndim; d++) rows += g.J[d];
     TabArgs tabs{{p->d_tab[0], p->d_tab[1], p->d_tab[2]}};
     int rc;
-    if ((rc = dev_alloc(p, &p->d_wts, sizeof(T) * (size_t)rows * g.M))) return rc;
-    point_weights_kernel<T><<<grid_for(g.M, 256, p->sm_count), 256, 0, st>>>(
-        g, tabs, (const T*)p->d_tm_s, p->d_pt_ko, (T*)p->d_wts);
-    CU(cudaGetLastError());
+    const bool packed = p->opt_fwd_pair && p->d_slots != nullptr;
+    if (packed) {
+        // forward weights in slot order: (weight, partner's weight) pairs
+        if ((rc = dev_alloc(p, &p->d_wts_f, 2 * sizeof(T) * (size_t)rows * p->n_slots))) return rc;
+        slot_weights_kernel<T><<<grid_for(p->n_slots, 256, p->sm_count), 256, 0, st>>>(
+            g, tabs, p->n_slots, p->d_slots, (const T*)p->d_tm_s, p->d_pt_ko,
+            (typename Cplx<T>::type*)p->d_wts_f);
+        CU(cudaGetLastError());
+        p->launches++;
+    }
+    // the sample-ordered weights of sort order A are read by the unpaired forward, the 2-D
+    // adjoint and the 3-D adjoint when it has no order of its own
+    if (!packed || g.ndim == 2 || !p->have_b) {
+        if ((rc = dev_alloc(p, &p->d_wts, sizeof(T) * (size_t)rows * g.M))) return rc;
+        point_weights_kernel<T><<<grid_for(g.M, 256, p->sm_count), 256, 0, st>>>(
+            g, tabs, (const T*)p->d_tm_s, p->d_pt_ko, (T*)p->d_wts);
+        CU(cudaGetLastError());
+    }
     if (p->have_b) {
         if ((rc = dev_alloc(p, &p->d_wts_b, sizeof(T) * (size_t)rows * g.M))) return rc;
         point_weights_kernel<T><<<grid_for(g.M, 256, p->sm_count), 256, 0, st>>>(
@@ -672,7 +814,8 @@ static int build_weights_t(b2n_plan* p, cudaStream_t st) {
 }
 
 static int ensure_weights(b2n_plan* p, cudaStream_t st) {
-    if (!p->opt_precomp || p->cplx_table || p->g.ndim < 2 || p->d_wts != nullptr || p->g.M == 0)
+    if (!p->opt_precomp || p->cplx_table || p->g.ndim < 2 || p->d_wts != nullptr ||
+        p->d_wts_f != nullptr || p->g.M == 0)
         return B2N_OK;
     if (!p->tables_set || !p->points_set) return B2N_OK;
     return p->precision == B2N_SINGLE ? build_weights_t<float>(p, st) : build_weights_t<double>(p, st);
@@ -712,11 +855,24 @@ static int interp_fwd_impl(b2n_plan* p, const void* grid, void* samples, int nba
     if (!p->opt_force_generic && !p->cplx_table) {
         const void* ph = phase ? p->d_phase_s : nullptr;
         const int fwd_flags = (int)((p->opt_use_tma ? 1 : 0) | (p->opt_fwd_pitch << 8));
+        const bool pairs = p->opt_fwd_pair && p->d_slots != nullptr;
+        const int4* fit = pairs ? p->d_items_f : p->d_items;
+        const int64_t nfit = pairs ? p->n_items_f : p->n_items;
+        SlotArgs sa;
+        if (pairs) {
+            sa.slots = p->d_slots;
+            sa.ns = p->n_slots;
+            sa.packed = p->d_wts_f != nullptr ? 1 : 0;
+            sa.wts2 = p->d_wts_f;
+            sa.kw = p->d_slot_kw;
+            sa.perm = p->d_slot_perm;
+            sa.phase2 = phase ? p->d_phase_f : nullptr;
+        }
         int rc = p->precision == B2N_SINGLE
-                     ? tiled_fwd_f32(p->g, p->tables_equal, table_ptrs(p), p->d_tm_s, p->d_wts, p->d_pt_ko, p->d_pt_kw, p->d_perm, p->d_items,
-                                     p->n_items, grid, samples, ph, nbatch, fwd_flags, st, &done)
-                     : tiled_fwd_f64(p->g, p->tables_equal, table_ptrs(p), p->d_tm_s, p->d_wts, p->d_pt_ko, p->d_pt_kw, p->d_perm, p->d_items,
-                                     p->n_items, grid, samples, ph, nbatch, fwd_flags, st, &done);
+                     ? tiled_fwd_f32(p->g, p->tables_equal, table_ptrs(p), p->d_tm_s, p->d_wts, p->d_pt_ko, p->d_pt_kw, p->d_perm, fit,
+                                     nfit, sa, grid, samples, ph, nbatch, fwd_flags, st, &done)
+                     : tiled_fwd_f64(p->g, p->tables_equal, table_ptrs(p), p->d_tm_s, p->d_wts, p->d_pt_ko, p->d_pt_kw, p->d_perm, fit,
+                                     nfit, sa, grid, samples, ph, nbatch, fwd_flags, st, &done);
         if (rc != 0) return fail(B2N_ECUDA, "tiled forward launch failed: " + std::string(cudaGetErrorString((cudaError_t)rc)));
     }
     if (!done) {

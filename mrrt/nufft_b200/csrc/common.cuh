@@ -58,6 +58,11 @@ struct Geom {
 // (template.c:870-873): p=(t-k)*L in T, n=floor(p), alf=p-n,
 // coef=(1-alf)*h[n]+alf*h[n+1].  The n+1 read is clamped to the last entry: it can
 // only exceed the table when alf==0 (the reference reads one past the end there).
+// The n read can fall one entry BEFORE the table when `t - J/2.` rounds to an integer in
+// the window-origin formula while t itself is a hair below it (e.g. K=32, J=6,
+// omega=-13*2pi/32 in float64: t=-13.000000000000002, koff=-15, last tap at
+// p=-3072.000000000002): the reference reads h[-1] there (undefined behaviour, weight
+// 1-alf ~ 1e-12); that entry is taken as 0 here.
 template <typename T>
 __device__ __forceinline__ T tap_real(const T* __restrict__ h, int ncenter, int tlen, T t, int k, int L) {
     const T p = (t - (T)k) * (T)L;
@@ -65,8 +70,9 @@ __device__ __forceinline__ T tap_real(const T* __restrict__ h, int ncenter, int 
     const int n = (int)fl;
     const T alf = p - fl;
     const int i0 = ncenter + n;
-    const int i1 = min(i0 + 1, tlen - 1);
-    return ((T)1 - alf) * h[i0] + alf * h[i1];
+    const int i1 = max(min(i0 + 1, tlen - 1), 0);
+    const T h0 = i0 >= 0 ? h[i0] : (T)0;
+    return ((T)1 - alf) * h0 + alf * h[i1];
 }
 
 template <typename T>
@@ -76,8 +82,8 @@ __device__ __forceinline__ cplx_t<T> tap_cplx(const cplx_t<T>* __restrict__ h, i
     const int n = (int)fl;
     const T alf = p - fl;
     const int i0 = ncenter + n;
-    const int i1 = min(i0 + 1, tlen - 1);
-    const cplx_t<T> a = h[i0], b = h[i1];
+    const int i1 = max(min(i0 + 1, tlen - 1), 0);
+    const cplx_t<T> a = i0 >= 0 ? h[i0] : make_c<T>(0, 0), b = h[i1];
     return make_c<T>(((T)1 - alf) * a.x + alf * b.x, ((T)1 - alf) * a.y + alf * b.y);
 }
 

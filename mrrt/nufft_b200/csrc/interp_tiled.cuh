@@ -70,13 +70,22 @@ struct TileShape {
 };
 
 // TAB: 0 table in global memory, 1 table staged in shared memory, 2 plan-time weights
-template <typename T, int NDIM, int J, int TAB>
+// PAIR: the work item ranges over SLOTS (one sample, or two consecutive sorted samples of
+//       the same cell, slots[s] = (first sample << 1) | has_partner): both samples of a
+//       slot share the window, so every tap is read from shared memory once for the two of
+//       them -- the kernel is shared-memory-bandwidth bound and 39 % of the bench
+//       trajectory's samples are the second one of such a pair.  PAIR 1 reads the
+//       sample-ordered arrays through slots[]; PAIR 2 (plan-time weights only) reads
+//       slot-ordered copies (weights of both samples as one vector load), which stay
+//       coalesced when the slots of a bin are stored column-interleaved.
+template <typename T, int NDIM, int J, int TAB, int PAIR>
 __global__ void __launch_bounds__(256)
 interp_fwd_tiled_kernel(const __grid_constant__ CUtensorMap tmap, Geom g, TileShape ts, int use_tma,
                         const T* __restrict__ tab, const T* __restrict__ wts,
                         const T* __restrict__ tm_s,
                         const int32_t* __restrict__ pt_ko, const int32_t* __restrict__ pt_kw,
                         const int32_t* __restrict__ perm, const int4* __restrict__ items,
+                        SlotArgs sa,
                         const cplx_t<T>* __restrict__ grid, cplx_t<T>* __restrict__ out,
                         const cplx_t<T>* __restrict__ phase_s) {
     using C = cplx_t<T>;
@@ -128,47 +137,105 @@ interp_fwd_tiled_kernel(const __grid_constant__ CUtensorMap tmap, Geom g, TileSh
     const T* __restrict__ h = TAB_SMEM ? stab : tab;
     const int64_t M = g.M;
     const int end = it.y + it.z;
-    for (int i = it.y + tid; i < end; i += blockDim.x) {
+    const uint32_t* __restrict__ slots = sa.slots;
+    const int64_t ns = sa.ns;
+    using T2 = typename Cplx<T>::type;      // (weight, partner's weight)
+    const T2* __restrict__ wts2 = (const T2*)sa.wts2;
+    for (int sidx = it.y + tid; sidx < end; sidx += blockDim.x) {
+        int i = sidx;
+        bool pair = false;
+        if (PAIR == 1) {
+            const uint32_t u = slots[sidx];
+            i = (int)(u >> 1);
+            pair = (u & 1u) != 0;
+        }
         T w[NDIM][J];
+        T wq[PAIR ? NDIM : 1][PAIR ? J : 1];   // partner's weights (zero when there is none)
         int c[NDIM];
 #pragma unroll
         for (int d = 0; d < NDIM; d++) {
             const int od = d == 0 ? o1 : (d == 1 ? o2 : o3);
+            if (PAIR == 2) {
+                c[d] = sa.kw[(int64_t)d * ns + sidx] - od;
+#pragma unroll
+                for (int j = 0; j < J; j++) {
+                    const T2 ww = wts2[(int64_t)(d * J + j) * ns + sidx];
+                    w[d][j] = ww.x;
+                    wq[d][j] = ww.y;
+                }
+                continue;
+            }
             c[d] = pt_kw[(int64_t)d * M + i] - od;           // wrapped origin inside the tile
             if (TAB == 2) {
 #pragma unroll
                 for (int j = 0; j < J; j++) w[d][j] = wts[(int64_t)(d * J + j) * M + i];
+                if (PAIR) {
+#pragma unroll
+                    for (int j = 0; j < J; j++)
+                        wq[d][j] = pair ? wts[(int64_t)(d * J + j) * M + i + 1] : (T)0;
+                }
             } else {
                 const T t = tm_s[(int64_t)d * M + i];
                 const int koff = pt_ko[(int64_t)d * M + i];  // 1 + floor(t - J/2.), plan time
 #pragma unroll
                 for (int j = 0; j < J; j++)
                     w[d][j] = tap_real<T>(h, g.ncenter[0], g.tlen[0], t, koff + j, g.L);
+                if (PAIR) {
+                    const T tq = tm_s[(int64_t)d * M + (pair ? i + 1 : i)];
+                    // same wrapped cell, but possibly whole periods away: its own origin
+                    const int koq = pt_ko[(int64_t)d * M + (pair ? i + 1 : i)];
+#pragma unroll
+                    for (int j = 0; j < J; j++)
+                        wq[d][j] = pair ? tap_real<T>(h, g.ncenter[0], g.tlen[0], tq, koq + j, g.L)
+                                        : (T)0;
+                }
             }
         }
-        C s3 = make_c<T>(0, 0);
+        C s3 = make_c<T>(0, 0), q3 = make_c<T>(0, 0);
 #pragma unroll
         for (int j3 = 0; j3 < (NDIM > 2 ? J : 1); j3++) {
-            C s2 = make_c<T>(0, 0);
+            C s2 = make_c<T>(0, 0), q2 = make_c<T>(0, 0);
 #pragma unroll
             for (int j2 = 0; j2 < (NDIM > 1 ? J : 1); j2++) {
                 int row = c[0];
                 if (NDIM == 2) row += (c[1] + j2) * ts.E1p;
                 if (NDIM == 3) row += ((c[NDIM > 2 ? 2 : 0] + j3) * ts.E2 + (c[1] + j2)) * ts.E1p;
                 const C* __restrict__ pr = tile + row;
-                C s1 = make_c<T>(0, 0);
+                C s1 = make_c<T>(0, 0), q1 = make_c<T>(0, 0);
 #pragma unroll
-                for (int j1 = 0; j1 < J; j1++) s1 = fma_w(w[0][j1], pr[j1], s1);   // FFMA2
+                for (int j1 = 0; j1 < J; j1++) {
+                    const C v = pr[j1];
+                    s1 = fma_w(w[0][j1], v, s1);                       // FFMA2
+                    if (PAIR) q1 = fma_w(wq[0][j1], v, q1);
+                }
                 s2 = fma_w(w[NDIM > 1 ? 1 : 0][j2], s1, s2);
+                if (PAIR) q2 = fma_w(wq[NDIM > 1 ? 1 : 0][j2], q1, q2);
             }
             if (NDIM > 2) {
                 s3 = fma_w(w[NDIM > 2 ? 2 : 0][j3], s2, s3);
+                if (PAIR) q3 = fma_w(wq[NDIM > 2 ? 2 : 0][j3], q2, q3);
             } else {
                 s3 = s2;
+                q3 = q2;
             }
+        }
+        if (PAIR == 2) {
+            const int pa = sa.perm[sidx], pb = sa.perm[ns + sidx];
+            if (sa.phase2 != nullptr) {
+                const C* __restrict__ ph2 = (const C*)sa.phase2;
+                s3 = cmul(s3, ph2[2 * (int64_t)sidx]);
+                q3 = cmul(q3, ph2[2 * (int64_t)sidx + 1]);
+            }
+            out[(int64_t)b * M + pa] = s3;
+            if (pb >= 0) out[(int64_t)b * M + pb] = q3;
+            continue;
         }
         if (phase_s != nullptr) s3 = cmul(s3, phase_s[i]);
         out[(int64_t)b * M + perm[i]] = s3;
+        if (PAIR && pair) {
+            if (phase_s != nullptr) q3 = cmul(q3, phase_s[i + 1]);
+            out[(int64_t)b * M + perm[i + 1]] = q3;
+        }
     }
 }
 
@@ -231,7 +298,7 @@ static bool make_grid_tmap(CUtensorMap* map, const Geom& g, const TileShape& ts,
 template <typename T, int NDIM, int J>
 static int launch_fwd_tiled(const Geom& g, const TablePtrs& tabs, const void* tm_s,
                             const void* wts, const int32_t* pt_ko, const int32_t* pt_kw, const int32_t* perm, const int4* items, int64_t n_items,
-                            const void* grid, void* out, const void* phase_s, int nbatch,
+                            const SlotArgs& sa, const void* grid, void* out, const void* phase_s, int nbatch,
                             int use_tma, cudaStream_t st, bool* done) {
     using C = cplx_t<T>;
     *done = false;
@@ -258,7 +325,7 @@ static int launch_fwd_tiled(const Geom& g, const TablePtrs& tabs, const void* tm
     cudaGetDevice(&dev);
     int max_smem = 0;
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    bool tab_smem = wts == nullptr;
+    bool tab_smem = wts == nullptr && !sa.packed;
     size_t smem = ts.tile_bytes + (tab_smem ? tab_bytes : 0);
     if (smem > (size_t)max_smem || smem > 100 * 1024) {
         tab_smem = false;
@@ -270,19 +337,26 @@ static int launch_fwd_tiled(const Geom& g, const TablePtrs& tabs, const void* tm
     const bool tma_ok = use_tma && make_grid_tmap<T, NDIM>(&map, g, ts, grid, nbatch);
     dim3 gridDim((unsigned)n_items, (unsigned)nbatch);
     cudaError_t e;
-#define B2N_LAUNCH_FWD(TABV)                                                                       \
+#define B2N_LAUNCH_FWD_P(TABV, PAIRV)                                                              \
     {                                                                                              \
-        auto k = interp_fwd_tiled_kernel<T, NDIM, J, TABV>;                                        \
+        auto k = interp_fwd_tiled_kernel<T, NDIM, J, TABV, PAIRV>;                                 \
         e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
         if (e != cudaSuccess) return (int)e;                                                       \
         k<<<gridDim, 256, smem, st>>>(map, g, ts, tma_ok ? 1 : 0, (const T*)tabs.h[0],             \
                                       (const T*)wts, (const T*)tm_s, pt_ko, pt_kw, perm, items,    \
-                                      (const C*)grid, (C*)out, (const C*)phase_s);                 \
+                                      sa, (const C*)grid, (C*)out, (const C*)phase_s);             \
     }
-    if (wts != nullptr) B2N_LAUNCH_FWD(2)
+    const int pairv = sa.slots == nullptr ? 0 : (sa.packed ? 2 : 1);
+#define B2N_LAUNCH_FWD(TABV)                                                                       \
+    {                                                                                              \
+        if (pairv) B2N_LAUNCH_FWD_P(TABV, 1) else B2N_LAUNCH_FWD_P(TABV, 0)                        \
+    }
+    if (pairv == 2) B2N_LAUNCH_FWD_P(2, 2)
+    else if (wts != nullptr) B2N_LAUNCH_FWD(2)
     else if (tab_smem) B2N_LAUNCH_FWD(1)
     else B2N_LAUNCH_FWD(0)
 #undef B2N_LAUNCH_FWD
+#undef B2N_LAUNCH_FWD_P
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
     *done = true;
@@ -292,17 +366,17 @@ static int launch_fwd_tiled(const Geom& g, const TablePtrs& tabs, const void* tm
 // returns 0 or a cudaError_t; *done tells whether the tiled kernel took the call
 template <typename T>
 static int tiled_fwd_t(const Geom& g, bool tables_equal, const TablePtrs& tabs, const void* tm_s,
-                       const void* wts, const int32_t* pt_ko, const int32_t* pt_kw, const int32_t* perm, const int4* items, int64_t n_items, const void* grid,
+                       const void* wts, const int32_t* pt_ko, const int32_t* pt_kw, const int32_t* perm, const int4* items, int64_t n_items, const SlotArgs& sa, const void* grid,
                        void* out, const void* phase_s, int nbatch, int use_tma, cudaStream_t st,
                        bool* done) {
     *done = false;
-    if (g.ndim < 2 || (!tables_equal && wts == nullptr) || n_items == 0 || n_items > 0x7fffffff ||
+    if (g.ndim < 2 || (!tables_equal && wts == nullptr && !sa.packed) || n_items == 0 || n_items > 0x7fffffff ||
         nbatch > 65535)
         return 0;
     for (int d = 1; d < g.ndim; d++)
         if (g.J[d] != g.J[0]) return 0;
 #define B2N_TILED(ND, JJ)                                                                      \
-    return launch_fwd_tiled<T, ND, JJ>(g, tabs, tm_s, wts, pt_ko, pt_kw, perm, items, n_items, grid, out, phase_s, \
+    return launch_fwd_tiled<T, ND, JJ>(g, tabs, tm_s, wts, pt_ko, pt_kw, perm, items, n_items, sa, grid, out, phase_s, \
                                        nbatch, use_tma, st, done)
     if (g.ndim == 2) {
         switch (g.J[0]) {

@@ -24,19 +24,24 @@ static inline int NAME(wrap)(int k, int K)
     return r < 0 ? r + K : r;
 }
 
-/* coefficient for one tap: linear interpolation of the centred table */
-static inline void NAME(coef)(const REAL *h, int h_cplx, int ncenter, REAL t,
+/* coefficient for one tap: linear interpolation of the centred table.
+ * The reference indexes h[n] and h[n+1] unguarded; n can be -1 (weight 1-alf ~ 1e-12,
+ * when `t - J/2.` rounds up to an integer in the window-origin formula) and n+1 can be
+ * one past the end (weight alf == 0): undefined behaviour there.  Both out-of-table
+ * entries count as 0 here, so that the checker never returns heap garbage. */
+static inline void NAME(coef)(const REAL *h, int h_cplx, int ncenter, int tlen, REAL t,
                               int k, int L, REAL *cr, REAL *ci)
 {
     const REAL p = (t - (REAL)k) * (REAL)L;
     const int n = (int)floor((double)p);
     const REAL alf = p - (REAL)n;
     const long i0 = (long)ncenter + n;
+    const int ok0 = i0 >= 0 && i0 < tlen, ok1 = i0 + 1 >= 0 && i0 + 1 < tlen;
     if (h_cplx) {
-        *cr = (1 - alf) * h[2 * i0] + alf * h[2 * (i0 + 1)];
-        *ci = (1 - alf) * h[2 * i0 + 1] + alf * h[2 * (i0 + 1) + 1];
+        *cr = (1 - alf) * (ok0 ? h[2 * i0] : 0) + alf * (ok1 ? h[2 * (i0 + 1)] : 0);
+        *ci = (1 - alf) * (ok0 ? h[2 * i0 + 1] : 0) + alf * (ok1 ? h[2 * (i0 + 1) + 1] : 0);
     } else {
-        *cr = (1 - alf) * h[i0] + alf * h[i0 + 1];
+        *cr = (1 - alf) * (ok0 ? h[i0] : 0) + alf * (ok1 ? h[i0 + 1] : 0);
         *ci = 0;
     }
 }
@@ -67,19 +72,19 @@ void NAME(interp_fwd)(int ndim, const int *K, const int *J, int L,
         for (int j3 = 0; j3 < J3; j3++) {
             REAL c3r = 1, c3i = 0;
             if (ndim > 2)
-                NAME(coef)(h3, h_cplx, nc3, t3, koff3 + j3, L, &c3r, &c3i);
+                NAME(coef)(h3, h_cplx, nc3, J3 * L + 1, t3, koff3 + j3, L, &c3r, &c3i);
             const long k3 = NAME(wrap)(koff3 + j3, K3);
             REAL s2r = 0, s2i = 0;
             for (int j2 = 0; j2 < J2; j2++) {
                 REAL c2r = 1, c2i = 0;
                 if (ndim > 1)
-                    NAME(coef)(h2, h_cplx, nc2, t2, koff2 + j2, L, &c2r, &c2i);
+                    NAME(coef)(h2, h_cplx, nc2, J2 * L + 1, t2, koff2 + j2, L, &c2r, &c2i);
                 const long k2 = NAME(wrap)(koff2 + j2, K2);
                 const long row = (k3 * K2 + k2) * K1;
                 REAL s1r = 0, s1i = 0;
                 for (int j1 = 0; j1 < J1; j1++) {
                     REAL c1r, c1i;
-                    NAME(coef)(h1, h_cplx, nc1, t1, koff1 + j1, L, &c1r, &c1i);
+                    NAME(coef)(h1, h_cplx, nc1, J1 * L + 1, t1, koff1 + j1, L, &c1r, &c1i);
                     const long kk = row + NAME(wrap)(koff1 + j1, K1);
                     const REAL gr = ck[2 * kk], gi = ck[2 * kk + 1];
                     s1r += c1r * gr - c1i * gi;
@@ -117,21 +122,21 @@ void NAME(interp_adj)(int ndim, const int *K, const int *J, int L,
         for (int j3 = 0; j3 < J3; j3++) {
             REAL c3r = 1, c3i = 0;
             if (ndim > 2)
-                NAME(coef)(h3, h_cplx, nc3, t3, koff3 + j3, L, &c3r, &c3i);
+                NAME(coef)(h3, h_cplx, nc3, J3 * L + 1, t3, koff3 + j3, L, &c3r, &c3i);
             const long k3 = NAME(wrap)(koff3 + j3, K3);
             const REAL v3r = c3r * fr + c3i * fi;
             const REAL v3i = c3r * fi - c3i * fr;
             for (int j2 = 0; j2 < J2; j2++) {
                 REAL c2r = 1, c2i = 0;
                 if (ndim > 1)
-                    NAME(coef)(h2, h_cplx, nc2, t2, koff2 + j2, L, &c2r, &c2i);
+                    NAME(coef)(h2, h_cplx, nc2, J2 * L + 1, t2, koff2 + j2, L, &c2r, &c2i);
                 const long k2 = NAME(wrap)(koff2 + j2, K2);
                 const long row = (k3 * K2 + k2) * K1;
                 const REAL v2r = c2r * v3r + c2i * v3i;
                 const REAL v2i = c2r * v3i - c2i * v3r;
                 for (int j1 = 0; j1 < J1; j1++) {
                     REAL c1r, c1i;
-                    NAME(coef)(h1, h_cplx, nc1, t1, koff1 + j1, L, &c1r, &c1i);
+                    NAME(coef)(h1, h_cplx, nc1, J1 * L + 1, t1, koff1 + j1, L, &c1r, &c1i);
                     const long kk = row + NAME(wrap)(koff1 + j1, K1);
                     ck[2 * kk] += c1r * v2r + c1i * v2i;
                     ck[2 * kk + 1] += c1r * v2i - c1i * v2r;

@@ -3,7 +3,8 @@
 Row pitch 32 complex64 == 0 mod 16 bank pairs, so for every tap the bank pair of a lane is
 (x1 + j1) mod 16: the wavefronts of one LDS.64 of a half-warp = max over columns c of the
 number of DISTINCT cells with x1 mod 16 == c among its 16 lanes.  Compares the cell-sorted
-order with the column-interleaved order (rank within column slowest, column fastest)."""
+order with the column-interleaved order (rank within column slowest, column fastest), for
+plain samples and for slots (pairs of same-cell samples, option fwd_pair)."""
 import sys
 import numpy as np
 sys.path.insert(0, ".")
@@ -36,26 +37,31 @@ def factor(cells_in_order):
     return tot, cnt
 
 
-t_old = t_new = n_hw = 0
-nsamp = 0
-for bb in sel_bins:
-    idx = np.nonzero(binid == bb)[0]
-    if len(idx) == 0:
-        continue
-    cl = cell[idx]
-    order = np.argsort(cl, kind="stable")
-    cs = cl[order]
-    a, n1 = factor(cs)
-    # interleaved: rank within column, then column
+def interleave(cs):
     col = cs % 16
     rank = np.zeros(len(cs), dtype=np.int64)
     o2 = np.argsort(col, kind="stable")
     sc = col[o2]
     start = np.searchsorted(sc, np.arange(16))
     rank[o2] = np.arange(len(cs)) - start[sc]
-    o3 = np.lexsort((col, rank))
-    bnew, n2 = factor(cs[o3])
-    t_old += a; t_new += bnew; n_hw += n1; nsamp += len(idx)
-print("samples", nsamp, "half-warps", n_hw)
-print("conflict factor cell-sorted  %.3f" % (t_old / n_hw))
-print("conflict factor interleaved  %.3f" % (t_new / n_hw))
+    return cs[np.lexsort((col, rank))]
+
+
+res = {k: [0, 0] for k in ("samples sorted", "samples interleaved", "slots sorted", "slots interleaved")}
+nsamp = 0
+for bb in sel_bins:
+    idx = np.nonzero(binid == bb)[0]
+    if len(idx) == 0:
+        continue
+    cs = np.sort(cell[idx])
+    u, cnt = np.unique(cs, return_counts=True)
+    slots = np.repeat(u, (cnt + 1) // 2)
+    for name, arr in (("samples sorted", cs), ("samples interleaved", interleave(cs)),
+                      ("slots sorted", slots), ("slots interleaved", interleave(slots))):
+        a, n = factor(arr)
+        res[name][0] += a
+        res[name][1] += n
+    nsamp += len(idx)
+print("samples", nsamp)
+for k, (a, n) in res.items():
+    print("%-20s half-warp LDS instructions %7d  wavefronts %7d  factor %.3f" % (k, n, a, a / n))

@@ -399,7 +399,11 @@ def test_wraparound_edges_vs_oracle(case, precision):
     x = (rs.standard_normal(Nd) + 1j * rs.standard_normal(Nd)).astype(A._cplx_dtype)
     y = (rs.standard_normal(A.M) + 1j * rs.standard_normal(A.M)).astype(A._cplx_dtype)
     tol = TOL[precision]
-    assert rel_l2(A.fft(x), O.fft(x)) <= tol
+    ya, yo = A.fft(x), O.fft(x)
+    assert np.isfinite(yo).all(), ("oracle", np.argwhere(~np.isfinite(yo)).ravel()[:8], om[~np.isfinite(yo)][:4])
+    assert np.isfinite(ya).all(), ("cuda", np.argwhere(~np.isfinite(ya)).ravel()[:8], om[~np.isfinite(ya)][:4],
+                                   A.option("n_slots"), A.option("last_fwd_kernel"))
+    assert rel_l2(ya, yo) <= tol
     assert rel_l2(A.adj(y), O.adj(y)) <= tol
 
 
