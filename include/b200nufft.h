@@ -109,6 +109,15 @@ int64_t b2n_plan_num_bins(b2n_plan *plan);
 int b2n_plan_get_points(b2n_plan *plan, void *tm_dev, int32_t *bin_ids_dev,
                         int64_t *keys_dev, int32_t *perm_dev, void *stream);
 
+/* Forward "slots" (no reference counterpart; part of the trajectory preprocessing): one or
+ * two sorted samples of the same grid cell that a thread of the forward kernel handles
+ * together.  slot = (sorted position of the first sample << 1) | has_partner (the partner
+ * is the next sorted position); pairs are formed greedily inside each run of equal sort
+ * keys, and the slots of a bin are stored ordered by (rank inside the bin's axis-1 column,
+ * column).  num_slots is 0 when the plan has none (1-D, complex table, option fwd_pair=0). */
+int64_t b2n_plan_num_slots(b2n_plan *plan);
+int b2n_plan_get_slots(b2n_plan *plan, uint32_t *slots_dev, void *stream);
+
 /* Interpolation only (the reference's grid_only switches).
  * grid_dev: complex[prod(Kd) * nbatch], first axis fastest, batch slowest.
  * samples_dev: complex[M * nbatch], acquisition order, batch slowest.

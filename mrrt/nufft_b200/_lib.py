@@ -38,6 +38,8 @@ SIGNATURES = {
     "b2n_plan_num_points": (c_i64, [c_vp]),
     "b2n_plan_num_bins": (c_i64, [c_vp]),
     "b2n_plan_get_points": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "b2n_plan_num_slots": (c_i64, [c_vp]),
+    "b2n_plan_get_slots": (c_int, [c_vp, c_vp, c_vp]),
     "b2n_interp_fwd": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_vp]),
     "b2n_interp_adj": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_vp]),
     "b2n_grid_fwd": (c_int, [c_vp, c_vp, c_vp, c_int, c_vp]),

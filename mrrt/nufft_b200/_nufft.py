@@ -373,6 +373,15 @@ class NufftBase(object):
                                                  perm.data_ptr(), self._stream()))
         return bins, keys, perm
 
+    def forward_slots(self):
+        """uint32 slot list of the paired forward kernel as an int64 device tensor
+        ((sorted position << 1) | has_partner); empty when the plan has none."""
+        n = int(self._lib.b2n_plan_num_slots(self._plan))
+        raw = torch.empty(max(n, 0), dtype=torch.int32, device=self.device)
+        if n > 0:
+            _lib.check(self._lib.b2n_plan_get_slots(self._plan, raw.data_ptr(), self._stream()))
+        return raw.to(torch.int64) & 0xFFFFFFFF
+
     @property
     def tile(self):
         return tuple(int(self._lib.b2n_plan_get_option(self._plan, ("tile%d" % (d + 1)).encode()))

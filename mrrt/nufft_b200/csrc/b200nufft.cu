@@ -715,6 +715,16 @@ extern "C" int b2n_plan_set_sample_phase(b2n_plan* p, const void* phase_dev, voi
 
 extern "C" int64_t b2n_plan_num_points(b2n_plan* p) { return p && p->points_set ? p->g.M : -1; }
 extern "C" int64_t b2n_plan_num_bins(b2n_plan* p) { return p ? (int64_t)p->g.nbin[0] * p->g.nbin[1] * p->g.nbin[2] : -1; }
+extern "C" int64_t b2n_plan_num_slots(b2n_plan* p) { return p && p->points_set ? p->n_slots : -1; }
+extern "C" int b2n_plan_get_slots(b2n_plan* p, uint32_t* slots_dev, void* stream) {
+    if (p == nullptr || slots_dev == nullptr) return fail(B2N_EINVAL, "NULL argument");
+    if (!p->points_set) return fail(B2N_ESTATE, "points not set");
+    CU(cudaSetDevice(p->device));
+    if (p->n_slots > 0)
+        CU(cudaMemcpyAsync(slots_dev, p->d_slots, sizeof(uint32_t) * p->n_slots,
+                           cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return B2N_OK;
+}
 extern "C" int64_t b2n_plan_device_bytes(b2n_plan* p) { return p ? p->dev_bytes : -1; }
 extern "C" int64_t b2n_plan_launch_count(b2n_plan* p) { return p ? p->launches : -1; }
 

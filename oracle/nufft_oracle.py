@@ -381,6 +381,44 @@ def bin_sort(tm, Jd, Kd, tile):
     return bin_id.astype(np.int32), keys, perm
 
 
+def forward_slots(keys, perm, tile):
+    """Slot list of the paired forward kernel (new preprocessing, no reference counterpart).
+
+    In sorted order, every run of equal sort keys (= samples of one grid cell) is cut
+    into pairs (positions 0|1, 2|3, ...; a last odd one stays single); a slot is
+    ``(sorted position of its first sample << 1) | has_partner``.  The slots of a bin are
+    then ordered by (rank inside the bin's axis-1 column, column), stable, so that
+    consecutive slots sit in different columns.  Returns int64 [n_slots].
+    """
+    ks = np.asarray(keys)[np.asarray(perm)]
+    M = ks.shape[0]
+    if M == 0:
+        return np.zeros(0, dtype=np.int64)
+    idx = np.arange(M)
+    head = np.ones(M, dtype=bool)
+    head[1:] = ks[1:] != ks[:-1]
+    runstart = np.maximum.accumulate(np.where(head, idx, 0))
+    first = ((idx - runstart) & 1) == 0
+    i = idx[first]
+    pair = np.zeros(i.shape[0], dtype=np.int64)
+    ok = i + 1 < M
+    pair[ok] = ks[i[ok] + 1] == ks[i[ok]]
+    slots = (i << 1) | pair
+    cpt = int(np.prod(tile))
+    kk = ks[i]
+    bins = kk // cpt
+    col = (kk % cpt) % int(tile[0])
+    o1 = np.lexsort((col, bins))                    # stable: by bin, then column
+    b1, c1 = bins[o1], col[o1]
+    g = b1 * int(tile[0]) + c1
+    gh = np.ones(g.shape[0], dtype=bool)
+    gh[1:] = g[1:] != g[:-1]
+    pos = np.arange(g.shape[0])
+    rank = pos - np.maximum.accumulate(np.where(gh, pos, 0))
+    o2 = np.lexsort((c1, rank, b1))                 # stable: by bin, rank, column
+    return slots[o1][o2]
+
+
 # ----------------------------------------------------------------------------
 # operator
 # ----------------------------------------------------------------------------

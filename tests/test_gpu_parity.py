@@ -107,6 +107,15 @@ def test_bin_sort_bit_exact(ndim, precision):
     assert np.array_equal(bins.cpu().numpy(), obins)
     assert np.array_equal(keys.cpu().numpy(), okeys)
     assert np.array_equal(perm.cpu().numpy(), operm)
+    # slot list of the paired forward kernel (2-D / 3-D): bit-exact too, and a partition
+    slots = A.forward_slots().cpu().numpy()
+    if ndim == 1:
+        assert slots.size == 0
+    else:
+        oslots = orc.forward_slots(okeys, operm, A.tile)
+        assert np.array_equal(slots, oslots)
+        covered = np.concatenate([slots >> 1, (slots >> 1)[(slots & 1) == 1] + 1])
+        assert np.array_equal(np.sort(covered), np.arange(M))
 
 
 def _radial3d(S, n):
