@@ -64,7 +64,7 @@ struct b2n_plan {
     long opt_order_b = 1;        // build the adjoint sort order (adj_kernel 3)
     long opt_fwd_pitch = 0;      // shared-memory row pitch of the forward tile (0 = automatic)
     long opt_win_lanes = 16;
-    long opt_fwd_pair = 1;       // tiled forward: same-cell sample pairs share one window pass
+    long opt_fwd_pair = 1;       // tiled forward: same-cell sample pairs share one window pass (1 = auto)
     long opt_fwd_interleave = 1; // ... and the slots of a bin are ordered column-interleaved
     // register-window adjoint: 0 register shifts, 1 lane ring, 2 fixed ring with rotated
     // weights, 3 last shift of a slide fused into the FMAs (default; fastest measured)
@@ -321,6 +321,7 @@ extern "C" int b2n_plan_set_option(b2n_plan* p, const char* name, long value) {
     } else if (n == "pruned_fft") {
         p->opt_pruned_fft = value;
     } else if (n == "fwd_pair") {
+        if (value < 0 || value > 2) return fail(B2N_EINVAL, "fwd_pair must be 0 (off), 1 (auto) or 2 (on)");
         p->opt_fwd_pair = value;
     } else if (n == "fwd_interleave") {
         p->opt_fwd_interleave = value;
@@ -549,7 +550,15 @@ static int set_points_t(b2n_plan* p, const void* coords, int64_t M, int kind, cu
     if ((rc = dev_alloc(p, (void**)&p->d_items, sizeof(int4) * (items.size() + 1)))) return rc;
     CU(cudaMemcpy(p->d_items, items.data(), sizeof(int4) * items.size(), cudaMemcpyHostToDevice));
     // forward slots: same-cell sample pairs share one pass over the window (tiled forward)
-    if (p->opt_fwd_pair && g.ndim >= 2 && !p->cplx_table) {
+    // fwd_pair: 0 off, 2 always, 1 (default) automatic = 3-D single precision, and only when
+    // at least 10 % of the samples are partners.  Measured: the paired kernel doubles the
+    // FMAs per shared-memory read, which pays where the forward kernel is shared-memory
+    // bound (3-D float: 3.17 -> 2.30 ms) and costs where it is not (double: FP64 pipe,
+    // 6.3 -> 8.0 ms; 2-D: per-slot overhead, configs[3] 0.157 -> 0.197 ms).
+    const bool want_pairs = g.ndim >= 2 && !p->cplx_table &&
+                            (p->opt_fwd_pair == 2 ||
+                             (p->opt_fwd_pair == 1 && g.ndim == 3 && p->precision == B2N_SINGLE));
+    if (want_pairs) {
         int32_t *head = nullptr, *isslot = nullptr, *slotidx = nullptr, *bss = nullptr;
         CU(scratch.alloc(&head, sizeof(int32_t) * M));
         CU(scratch.alloc(&isslot, sizeof(int32_t) * M));
@@ -576,6 +585,12 @@ static int set_points_t(b2n_plan* p, const void* coords, int64_t M, int kind, cu
         CU(cudaMemcpyAsync(hss.data(), bss, sizeof(int32_t) * p->nbins, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         p->n_slots = (int64_t)last_idx + last_flag;
+        if (p->opt_fwd_pair == 1 && (double)p->n_slots > 0.9 * (double)M) {
+            p->n_slots = 0;          // too few pairs to pay for the doubled FMAs
+            p->launches += 4;
+            p->points_set = true;
+            return B2N_OK;
+        }
         if ((rc = dev_alloc(p, (void**)&p->d_slots, sizeof(uint32_t) * (p->n_slots + 1)))) return rc;
         slot_write_kernel<<<grid_for(M, 256, p->sm_count), 256, 0, st>>>(M, keys_s, isslot, slotidx,
                                                                          p->d_slots);

@@ -92,5 +92,5 @@ if __name__ == "__main__":
         for r in ROWS:
             f.write("| %s (%s) | %s | %d | %d | %.3f | %.3f | %.3f | %.3f | %.2f | %.3f | %.0f | %d/%d |\n" % (
                 r["config"], r["mode"], r["precision"], r["M"], r["coils"], r["interp_fwd_ms"],
-                r["interp_adj_ms"], r["full_fwd_ms"], r["full_adj_ms"], r["gpts_per_s"] / 1e3,
+                r["interp_adj_ms"], r["full_fwd_ms"], r["full_adj_ms"], r["gpts_per_s"],
                 r["pair_algorithmic_GB"], r["hbm_GBps"], r["fwd_kernel"], r["adj_kernel"]))

@@ -15,7 +15,7 @@ def _op(cfg, omega, **extra):
     return NufftBase(omega=omega, on_gpu=True, **ctor_kwargs(cfg), **extra)
 
 
-@pytest.mark.parametrize("variant", ["auto", "generic"])
+@pytest.mark.parametrize("variant", ["auto", "generic", "paired"])
 @pytest.mark.parametrize("name", case_names())
 def test_golden(name, variant):
     """fft / adj / grid_only stages vs what the reference package produced."""
@@ -23,7 +23,9 @@ def test_golden(name, variant):
 
     cfg, z = load_case(name)
     tol = TOL[cfg["precision"]]
-    opts = {"force_generic": 1} if variant == "generic" else {}
+    # "paired": same-cell sample pairs in the forward kernel forced on (automatic only for
+    # 3-D single precision with enough pairs)
+    opts = {"generic": {"force_generic": 1}, "paired": {"fwd_pair": 2}, "auto": {}}[variant]
     A = _op(cfg, z["omega"], options=opts)
     # plan arrays: bit-exact
     assert np.array_equal(A.sn, z["sn"])
@@ -99,7 +101,7 @@ def test_bin_sort_bit_exact(ndim, precision):
     om[60:70] = -np.pi
     from mrrt.nufft_b200 import NufftBase
 
-    A = NufftBase(Nd=Nd, omega=om, Jd=6, Kd=Kd, precision=precision)
+    A = NufftBase(Nd=Nd, omega=om, Jd=6, Kd=Kd, precision=precision, options={"fwd_pair": 2})
     O = orc.OracleNufft(Nd=Nd, omega=om, Jd=6, Kd=Kd, precision=precision)
     assert np.array_equal(A.tm.cpu().numpy(), O.tm)
     bins, keys, perm = A.bin_sort()
@@ -130,7 +132,8 @@ def _radial3d(S, n):
 
 @pytest.mark.parametrize("precision", ["single", "double"])
 @pytest.mark.parametrize("variant", ["auto", "generic", "no_tma", "slide", "tile", "window_a",
-                                     "window_32", "table_in_kernel", "window_ring", "window_rot", "window_fuse", "window_shift"])
+                                     "window_32", "table_in_kernel", "window_ring", "window_rot", "window_fuse", "window_shift", "pair_on", "pair_off",
+                                     "pair_sorted", "pair_table"])
 def test_mid_3d_radial_vs_oracle(precision, variant):
     """3-D radial, J=6, Kd=1.5N (BASELINE configs[4] scaled down) vs the live oracle."""
     from oracle import nufft_oracle as orc
@@ -144,7 +147,9 @@ def test_mid_3d_radial_vs_oracle(precision, variant):
             "window_a": {"adj_kernel": 3, "order_b": 0}, "window_32": {"win_lanes": 32},
             "table_in_kernel": {"precomp_weights": 0}, "window_ring": {"win_ring": 1},
             "window_rot": {"win_ring": 2}, "window_fuse": {"win_ring": 3},
-            "window_shift": {"win_ring": 0}}[variant]
+            "window_shift": {"win_ring": 0}, "pair_on": {"fwd_pair": 2},
+            "pair_off": {"fwd_pair": 0}, "pair_sorted": {"fwd_pair": 2, "fwd_interleave": 0},
+            "pair_table": {"fwd_pair": 2, "precomp_weights": 0}}[variant]
     A = NufftBase(Nd=Nd, omega=om, Jd=6, Kd=Kd, precision=precision, options=opts)
     eng = "reference" if orc.have_reference_engine() else "port"
     O = orc.OracleNufft(Nd=Nd, omega=om, Jd=6, Kd=Kd, precision=precision, engine=eng)
@@ -400,7 +405,8 @@ def test_wraparound_edges_vs_oracle(case, precision):
     # J > K: the reference's table builder raises IndexError there, its sparse mode works
     # (duplicate columns are summed, _nufft.py:854-873) -- so that case is checked in sparse mode
     mode = "sparse" if case == "J_gt_K" else "table"
-    A = NufftBase(Nd=Nd, omega=om, Jd=Jd, Kd=Kd, precision=precision, mode=mode)
+    A = NufftBase(Nd=Nd, omega=om, Jd=Jd, Kd=Kd, precision=precision, mode=mode,
+                  options={"fwd_pair": 2})       # pairs across periods are the corner case
     eng = "reference" if orc.have_reference_engine() else "port"
     O = orc.OracleNufft(Nd=Nd, omega=om, Jd=Jd, Kd=Kd, precision=precision, engine=eng, mode=mode)
     if mode == "table":
