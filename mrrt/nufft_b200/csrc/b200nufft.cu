@@ -550,14 +550,16 @@ static int set_points_t(b2n_plan* p, const void* coords, int64_t M, int kind, cu
     if ((rc = dev_alloc(p, (void**)&p->d_items, sizeof(int4) * (items.size() + 1)))) return rc;
     CU(cudaMemcpy(p->d_items, items.data(), sizeof(int4) * items.size(), cudaMemcpyHostToDevice));
     // forward slots: same-cell sample pairs share one pass over the window (tiled forward)
-    // fwd_pair: 0 off, 2 always, 1 (default) automatic = 3-D single precision, and only when
+    // fwd_pair: 0 off, 2 always, 1 (default) automatic = 3-D single precision with J >= 6, and only when
     // at least 10 % of the samples are partners.  Measured: the paired kernel doubles the
     // FMAs per shared-memory read, which pays where the forward kernel is shared-memory
     // bound (3-D float: 3.17 -> 2.30 ms) and costs where it is not (double: FP64 pipe,
-    // 6.3 -> 8.0 ms; 2-D: per-slot overhead, configs[3] 0.157 -> 0.197 ms).
+    // 6.3 -> 8.0 ms; 2-D: per-slot overhead, configs[3] 0.157 -> 0.197 ms; J = 4: 64 taps
+    // per sample are too few, configs[2] 0.176 -> 0.182 ms).
     const bool want_pairs = g.ndim >= 2 && !p->cplx_table &&
                             (p->opt_fwd_pair == 2 ||
-                             (p->opt_fwd_pair == 1 && g.ndim == 3 && p->precision == B2N_SINGLE));
+                             (p->opt_fwd_pair == 1 && g.ndim == 3 && p->precision == B2N_SINGLE &&
+                              g.J[0] >= 6));
     if (want_pairs) {
         int32_t *head = nullptr, *isslot = nullptr, *slotidx = nullptr, *bss = nullptr;
         CU(scratch.alloc(&head, sizeof(int32_t) * M));
