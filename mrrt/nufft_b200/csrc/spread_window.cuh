@@ -70,7 +70,7 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
                        const int32_t* __restrict__ pt_ko, const int32_t* __restrict__ pt_kw,
                        const int32_t* __restrict__ perm, const cplx_t<T>* __restrict__ samples,
                        cplx_t<T>* __restrict__ grid, const cplx_t<T>* __restrict__ phase_s,
-                       int pts_per_warp) {
+                       int pts_per_warp, int max_slide) {
     using C = cplx_t<T>;
     constexpr int R = J * J;
     constexpr int RPL = (R + G - 1) / G;
@@ -193,7 +193,9 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
                 qC = __shfl_up_sync(FULL, kC, 1, G);
             if (lg == 0) { qA = pkA; qB = pkB; qC = pkC; }
             const int d = kA - qA;
-            const int act = (kB == qB && kC == qC && d >= 0 && d < J) ? d : -1;
+            // slides longer than max_slide cells cost more instructions than flushing the
+            // whole window and starting a new one
+            const int act = (kB == qB && kC == qC && d >= 0 && d <= max_slide) ? d : -1;
             if (lg < cnt) actions[lane] = make_int4(kA, kB, kC, act);
             const int last = cnt > 0 ? cnt - 1 : 0;
             const int nA = __shfl_sync(FULL, kA, last, G), nB = __shfl_sync(FULL, kB, last, G),
@@ -435,6 +437,8 @@ static int launch_window(const Geom& g, const TablePtrs& tabs, int slide_axis, c
     const bool ring = (slide_axis & 256) != 0;
     const bool rot = (slide_axis & 512) != 0;     // bit 9: fixed ring with rotated weights
     const bool fuse = (slide_axis & 1024) != 0;   // bit 10: last shift fused into the FMAs
+    int max_slide = (slide_axis >> 12) & 15;      // bits 12-15: longest slide (0 = J - 1)
+    if (max_slide <= 0 || max_slide > J - 1) max_slide = J - 1;
     slide_axis &= 255;
     pts_per_warp = (pts_per_warp + 31) / 32 * 32;
     using C = cplx_t<T>;
@@ -459,7 +463,7 @@ static int launch_window(const Geom& g, const TablePtrs& tabs, int slide_axis, c
         k<<<gd, 128, (SMEM), st>>>(g, wa, (const T*)tabs.h[0], (const T*)tabs.h[1],                \
                                    (const T*)tabs.h[2], (const T*)tm_s, (const T*)wts, pt_ko, pt_kw, \
                                    perm, (const C*)samples, (C*)grid, (const C*)phase_s,           \
-                                   pts_per_warp);                                                  \
+                                   pts_per_warp, max_slide);                                       \
     } else if (lanes_per_sample == 16 && fuse) {                                                   \
         auto k = spread_window3d_kernel<T, J, TABV, 16, 3>;                                        \
         e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM));     \
@@ -467,7 +471,7 @@ static int launch_window(const Geom& g, const TablePtrs& tabs, int slide_axis, c
         k<<<gd, 128, (SMEM), st>>>(g, wa, (const T*)tabs.h[0], (const T*)tabs.h[1],                \
                                    (const T*)tabs.h[2], (const T*)tm_s, (const T*)wts, pt_ko, pt_kw, \
                                    perm, (const C*)samples, (C*)grid, (const C*)phase_s,           \
-                                   pts_per_warp);                                                  \
+                                   pts_per_warp, max_slide);                                       \
     } else if (lanes_per_sample == 16 && rot) {                                                    \
         auto k = spread_window3d_kernel<T, J, TABV, 16, 2>;                                        \
         e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM));     \
@@ -475,7 +479,7 @@ static int launch_window(const Geom& g, const TablePtrs& tabs, int slide_axis, c
         k<<<gd, 128, (SMEM), st>>>(g, wa, (const T*)tabs.h[0], (const T*)tabs.h[1],                \
                                    (const T*)tabs.h[2], (const T*)tm_s, (const T*)wts, pt_ko, pt_kw, \
                                    perm, (const C*)samples, (C*)grid, (const C*)phase_s,           \
-                                   pts_per_warp);                                                  \
+                                   pts_per_warp, max_slide);                                       \
     } else if (lanes_per_sample == 16 && ring) {                                                   \
         auto k = spread_window3d_kernel<T, J, TABV, 16, 1>;                                        \
         e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM));     \
@@ -483,7 +487,7 @@ static int launch_window(const Geom& g, const TablePtrs& tabs, int slide_axis, c
         k<<<gd, 128, (SMEM), st>>>(g, wa, (const T*)tabs.h[0], (const T*)tabs.h[1],                \
                                    (const T*)tabs.h[2], (const T*)tm_s, (const T*)wts, pt_ko, pt_kw, \
                                    perm, (const C*)samples, (C*)grid, (const C*)phase_s,           \
-                                   pts_per_warp);                                                  \
+                                   pts_per_warp, max_slide);                                       \
     } else if (lanes_per_sample == 16) {                                                           \
         auto k = spread_window3d_kernel<T, J, TABV, 16, 0>;                                           \
         e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM));     \
@@ -491,7 +495,7 @@ static int launch_window(const Geom& g, const TablePtrs& tabs, int slide_axis, c
         k<<<gd, 128, (SMEM), st>>>(g, wa, (const T*)tabs.h[0], (const T*)tabs.h[1],                \
                                    (const T*)tabs.h[2], (const T*)tm_s, (const T*)wts, pt_ko, pt_kw, \
                                    perm, (const C*)samples, (C*)grid, (const C*)phase_s,           \
-                                   pts_per_warp);                                                  \
+                                   pts_per_warp, max_slide);                                       \
     } else {                                                                                       \
         auto k = spread_window3d_kernel<T, J, TABV, 32, 0>;                                           \
         e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM));     \
@@ -499,7 +503,7 @@ static int launch_window(const Geom& g, const TablePtrs& tabs, int slide_axis, c
         k<<<gd, 128, (SMEM), st>>>(g, wa, (const T*)tabs.h[0], (const T*)tabs.h[1],                \
                                    (const T*)tabs.h[2], (const T*)tm_s, (const T*)wts, pt_ko, pt_kw, \
                                    perm, (const C*)samples, (C*)grid, (const C*)phase_s,           \
-                                   pts_per_warp);                                                  \
+                                   pts_per_warp, max_slide);                                       \
     }
     if (wts != nullptr) B2N_LAUNCH_WIN(2, stage_bytes)
     else if (tab_smem) B2N_LAUNCH_WIN(1, stage_bytes + (size_t)g.tlen[0] * sizeof(T))

@@ -440,3 +440,22 @@ def test_many_repetitions():
     xa = A.adj(y)
     assert xa.shape == (8, reps)
     assert rel_l2(xa[:, sel], O.adj(y[:, sel])) <= 1e-5
+
+
+@pytest.mark.parametrize("mode", ["table", "sparse"])
+@pytest.mark.parametrize("name,rtol,atol", [("d1_table_double_real", 1e-3, 1e-5),
+                                            ("d2_table_double_real_K32_J6", 1e-3, 1e-5),
+                                            ("d3_table_double_real", 1e-2, 1e-4)])
+def test_vs_exact_dtft(name, rtol, atol, mode):
+    """The reference's own acceptance test (tests/test_nufft.py:99-324): fft / adj against
+    the exact non-uniform DFT at its tolerances, here for the CUDA operator."""
+    from oracle import nufft_oracle as orc
+
+    from mrrt.nufft_b200 import NufftBase
+
+    cfg, z = load_case(name)
+    A = NufftBase(omega=z["omega"], on_gpu=True, **dict(ctor_kwargs(cfg), mode=mode))
+    y_true = orc.dtft(z["x"], z["omega"], A.Nd, A.n_shift)
+    np.testing.assert_allclose(A.fft(z["x"]), y_true, rtol=rtol, atol=atol)
+    x_true = orc.dtft_adj(z["y"], z["omega"], A.Nd, A.n_shift)
+    np.testing.assert_allclose(A.adj(z["y"]), x_true, rtol=rtol, atol=atol)
