@@ -149,6 +149,12 @@ interp_fwd_tiled_kernel(const __grid_constant__ CUtensorMap tmap, Geom g, TileSh
             i = (int)(u >> 1);
             pair = (u & 1u) != 0;
         }
+        // output positions first: their latency hides behind the gather
+        int pa = 0, pb = -1;
+        if (PAIR == 2) {
+            pa = __ldg(sa.perm + sidx);
+            pb = __ldg(sa.perm + ns + sidx);
+        }
         T w[NDIM][J];
         T wq[PAIR ? NDIM : 1][PAIR ? J : 1];   // partner's weights (zero when there is none)
         int c[NDIM];
@@ -156,7 +162,7 @@ interp_fwd_tiled_kernel(const __grid_constant__ CUtensorMap tmap, Geom g, TileSh
         for (int d = 0; d < NDIM; d++) {
             const int od = d == 0 ? o1 : (d == 1 ? o2 : o3);
             if (PAIR == 2) {
-                c[d] = sa.kw[(int64_t)d * ns + sidx] - od;
+                c[d] = __ldg(sa.kw + (int64_t)d * ns + sidx) - od;
 #pragma unroll
                 for (int j = 0; j < J; j++) {
                     const T2 ww = wts2[(int64_t)(d * J + j) * ns + sidx];
@@ -220,7 +226,6 @@ interp_fwd_tiled_kernel(const __grid_constant__ CUtensorMap tmap, Geom g, TileSh
             }
         }
         if (PAIR == 2) {
-            const int pa = sa.perm[sidx], pb = sa.perm[ns + sidx];
             if (sa.phase2 != nullptr) {
                 const C* __restrict__ ph2 = (const C*)sa.phase2;
                 s3 = cmul(s3, ph2[2 * (int64_t)sidx]);
