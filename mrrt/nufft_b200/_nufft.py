@@ -466,18 +466,36 @@ class NufftBase(object):
             for k in range(self.host_chunks):
                 lo, hi = shard_range(self.M, self.host_chunks, k)
                 self._children.append((lo, hi, NufftBase(self.Nd, self._omega_host[lo:hi], **kw)))
-            self._copy_stream = torch.cuda.Stream(device=self.device)
+            # one stream per copy direction: the two DMA directions of the link are
+            # independent, so the samples of one call can travel back while the inputs of
+            # the next call come in
+            self._h2d_stream = torch.cuda.Stream(device=self.device)
+            self._d2h_stream = torch.cuda.Stream(device=self.device)
         return self._children
+
+    def synchronize(self):
+        """Wait for every transform issued with ``non_blocking=True`` (and everything else
+        on this operator's streams); their host results are valid afterwards."""
+        with torch.cuda.device(self.device):
+            torch.cuda.current_stream(self.device).synchronize()
+            if self._children is not None:
+                self._h2d_stream.synchronize()
+                self._d2h_stream.synchronize()
 
     def _host_tensor(self, x):
         t = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.asarray(x))
         cdt = _TORCH_C[self._cplx_dtype]
         return t if t.dtype == cdt else t.to(cdt)
 
-    def _fft_host(self, x, kind):
+    def _fft_host(self, x, kind, non_blocking=False):
         """fft for a HOST array: H2D image, one spectrum, then per sample range the
         interpolation on the compute stream while the previous range's samples travel
-        back on the copy stream."""
+        back on the D2H stream.
+
+        Buffer lifetimes follow the caching allocator's stream rules: a buffer written by a
+        copy stream is allocated under that stream and ``record_stream``-ed for the compute
+        stream (and vice versa), so no host synchronisation is needed to keep it alive and
+        ``non_blocking=True`` can return while the copies are still in flight."""
         xt = self._host_tensor(x)
         if self.order == "C":
             xt = self._swap_reps(xt, self.nargin1)
@@ -490,24 +508,29 @@ class NufftBase(object):
         cdt = _TORCH_C[self._cplx_dtype]
         with torch.cuda.device(self.device):
             main = torch.cuda.current_stream(self.device)
+            h2d, d2h = self._h2d_stream, self._d2h_stream
             mem_h = _f_order_memory(xt, self.Nd).reshape(n_reps, self.nargin1)
-            mem = mem_h.to(self.device, non_blocking=True)
+            with torch.cuda.stream(h2d):
+                mem = torch.empty(mem_h.shape, dtype=cdt, device=self.device)
+                mem.copy_(mem_h, non_blocking=True)
+            mem.record_stream(main)
+            main.wait_stream(h2d)
             grid = torch.empty((n_reps, _prod(self.Kd)), dtype=cdt, device=self.device)
             _lib.check(self._lib.b2n_grid_fwd(self._plan, mem.data_ptr(), grid.data_ptr(), n_reps,
                                               self._stream()))
             out_h = torch.empty((n_reps, self.M), dtype=cdt, pin_memory=True)
-            keep = []
             for lo, hi, ch in children:
                 out_k = torch.empty((n_reps, hi - lo), dtype=cdt, device=self.device)
                 _lib.check(self._lib.b2n_interp_fwd(ch._plan, grid.data_ptr(), out_k.data_ptr(),
                                                     n_reps, 1, self._stream()))
                 ev = torch.cuda.Event()
                 ev.record(main)
-                with torch.cuda.stream(self._copy_stream):
-                    self._copy_stream.wait_event(ev)
+                out_k.record_stream(d2h)
+                with torch.cuda.stream(d2h):
+                    d2h.wait_event(ev)
                     out_h[:, lo:hi].copy_(out_k, non_blocking=True)
-                keep.append(out_k)
-            self._copy_stream.synchronize()
+            if not non_blocking:
+                d2h.synchronize()
         out = out_h.t()
         if n_reps == 1:
             out = out[..., 0]
@@ -515,9 +538,10 @@ class NufftBase(object):
             out = self._unswap_reps(out, self.nargout1)
         return out.numpy() if kind.kind == "numpy" else out
 
-    def _adj_host(self, k, kind):
-        """adj for a HOST array: sample ranges are copied in on the copy stream while the
-        previous range is gridded (accumulating into one grid) on the compute stream."""
+    def _adj_host(self, k, kind, non_blocking=False):
+        """adj for a HOST array: sample ranges are copied in on the H2D stream while the
+        previous range is gridded (accumulating into one grid) on the compute stream; the
+        image travels back on the D2H stream."""
         kt = self._host_tensor(k)
         if self.order == "C":
             kt = self._swap_reps(kt, self.nargout1)
@@ -528,26 +552,32 @@ class NufftBase(object):
         cdt = _TORCH_C[self._cplx_dtype]
         with torch.cuda.device(self.device):
             main = torch.cuda.current_stream(self.device)
+            h2d, d2h = self._h2d_stream, self._d2h_stream
             mem_h = _f_order_memory(kt, (self.M,)).reshape(n_reps, self.M)
             grid = torch.empty((n_reps, _prod(self.Kd)), dtype=cdt, device=self.device)
-            keep = []
             for idx, (lo, hi, ch) in enumerate(children):
-                buf = torch.empty((n_reps, hi - lo), dtype=cdt, device=self.device)
                 ev = torch.cuda.Event()
-                with torch.cuda.stream(self._copy_stream):
+                with torch.cuda.stream(h2d):
+                    buf = torch.empty((n_reps, hi - lo), dtype=cdt, device=self.device)
                     buf.copy_(mem_h[:, lo:hi], non_blocking=True)
-                    ev.record(self._copy_stream)
+                    ev.record(h2d)
+                buf.record_stream(main)
                 main.wait_event(ev)
                 # bit 0: apply the sample phase, bit 1: accumulate into the grid
                 _lib.check(self._lib.b2n_interp_adj(ch._plan, buf.data_ptr(), grid.data_ptr(), n_reps,
                                                     1 | (2 if idx > 0 else 0), self._stream()))
-                keep.append(buf)
             out = torch.empty((n_reps,) + tuple(reversed(self.Nd)), dtype=cdt, device=self.device)
             _lib.check(self._lib.b2n_grid_adj(self._plan, grid.data_ptr(), out.data_ptr(), n_reps,
                                               self._stream()))
             out_h = torch.empty(out.shape, dtype=cdt, pin_memory=True)
-            out_h.copy_(out, non_blocking=False)
-            self._copy_stream.synchronize()
+            ev = torch.cuda.Event()
+            ev.record(main)
+            out.record_stream(d2h)
+            with torch.cuda.stream(d2h):
+                d2h.wait_event(ev)
+                out_h.copy_(out, non_blocking=True)
+            if not non_blocking:
+                d2h.synchronize()
         x = out_h.permute(*reversed(range(out_h.dim())))
         if n_reps == 1:
             x = x[..., 0]
@@ -555,16 +585,21 @@ class NufftBase(object):
             x = self._unswap_reps(x, self.nargin1)
         return x.numpy() if kind.kind == "numpy" else x
 
-    def fft(self, x):
+    def fft(self, x, non_blocking=False):
         """Forward NUFFT (uniform spatial -> non-uniform frequency).
 
         ``x`` has shape ``Nd`` (plus a trailing repetition axis for ``order="F"``, a
         leading one for ``order="C"``).  Returns ``(M,)`` / ``(M, reps)`` / ``(reps, M)``.
         Reference: _nufft.py:425-452.
+
+        ``non_blocking=True`` (pinned HOST torch tensors with ``host_chunks > 1`` only; as
+        in ``torch.Tensor.to``): the call returns a pinned host tensor while its copies are
+        still in flight, so the host<->device traffic of consecutive calls overlaps in both
+        link directions; the result is valid after ``synchronize()``.
         """
         kind = _ArrayKind(x)
         if self._pipelined(kind):
-            return self._fft_host(x, kind)
+            return self._fft_host(x, kind, non_blocking and kind.kind == "torch" and kind.pinned)
         xt = kind.to_torch(x, self.device)
         if self.order == "C":
             xt = self._swap_reps(xt, self.nargin1)
@@ -573,12 +608,12 @@ class NufftBase(object):
             k = self._unswap_reps(k, self.nargout1)
         return kind.from_torch(k)
 
-    def adj(self, k):
+    def adj(self, k, non_blocking=False):
         """Adjoint NUFFT (non-uniform frequency -> uniform spatial).
-        Reference: _nufft.py:454-482."""
+        Reference: _nufft.py:454-482.  ``non_blocking``: see ``fft``."""
         kind = _ArrayKind(k)
         if self._pipelined(kind):
-            return self._adj_host(k, kind)
+            return self._adj_host(k, kind, non_blocking and kind.kind == "torch" and kind.pinned)
         kt = kind.to_torch(k, self.device)
         if self.order == "C":
             kt = self._swap_reps(kt, self.nargout1)
