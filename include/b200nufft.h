@@ -144,6 +144,21 @@ int b2n_nufft_fwd(b2n_plan *plan, const void *image_dev, void *samples_dev, int 
 int b2n_nufft_adj(b2n_plan *plan, const void *samples_dev, void *image_dev, int nbatch,
                   void *stream);
 
+/* Coil-sensitivity encoding fused around the full transforms.
+ * The reference's callers (mrrt.operators / mrrt.mri MRI_Operator, named at _nufft.py:3-5
+ * and :200-201; not in its tree) multiply the image by the coil maps before NufftBase.fft
+ * and conjugate-multiply-and-sum the coil images after NufftBase.adj; here those steps are
+ * part of the scale/zero-pad kernel and of the crop/scale kernel, so the coil images never
+ * travel through HBM.
+ *   forward: samples[:, c] = NUFFT(image * smaps[:, c])                    c = 0..ncoil-1
+ *   adjoint: image = sum_c conj(smaps[:, c]) * NUFFT^H(samples[:, c])
+ * image_dev complex[prod(Nd)]; smaps_dev complex[prod(Nd) * ncoil] (coil slowest);
+ * samples_dev complex[M * ncoil] (coil slowest); all in the precision dtype. */
+int b2n_sense_fwd(b2n_plan *plan, const void *image_dev, const void *smaps_dev,
+                  void *samples_dev, int ncoil, void *stream);
+int b2n_sense_adj(b2n_plan *plan, const void *samples_dev, const void *smaps_dev,
+                  void *image_dev, int ncoil, void *stream);
+
 /* Sparse mode.  coef[d]: DEVICE [Jd[d], M] (tap fastest) per-axis coefficient, double
  * (real table) or interleaved complex double; kidx[d]: DEVICE int32 [Jd[d], M] wrapped
  * grid index per tap.  The ELL matrix (prod(Jd) entries per row) is formed on the device

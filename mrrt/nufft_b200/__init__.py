@@ -4,6 +4,7 @@ double precision).  Host code is Python; all transforms run in pre-built CUDA lo
 through a C ABI (include/b200nufft.h).  No CPU fallback."""
 from ._kernels import BeattyKernel, KaiserBesselKernel, kaiser_bessel, kaiser_bessel_ft
 from ._nufft import NufftBase, nufft_adj, nufft_forward
+from ._sense import SenseNufft
 from ._sharded import CoilShardedNufft, SampleShardedNufft, shard_range
 
 __all__ = [
@@ -17,5 +18,6 @@ __all__ = [
     "SampleShardedNufft",
     "CoilShardedNufft",
     "shard_range",
+    "SenseNufft",
 ]
 __version__ = "0.1.0"

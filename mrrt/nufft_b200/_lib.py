@@ -46,6 +46,8 @@ SIGNATURES = {
     "b2n_grid_adj": (c_int, [c_vp, c_vp, c_vp, c_int, c_vp]),
     "b2n_nufft_fwd": (c_int, [c_vp, c_vp, c_vp, c_int, c_vp]),
     "b2n_nufft_adj": (c_int, [c_vp, c_vp, c_vp, c_int, c_vp]),
+    "b2n_sense_fwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_vp]),
+    "b2n_sense_adj": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_vp]),
     "b2n_plan_set_sparse": (c_int, [c_vp, PP, PP, c_i64, c_vp, c_vp]),
     "b2n_plan_sparse_nnz": (c_i64, [c_vp]),
     "b2n_plan_get_sparse": (c_int, [c_vp, c_vp, c_vp, c_vp]),

@@ -274,10 +274,16 @@ struct AxisPtrs {
 // array re-formed on the fly: ((s1*s2)*s3) in double, then cast (:737-748).
 // One thread handles VEC consecutive cells of a grid row, so the row decode (integer
 // divisions) is amortised and the stores are 16-32 bytes wide.
-template <typename T, int VEC>
+//
+// SENSE = true (b2n_sense_fwd): ONE image is encoded by nbatch coil sensitivity maps,
+// grid[b] = pad((x * smaps[b]) * sn): the coil images x * smaps[b] that a caller of the
+// reference forms before NufftBase.fft (mrrt.operators' MRI_Operator, _nufft.py:3-5) are
+// never written to memory.  Same rounding order as the unfused sequence.
+template <typename T, int VEC, bool SENSE = false>
 __global__ void pre_scale_pad_kernel(Geom g, AxisPtrs ax, T fwd_scale, int apply_scale,
                                      const cplx_t<T>* __restrict__ image,
-                                     cplx_t<T>* __restrict__ grid, int nbatch) {
+                                     cplx_t<T>* __restrict__ grid, int nbatch,
+                                     const cplx_t<T>* __restrict__ smaps = nullptr) {
     using C = cplx_t<T>;
     const int cpr = (g.K[0] + VEC - 1) / VEC;               // chunks per row
     const int64_t rows = (g.PK / g.K[0]) * nbatch;
@@ -292,7 +298,7 @@ __global__ void pre_scale_pad_kernel(Geom g, AxisPtrs ax, T fwd_scale, int apply
         const int64_t b = g.ndim > 2 ? r2 / g.K[2] : r2;
         const bool row_in = (g.ndim < 2 || k2 < g.N[1]) && (g.ndim < 3 || k3 < g.N[2]);
         double s23 = 1.0;
-        int64_t nrow = b * g.PN;
+        int64_t nrow = SENSE ? 0 : b * g.PN;
         if (row_in) {
             if (g.ndim > 1) nrow += (int64_t)k2 * g.N[0];
             if (g.ndim > 2) nrow += (int64_t)k3 * g.N[0] * g.N[1];
@@ -307,7 +313,11 @@ __global__ void pre_scale_pad_kernel(Geom g, AxisPtrs ax, T fwd_scale, int apply
                 if (g.ndim > 1) s *= ax.sn[1][k2];
                 if (g.ndim > 2) s *= ax.sn[2][k3];
                 const T st = (T)s;
-                const C x = image[nrow + k1];
+                C x = image[nrow + k1];
+                if (SENSE) {
+                    const C c = smaps[b * g.PN + nrow + k1];
+                    x = make_c<T>(x.x * c.x - x.y * c.y, x.x * c.y + x.y * c.x);
+                }
                 v[e] = make_c<T>(x.x * st, x.y * st);
                 if (apply_scale) { v[e].x *= fwd_scale; v[e].y *= fwd_scale; }
             }
@@ -426,6 +436,41 @@ __global__ void post_crop_scale_kernel(Geom g, AxisPtrs ax, T adj_scale, int app
         C v = grid[b * g.PK + k];
         if (apply_scale) { v.x *= adj_scale; v.y *= adj_scale; }
         image[idx] = make_c<T>(v.x * st, v.y * st);
+    }
+}
+
+// image[n] = sum_b conj(smaps[b][n]) * (grid[b][n (corner)] * adj_scale * sn[n]):
+// the crop/scale of every coil (as post_crop_scale_kernel) and the coil combination a
+// caller of the reference performs after NufftBase.adj, without writing the coil images.
+// Coils are summed in index order in the precision dtype, like the unfused sequence.
+template <typename T>
+__global__ void sense_crop_combine_kernel(Geom g, AxisPtrs ax, T adj_scale, int apply_scale,
+                                          const cplx_t<T>* __restrict__ grid,
+                                          const cplx_t<T>* __restrict__ smaps,
+                                          cplx_t<T>* __restrict__ image, int ncoil) {
+    using C = cplx_t<T>;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < g.PN;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = idx;
+        const int n1 = (int)(r % g.N[0]);
+        r /= g.N[0];
+        const int n2 = g.ndim > 1 ? (int)(r % g.N[1]) : 0;
+        const int n3 = g.ndim > 2 ? (int)(r / g.N[1]) : 0;
+        double s = ax.sn[0][n1];
+        int64_t k = n1;
+        if (g.ndim > 1) { s *= ax.sn[1][n2]; k += (int64_t)n2 * g.K[0]; }
+        if (g.ndim > 2) { s *= ax.sn[2][n3]; k += (int64_t)n3 * g.K[0] * g.K[1]; }
+        const T st = (T)s;
+        C acc = make_c<T>(0, 0);
+        for (int b = 0; b < ncoil; b++) {
+            C v = grid[b * g.PK + k];
+            if (apply_scale) { v.x *= adj_scale; v.y *= adj_scale; }
+            v = make_c<T>(v.x * st, v.y * st);
+            const C c = smaps[b * g.PN + idx];
+            acc.x += c.x * v.x + c.y * v.y;
+            acc.y += c.x * v.y - c.y * v.x;
+        }
+        image[idx] = acc;
     }
 }
 

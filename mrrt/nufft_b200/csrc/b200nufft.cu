@@ -1240,16 +1240,22 @@ static AxisPtrs axis_ptrs(b2n_plan* p) {
 }
 
 // image -> oversampled spectrum on the Kd grid (scale, zero-pad, FFT, phase_before)
+// (smaps != nullptr: one image times nbatch coil maps, see pre_scale_pad_kernel)
 template <typename T>
-static int grid_fwd_t(b2n_plan* p, const void* image, void* grid, int nbatch, cudaStream_t st) {
+static int grid_fwd_t(b2n_plan* p, const void* image, void* grid, int nbatch, cudaStream_t st,
+                      const void* smaps = nullptr) {
     using C = cplx_t<T>;
     const Geom& g = p->g;
     int rc;
     AxisPtrs ax = axis_ptrs(p);
     C* work = (C*)grid;
     constexpr int VEC = 32 / (int)sizeof(C);   // 32 bytes of grid per thread
-    pre_scale_pad_kernel<T, VEC><<<grid_for(g.PK * nbatch / VEC + 1, 256, p->sm_count, 32), 256, 0, st>>>(
-        g, ax, (T)p->fwd_scale, p->fwd_scale != 1.0, (const C*)image, work, nbatch);
+    if (smaps != nullptr)
+        pre_scale_pad_kernel<T, VEC, true><<<grid_for(g.PK * nbatch / VEC + 1, 256, p->sm_count, 32), 256, 0, st>>>(
+            g, ax, (T)p->fwd_scale, p->fwd_scale != 1.0, (const C*)image, work, nbatch, (const C*)smaps);
+    else
+        pre_scale_pad_kernel<T, VEC><<<grid_for(g.PK * nbatch / VEC + 1, 256, p->sm_count, 32), 256, 0, st>>>(
+            g, ax, (T)p->fwd_scale, p->fwd_scale != 1.0, (const C*)image, work, nbatch);
     CU(cudaGetLastError());
     if ((rc = run_fft<T>(p, work, nbatch, CUFFT_FORWARD, st))) return rc;
     p->launches += 1;
@@ -1263,8 +1269,10 @@ static int grid_fwd_t(b2n_plan* p, const void* image, void* grid, int nbatch, cu
 }
 
 // gridded spectrum -> image (conj phase_before, inverse FFT, crop, scale); grid is overwritten
+// (smaps != nullptr: the nbatch coil images are combined into one, see sense_crop_combine_kernel)
 template <typename T>
-static int grid_adj_t(b2n_plan* p, void* grid, void* image, int nbatch, cudaStream_t st) {
+static int grid_adj_t(b2n_plan* p, void* grid, void* image, int nbatch, cudaStream_t st,
+                      const void* smaps = nullptr) {
     using C = cplx_t<T>;
     const Geom& g = p->g;
     int rc;
@@ -1278,20 +1286,26 @@ static int grid_adj_t(b2n_plan* p, void* grid, void* image, int nbatch, cudaStre
         p->launches++;
     }
     if ((rc = run_fft<T>(p, work, nbatch, CUFFT_INVERSE, st))) return rc;
-    post_crop_scale_kernel<T><<<grid_for(g.PN * nbatch, 256, p->sm_count, 32), 256, 0, st>>>(
-        g, ax, (T)p->adj_scale, p->adj_scale != 1.0, work, (C*)image, nbatch);
+    if (smaps != nullptr)
+        sense_crop_combine_kernel<T><<<grid_for(g.PN, 256, p->sm_count, 32), 256, 0, st>>>(
+            g, ax, (T)p->adj_scale, p->adj_scale != 1.0, work, (const C*)smaps, (C*)image, nbatch);
+    else
+        post_crop_scale_kernel<T><<<grid_for(g.PN * nbatch, 256, p->sm_count, 32), 256, 0, st>>>(
+            g, ax, (T)p->adj_scale, p->adj_scale != 1.0, work, (C*)image, nbatch);
     CU(cudaGetLastError());
     p->launches += 1;
     return B2N_OK;
 }
 
-static int grid_fwd(b2n_plan* p, const void* image, void* grid, int nbatch, cudaStream_t st) {
-    return p->precision == B2N_SINGLE ? grid_fwd_t<float>(p, image, grid, nbatch, st)
-                                      : grid_fwd_t<double>(p, image, grid, nbatch, st);
+static int grid_fwd(b2n_plan* p, const void* image, void* grid, int nbatch, cudaStream_t st,
+                    const void* smaps = nullptr) {
+    return p->precision == B2N_SINGLE ? grid_fwd_t<float>(p, image, grid, nbatch, st, smaps)
+                                      : grid_fwd_t<double>(p, image, grid, nbatch, st, smaps);
 }
-static int grid_adj(b2n_plan* p, void* grid, void* image, int nbatch, cudaStream_t st) {
-    return p->precision == B2N_SINGLE ? grid_adj_t<float>(p, grid, image, nbatch, st)
-                                      : grid_adj_t<double>(p, grid, image, nbatch, st);
+static int grid_adj(b2n_plan* p, void* grid, void* image, int nbatch, cudaStream_t st,
+                    const void* smaps = nullptr) {
+    return p->precision == B2N_SINGLE ? grid_adj_t<float>(p, grid, image, nbatch, st, smaps)
+                                      : grid_adj_t<double>(p, grid, image, nbatch, st, smaps);
 }
 
 extern "C" int b2n_grid_fwd(b2n_plan* p, const void* image_dev, void* grid_dev, int nbatch,
@@ -1313,21 +1327,23 @@ extern "C" int b2n_grid_adj(b2n_plan* p, void* grid_dev, void* image_dev, int nb
     return grid_adj(p, grid_dev, image_dev, nbatch, (cudaStream_t)stream);
 }
 
-static int nufft_fwd_impl(b2n_plan* p, const void* image, void* samples, int nbatch, cudaStream_t st) {
+static int nufft_fwd_impl(b2n_plan* p, const void* image, void* samples, int nbatch, cudaStream_t st,
+                          const void* smaps = nullptr) {
     int rc;
     if ((rc = ensure_work(p, nbatch))) return rc;
-    if ((rc = grid_fwd(p, image, p->d_work, nbatch, st))) return rc;
+    if ((rc = grid_fwd(p, image, p->d_work, nbatch, st, smaps))) return rc;
     if (p->opt_sparse_mode) return spmv_impl(p, true, p->d_work, samples, nbatch, p->d_phase_s != nullptr, st);
     return interp_fwd_impl(p, p->d_work, samples, nbatch, p->d_phase_s != nullptr, st);
 }
 
-static int nufft_adj_impl(b2n_plan* p, const void* samples, void* image, int nbatch, cudaStream_t st) {
+static int nufft_adj_impl(b2n_plan* p, const void* samples, void* image, int nbatch, cudaStream_t st,
+                          const void* smaps = nullptr) {
     int rc;
     if ((rc = ensure_work(p, nbatch))) return rc;
     if (p->opt_sparse_mode) rc = spmv_impl(p, false, samples, p->d_work, nbatch, p->d_phase_s != nullptr, st);
     else rc = interp_adj_impl(p, samples, p->d_work, nbatch, p->d_phase_s != nullptr, st);
     if (rc) return rc;
-    return grid_adj(p, p->d_work, image, nbatch, st);
+    return grid_adj(p, p->d_work, image, nbatch, st, smaps);
 }
 
 extern "C" int b2n_nufft_fwd(b2n_plan* p, const void* image_dev, void* samples_dev, int nbatch,
@@ -1348,4 +1364,25 @@ extern "C" int b2n_nufft_adj(b2n_plan* p, const void* samples_dev, void* image_d
     if (!p->scaling_set) return fail(B2N_ESTATE, "scaling not set");
     CU(cudaSetDevice(p->device));
     return nufft_adj_impl(p, samples_dev, image_dev, nbatch, (cudaStream_t)stream);
+}
+
+// Coil-sensitivity encoding fused around the transforms.
+extern "C" int b2n_sense_fwd(b2n_plan* p, const void* image_dev, const void* smaps_dev,
+                             void* samples_dev, int ncoil, void* stream) {
+    int rc = check_ready(p, image_dev, samples_dev, ncoil);
+    if (rc) return rc;
+    if (image_dev == nullptr || smaps_dev == nullptr) return fail(B2N_EINVAL, "NULL array");
+    if (!p->scaling_set) return fail(B2N_ESTATE, "scaling not set");
+    CU(cudaSetDevice(p->device));
+    return nufft_fwd_impl(p, image_dev, samples_dev, ncoil, (cudaStream_t)stream, smaps_dev);
+}
+
+extern "C" int b2n_sense_adj(b2n_plan* p, const void* samples_dev, const void* smaps_dev,
+                             void* image_dev, int ncoil, void* stream) {
+    int rc = check_ready(p, samples_dev, image_dev, ncoil);
+    if (rc) return rc;
+    if (image_dev == nullptr || smaps_dev == nullptr) return fail(B2N_EINVAL, "NULL array");
+    if (!p->scaling_set) return fail(B2N_ESTATE, "scaling not set");
+    CU(cudaSetDevice(p->device));
+    return nufft_adj_impl(p, samples_dev, image_dev, ncoil, (cudaStream_t)stream, smaps_dev);
 }

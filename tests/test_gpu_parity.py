@@ -308,6 +308,16 @@ def test_host_pipeline_matches_golden(name):
     yt = A.fft(xt)
     assert isinstance(yt, torch.Tensor) and not yt.is_cuda
     assert rel_l2(yt.numpy(), z["y"]) <= tol
+    # non-blocking calls: several transforms in flight, results valid after synchronize()
+    kt = torch.from_numpy(np.asfortranarray(z["y"]).astype(A._cplx_dtype)).pin_memory()
+    outs = []
+    for _ in range(3):
+        outs.append((A.fft(xt, non_blocking=True), A.adj(kt, non_blocking=True)))
+    A.synchronize()
+    for y_nb, x_nb in outs:
+        assert not y_nb.is_cuda and y_nb.is_pinned() and x_nb.is_pinned()
+        assert rel_l2(y_nb.numpy(), z["y"]) <= tol
+        assert rel_l2(x_nb.numpy(), z["x_adj"]) <= tol
 
 
 def test_array_kinds_and_dtypes():
@@ -459,3 +469,57 @@ def test_vs_exact_dtft(name, rtol, atol, mode):
     np.testing.assert_allclose(A.fft(z["x"]), y_true, rtol=rtol, atol=atol)
     x_true = orc.dtft_adj(z["y"], z["omega"], A.Nd, A.n_shift)
     np.testing.assert_allclose(A.adj(z["y"]), x_true, rtol=rtol, atol=atol)
+
+
+@pytest.mark.parametrize("case", ["2d_single_table", "2d_double_sparse", "3d_single_table",
+                                  "3d_double_table_ortho", "1d_double_complex"])
+def test_sense_fused_vs_oracle(case):
+    """Coil-sensitivity encoding fused around the transforms: fft / adj / norm
+    of `SenseNufft` against the reference sequence -- multiply by the maps, the oracle's
+    NufftBase.fft per coil; its adj per coil, conjugate-multiply and sum -- and against the
+    same sequence through the unfused CUDA operator."""
+    from oracle import nufft_oracle as orc
+    from mrrt.nufft_b200 import NufftBase, SenseNufft
+
+    spec = {
+        "2d_single_table": dict(Nd=(48, 40), Kd=(72, 64), Jd=6, precision="single", mode="table", nc=5),
+        "2d_double_sparse": dict(Nd=(32, 32), Kd=(64, 64), Jd=5, precision="double", mode="sparse", nc=3),
+        "3d_single_table": dict(Nd=(24, 20, 16), Kd=(36, 32, 24), Jd=6, precision="single", mode="table", nc=4),
+        "3d_double_table_ortho": dict(Nd=(16, 16, 12), Kd=(24, 24, 20), Jd=4, precision="double",
+                                      mode="table", nc=2, ortho=True, n_shift=(8, 8, 6)),
+        "1d_double_complex": dict(Nd=(64,), Kd=(128,), Jd=6, precision="double", mode="table", nc=1,
+                                  phasing="complex"),
+    }[case]
+    nc = spec.pop("nc")
+    Nd = spec["Nd"]
+    rs = np.random.RandomState(len(case))
+    rdt = np.float32 if spec["precision"] == "single" else np.float64
+    om = ((rs.rand(6000, len(Nd)) * 2 - 1) * np.pi).astype(rdt)
+    S = SenseNufft(omega=om, smaps=rs.standard_normal(Nd + (nc,)) + 1j * rs.standard_normal(Nd + (nc,)),
+                   **spec)
+    smaps = S.smaps.cpu().numpy()
+    A = NufftBase(omega=om, **spec)
+    O = orc.OracleNufft(omega=om, **spec)
+    cdt = A._cplx_dtype
+    tol = TOL[spec["precision"]]
+    x = (rs.standard_normal(Nd) + 1j * rs.standard_normal(Nd)).astype(cdt)
+    coil_imgs = (x[..., None] * smaps).astype(cdt)
+    yo = O.fft(coil_imgs).reshape(A.M, nc)
+    y = S.fft(x)
+    assert isinstance(y, np.ndarray) and y.shape == (A.M, nc) and y.dtype == cdt
+    assert rel_l2(y, yo) <= tol
+    assert rel_l2(y, A.fft(coil_imgs).reshape(A.M, nc)) <= tol / 4
+    xo = np.sum(np.conj(smaps) * O.adj(yo).reshape(Nd + (nc,)), axis=-1)
+    xa = S.adj(yo)
+    assert xa.shape == Nd and xa.dtype == cdt
+    assert rel_l2(xa, xo) <= tol
+    xu = np.sum(np.conj(smaps) * A.adj(yo).reshape(Nd + (nc,)), axis=-1)
+    assert rel_l2(xa, xu) <= tol / 4
+    assert rel_l2(S.norm(x), np.sum(np.conj(smaps) * O.adj(O.fft(coil_imgs)).reshape(Nd + (nc,)),
+                                    axis=-1)) <= 2 * tol
+    with pytest.raises(ValueError):
+        S.fft(np.zeros(Nd + (2,)))
+    with pytest.raises(ValueError):
+        S.adj(np.zeros(A.M * nc + 1))
+    with pytest.raises(ValueError):
+        SenseNufft(omega=om, smaps=np.zeros((3,) + Nd), **spec)
