@@ -490,6 +490,13 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
+    # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its
+    # version banner to fd 1 when NCCL_DEBUG is set on the box), so fd 1 is pointed at
+    # stderr for the duration of the run and the JSON line goes to the real stdout.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
     if args.impl == "reference":
         run_reference_arm(args)
     elif args.workload == "coils":
