@@ -138,6 +138,15 @@ int b2n_grid_fwd(b2n_plan *plan, const void *image_dev, void *grid_dev, int nbat
                  void *stream);
 int b2n_grid_adj(b2n_plan *plan, void *grid_dev, void *image_dev, int nbatch, void *stream);
 
+/* grid_dev[b][k] *= kernel_dev[k] (complex, precision dtype) for b < nbatch: the middle
+ * step of the Toeplitz normal operator (the reference only hints at
+ * it with return_psf, _nufft.py:1459,1495,1517-1518): on a plan with Kd = 2*Nd, unit
+ * deapodization and no phase_before, b2n_grid_fwd (zero-pad + FFT), this call with the
+ * spectrum of the point-spread function, and b2n_grid_adj (inverse FFT + crop + scale)
+ * apply A^H W A without touching the non-uniform samples. */
+int b2n_grid_multiply(b2n_plan *plan, void *grid_dev, const void *kernel_dev, int nbatch,
+                      void *stream);
+
 /* Full transforms.  image_dev: complex[prod(Nd) * nbatch] first axis fastest. */
 int b2n_nufft_fwd(b2n_plan *plan, const void *image_dev, void *samples_dev, int nbatch,
                   void *stream);

@@ -5,6 +5,7 @@ through a C ABI (include/b200nufft.h).  No CPU fallback."""
 from ._kernels import BeattyKernel, KaiserBesselKernel, kaiser_bessel, kaiser_bessel_ft
 from ._nufft import NufftBase, nufft_adj, nufft_forward
 from ._sense import SenseNufft
+from ._toeplitz import ToeplitzNorm
 from ._sharded import CoilShardedNufft, SampleShardedNufft, shard_range
 
 __all__ = [
@@ -19,5 +20,6 @@ __all__ = [
     "CoilShardedNufft",
     "shard_range",
     "SenseNufft",
+    "ToeplitzNorm",
 ]
 __version__ = "0.1.0"

@@ -44,6 +44,7 @@ SIGNATURES = {
     "b2n_interp_adj": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_vp]),
     "b2n_grid_fwd": (c_int, [c_vp, c_vp, c_vp, c_int, c_vp]),
     "b2n_grid_adj": (c_int, [c_vp, c_vp, c_vp, c_int, c_vp]),
+    "b2n_grid_multiply": (c_int, [c_vp, c_vp, c_vp, c_int, c_vp]),
     "b2n_nufft_fwd": (c_int, [c_vp, c_vp, c_vp, c_int, c_vp]),
     "b2n_nufft_adj": (c_int, [c_vp, c_vp, c_vp, c_int, c_vp]),
     "b2n_sense_fwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_vp]),

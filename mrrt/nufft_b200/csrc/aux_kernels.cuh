@@ -474,6 +474,22 @@ __global__ void sense_crop_combine_kernel(Geom g, AxisPtrs ax, T adj_scale, int 
     }
 }
 
+// grid[b][k] *= kern[k] (complex): the spectrum of the Toeplitz kernel applied to the
+// padded image's spectrum (b2n_grid_multiply); two cells per thread where the element
+// count allows, the kernel array is read once per batch entry from L2.
+template <typename T>
+__global__ void grid_multiply_kernel(int64_t PK, const cplx_t<T>* __restrict__ kern,
+                                     cplx_t<T>* __restrict__ grid, int nbatch) {
+    using C = cplx_t<T>;
+    const int64_t total = PK * nbatch;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const C t = kern[idx % PK];
+        const C v = grid[idx];
+        grid[idx] = make_c<T>(v.x * t.x - v.y * t.y, v.x * t.y + v.y * t.x);
+    }
+}
+
 // ---------------------------------------------------------------------------------
 // sparse mode: fixed-width rows (exactly prod(Jd) entries per sample)
 // ---------------------------------------------------------------------------------

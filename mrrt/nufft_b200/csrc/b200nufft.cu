@@ -1386,3 +1386,26 @@ extern "C" int b2n_sense_adj(b2n_plan* p, const void* samples_dev, const void* s
     CU(cudaSetDevice(p->device));
     return nufft_adj_impl(p, samples_dev, image_dev, ncoil, (cudaStream_t)stream, smaps_dev);
 }
+
+// grid[b] *= kernel (pointwise, complex) for every batch entry: the middle step of the
+// Toeplitz normal operator (pad + FFT by b2n_grid_fwd, this, inverse FFT + crop by
+// b2n_grid_adj on a plan with Kd = 2 Nd).
+extern "C" int b2n_grid_multiply(b2n_plan* p, void* grid_dev, const void* kernel_dev, int nbatch,
+                                 void* stream) {
+    if (p == nullptr) return fail(B2N_EINVAL, "NULL plan");
+    if (nbatch < 1) return fail(B2N_EINVAL, "nbatch must be >= 1");
+    if (grid_dev == nullptr || kernel_dev == nullptr) return fail(B2N_EINVAL, "NULL array");
+    CU(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const Geom& g = p->g;
+    const int nb = grid_for(g.PK * nbatch, 256, p->sm_count, 32);
+    if (p->precision == B2N_SINGLE)
+        grid_multiply_kernel<float><<<nb, 256, 0, st>>>(g.PK, (const cplx_t<float>*)kernel_dev,
+                                                        (cplx_t<float>*)grid_dev, nbatch);
+    else
+        grid_multiply_kernel<double><<<nb, 256, 0, st>>>(g.PK, (const cplx_t<double>*)kernel_dev,
+                                                         (cplx_t<double>*)grid_dev, nbatch);
+    CU(cudaGetLastError());
+    p->launches += 1;
+    return B2N_OK;
+}
