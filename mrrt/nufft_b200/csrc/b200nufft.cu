@@ -69,6 +69,8 @@ struct b2n_plan {
     // register-window adjoint: 0 register shifts, 1 lane ring, 2 fixed ring with rotated
     // weights, 3 last shift of a slide fused into the FMAs (default; fastest measured)
     long opt_win_ring = 3;
+    long opt_win_facew = -1;     // window adjoint: face-weight staging (-1 = automatic: J = 6 only, the
+                                 // measured case: float 2 (5 CTAs/SM), double 1; 0 = off)
     long opt_win_maxslide = 0;   // longest window slide in cells before a new window is started (0 = J-1)
     bool tile_user_set = false;
     bool tile_b_user_set = false;
@@ -329,6 +331,9 @@ extern "C" int b2n_plan_set_option(b2n_plan* p, const char* name, long value) {
     } else if (n == "win_maxslide") {
         if (value < 0 || value > 15) return fail(B2N_EINVAL, "win_maxslide must be in 0..15");
         p->opt_win_maxslide = value;
+    } else if (n == "win_facew") {
+        if (value < -1 || value > 2) return fail(B2N_EINVAL, "win_facew must be -1 (auto), 0, 1 or 2");
+        p->opt_win_facew = value;
     } else if (n == "win_ring") {
         if (value < 0 || value > 3) return fail(B2N_EINVAL, "win_ring must be in 0..3");
         p->opt_win_ring = value;
@@ -950,8 +955,11 @@ static int interp_adj_impl(b2n_plan* p, const void* samples, void* grid, int nba
         const int32_t* ko = ob ? p->d_pt_ko_b : p->d_pt_ko;
         const int32_t* kw = ob ? p->d_pt_kw_b : p->d_pt_kw;
         const int32_t* pm = ob ? p->d_perm_b : p->d_perm;
+        long facew = p->opt_win_facew;
+        if (facew < 0) facew = p->g.J[0] == 6 ? (p->precision == B2N_SINGLE ? 2 : 1) : 0;
         const int slide_axis = (ob ? 2 : 0) | (p->opt_win_ring == 1 ? 256 : 0) | (p->opt_win_ring == 2 ? 512 : 0) |
-                               (p->opt_win_ring == 3 ? 1024 : 0) | (int)((p->opt_win_maxslide & 15) << 12);
+                               (p->opt_win_ring == 3 ? 1024 : 0) | (facew ? 2048 : 0) | (facew == 2 ? (1 << 16) : 0) |
+                               (int)((p->opt_win_maxslide & 15) << 12);
         const int wpts = (int)(p->opt_win_lanes == 32 ? -p->opt_slide_pts
                                : (p->opt_win_lanes == 8 ? p->opt_slide_pts + (1 << 20) : p->opt_slide_pts));
         int rc = p->precision == B2N_SINGLE

@@ -32,7 +32,7 @@ struct WindowAxes {
 // Staging of one 32-sample batch: per sample a record of kW values (3J weights, fx, fy)
 // with an ODD pitch in elements, so that the 32 lanes' scalar stores (lane = sample)
 // fall in 32 different banks, plus a separate int4 (kA, kB, kC, action) per sample.
-template <typename T, int J> struct WinRec {
+template <typename T, int J, bool FW = false> struct WinRec {
     static constexpr int kW = 3 * J + 2;                         // weights + fx, fy
     // odd pitch in units of sizeof(T): float records spread over all 32 banks, double
     // records over all 16 bank pairs, and every element stays naturally aligned
@@ -42,6 +42,38 @@ template <typename T, int J> struct WinRec {
     static constexpr int kRecBytes = ((32 * kPitch + 15) / 16) * 16;
     static constexpr int kBytes = kRecBytes + 32 * 16;           // per warp
 };
+
+// FW (face weights) staging.  Per sample a 16-byte aligned HEAD = {J slide-axis weights, fx,
+// fy, (kA, kB, kC, action)} written by the batch phase with 16-byte vector stores and read
+// by the sample loop with 16-byte broadcast loads (3 for float J=6 instead of 9 scalar
+// ones), and a FACE record of the J*J products wb[jb]*wc[jc] in face order r = jb + J*jc,
+// so a lane fetches its face weights from ONE lane-dependent base (+G per slot) instead
+// of two table-indexed reads and one multiply per slot.  Head pitch = 16 bytes x odd: the
+// 8 lanes of a quarter-warp store phase then cover all 32 banks exactly once.
+template <typename T, int J> struct WinRec<T, J, true> {
+    static constexpr int kHeadInt = (((J + 2) * (int)sizeof(T) + 15) / 16) * 16;   // offset of the int4
+    static constexpr int kHeadMin = kHeadInt + 16;
+    static constexpr int kHead = (kHeadMin / 16) % 2 == 1 ? kHeadMin : kHeadMin + 16;
+    static constexpr int kFaceElems = (J * J) % 2 == 1 ? J * J : J * J + 1;          // odd pitch
+    // slots past the face (r >= J*J) read up to 31 elements past a record: keep them inside
+    static constexpr int kFaceBytes = ((32 * kFaceElems + 32) * (int)sizeof(T) + 15) / 16 * 16;
+    static constexpr int kBytes = 32 * kHead + kFaceBytes;       // per warp
+};
+
+__device__ __forceinline__ void store16(void* dst, const float* v) {
+    *(float4*)dst = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void store16(void* dst, const double* v) {
+    *(double2*)dst = make_double2(v[0], v[1]);
+}
+__device__ __forceinline__ void load16(const void* src, float* v) {
+    const float4 t = *(const float4*)src;
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+__device__ __forceinline__ void load16(const void* src, double* v) {
+    const double2 t = *(const double2*)src;
+    v[0] = t.x; v[1] = t.y;
+}
 
 // TAB: 0 table in global memory, 1 table staged in shared memory, 2 plan-time weights.
 // G:   lanes per sample (32 or 16).  With G = 16 every half-warp walks its OWN run of
@@ -62,8 +94,10 @@ __device__ __forceinline__ int rot_slot(int m, int j) {
     return r >= J ? r - J : r;
 }
 
-template <typename T, int J, int TAB, int G, int RING>
-__global__ void __launch_bounds__(128)
+// FWV: 0 = scalar staging records; 1 = face-weight staging (below); 2 = the same compiled for
+//      5 CTAs per SM (float J=6: 96 registers with a 48-byte spill instead of 110).
+template <typename T, int J, int TAB, int G, int RING, int FWV = 0>
+__global__ void __launch_bounds__(128, FWV == 2 ? 5 : 1)
 spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T* __restrict__ h2,
                        const T* __restrict__ h3, const T* __restrict__ tm_s,
                        const T* __restrict__ wts,
@@ -72,18 +106,26 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
                        cplx_t<T>* __restrict__ grid, const cplx_t<T>* __restrict__ phase_s,
                        int pts_per_warp, int max_slide) {
     using C = cplx_t<T>;
+    constexpr bool FW = FWV != 0;
     constexpr int R = J * J;
     constexpr int RPL = (R + G - 1) / G;
     constexpr int NG = 32 / G;                                    // sample groups per warp
-    constexpr int RB = WinRec<T, J>::kPitch;
-    constexpr int WB = WinRec<T, J>::kBytes;
+    static_assert(!FW || (TAB == 2 && RING != 1 && RING != 2), "face weights: plan-time weights, shift/fuse windows");
+    constexpr int RB = WinRec<T, J, false>::kPitch;               // (not used with FW)
+    constexpr int WB = WinRec<T, J, FW>::kBytes;
+    constexpr int HP = WinRec<T, J, true>::kHead;                 // FW: head pitch (bytes)
+    constexpr int HI = WinRec<T, J, true>::kHeadInt;              // FW: offset of (kA, kB, kC, act)
+    constexpr int FP = WinRec<T, J, true>::kFaceElems;            // FW: face pitch (elements)
+    constexpr int HV = HI / (int)sizeof(T);                       // FW: head values incl. padding
+    constexpr int VPC = 16 / (int)sizeof(T);                      // values per 16-byte chunk
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     const T* stab = (const T*)(dyn_smem + 4 * WB);
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     unsigned char* stage = dyn_smem + wib * WB;                   // this warp's records
-    int4* actions = (int4*)(stage + WinRec<T, J>::kRecBytes);     // this warp's action codes
+    int4* actions = (int4*)(stage + WinRec<T, J, false>::kRecBytes);  // this warp's action codes (not FW)
+    T* face = (T*)(stage + 32 * HP);                              // FW: this warp's face records
     const int64_t M = g.M;
     constexpr bool TAB_SMEM = TAB == 1;
     if (TAB_SMEM) {
@@ -163,7 +205,29 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
             kC = pt_kw[(int64_t)aC * M + i];
             // ROT: the slide-axis weight of cell kA + j goes to ring slot (kA + j) mod J
             const int mrot = ROT ? kA % J : 0;
-            if (TAB == 2) {
+            if constexpr (FW) {
+                T hv[HV], wB[J], wC[J];
+#pragma unroll
+                for (int e = 0; e < HV; e++) hv[e] = (T)0;
+#pragma unroll
+                for (int j = 0; j < J; j++) {
+                    hv[j] = wts[(int64_t)(aA * J + j) * M + i];
+                    wB[j] = wts[(int64_t)(aB * J + j) * M + i];
+                    wC[j] = wts[(int64_t)(aC * J + j) * M + i];
+                }
+                C f = sb[perm[i]];
+                if (phase_s != nullptr) f = cmul_conj(f, phase_s[i]);
+                hv[J] = f.x;
+                hv[J + 1] = f.y;
+                unsigned char* hb = stage + lane * HP;
+#pragma unroll
+                for (int c = 0; c < HV / VPC; c++) store16(hb + 16 * c, hv + VPC * c);
+                T* fr = face + lane * FP;
+#pragma unroll
+                for (int jc = 0; jc < J; jc++)
+#pragma unroll
+                    for (int jb = 0; jb < J; jb++) fr[jb + J * jc] = wB[jb] * wC[jc];
+            } else if (TAB == 2) {
 #pragma unroll
                 for (int j = 0; j < J; j++) {
                     w[rot_slot<J>(mrot, j)] = wts[(int64_t)(aA * J + j) * M + i];
@@ -182,10 +246,12 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
                     w[2 * J + j] = tap_real<T>(tabC, ncC, tlC, tC, oC + j, g.L);
                 }
             }
-            C f = sb[perm[i]];
-            if (phase_s != nullptr) f = cmul_conj(f, phase_s[i]);
-            w[3 * J] = f.x;
-            w[3 * J + 1] = f.y;
+            if constexpr (!FW) {
+                C f = sb[perm[i]];
+                if (phase_s != nullptr) f = cmul_conj(f, phase_s[i]);
+                w[3 * J] = f.x;
+                w[3 * J + 1] = f.y;
+            }
         }
         // window action: slide distance along a, or -1 = new window
         {
@@ -196,7 +262,10 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
             // slides longer than max_slide cells cost more instructions than flushing the
             // whole window and starting a new one
             const int act = (kB == qB && kC == qC && d >= 0 && d <= max_slide) ? d : -1;
-            if (lg < cnt) actions[lane] = make_int4(kA, kB, kC, act);
+            if (lg < cnt) {
+                if constexpr (FW) *(int4*)(stage + lane * HP + HI) = make_int4(kA, kB, kC, act);
+                else actions[lane] = make_int4(kA, kB, kC, act);
+            }
             const int last = cnt > 0 ? cnt - 1 : 0;
             const int nA = __shfl_sync(FULL, kA, last, G), nB = __shfl_sync(FULL, kB, last, G),
                       nC = __shfl_sync(FULL, kC, last, G);
@@ -204,7 +273,13 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
         }
         __syncwarp();
         // ---- sample loop: all lanes of a group work on one sample
-        int4 kk_next = actions[grp * G];
+        // FW: only the action code is prefetched (one register); the origin (kA, kB, kC) is read
+        // by the new-window path itself, and the record pointers advance by a constant
+        int4 kk_next = make_int4(0, 0, 0, 0);
+        if constexpr (FW) kk_next.w = *(const int*)(stage + (grp * G) * HP + HI + 12);
+        else kk_next = actions[grp * G];
+        const unsigned char* recf = stage + (grp * G) * HP;
+        const T* wff = face + (grp * G) * FP + lg;
         if constexpr (RING == 1) {
             for (int q = 0; q < cnt; q++) {
                 const unsigned char* rec = stage + (grp * G + q) * RB;
@@ -289,23 +364,50 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
             }
             continue;
         }
-        for (int q = 0; q < cnt; q++) {
-            const unsigned char* rec = stage + (grp * G + q) * RB;
+        for (int q = 0; q < cnt; q++, recf += HP, wff += FP) {
+            const unsigned char* rec = FW ? recf : stage + (grp * G + q) * RB;
             const int4 kk = kk_next;
-            if (q + 1 < cnt) kk_next = actions[grp * G + q + 1];
+            if (q + 1 < cnt) {
+                if constexpr (FW) kk_next.w = *(const int*)(rec + HP + HI + 12);
+                else kk_next = actions[grp * G + q + 1];
+            }
             // operands of this sample are fetched before the window update so that their
             // shared-memory latency overlaps it
             const T* w = (const T*)rec;
-            T wA[J];
-#pragma unroll
-            for (int j = 0; j < J; j++) wA[j] = w[j];
-            const T fx = w[3 * J], fy = w[3 * J + 1];
+            T wA[J], fx, fy;
             T wb[RPL], wc[RPL];
+            if constexpr (FW) {
+                T hv[HV];
 #pragma unroll
-            for (int s = 0; s < RPL; s++) {
-                wb[s] = w[J + rjb[s]];
-                wc[s] = w[2 * J + rjc[s]];
+                for (int c = 0; c < HV / VPC; c++) load16(rec + 16 * c, hv + VPC * c);
+#pragma unroll
+                for (int j = 0; j < J; j++) wA[j] = hv[j];
+                fx = hv[J];
+                fy = hv[J + 1];
+                // one lane-dependent base, slots at a fixed distance (r = lg + G*s).  Slots past
+                // the face (r >= J*J) read up to G*RPL - J*J elements past the record: still
+                // inside this warp's face area (next record / tail padding); never flushed.
+                const T* wf = wff;
+#pragma unroll
+                for (int s = 0; s < RPL; s++) {
+                    wb[s] = wf[G * s];
+                    wc[s] = (T)1;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < J; j++) wA[j] = w[j];
+                fx = w[3 * J];
+                fy = w[3 * J + 1];
+#pragma unroll
+                for (int s = 0; s < RPL; s++) {
+                    wb[s] = w[J + rjb[s]];
+                    wc[s] = w[2 * J + rjc[s]];
+                }
             }
+            if (FW && kk.w == 0) {
+                // same cell as the previous sample (the common case in the dense centre):
+                // straight to the FMAs
+            } else
             if (kk.w < 0) {
                 if (have) {
 #pragma unroll
@@ -323,12 +425,13 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
                     }
                 }
                 have = true;
-                WA = kk.x;
+                const int4 ko = FW ? *(const int4*)(rec + HI) : kk;     // this sample's origin
+                WA = ko.x;
                 if (ROT) mA = WA % J;
 #pragma unroll
                 for (int s = 0; s < RPL; s++) {
-                    int kb = kk.y + rjb[s]; if (kb >= KB) kb -= KB;
-                    int kc = kk.z + rjc[s]; if (kc >= KC) kc -= KC;
+                    int kb = ko.y + rjb[s]; if (kb >= KB) kb -= KB;
+                    int kc = ko.z + rjc[s]; if (kc >= KC) kc -= KC;
                     faceptr[s] = gb + ((int64_t)kb * sB + (int64_t)kc * sC);
                 }
             } else {
@@ -371,7 +474,8 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
                         for (int s = 0; s < RPL; s++) {
                             if (rvalid[s]) {
                                 atomic_add_c(faceptr[s] + (int64_t)WA * sA, acc[s][0]);
-                                const C v2 = mul_w(wb[s], mul_w(wc[s], make_c<T>(fx, fy)));
+                                const C v2 = FW ? mul_w(wb[s], make_c<T>(fx, fy))
+                                                : mul_w(wb[s], mul_w(wc[s], make_c<T>(fx, fy)));
 #pragma unroll
                                 for (int j = 0; j + 1 < J; j++)
                                     acc[s][j] = fma_w(wA[j], v2, acc[s][j + 1]);
@@ -387,7 +491,8 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
             for (int s = 0; s < RPL; s++) {
                 if (rvalid[s]) {
                     // (coef_c * f) * coef_b, then * coef_a per cell; packed re/im arithmetic
-                    const C v2 = mul_w(wb[s], mul_w(wc[s], make_c<T>(fx, fy)));
+                    const C v2 = FW ? mul_w(wb[s], make_c<T>(fx, fy))
+                                    : mul_w(wb[s], mul_w(wc[s], make_c<T>(fx, fy)));
 #pragma unroll
                     for (int j = 0; j < J; j++) acc[s][j] = fma_w(wA[j], v2, acc[s][j]);
                 }
@@ -437,6 +542,8 @@ static int launch_window(const Geom& g, const TablePtrs& tabs, int slide_axis, c
     const bool ring = (slide_axis & 256) != 0;
     const bool rot = (slide_axis & 512) != 0;     // bit 9: fixed ring with rotated weights
     const bool fuse = (slide_axis & 1024) != 0;   // bit 10: last shift fused into the FMAs
+    const bool facew = (slide_axis & 2048) != 0;  // bit 11: face-weight staging
+    const bool facew5 = (slide_axis & (1 << 16)) != 0;  // bit 16: ... compiled for 5 CTAs per SM
     int max_slide = (slide_axis >> 12) & 15;      // bits 12-15: longest slide (0 = J - 1)
     if (max_slide <= 0 || max_slide > J - 1) max_slide = J - 1;
     slide_axis &= 255;
@@ -455,6 +562,25 @@ static int launch_window(const Geom& g, const TablePtrs& tabs, int slide_axis, c
                           (size_t)g.tlen[0] * sizeof(T) <= 56 * 1024;
     const size_t stage_bytes = (size_t)4 * WinRec<T, J>::kBytes;
     cudaError_t e;
+    if (wts != nullptr && lanes_per_sample == 16 && fuse && facew) {
+        const size_t smem = (size_t)4 * WinRec<T, J, true>::kBytes;
+#define B2N_LAUNCH_FW(FWV)                                                                         \
+        {                                                                                          \
+            auto k = spread_window3d_kernel<T, J, 2, 16, 3, FWV>;                                  \
+            e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
+            if (e != cudaSuccess) return (int)e;                                                   \
+            k<<<gd, 128, smem, st>>>(g, wa, (const T*)tabs.h[0], (const T*)tabs.h[1],              \
+                                     (const T*)tabs.h[2], (const T*)tm_s, (const T*)wts, pt_ko,    \
+                                     pt_kw, perm, (const C*)samples, (C*)grid, (const C*)phase_s,  \
+                                     pts_per_warp, max_slide);                                     \
+        }
+        if (facew5 && sizeof(T) == 4 && J <= 6) B2N_LAUNCH_FW(2) else B2N_LAUNCH_FW(1)
+#undef B2N_LAUNCH_FW
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return (int)e;
+        *done = true;
+        return 0;
+    }
 #define B2N_LAUNCH_WIN(TABV, SMEM)                                                                 \
     if (lanes_per_sample == 8) {                                                                   \
         auto k = spread_window3d_kernel<T, J, TABV, 8, 0>;                                            \
