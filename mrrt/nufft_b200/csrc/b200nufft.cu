@@ -69,8 +69,9 @@ struct b2n_plan {
     // register-window adjoint: 0 register shifts, 1 lane ring, 2 fixed ring with rotated
     // weights, 3 last shift of a slide fused into the FMAs (default; fastest measured)
     long opt_win_ring = 3;
-    long opt_win_facew = -1;     // window adjoint: face-weight staging (-1 = automatic: J = 6 only, the
-                                 // measured case: float 2 (5 CTAs/SM), double 1; 0 = off)
+    long opt_win_facew = -1;     // window adjoint: face-weight staging.  -1 = automatic: J <= 6 (measured at
+                                 // J = 4 and 6): float 2 (5 CTAs/SM), double 1; 0 = off; 3 = plan-time
+                                 // window records (tested option: no faster, 192 B/sample of plan memory)
     long opt_win_maxslide = 0;   // longest window slide in cells before a new window is started (0 = J-1)
     bool tile_user_set = false;
     bool tile_b_user_set = false;
@@ -103,6 +104,8 @@ struct b2n_plan {
     // plan-time interpolation weights [sum(J)][M] for each sort order (real tables)
     void* d_wts = nullptr;
     void* d_wts_b = nullptr;
+    void* d_win_recs = nullptr;  // plan-time window records of the adjoint kernel (win_facew 3)
+    long win_recs_pts = -1, win_recs_slide = -1;
     long opt_precomp = 1;
     void* d_phase_s = nullptr;   // sorted sample phase or null
     int64_t nbins = 0;
@@ -261,6 +264,9 @@ static void free_points(b2n_plan* p) {
     dev_free(p->d_phase_sb);
     dev_free(p->d_wts); dev_free(p->d_wts_b); dev_free(p->d_wts_f);
     p->d_wts = p->d_wts_b = p->d_wts_f = nullptr;
+    dev_free(p->d_win_recs);
+    p->d_win_recs = nullptr;
+    p->win_recs_pts = p->win_recs_slide = -1;
     p->d_tm_sb = p->d_phase_sb = nullptr;
     p->d_perm_b = p->d_pt_ko_b = p->d_pt_kw_b = nullptr;
     p->have_b = false;
@@ -332,7 +338,7 @@ extern "C" int b2n_plan_set_option(b2n_plan* p, const char* name, long value) {
         if (value < 0 || value > 15) return fail(B2N_EINVAL, "win_maxslide must be in 0..15");
         p->opt_win_maxslide = value;
     } else if (n == "win_facew") {
-        if (value < -1 || value > 2) return fail(B2N_EINVAL, "win_facew must be -1 (auto), 0, 1 or 2");
+        if (value < -1 || value > 3) return fail(B2N_EINVAL, "win_facew must be -1 (auto), 0, 1, 2 or 3");
         p->opt_win_facew = value;
     } else if (n == "win_ring") {
         if (value < 0 || value > 3) return fail(B2N_EINVAL, "win_ring must be in 0..3");
@@ -956,10 +962,39 @@ static int interp_adj_impl(b2n_plan* p, const void* samples, void* grid, int nba
         const int32_t* kw = ob ? p->d_pt_kw_b : p->d_pt_kw;
         const int32_t* pm = ob ? p->d_perm_b : p->d_perm;
         long facew = p->opt_win_facew;
-        if (facew < 0) facew = p->g.J[0] == 6 ? (p->precision == B2N_SINGLE ? 2 : 1) : 0;
+        if (facew < 0) facew = p->g.J[0] <= 6 ? (p->precision == B2N_SINGLE ? 2 : 1) : 0;
+        // variant 3 (plan-time window records) needs the plan-time weights, 16 lanes per sample
+        // and the fused slide; the records follow the run partition and the longest slide
+        if (facew == 3 && (wts == nullptr || p->opt_win_lanes != 16 || p->opt_win_ring != 3 || nbatch > 65535))
+            facew = p->precision == B2N_SINGLE ? 2 : 1;
+        if (facew == 3) {
+            const size_t rs = p->precision == B2N_SINGLE ? window_record_bytes_f32(p->g.J[0])
+                                                         : window_record_bytes_f64(p->g.J[0]);
+            if (rs == 0) facew = 0;
+            else if (p->d_win_recs == nullptr || p->win_recs_pts != p->opt_slide_pts ||
+                     p->win_recs_slide != p->opt_win_maxslide) {
+                if (p->d_win_recs) {
+                    dev_free(p->d_win_recs);
+                    p->d_win_recs = nullptr;
+                }
+                int rcb = dev_alloc(p, &p->d_win_recs, rs * (size_t)p->g.M + 16);
+                if (rcb) return rcb;
+                const int sa = ob ? 2 : 0;
+                rcb = p->precision == B2N_SINGLE
+                          ? window_records_build_f32(p->g, sa, wts, kw, (int)p->opt_slide_pts,
+                                                     (int)p->opt_win_maxslide, p->d_win_recs, p->sm_count, st)
+                          : window_records_build_f64(p->g, sa, wts, kw, (int)p->opt_slide_pts,
+                                                     (int)p->opt_win_maxslide, p->d_win_recs, p->sm_count, st);
+                if (rcb != 0) return fail(B2N_ECUDA, "window record build failed: " + std::string(cudaGetErrorString((cudaError_t)rcb)));
+                p->win_recs_pts = p->opt_slide_pts;
+                p->win_recs_slide = p->opt_win_maxslide;
+                p->launches += 1;
+            }
+        }
+        if (facew == 3) wts = p->d_win_recs;
         const int slide_axis = (ob ? 2 : 0) | (p->opt_win_ring == 1 ? 256 : 0) | (p->opt_win_ring == 2 ? 512 : 0) |
                                (p->opt_win_ring == 3 ? 1024 : 0) | (facew ? 2048 : 0) | (facew == 2 ? (1 << 16) : 0) |
-                               (int)((p->opt_win_maxslide & 15) << 12);
+                               (facew == 3 ? (1 << 17) : 0) | (int)((p->opt_win_maxslide & 15) << 12);
         const int wpts = (int)(p->opt_win_lanes == 32 ? -p->opt_slide_pts
                                : (p->opt_win_lanes == 8 ? p->opt_slide_pts + (1 << 20) : p->opt_slide_pts));
         int rc = p->precision == B2N_SINGLE

@@ -47,7 +47,11 @@ struct SlotArgs {
     int window_adj_##SUF(const Geom& g, const TablePtrs& tabs, int slide_axis, const void* tm_s, \
                          const void* wts, const int32_t* pt_ko, const int32_t* pt_kw, const int32_t* perm,        \
                          const void* samples, void* grid, const void* phase_s, int nbatch,       \
-                         int pts_per_warp, cudaStream_t st, bool* done);
+                         int pts_per_warp, cudaStream_t st, bool* done);                         \
+    size_t window_record_bytes_##SUF(int J);                                                     \
+    int window_records_build_##SUF(const Geom& g, int slide_axis, const void* wts,               \
+                                   const int32_t* pt_kw, int pts_per_warp, int max_slide,        \
+                                   void* recs, int sm_count, cudaStream_t st);
 #define B2N_DECLARE4(SUF)                                                                        \
     int window2d_adj_##SUF(const Geom& g, const TablePtrs& tabs, const void* tm_s, const void* wts, \
                            const int32_t* pt_ko, const int32_t* pt_kw, const int32_t* perm,      \

@@ -75,6 +75,62 @@ __device__ __forceinline__ void load16(const void* src, double* v) {
     v[0] = t.x; v[1] = t.y;
 }
 
+// Plan-time window RECORDS (FWV = 3): everything the staging area holds except the sample
+// value is a function of the trajectory only, so it is laid out once, in the adjoint order,
+// exactly as the sample loop wants it in shared memory:
+//   [wA[J] | fx fy (filled per launch) | pad | kA kB kC action | face J*J products | pad]
+// and the batch phase becomes a coalesced 16-byte-chunk copy global -> shared plus the
+// sample fetch.  The action code (slide distance or -1 = new window) depends on the run
+// partition (samples per lane group) and on the longest allowed slide: the records are
+// rebuilt when those options change.
+template <typename T, int J> struct WinRecG {
+    static constexpr int kF = J * (int)sizeof(T);                                   // offset of fx, fy
+    static constexpr int kInt = (((J + 2) * (int)sizeof(T) + 15) / 16) * 16;        // offset of the int4
+    static constexpr int kFace = kInt + 16;                                         // offset of the face
+    static constexpr int kSize = ((kFace + J * J * (int)sizeof(T) + 15) / 16) * 16; // record bytes
+    static constexpr int kBytes = 32 * kSize + 64 * (int)sizeof(T);                 // per warp (+ overread pad)
+};
+
+template <typename T, int J>
+__global__ void window_records_kernel(int64_t M, int aA, int aB, int aC, int per_group, int max_slide,
+                                      const T* __restrict__ wts, const int32_t* __restrict__ pt_kw,
+                                      unsigned char* __restrict__ recs) {
+    using RG = WinRecG<T, J>;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < M;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        unsigned char* r = recs + i * RG::kSize;
+        T wA[J], wB[J], wC[J];
+#pragma unroll
+        for (int j = 0; j < J; j++) {
+            wA[j] = wts[(int64_t)(aA * J + j) * M + i];
+            wB[j] = wts[(int64_t)(aB * J + j) * M + i];
+            wC[j] = wts[(int64_t)(aC * J + j) * M + i];
+        }
+        const int kA = pt_kw[(int64_t)aA * M + i], kB = pt_kw[(int64_t)aB * M + i],
+                  kC = pt_kw[(int64_t)aC * M + i];
+        int act = -1;
+        if (i % per_group != 0) {   // the first sample of a lane group's run starts a window
+            const int qA = pt_kw[(int64_t)aA * M + i - 1], qB = pt_kw[(int64_t)aB * M + i - 1],
+                      qC = pt_kw[(int64_t)aC * M + i - 1];
+            const int d = kA - qA;
+            if (kB == qB && kC == qC && d >= 0 && d <= max_slide) act = d;
+        }
+        T* w = (T*)r;
+#pragma unroll
+        for (int j = 0; j < J; j++) w[j] = wA[j];
+#pragma unroll
+        for (int e = J; e < RG::kInt / (int)sizeof(T); e++) w[e] = (T)0;
+        *(int4*)(r + RG::kInt) = make_int4(kA, kB, kC, act);
+        T* f = (T*)(r + RG::kFace);
+#pragma unroll
+        for (int jc = 0; jc < J; jc++)
+#pragma unroll
+            for (int jb = 0; jb < J; jb++) f[jb + J * jc] = wB[jb] * wC[jc];
+#pragma unroll
+        for (int e = J * J; e < (RG::kSize - RG::kFace) / (int)sizeof(T); e++) f[e] = (T)0;
+    }
+}
+
 // TAB: 0 table in global memory, 1 table staged in shared memory, 2 plan-time weights.
 // G:   lanes per sample (32 or 16).  With G = 16 every half-warp walks its OWN run of
 //      samples with its own register window: the per-sample instructions (operand loads,
@@ -97,7 +153,7 @@ __device__ __forceinline__ int rot_slot(int m, int j) {
 // FWV: 0 = scalar staging records; 1 = face-weight staging (below); 2 = the same compiled for
 //      5 CTAs per SM (float J=6: 96 registers with a 48-byte spill instead of 110).
 template <typename T, int J, int TAB, int G, int RING, int FWV = 0>
-__global__ void __launch_bounds__(128, FWV == 2 ? 5 : 1)
+__global__ void __launch_bounds__(128, (FWV == 2 || (FWV == 3 && sizeof(T) == 4 && J <= 6)) ? 5 : 1)
 spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T* __restrict__ h2,
                        const T* __restrict__ h3, const T* __restrict__ tm_s,
                        const T* __restrict__ wts,
@@ -112,10 +168,12 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
     constexpr int NG = 32 / G;                                    // sample groups per warp
     static_assert(!FW || (TAB == 2 && RING != 1 && RING != 2), "face weights: plan-time weights, shift/fuse windows");
     constexpr int RB = WinRec<T, J, false>::kPitch;               // (not used with FW)
-    constexpr int WB = WinRec<T, J, FW>::kBytes;
-    constexpr int HP = WinRec<T, J, true>::kHead;                 // FW: head pitch (bytes)
-    constexpr int HI = WinRec<T, J, true>::kHeadInt;              // FW: offset of (kA, kB, kC, act)
-    constexpr int FP = WinRec<T, J, true>::kFaceElems;            // FW: face pitch (elements)
+    constexpr bool REC = FWV == 3;                                // plan-time records (WinRecG)
+    constexpr int WB = REC ? WinRecG<T, J>::kBytes : WinRec<T, J, FW>::kBytes;
+    constexpr int HP = REC ? WinRecG<T, J>::kSize : WinRec<T, J, true>::kHead;     // FW: head pitch (bytes)
+    constexpr int HI = REC ? WinRecG<T, J>::kInt : WinRec<T, J, true>::kHeadInt;   // FW: offset of (kA, kB, kC, act)
+    constexpr int FP = REC ? WinRecG<T, J>::kSize / (int)sizeof(T)
+                           : WinRec<T, J, true>::kFaceElems;      // FW: face pitch (elements)
     constexpr int HV = HI / (int)sizeof(T);                       // FW: head values incl. padding
     constexpr int VPC = 16 / (int)sizeof(T);                      // values per 16-byte chunk
     constexpr unsigned FULL = 0xffffffffu;
@@ -125,7 +183,8 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
     const int wib = threadIdx.x >> 5;
     unsigned char* stage = dyn_smem + wib * WB;                   // this warp's records
     int4* actions = (int4*)(stage + WinRec<T, J, false>::kRecBytes);  // this warp's action codes (not FW)
-    T* face = (T*)(stage + 32 * HP);                              // FW: this warp's face records
+    T* face = REC ? (T*)(stage + WinRecG<T, J>::kFace)            // FW: this warp's face records
+                  : (T*)(stage + 32 * HP);
     const int64_t M = g.M;
     constexpr bool TAB_SMEM = TAB == 1;
     if (TAB_SMEM) {
@@ -195,9 +254,31 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
         const int64_t base = begin + it;
         const int cnt = (int)(base >= end ? 0 : (end - base < G ? end - base : G));
         __syncwarp();
+        if constexpr (REC) {
+            // ---- batch phase with plan-time records: fetch this lane's sample, copy the lane
+            // group's cnt records (16-byte chunks, coalesced), then drop the sample value in
+            C f = make_c<T>(0, 0);
+            if (lg < cnt) {
+                const int64_t i = base + lg;
+                f = sb[perm[i]];
+                if (phase_s != nullptr) f = cmul_conj(f, phase_s[i]);
+            }
+            constexpr int CPR = HP / 16;                          // chunks per record
+            const int4* __restrict__ gsrc = (const int4*)((const unsigned char*)wts + base * HP);
+            int4* sdst = (int4*)(stage + (grp * G) * HP);
+            const int nch = cnt * CPR;
+#pragma unroll
+            for (int c = 0; c < CPR; c++) {
+                const int e = lg + G * c;
+                if (e < nch) sdst[e] = __ldg(gsrc + e);
+            }
+            __syncwarp();
+            if (lg < cnt) *(C*)(stage + lane * HP + J * sizeof(T)) = f;
+            __syncwarp();
+        }
         // ---- batch phase: lane = sample (record index = lane)
         int kA = 0, kB = 0, kC = 0;
-        if (lg < cnt) {
+        if (!REC && lg < cnt) {
             const int64_t i = base + lg;
             T* w = (T*)(stage + lane * RB);
             kA = pt_kw[(int64_t)aA * M + i];
@@ -254,7 +335,7 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
             }
         }
         // window action: slide distance along a, or -1 = new window
-        {
+        if constexpr (!REC) {
             int qA = __shfl_up_sync(FULL, kA, 1, G), qB = __shfl_up_sync(FULL, kB, 1, G),
                 qC = __shfl_up_sync(FULL, kC, 1, G);
             if (lg == 0) { qA = pkA; qB = pkB; qC = pkC; }
@@ -544,6 +625,7 @@ static int launch_window(const Geom& g, const TablePtrs& tabs, int slide_axis, c
     const bool fuse = (slide_axis & 1024) != 0;   // bit 10: last shift fused into the FMAs
     const bool facew = (slide_axis & 2048) != 0;  // bit 11: face-weight staging
     const bool facew5 = (slide_axis & (1 << 16)) != 0;  // bit 16: ... compiled for 5 CTAs per SM
+    const bool facerec = (slide_axis & (1 << 17)) != 0; // bit 17: `wts` holds plan-time window records
     int max_slide = (slide_axis >> 12) & 15;      // bits 12-15: longest slide (0 = J - 1)
     if (max_slide <= 0 || max_slide > J - 1) max_slide = J - 1;
     slide_axis &= 255;
@@ -563,7 +645,7 @@ static int launch_window(const Geom& g, const TablePtrs& tabs, int slide_axis, c
     const size_t stage_bytes = (size_t)4 * WinRec<T, J>::kBytes;
     cudaError_t e;
     if (wts != nullptr && lanes_per_sample == 16 && fuse && facew) {
-        const size_t smem = (size_t)4 * WinRec<T, J, true>::kBytes;
+        const size_t smem = (size_t)4 * (facerec ? WinRecG<T, J>::kBytes : WinRec<T, J, true>::kBytes);
 #define B2N_LAUNCH_FW(FWV)                                                                         \
         {                                                                                          \
             auto k = spread_window3d_kernel<T, J, 2, 16, 3, FWV>;                                  \
@@ -574,7 +656,8 @@ static int launch_window(const Geom& g, const TablePtrs& tabs, int slide_axis, c
                                      pt_kw, perm, (const C*)samples, (C*)grid, (const C*)phase_s,  \
                                      pts_per_warp, max_slide);                                     \
         }
-        if (facew5 && sizeof(T) == 4 && J <= 6) B2N_LAUNCH_FW(2) else B2N_LAUNCH_FW(1)
+        if (facerec) B2N_LAUNCH_FW(3)
+        else if (facew5 && sizeof(T) == 4 && J <= 6) B2N_LAUNCH_FW(2) else B2N_LAUNCH_FW(1)
 #undef B2N_LAUNCH_FW
         e = cudaGetLastError();
         if (e != cudaSuccess) return (int)e;
@@ -639,6 +722,49 @@ static int launch_window(const Geom& g, const TablePtrs& tabs, int slide_axis, c
     if (e != cudaSuccess) return (int)e;
     *done = true;
     return 0;
+}
+
+// bytes per plan-time window record (0 = this J has no record variant)
+template <typename T>
+static size_t window_record_bytes_t(int J) {
+    switch (J) {
+        case 4: return WinRecG<T, 4>::kSize;
+        case 5: return WinRecG<T, 5>::kSize;
+        case 6: return WinRecG<T, 6>::kSize;
+        case 7: return WinRecG<T, 7>::kSize;
+        case 8: return WinRecG<T, 8>::kSize;
+        default: return 0;
+    }
+}
+
+// builds recs[M] (adjoint order) from the plan-time weights [3J][M] and wrapped origins
+template <typename T>
+static int window_records_build_t(const Geom& g, int slide_axis, const void* wts, const int32_t* pt_kw,
+                                  int pts_per_warp, int max_slide, void* recs, int sm_count,
+                                  cudaStream_t st) {
+    const int J = g.J[0];
+    if (max_slide <= 0 || max_slide > J - 1) max_slide = J - 1;
+    pts_per_warp = (pts_per_warp + 31) / 32 * 32;
+    const int per_group = pts_per_warp / 2;                    // 16 lanes per sample
+    int aA = 0, aB = 1, aC = 2;
+    if ((slide_axis & 255) == 2) { aA = 2; aB = 0; aC = 1; }
+    int64_t nb = (g.M + 127) / 128;
+    const int64_t cap = (int64_t)sm_count * 32;
+    if (nb > cap) nb = cap;
+    if (nb < 1) nb = 1;
+#define B2N_REC(JJ)                                                                                 \
+    window_records_kernel<T, JJ><<<(unsigned)nb, 128, 0, st>>>(g.M, aA, aB, aC, per_group, max_slide, \
+                                                               (const T*)wts, pt_kw, (unsigned char*)recs)
+    switch (J) {
+        case 4: B2N_REC(4); break;
+        case 5: B2N_REC(5); break;
+        case 6: B2N_REC(6); break;
+        case 7: B2N_REC(7); break;
+        case 8: B2N_REC(8); break;
+        default: return (int)cudaErrorInvalidValue;
+    }
+#undef B2N_REC
+    return (int)cudaGetLastError();
 }
 
 template <typename T>

@@ -29,14 +29,20 @@ def timeit(f, n=10, warm=3):
 
 if __name__ == "__main__":
     small = os.environ.get("AB_SMALL") == "1"
-    om = bench.radial3d(bench.SPOKES // (8 if small else 1), bench.NREAD // (2 if small else 1))
-    Nd, Kd = ((128,) * 3, (192,) * 3) if small else (bench.ND, bench.KD)
+    JJ = int(os.environ.get("AB_J", "6"))
+    if os.environ.get("AB_CASE") == "c3":
+        # BASELINE configs[2]: 3-D 128^3 stack-of-stars 201 x 256 x 128, Kd = 192^3
+        from sense_bench import stack_of_stars
+        om, Nd, Kd = stack_of_stars(201, 256, 128), (128,) * 3, (192,) * 3
+    else:
+        om = bench.radial3d(bench.SPOKES // (8 if small else 1), bench.NREAD // (2 if small else 1))
+        Nd, Kd = ((128,) * 3, (192,) * 3) if small else (bench.ND, bench.KD)
     variants = [{}] + [json.loads(a) for a in sys.argv[1:]]
     y = g = ref_a = ref_f = None
     prec = os.environ.get("AB_PRECISION", "single")
     cdt = torch.complex64 if prec == "single" else torch.complex128
     for opts in variants:
-        A = NufftBase(Nd=Nd, omega=om, Jd=6, Kd=Kd, precision=prec, options=opts)
+        A = NufftBase(Nd=Nd, omega=om, Jd=JJ, Kd=Kd, precision=prec, options=opts)
         if y is None:
             y = torch.randn(A.M, dtype=cdt, device="cuda")
             g = torch.randn(int(np.prod(Kd)), dtype=cdt, device="cuda")
