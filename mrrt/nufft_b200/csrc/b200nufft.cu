@@ -338,7 +338,7 @@ extern "C" int b2n_plan_set_option(b2n_plan* p, const char* name, long value) {
         if (value < 0 || value > 15) return fail(B2N_EINVAL, "win_maxslide must be in 0..15");
         p->opt_win_maxslide = value;
     } else if (n == "win_facew") {
-        if (value < -1 || value > 3) return fail(B2N_EINVAL, "win_facew must be -1 (auto), 0, 1, 2 or 3");
+        if (value < -1 || value > 4) return fail(B2N_EINVAL, "win_facew must be -1 (auto) or 0..4");
         p->opt_win_facew = value;
     } else if (n == "win_ring") {
         if (value < 0 || value > 3) return fail(B2N_EINVAL, "win_ring must be in 0..3");
@@ -965,6 +965,8 @@ static int interp_adj_impl(b2n_plan* p, const void* samples, void* grid, int nba
         if (facew < 0) facew = p->g.J[0] <= 6 ? (p->precision == B2N_SINGLE ? 2 : 1) : 0;
         // variant 3 (plan-time window records) needs the plan-time weights, 16 lanes per sample
         // and the fused slide; the records follow the run partition and the longest slide
+        const bool rec_async = facew == 4;
+        if (facew == 4) facew = 3;
         if (facew == 3 && (wts == nullptr || p->opt_win_lanes != 16 || p->opt_win_ring != 3 || nbatch > 65535))
             facew = p->precision == B2N_SINGLE ? 2 : 1;
         if (facew == 3) {
@@ -994,7 +996,8 @@ static int interp_adj_impl(b2n_plan* p, const void* samples, void* grid, int nba
         if (facew == 3) wts = p->d_win_recs;
         const int slide_axis = (ob ? 2 : 0) | (p->opt_win_ring == 1 ? 256 : 0) | (p->opt_win_ring == 2 ? 512 : 0) |
                                (p->opt_win_ring == 3 ? 1024 : 0) | (facew ? 2048 : 0) | (facew == 2 ? (1 << 16) : 0) |
-                               (facew == 3 ? (1 << 17) : 0) | (int)((p->opt_win_maxslide & 15) << 12);
+                               (facew == 3 ? (1 << 17) : 0) | ((facew == 3 && rec_async) ? (1 << 18) : 0) |
+                               (int)((p->opt_win_maxslide & 15) << 12);
         const int wpts = (int)(p->opt_win_lanes == 32 ? -p->opt_slide_pts
                                : (p->opt_win_lanes == 8 ? p->opt_slide_pts + (1 << 20) : p->opt_slide_pts));
         int rc = p->precision == B2N_SINGLE

@@ -153,7 +153,7 @@ __device__ __forceinline__ int rot_slot(int m, int j) {
 // FWV: 0 = scalar staging records; 1 = face-weight staging (below); 2 = the same compiled for
 //      5 CTAs per SM (float J=6: 96 registers with a 48-byte spill instead of 110).
 template <typename T, int J, int TAB, int G, int RING, int FWV = 0>
-__global__ void __launch_bounds__(128, (FWV == 2 || (FWV == 3 && sizeof(T) == 4 && J <= 6)) ? 5 : 1)
+__global__ void __launch_bounds__(128, (FWV == 2 || (FWV >= 3 && sizeof(T) == 4 && J <= 6)) ? 5 : 1)
 spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T* __restrict__ h2,
                        const T* __restrict__ h3, const T* __restrict__ tm_s,
                        const T* __restrict__ wts,
@@ -168,7 +168,9 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
     constexpr int NG = 32 / G;                                    // sample groups per warp
     static_assert(!FW || (TAB == 2 && RING != 1 && RING != 2), "face weights: plan-time weights, shift/fuse windows");
     constexpr int RB = WinRec<T, J, false>::kPitch;               // (not used with FW)
-    constexpr bool REC = FWV == 3;                                // plan-time records (WinRecG)
+    constexpr bool ASY = FWV == 4;                                // records copied with cp.async, double-buffered
+    constexpr bool REC = FWV == 3 || ASY;                         // plan-time records (WinRecG)
+    constexpr int BSZ = ASY ? 8 : G;                              // samples per lane group and batch
     constexpr int WB = REC ? WinRecG<T, J>::kBytes : WinRec<T, J, FW>::kBytes;
     constexpr int HP = REC ? WinRecG<T, J>::kSize : WinRec<T, J, true>::kHead;     // FW: head pitch (bytes)
     constexpr int HI = REC ? WinRecG<T, J>::kInt : WinRec<T, J, true>::kHeadInt;   // FW: offset of (kA, kB, kC, act)
@@ -249,11 +251,63 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
     bool have = false;
     int pkA = -1 << 30, pkB = -1, pkC = -1;   // previous sample's wrapped origin
 
-    for (int it = 0; it < per_group; it += G) {
+    // ASY: a warp's staging area holds two buffers of NG * BSZ records; while the sample loop
+    // works on one, the next batch's records arrive in the other (cp.async, no registers) and
+    // the next batch's sample values are fetched into two registers
+    [[maybe_unused]] C fnext = make_c<T>(0, 0);
+    [[maybe_unused]] int buf = 0;
+    if constexpr (ASY) {
+        static_assert(G == 16, "ASY: 16 lanes per sample");
+        constexpr int CPR = HP / 16;
+        const int cnt0 = (int)(begin >= end ? 0 : (end - begin < BSZ ? end - begin : BSZ));
+        const unsigned char* gsrc = (const unsigned char*)wts + begin * HP;
+        const unsigned sdst = (unsigned)__cvta_generic_to_shared(stage + (grp * BSZ) * HP);
+#pragma unroll
+        for (int c = 0; c < (BSZ * CPR + G - 1) / G; c++) {
+            const int e = lg + G * c;
+            if (e < cnt0 * CPR)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst + 16 * e), "l"(gsrc + 16 * e));
+        }
+        asm volatile("cp.async.commit_group;");
+        if (lg < cnt0) {
+            fnext = sb[perm[begin + lg]];
+            if (phase_s != nullptr) fnext = cmul_conj(fnext, phase_s[begin + lg]);
+        }
+    }
+    for (int it = 0; it < per_group; it += BSZ) {
         // (uniform trip count for the whole warp; groups past their end idle)
         const int64_t base = begin + it;
-        const int cnt = (int)(base >= end ? 0 : (end - base < G ? end - base : G));
+        const int cnt = (int)(base >= end ? 0 : (end - base < BSZ ? end - base : BSZ));
         __syncwarp();
+        if constexpr (ASY) {
+            constexpr int CPR = HP / 16;
+            constexpr int BUFB = NG * BSZ * HP;                   // bytes per buffer
+            const C fcur = fnext;
+            // next batch: records into the other buffer, sample values into registers
+            const int64_t nbase = base + BSZ;
+            const int ncnt = (it + BSZ >= per_group || nbase >= end) ? 0
+                             : (int)(end - nbase < BSZ ? end - nbase : BSZ);
+            {
+                const unsigned char* gsrc = (const unsigned char*)wts + nbase * HP;
+                const unsigned sdst = (unsigned)__cvta_generic_to_shared(
+                    stage + (buf ^ 1) * BUFB + (grp * BSZ) * HP);
+#pragma unroll
+                for (int c = 0; c < (BSZ * CPR + G - 1) / G; c++) {
+                    const int e = lg + G * c;
+                    if (e < ncnt * CPR)
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst + 16 * e), "l"(gsrc + 16 * e));
+                }
+                asm volatile("cp.async.commit_group;");
+                if (lg < ncnt) {
+                    fnext = sb[perm[nbase + lg]];
+                    if (phase_s != nullptr) fnext = cmul_conj(fnext, phase_s[nbase + lg]);
+                }
+            }
+            asm volatile("cp.async.wait_group 1;" ::: "memory");  // this batch's records have landed
+            __syncwarp();
+            if (lg < cnt) *(C*)(stage + buf * BUFB + (grp * BSZ + lg) * HP + J * sizeof(T)) = fcur;
+            __syncwarp();
+        } else
         if constexpr (REC) {
             // ---- batch phase with plan-time records: fetch this lane's sample, copy the lane
             // group's cnt records (16-byte chunks, coalesced), then drop the sample value in
@@ -357,10 +411,11 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
         // FW: only the action code is prefetched (one register); the origin (kA, kB, kC) is read
         // by the new-window path itself, and the record pointers advance by a constant
         int4 kk_next = make_int4(0, 0, 0, 0);
-        if constexpr (FW) kk_next.w = *(const int*)(stage + (grp * G) * HP + HI + 12);
+        const unsigned char* recf = stage + (ASY ? buf * (NG * BSZ * HP) : 0) + (grp * BSZ) * HP;
+        const T* wff = (REC ? (const T*)(recf + WinRecG<T, J>::kFace) : face + (grp * G) * FP) + lg;
+        if constexpr (FW) kk_next.w = *(const int*)(recf + HI + 12);
         else kk_next = actions[grp * G];
-        const unsigned char* recf = stage + (grp * G) * HP;
-        const T* wff = face + (grp * G) * FP + lg;
+        if constexpr (ASY) buf ^= 1;
         if constexpr (RING == 1) {
             for (int q = 0; q < cnt; q++) {
                 const unsigned char* rec = stage + (grp * G + q) * RB;
@@ -626,6 +681,7 @@ static int launch_window(const Geom& g, const TablePtrs& tabs, int slide_axis, c
     const bool facew = (slide_axis & 2048) != 0;  // bit 11: face-weight staging
     const bool facew5 = (slide_axis & (1 << 16)) != 0;  // bit 16: ... compiled for 5 CTAs per SM
     const bool facerec = (slide_axis & (1 << 17)) != 0; // bit 17: `wts` holds plan-time window records
+    const bool faceasy = (slide_axis & (1 << 18)) != 0; // bit 18: ... copied with cp.async, double-buffered
     int max_slide = (slide_axis >> 12) & 15;      // bits 12-15: longest slide (0 = J - 1)
     if (max_slide <= 0 || max_slide > J - 1) max_slide = J - 1;
     slide_axis &= 255;
@@ -656,7 +712,8 @@ static int launch_window(const Geom& g, const TablePtrs& tabs, int slide_axis, c
                                      pt_kw, perm, (const C*)samples, (C*)grid, (const C*)phase_s,  \
                                      pts_per_warp, max_slide);                                     \
         }
-        if (facerec) B2N_LAUNCH_FW(3)
+        if (facerec && faceasy) B2N_LAUNCH_FW(4)
+        else if (facerec) B2N_LAUNCH_FW(3)
         else if (facew5 && sizeof(T) == 4 && J <= 6) B2N_LAUNCH_FW(2) else B2N_LAUNCH_FW(1)
 #undef B2N_LAUNCH_FW
         e = cudaGetLastError();

@@ -132,7 +132,7 @@ def _radial3d(S, n):
 
 @pytest.mark.parametrize("precision", ["single", "double"])
 @pytest.mark.parametrize("variant", ["auto", "generic", "no_tma", "slide", "tile", "window_a",
-                                     "window_32", "table_in_kernel", "window_ring", "window_rot", "window_fuse", "window_shift", "window_facew", "window_facew5", "window_records", "pair_on", "pair_off",
+                                     "window_32", "table_in_kernel", "window_ring", "window_rot", "window_fuse", "window_shift", "window_facew", "window_facew5", "window_records", "window_records_async", "pair_on", "pair_off",
                                      "pair_sorted", "pair_table"])
 def test_mid_3d_radial_vs_oracle(precision, variant):
     """3-D radial, J=6, Kd=1.5N (BASELINE configs[4] scaled down) vs the live oracle."""
@@ -147,7 +147,7 @@ def test_mid_3d_radial_vs_oracle(precision, variant):
             "window_a": {"adj_kernel": 3, "order_b": 0}, "window_32": {"win_lanes": 32},
             "table_in_kernel": {"precomp_weights": 0}, "window_ring": {"win_ring": 1},
             "window_rot": {"win_ring": 2}, "window_fuse": {"win_ring": 3},
-            "window_shift": {"win_ring": 0}, "window_facew": {"win_facew": 1}, "window_facew5": {"win_facew": 2}, "window_records": {"win_facew": 3}, "pair_on": {"fwd_pair": 2},
+            "window_shift": {"win_ring": 0}, "window_facew": {"win_facew": 1}, "window_facew5": {"win_facew": 2}, "window_records": {"win_facew": 3}, "window_records_async": {"win_facew": 4}, "pair_on": {"fwd_pair": 2},
             "pair_off": {"fwd_pair": 0}, "pair_sorted": {"fwd_pair": 2, "fwd_interleave": 0},
             "pair_table": {"fwd_pair": 2, "precomp_weights": 0}}[variant]
     A = NufftBase(Nd=Nd, omega=om, Jd=6, Kd=Kd, precision=precision, options=opts)
