@@ -67,10 +67,26 @@ int b2n_plan_create(int ndim, const int *Nd, const int *Kd, const int *Jd, int L
                     int precision, int table_is_complex, int device, b2n_plan **out);
 int b2n_plan_destroy(b2n_plan *plan);
 
-/* integer options: "tile1","tile2","tile3" (bin shape in grid cells), "chunk"
- * (max samples per work item), "slide_pts" (samples per warp in the sliding-window
- * adjoint), "profile", "force_generic" (1 = never use the tiled / sliding
- * kernels), "use_tma" (0 = cooperative tile loads only).  Must precede set_points. */
+/* Integer options.  Layout options must precede b2n_plan_set_points; launch options may
+ * change between transforms.  Every non-default value is a tested variant (tests/).
+ *   layout:  "tile1","tile2","tile3" bin shape in grid cells; "chunk" max samples per forward
+ *            work item; "order_b" 1 = also build the adjoint sort order (3-D);
+ *            "precomp_weights" 1 = plan-time interpolation weights (0 = table lookups in the
+ *            kernels); "fwd_pair" 0/1/2 = same-cell sample pairs in the forward kernel off /
+ *            automatic / on; "fwd_interleave" column-interleaved slot order.
+ *   launch:  "force_generic" 1 = one-thread-per-sample kernels only; "use_tma" 0 = cooperative
+ *            tile loads; "fwd_pitch" shared-memory row pitch of the forward tile (0 = auto);
+ *            "adj_kernel" 3 register window (default) / 2 shared-memory tile + TMA reduce / 1
+ *            first-generation sliding window; "slide_pts" samples per warp of the window
+ *            kernels; "win_lanes" 8/16/32 lanes per sample; "win_ring" 0..3 window shift
+ *            variants (3 = last shift fused into the FMAs, default); "win_maxslide" longest
+ *            slide in cells (0 = J-1); "win_facew" -1 auto / 0 off / 1,2 face-weight staging /
+ *            3,4 plan-time window records (plain copy / cp.async double buffer);
+ *            "pruned_fft" 1 = skip the all-zero planes of the padded FFT; "profile" 1 = CUDA
+ *            events around the interpolation kernels; "sparse_mode" (set by the host for
+ *            mode="sparse").
+ *   read-only (b2n_plan_get_option): "last_fwd_kernel", "last_adj_kernel", "n_items",
+ *            "n_slots", "lib_calls". */
 int b2n_plan_set_option(b2n_plan *plan, const char *name, long value);
 long b2n_plan_get_option(b2n_plan *plan, const char *name);
 

@@ -377,6 +377,10 @@ extern "C" long b2n_plan_get_option(b2n_plan* p, const char* name) {
     if (n == "lib_calls") return (long)p->lib_calls;
     if (n == "n_items") return (long)p->n_items;
     if (n == "n_slots") return (long)p->n_slots;
+    if (n == "win_facew") return (long)p->opt_win_facew;
+    if (n == "win_ring") return (long)p->opt_win_ring;
+    if (n == "win_lanes") return (long)p->opt_win_lanes;
+    if (n == "win_maxslide") return (long)p->opt_win_maxslide;
     if (n == "fwd_pair") return (long)p->opt_fwd_pair;
     if (n == "fwd_interleave") return (long)p->opt_fwd_interleave;
     if (n == "last_fwd_kernel") return p->last_fwd_kernel;
