@@ -127,6 +127,15 @@ class CpuReference(object):
 
         self.engine = "reference" if orc.have_reference_engine() else "port"
         self.frac = frac
+        # all the host threads this process may use, whatever OMP_NUM_THREADS says (torchrun
+        # sets it to 1 for every rank): the reference's forward interpolator is OpenMP-parallel
+        self.cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        try:
+            import ctypes
+
+            ctypes.CDLL("libgomp.so.1").omp_set_num_threads(int(self.cores))
+        except OSError:  # pragma: no cover
+            pass
         idx = np.arange(0, SPOKES, frac)
         om = np.concatenate([radial3d(SPOKES, NREAD, int(s), int(s) + 1) for s in idx], 0)
         t0 = time.perf_counter()
@@ -158,7 +167,7 @@ class CpuReference(object):
             "kind": "reference" if self.engine == "reference" else "port",
             "pts_per_s_sample": 2 * self.Ms / (t_fwd + t_adj),
             "pts_per_s_full": 2 * M / t_full,
-            "cores": os.cpu_count(),
+            "cores": self.cores,
             "sample": ("1/%d of the spokes (evenly strided, M=%d): fwd %.2fs (interp %.2fs, OpenMP over "
                        "samples) adj %.2fs (interp %.2fs, one thread per coil as in the reference), "
                        "numpy.fft for the 384^3 FFT; value = 2*M_full/(FFT+scaling time + interp time"
