@@ -82,7 +82,9 @@ int b2n_plan_destroy(b2n_plan *plan);
  *            variants (3 = last shift fused into the FMAs, default); "win_maxslide" longest
  *            slide in cells (0 = J-1); "win_facew" -1 auto / 0 off / 1,2 face-weight staging /
  *            3,4 plan-time window records (plain copy / cp.async double buffer);
- *            "pruned_fft" 1 = skip the all-zero planes of the padded FFT; "profile" 1 = CUDA
+ *            "pruned_fft" 1 = skip the all-zero planes of the padded FFT; "own_fft3" 1 = the
+ *            axis-3 pass of the pruned FFT by the fused kernel of csrc/fft_axis3.cuh (zero
+ *            padding, phase_before and crop inside the pass; break-even, off by default); "profile" 1 = CUDA
  *            events around the interpolation kernels; "sparse_mode" (set by the host for
  *            mode="sparse").
  *   read-only (b2n_plan_get_option): "last_fwd_kernel", "last_adj_kernel", "n_items",

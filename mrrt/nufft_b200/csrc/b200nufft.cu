@@ -14,6 +14,7 @@
 
 #include "../../../include/b200nufft.h"
 #include "aux_kernels.cuh"
+#include "fft_axis3.cuh"
 #include "common.cuh"
 #include "dispatch.h"
 
@@ -131,6 +132,10 @@ struct b2n_plan {
     bool fft_pruned_ready = false;
     cufftHandle fft_2d = 0, fft_1d = 0;
     long opt_pruned_fft = 1;
+    long opt_own_fft3 = 0;       // pruned FFT: own axis-3 pass fused with the zero-padding, phase_before and the crop
+    Axis3Plan ax3{};             // its radix schedule, and the K3-entry twiddle table (precision dtype)
+    int ax3_state = 0;           // 0 = not prepared, 1 = ready, -1 = K3 not supported
+    void* d_tw3 = nullptr;
     void* d_work = nullptr;
     size_t work_bytes = 0;
     int64_t dev_bytes = 0;
@@ -280,6 +285,7 @@ extern "C" int b2n_plan_destroy(b2n_plan* p) {
     cudaSetDevice(p->device);
     for (auto& kv : p->fft_plans) cufftDestroy(kv.second);
     if (p->fft_pruned_ready) { cufftDestroy(p->fft_2d); cufftDestroy(p->fft_1d); }
+    dev_free(p->d_tw3);
     free_points(p);
     for (int d = 0; d < 3; d++) {
         bool dup = false;
@@ -329,6 +335,8 @@ extern "C" int b2n_plan_set_option(b2n_plan* p, const char* name, long value) {
         p->opt_fwd_pitch = value;
     } else if (n == "pruned_fft") {
         p->opt_pruned_fft = value;
+    } else if (n == "own_fft3") {
+        p->opt_own_fft3 = value;
     } else if (n == "fwd_pair") {
         if (value < 0 || value > 2) return fail(B2N_EINVAL, "fwd_pair must be 0 (off), 1 (auto) or 2 (on)");
         p->opt_fwd_pair = value;
@@ -377,6 +385,8 @@ extern "C" long b2n_plan_get_option(b2n_plan* p, const char* name) {
     if (n == "lib_calls") return (long)p->lib_calls;
     if (n == "n_items") return (long)p->n_items;
     if (n == "n_slots") return (long)p->n_slots;
+    if (n == "own_fft3") return (long)p->opt_own_fft3;
+    if (n == "pruned_fft") return (long)p->opt_pruned_fft;
     if (n == "win_facew") return (long)p->opt_win_facew;
     if (n == "win_ring") return (long)p->opt_win_ring;
     if (n == "win_lanes") return (long)p->opt_win_lanes;
@@ -1234,6 +1244,34 @@ static int get_pruned_fft(b2n_plan* p, cufftHandle* plan2d, cufftHandle* plan1d)
     return B2N_OK;
 }
 
+// own axis-3 pass (fft_axis3.cuh): radix schedule + twiddle table, prepared on first use
+template <typename T>
+static int prepare_axis3(b2n_plan* p) {
+    if (p->ax3_state != 0) return B2N_OK;
+    const int L = p->g.K[2];
+    int max_smem = 0;
+    CU(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, p->device));
+    if (!axis3_factor(L, &p->ax3) || Axis3Cfg<T>::smem(L) > (size_t)max_smem) {
+        p->ax3_state = -1;
+        return B2N_OK;
+    }
+    std::vector<T> tw(2 * (size_t)L);
+    for (int t = 0; t < L; t++) {
+        const double a = -2.0 * M_PI * (double)t / (double)L;
+        tw[2 * t] = (T)std::cos(a);
+        tw[2 * t + 1] = (T)std::sin(a);
+    }
+    int rc = dev_alloc(p, &p->d_tw3, sizeof(T) * 2 * (size_t)L);
+    if (rc) return rc;
+    CU(cudaMemcpy(p->d_tw3, tw.data(), sizeof(T) * 2 * (size_t)L, cudaMemcpyHostToDevice));
+    p->ax3_state = 1;
+    return B2N_OK;
+}
+
+// true when run_fft will apply phase_before / conj(phase_before) itself
+template <typename T>
+static bool axis3_fused(b2n_plan* p, int nbatch);
+
 template <typename T>
 static int exec_fft(cufftHandle h, void* data, int dir) {
     if (sizeof(T) == 4) FFT(cufftExecC2C(h, (cufftComplex*)data, (cufftComplex*)data, dir));
@@ -1243,6 +1281,13 @@ static int exec_fft(cufftHandle h, void* data, int dir) {
 
 // forward: in-plane passes on the non-zero planes, then axis 3; inverse: the reverse
 template <typename T>
+static bool axis3_fused(b2n_plan* p, int nbatch) {
+    if (!p->opt_own_fft3 || !pruned_ok(p, nbatch)) return false;
+    if (prepare_axis3<T>(p) != B2N_OK) return false;
+    return p->ax3_state == 1;
+}
+
+template <typename T>
 static int run_fft(b2n_plan* p, void* data, int nbatch, int dir, cudaStream_t st) {
     int rc;
     if (pruned_ok(p, nbatch)) {
@@ -1250,6 +1295,23 @@ static int run_fft(b2n_plan* p, void* data, int nbatch, int dir, cudaStream_t st
         if ((rc = get_pruned_fft(p, &h2, &h1))) return rc;
         FFT(cufftSetStream(h2, st));
         FFT(cufftSetStream(h1, st));
+        if (axis3_fused<T>(p, nbatch)) {
+            // in-plane passes by cuFFT on the N3 planes; axis 3 by the fused kernel, which also
+            // applies phase_before (forward, on store) / conj(phase_before) (inverse, on load)
+            const void* a1 = p->have_pb ? p->d_pb[0] : nullptr;
+            if (dir == CUFFT_FORWARD) {
+                if ((rc = exec_fft<T>(h2, data, dir))) return rc;
+                rc = fft_axis3_launch<T>(p->ax3, p->g, false, p->d_tw3, a1, p->d_pb[1], p->d_pb[2], data, st);
+                if (rc != 0) return fail(B2N_ECUDA, "axis-3 FFT launch failed: " + std::string(cudaGetErrorString((cudaError_t)rc)));
+            } else {
+                rc = fft_axis3_launch<T>(p->ax3, p->g, true, p->d_tw3, a1, p->d_pb[1], p->d_pb[2], data, st);
+                if (rc != 0) return fail(B2N_ECUDA, "axis-3 FFT launch failed: " + std::string(cudaGetErrorString((cudaError_t)rc)));
+                if ((rc = exec_fft<T>(h2, data, dir))) return rc;
+            }
+            p->lib_calls += 1;
+            p->launches += 1;
+            return B2N_OK;
+        }
         if (dir == CUFFT_FORWARD) {
             if ((rc = exec_fft<T>(h2, data, dir))) return rc;
             if ((rc = exec_fft<T>(h1, data, dir))) return rc;
@@ -1309,7 +1371,7 @@ static int grid_fwd_t(b2n_plan* p, const void* image, void* grid, int nbatch, cu
     CU(cudaGetLastError());
     if ((rc = run_fft<T>(p, work, nbatch, CUFFT_FORWARD, st))) return rc;
     p->launches += 1;
-    if (p->have_pb) {
+    if (p->have_pb && !axis3_fused<T>(p, nbatch)) {
         phase_before_kernel<T, VEC><<<grid_for(g.PK * nbatch / VEC + 1, 256, p->sm_count, 32), 256, 0, st>>>(
             g, ax, 0, work, nbatch);
         CU(cudaGetLastError());
@@ -1328,7 +1390,7 @@ static int grid_adj_t(b2n_plan* p, void* grid, void* image, int nbatch, cudaStre
     int rc;
     AxisPtrs ax = axis_ptrs(p);
     C* work = (C*)grid;
-    if (p->have_pb) {
+    if (p->have_pb && !axis3_fused<T>(p, nbatch)) {
         constexpr int VEC = 32 / (int)sizeof(C);
         phase_before_kernel<T, VEC><<<grid_for(g.PK * nbatch / VEC + 1, 256, p->sm_count, 32), 256, 0, st>>>(
             g, ax, 1, work, nbatch);

@@ -1,0 +1,240 @@
+// Axis-3 pass of the pruned oversampled 3-D FFT, fused with what surrounds it.
+//
+// The pruned FFT (b200nufft.cu: run_fft) does the two in-plane passes with a batched 2-D
+// cuFFT plan on the N3 non-zero planes and the pass along axis 3 on all K1*K2 columns.
+// This kernel IS that last pass (first pass of the inverse), written here so that the work
+// the reference does in separate full-grid sweeps rides along:
+//   forward  (_nufft.py:1331-1371): the zero planes k3 >= N3 are never read (the padding is
+//            created in shared memory), and phase_before is multiplied into the output as
+//            it is stored -- one read of N3 planes + one write of K3 planes instead of a
+//            strided FFT pass (r+w K3 planes) and a phase pass (r+w K3 planes);
+//   adjoint  (_nufft.py:1519-1559): conj(phase_before) is applied as the columns are loaded
+//            and only the planes k3 < N3, which survive the crop, are stored.
+// A CTA owns COLS adjacent columns (adjacent along axis 1, so every global access is a run
+// of COLS complex values), keeps them in shared memory and runs a mixed-radix (8, 4, 2, 3)
+// Stockham autosort FFT of length K3 on them: per pass one butterfly per thread, rows of
+// COLS values per shared-memory access (conflict-free), twiddles from a K3-entry table
+// evaluated in double precision on the host.  Unnormalised in both directions, like cuFFT.
+#pragma once
+#include "aux_kernels.cuh"
+#include "common.cuh"
+
+namespace b2n {
+
+struct Axis3Plan {
+    int L;            // transform length K3
+    int npass;
+    int radix[12];
+};
+
+// radices 4.., 2, 3..; returns false when L has another prime factor
+static inline bool axis3_factor(int L, Axis3Plan* ap) {
+    ap->L = L;
+    ap->npass = 0;
+    if (L < 2) return false;
+    while (L % 8 == 0) { ap->radix[ap->npass++] = 8; L /= 8; }
+    while (L % 4 == 0) { ap->radix[ap->npass++] = 4; L /= 4; }
+    while (L % 2 == 0) { ap->radix[ap->npass++] = 2; L /= 2; }
+    while (L % 3 == 0) { ap->radix[ap->npass++] = 3; L /= 3; }
+    return L == 1 && ap->npass <= 12;
+}
+
+template <typename T>
+__device__ __forceinline__ cplx_t<T> cmulc(cplx_t<T> a, cplx_t<T> b) {      // a * b
+    return make_c<T>(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+
+template <typename T> __device__ __forceinline__ cplx_t<T> cadd(cplx_t<T> a, cplx_t<T> b) { return make_c<T>(a.x + b.x, a.y + b.y); }
+template <typename T> __device__ __forceinline__ cplx_t<T> csub(cplx_t<T> a, cplx_t<T> b) { return make_c<T>(a.x - b.x, a.y - b.y); }
+// (+i) * a for the inverse transform, (-i) * a for the forward one
+template <typename T, bool INV> __device__ __forceinline__ cplx_t<T> rot90(cplx_t<T> a) {
+    return INV ? make_c<T>(-a.y, a.x) : make_c<T>(a.y, -a.x);
+}
+
+// length-4 DFT of (a0, a1, a2, a3) in place
+template <typename T, bool INV>
+__device__ __forceinline__ void dft4(cplx_t<T>& a0, cplx_t<T>& a1, cplx_t<T>& a2, cplx_t<T>& a3) {
+    using C = cplx_t<T>;
+    const C s02 = cadd<T>(a0, a2), d02 = csub<T>(a0, a2), s13 = cadd<T>(a1, a3);
+    const C id13 = rot90<T, INV>(csub<T>(a1, a3));
+    a0 = cadd<T>(s02, s13);
+    a1 = cadd<T>(d02, id13);
+    a2 = csub<T>(s02, s13);
+    a3 = csub<T>(d02, id13);
+}
+
+// One Stockham pass of radix R over the CTA's COLS columns: butterfly j reads rows
+// j + r*L/R, multiplies by the twiddles W^(r*k*L/(Ns*R)), k = j mod Ns, and writes rows
+// (j div Ns)*Ns*R + k + r*Ns.
+template <typename T, bool INV, int COLS, int R, int NT>
+__device__ __forceinline__ void axis3_pass(const cplx_t<T>* __restrict__ in, cplx_t<T>* __restrict__ out,
+                                           const cplx_t<T>* __restrict__ twS, int L, int Ns, int sh,
+                                           bool pow2, int tid) {
+    using C = cplx_t<T>;
+    const int c = tid % COLS;
+    const int Tn = L / R;
+    const int tstep = Tn / Ns;                       // = L / (Ns * R)
+    for (int j = tid / COLS; j < Tn; j += NT / COLS) {
+        const int k = pow2 ? (j & (Ns - 1)) : j % Ns;
+        const int jq = pow2 ? (j >> sh) : j / Ns;
+        const int j0 = jq * Ns * R + k;
+        C v[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) v[r] = in[(j + r * Tn) * COLS + c];
+        if (k != 0) {
+#pragma unroll
+            for (int r = 1; r < R; r++) v[r] = cmulc<T>(v[r], twS[r * k * tstep]);
+        }
+        if (R == 2) {
+            const C a = v[0];
+            v[0] = cadd<T>(a, v[1]);
+            v[1] = csub<T>(a, v[1]);
+        } else if (R == 3) {
+            // w = exp(-+ 2 pi i / 3) = (-1/2, -+ sqrt(3)/2)
+            const T hs = (T)0.86602540378443864676 * (INV ? (T)1 : (T)-1);
+            const C s12 = cadd<T>(v[1], v[2]), d12 = csub<T>(v[1], v[2]);
+            const C m = make_c<T>(v[0].x - (T)0.5 * s12.x, v[0].y - (T)0.5 * s12.y);
+            const C rr = make_c<T>(-hs * d12.y, hs * d12.x);                // i * hs * d12
+            v[0] = cadd<T>(v[0], s12);
+            v[1] = cadd<T>(m, rr);
+            v[2] = csub<T>(m, rr);
+        } else if (R == 4) {
+            dft4<T, INV>(v[0], v[1], v[2], v[3]);
+        } else {                                     // R == 8: two length-4 DFTs + one radix-2 stage
+            dft4<T, INV>(v[0], v[2], v[4], v[6]);
+            dft4<T, INV>(v[1], v[3], v[5], v[7]);
+            // odd half times w8^q, w8 = exp(-+ 2 pi i / 8)
+            const T h = (T)0.70710678118654752440;
+            const C b1 = v[3], b3 = v[7];
+            // w8^1 = (h, -+h), w8^2 = -+i, w8^3 = (-h, -+h)
+            const C t1 = INV ? make_c<T>(h * (b1.x - b1.y), h * (b1.x + b1.y))
+                             : make_c<T>(h * (b1.x + b1.y), h * (b1.y - b1.x));
+            const C t2 = rot90<T, INV>(v[5]);
+            const C t3 = INV ? make_c<T>(-h * (b3.x + b3.y), h * (b3.x - b3.y))
+                             : make_c<T>(h * (b3.y - b3.x), -h * (b3.x + b3.y));
+            const C e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6], o0 = v[1];
+            v[0] = cadd<T>(e0, o0); v[4] = csub<T>(e0, o0);
+            v[1] = cadd<T>(e1, t1); v[5] = csub<T>(e1, t1);
+            v[2] = cadd<T>(e2, t2); v[6] = csub<T>(e2, t2);
+            v[3] = cadd<T>(e3, t3); v[7] = csub<T>(e3, t3);
+        }
+#pragma unroll
+        for (int r = 0; r < R; r++) out[(j0 + r * Ns) * COLS + c] = v[r];
+    }
+}
+
+// INV = false: exp(-i...) (cuFFT forward); INV = true: exp(+i...)
+template <typename T, bool INV, int COLS, int NT>
+__global__ void __launch_bounds__(NT)
+fft_axis3_kernel(Axis3Plan ap, int64_t plane, int K1, int NZ, const cplx_t<T>* __restrict__ tw,
+                 const T* __restrict__ a1, const T* __restrict__ a2, const T* __restrict__ a3,
+                 cplx_t<T>* __restrict__ data) {
+    using C = cplx_t<T>;
+    extern __shared__ __align__(16) unsigned char fft3_smem[];
+    const int L = ap.L;
+    C* bufA = (C*)fft3_smem;
+    C* bufB = bufA + (size_t)L * COLS;
+    C* twS = bufB + (size_t)L * COLS;
+    const int tid = threadIdx.x;
+    const int64_t col0 = (int64_t)blockIdx.x * COLS;
+    const bool phase = a1 != nullptr;
+
+    for (int e = tid; e < L; e += NT) {
+        C w = tw[e];
+        if (INV) w.y = -w.y;
+        twS[e] = w;
+    }
+    // this thread's column (fixed: NT % COLS == 0) and its in-plane phase angle
+    const int c = tid % COLS;
+    const int64_t col = col0 + c;
+    const bool col_ok = col < plane;
+    T a12 = (T)0;
+    if (phase && col_ok) {
+        const int k1 = (int)(col % K1), k2 = (int)(col / K1);
+        a12 = a1[k1] + a2[k2];                       // the reference's summation order
+    }
+    // ---- load (forward: only the non-zero planes; the rest of the column is padding)
+    const int rows_in = INV ? L : NZ;
+    for (int k3 = tid / COLS; k3 < L; k3 += NT / COLS) {
+        C v = make_c<T>(0, 0);
+        if (k3 < rows_in && col_ok) {
+            v = data[(int64_t)k3 * plane + col];
+            if (INV && phase) {
+                T s, co;
+                sincos_t(a12 + a3[k3], &s, &co);
+                v = make_c<T>(v.x * co + v.y * s, v.y * co - v.x * s);      // * conj(phase)
+            }
+        }
+        bufA[k3 * COLS + c] = v;
+    }
+    __syncthreads();
+    // ---- Stockham passes (radix dispatch is uniform; Ns is a power of two until the first
+    // radix-3 pass, so the index split is a shift and a mask there)
+    C* in = bufA;
+    C* out = bufB;
+    int Ns = 1;
+    for (int p = 0; p < ap.npass; p++) {
+        const int R = ap.radix[p];
+        const bool pow2 = (Ns & (Ns - 1)) == 0;
+        const int sh = 31 - __clz(Ns);
+        if (R == 8) axis3_pass<T, INV, COLS, 8, NT>(in, out, twS, L, Ns, sh, pow2, tid);
+        else if (R == 4) axis3_pass<T, INV, COLS, 4, NT>(in, out, twS, L, Ns, sh, pow2, tid);
+        else if (R == 2) axis3_pass<T, INV, COLS, 2, NT>(in, out, twS, L, Ns, sh, pow2, tid);
+        else axis3_pass<T, INV, COLS, 3, NT>(in, out, twS, L, Ns, sh, pow2, tid);
+        __syncthreads();
+        C* t = in; in = out; out = t;
+        Ns *= R;
+    }
+    // ---- store (adjoint: only the planes that survive the crop)
+    if (!col_ok) return;
+    const int rows_out = INV ? NZ : L;
+    for (int k3 = tid / COLS; k3 < rows_out; k3 += NT / COLS) {
+        C v = in[k3 * COLS + c];
+        if (!INV && phase) {
+            T s, co;
+            sincos_t(a12 + a3[k3], &s, &co);
+            v = make_c<T>(v.x * co - v.y * s, v.x * s + v.y * co);          // * phase
+        }
+        data[(int64_t)k3 * plane + col] = v;
+    }
+}
+
+template <typename T> struct Axis3Cfg {
+    // 8 (4) columns = 64-byte runs per global access, 256 threads; at K3 = 384 the two buffers
+    // take 48 KB: 4 CTAs = 32 warps per SM.  Measured on the bench workload against cuFFT's
+    // strided pass + the phase kernel (fft / adj, ms): 16 columns x 256 threads +0.10 / +0.33,
+    // 16 x 512 -0.03 / +0.08, 8 x 256 -0.06 / +0.02 -- break-even, so the option stays off.
+    static constexpr int COLS = sizeof(T) == 4 ? 8 : 4;
+    static constexpr int NT = 256;
+    static size_t smem(int L) { return (size_t)(2 * L * COLS + L) * 2 * sizeof(T); }
+};
+
+// returns 0 or a cudaError_t
+template <typename T>
+static int fft_axis3_launch(const Axis3Plan& ap, const Geom& g, bool inverse, const void* tw,
+                            const void* a1, const void* a2, const void* a3, void* data,
+                            cudaStream_t st) {
+    using C = cplx_t<T>;
+    constexpr int COLS = Axis3Cfg<T>::COLS;
+    constexpr int NT = Axis3Cfg<T>::NT;
+    const int64_t plane = (int64_t)g.K[0] * g.K[1];
+    const size_t smem = Axis3Cfg<T>::smem(ap.L);
+    const unsigned nb = (unsigned)((plane + COLS - 1) / COLS);
+    cudaError_t e;
+    if (inverse) {
+        auto k = fft_axis3_kernel<T, true, COLS, NT>;
+        e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        k<<<nb, NT, smem, st>>>(ap, plane, g.K[0], g.N[2], (const C*)tw, (const T*)a1, (const T*)a2,
+                                 (const T*)a3, (C*)data);
+    } else {
+        auto k = fft_axis3_kernel<T, false, COLS, NT>;
+        e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        k<<<nb, NT, smem, st>>>(ap, plane, g.K[0], g.N[2], (const C*)tw, (const T*)a1, (const T*)a2,
+                                 (const T*)a3, (C*)data);
+    }
+    return (int)cudaGetLastError();
+}
+
+}  // namespace b2n

@@ -50,7 +50,9 @@ if __name__ == "__main__":
         gf = nufft_forward(A, g, grid_only=True)
         if ref_a is None:
             ref_a, ref_f = ga.clone(), gf.clone()
-        r = {"opts": opts, "adj_ms": timeit(lambda: nufft_adj(A, y, grid_only=True)),
+        xim = torch.randn(tuple(reversed(Nd)), dtype=cdt, device="cuda").permute(2, 1, 0)
+        r = {"opts": opts, "fft_full_ms": timeit(lambda: A.fft(xim)), "adj_full_ms": timeit(lambda: A.adj(y)),
+             "adj_ms": timeit(lambda: nufft_adj(A, y, grid_only=True)),
              "fwd_ms": timeit(lambda: nufft_forward(A, g, grid_only=True)),
              "adj_rel_vs_base": float((ga - ref_a).norm() / ref_a.norm()),
              "fwd_rel_vs_base": float((gf - ref_f).norm() / ref_f.norm()),

@@ -567,3 +567,39 @@ def test_toeplitz_norm_vs_exact_gram(case):
     assert rel_l2(y, ya) <= 2 * tol
     with pytest.raises(ValueError):
         T.norm(np.zeros(int(np.prod(Nd)) + 1))
+
+
+@pytest.mark.parametrize("name", [n for n in case_names() if n.startswith("d3_")])
+def test_own_axis3_fft_golden(name):
+    """Option own_fft3: the axis-3 pass of the pruned FFT done by the fused kernel (zero
+    padding in shared memory, phase_before on store / conj(phase_before) on load, cropped
+    store) instead of cuFFT + the phase kernel -- every 3-D golden case of the reference."""
+    cfg, z = load_case(name)
+    tol = TOL[cfg["precision"]]
+    A = _op(cfg, z["omega"], options={"own_fft3": 1})
+    assert rel_l2(A.fft(z["x"]), z["y"]) <= tol
+    assert rel_l2(A.adj(z["y"]), z["x_adj"]) <= tol
+    B = _op(cfg, z["omega"])
+    assert rel_l2(A.fft(z["x"]), B.fft(z["x"])) <= tol / 4
+    assert rel_l2(A.adj(z["y"]), B.adj(z["y"])) <= tol / 4
+
+
+@pytest.mark.parametrize("precision", ["single", "double"])
+@pytest.mark.parametrize("Kd", [(48, 40, 96), (40, 48, 54), (36, 36, 35)])
+def test_own_axis3_fft_vs_oracle(precision, Kd):
+    """own_fft3 on grids whose axis-3 length is 4*4*2*3, 2*3*3*3 and 5*7 (the last one is not
+    supported by the radix schedule and must fall back to cuFFT)."""
+    from oracle import nufft_oracle as orc
+    from mrrt.nufft_b200 import NufftBase
+
+    Nd = (24, 20, 30)
+    rs = np.random.RandomState(3)
+    rdt = np.float32 if precision == "single" else np.float64
+    om = ((rs.rand(5000, 3) * 2 - 1) * np.pi).astype(rdt)
+    A = NufftBase(Nd=Nd, omega=om, Jd=6, Kd=Kd, precision=precision, n_shift=(3, 0, 7),
+                  options={"own_fft3": 1})
+    O = orc.OracleNufft(Nd=Nd, omega=om, Jd=6, Kd=Kd, precision=precision, n_shift=(3, 0, 7))
+    x = (rs.standard_normal(Nd) + 1j * rs.standard_normal(Nd)).astype(A._cplx_dtype)
+    yo = O.fft(x)
+    assert rel_l2(A.fft(x), yo) <= TOL[precision]
+    assert rel_l2(A.adj(yo), O.adj(yo)) <= TOL[precision]
