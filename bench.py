@@ -494,7 +494,7 @@ def main():
                     help="N>1, c5 workload: coils = one coil of the volume per GPU, no collective "
                          "(weak scaling, default); samples = one coil, spokes sharded, NCCL "
                          "all-reduce of the adjoint image (strong scaling)")
-    ap.add_argument("--host-chunks", type=int, default=8,
+    ap.add_argument("--host-chunks", type=int, default=4,
                     help="sample ranges pipelined against host<->device copies in the e2e leg")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
