@@ -657,3 +657,50 @@ def dtft_adj(xk, omega, shape, n_shift=None):
     out = np.dot(np.exp(1j * ph), xk)
     out = out.reshape(tuple(shape) + (-1,), order="F")
     return out[..., 0] if out.shape[-1] == 1 else out
+
+
+# ---------------------------------------------------------------------------------------
+# Restatement of the axis-3 FFT pass of mrrt/nufft_b200/csrc/fft_axis3.cuh (option own_fft3):
+# the same radix schedule and the same Stockham index arithmetic, in NumPy, so that the
+# schedule is pinned against numpy.fft on the CPU (tests/test_oracle.py).  The reference has
+# no counterpart (it calls numpy.fft / cuFFT, _nufft.py:1331, :1335-1369).
+# ---------------------------------------------------------------------------------------
+def axis3_radices(L):
+    """Radix schedule of ``axis3_factor``: 8s, 4s, 2s, then 3s; None if L has another factor."""
+    if L < 2:
+        return None
+    out = []
+    for r in (8, 4, 2, 3):
+        while L % r == 0:
+            out.append(r)
+            L //= r
+    return out if L == 1 else None
+
+
+def axis3_stockham(x, inverse=False):
+    """Unnormalised DFT of the last axis of ``x`` by the kernel's Stockham passes: butterfly
+    ``j`` of a radix-``R`` pass reads rows ``j + r*L/R``, multiplies by
+    ``W^(r*k*L/(Ns*R))`` with ``k = j mod Ns`` and writes rows ``(j div Ns)*Ns*R + k + r*Ns``."""
+    x = np.asarray(x, dtype=np.complex128)
+    L = x.shape[-1]
+    rad = axis3_radices(L)
+    if rad is None:
+        raise ValueError("length %d is not of the form 2^a 3^b" % L)
+    sign = 1.0 if inverse else -1.0
+    W = np.exp(sign * 2j * np.pi * np.arange(L) / L)
+    a = x.copy()
+    Ns = 1
+    for R in rad:
+        b = np.empty_like(a)
+        Tn = L // R
+        tstep = Tn // Ns
+        j = np.arange(Tn)
+        k = j % Ns
+        j0 = (j // Ns) * Ns * R + k
+        v = [a[..., j + r * Tn] * W[(r * k * tstep) % L] for r in range(R)]
+        small = np.exp(sign * 2j * np.pi * np.outer(np.arange(R), np.arange(R)) / R)
+        for q in range(R):
+            b[..., j0 + q * Ns] = sum(small[q, r] * v[r] for r in range(R))
+        a = b
+        Ns *= R
+    return a

@@ -119,3 +119,14 @@ def test_bin_sort_properties():
     assert np.all(np.diff(perm)[same] > 0)
     nb = [-(-k // t) for k, t in zip(Kd, tile)]
     assert bins.min() >= 0 and bins.max() < np.prod(nb)
+
+
+@pytest.mark.parametrize("L", [384, 192, 96, 54, 48, 36, 12, 8, 6, 2])
+def test_axis3_stockham_schedule(L):
+    """The radix schedule / index arithmetic of the own axis-3 FFT pass (csrc/fft_axis3.cuh,
+    restated in the oracle) is a DFT: against numpy.fft in both directions."""
+    rs = np.random.RandomState(L)
+    x = rs.standard_normal((3, L)) + 1j * rs.standard_normal((3, L))
+    assert np.allclose(orc.axis3_stockham(x), np.fft.fft(x, axis=-1), rtol=0, atol=1e-11)
+    assert np.allclose(orc.axis3_stockham(x, inverse=True), np.fft.ifft(x, axis=-1) * L, rtol=0, atol=1e-11)
+    assert orc.axis3_radices(35) is None and orc.axis3_radices(384) == [8, 8, 2, 3]
