@@ -603,3 +603,26 @@ def test_own_axis3_fft_vs_oracle(precision, Kd):
     yo = O.fft(x)
     assert rel_l2(A.fft(x), yo) <= TOL[precision]
     assert rel_l2(A.adj(yo), O.adj(yo)) <= TOL[precision]
+
+
+@pytest.mark.parametrize("precision", ["single", "double"])
+@pytest.mark.parametrize("J", [5, 7, 8])
+def test_3d_window_kernels_other_J(J, precision):
+    """3-D register-window adjoint / tiled forward at the kernel sizes the golden cases do not
+    reach (J = 5 with the face-weight staging, J = 7 and 8 without), vs the oracle."""
+    from oracle import nufft_oracle as orc
+    from mrrt.nufft_b200 import NufftBase
+
+    Nd, Kd = (20, 18, 16), (32, 28, 24)
+    rdt = np.float32 if precision == "single" else np.float64
+    om = _radial3d(150, 48).astype(rdt)
+    A = NufftBase(Nd=Nd, omega=om, Jd=J, Kd=Kd, precision=precision)
+    O = orc.OracleNufft(Nd=Nd, omega=om, Jd=J, Kd=Kd, precision=precision)
+    rs = np.random.RandomState(J)
+    x = (rs.standard_normal(Nd) + 1j * rs.standard_normal(Nd)).astype(A._cplx_dtype)
+    yo = O.fft(x)
+    assert rel_l2(A.fft(x), yo) <= TOL[precision]
+    xa = A.adj(yo)
+    assert A.option("last_adj_kernel") == 3
+    # float32: the reference's own sequential accumulation noise dominates (DESIGN section 2)
+    assert rel_l2(xa, O.adj(yo)) <= (2e-5 if precision == "single" else TOL[precision])
