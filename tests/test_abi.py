@@ -97,3 +97,36 @@ def test_kernel_objects():
     assert abs(kaiser_bessel(np.array([0.0]), 6, k.alpha[0])[0] - 1.0) < 1e-15
     with pytest.raises(ValueError):
         BeattyKernel((6, 6), (64,), (128, 128))
+
+
+def test_kaiser_bessel_matches_reference_values():
+    """kaiser_bessel / kaiser_bessel_ft / BeattyKernel against values produced by the real
+    reference package (tests/golden/make_golden_kaiser.py) at the reference's own test
+    parameters (tests/test_kaiser.py:18-88, tests/test_kernels.py:17-58)."""
+    import os
+    import warnings
+
+    from mrrt.nufft_b200 import BeattyKernel, kaiser_bessel, kaiser_bessel_ft
+
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "extra", "kaiser.npz"))
+    for m in (-4, 0, 2, 7):
+        got = kaiser_bessel(z["kb_x"], 8, 2.34 * 8, m)
+        np.testing.assert_allclose(got, z["kb_J8_m%d" % m], rtol=1e-12, atol=1e-14)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for m in (-2, 0, 2, 7):
+            np.testing.assert_allclose(kaiser_bessel(z["kbx_x"], 5, 6.8, m), z["kbx_J5_m%d" % m],
+                                       rtol=1e-12, atol=1e-14)
+            np.testing.assert_allclose(kaiser_bessel_ft(z["ft_u"], 5, 6.8, m, 1), z["ft_J5_m%d" % m],
+                                       rtol=1e-11, atol=1e-13)
+    shapes = {"c1": ((6, 6), (256, 256), (512, 512)), "c3": ((4, 4, 4), (128,) * 3, (192,) * 3),
+              "c5": ((6, 6, 6), (256,) * 3, (384,) * 3), "odd": ((3, 4), (64, 64), (128, 128)),
+              "t": ((4, 4), (24, 16), (32, 32))}
+    for tag, (shape, grid, os_grid) in shapes.items():
+        k = BeattyKernel(shape, grid, os_grid)
+        assert np.array_equal(np.asarray(k.alpha, dtype=np.float64), z["beatty_%s_alpha" % tag])
+        assert np.array_equal(np.asarray(k.m, dtype=np.float64), z["beatty_%s_m" % tag])
+        for d in range(len(shape)):
+            xs = np.linspace(-shape[d] / 2 - 0.5, shape[d] / 2 + 0.5, 301)
+            np.testing.assert_allclose(k.kernels[d](xs), z["beatty_%s_k%d" % (tag, d)],
+                                       rtol=1e-12, atol=1e-14)
