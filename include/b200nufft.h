@@ -69,26 +69,31 @@ int b2n_plan_destroy(b2n_plan *plan);
 
 /* Integer options.  Layout options must precede b2n_plan_set_points; launch options may
  * change between transforms.  Every non-default value is a tested variant (tests/).
- *   layout:  "tile1","tile2","tile3" bin shape in grid cells; "chunk" max samples per forward
- *            work item; "order_b" 1 = also build the adjoint sort order (3-D);
- *            "precomp_weights" 1 = plan-time interpolation weights (0 = table lookups in the
- *            kernels); "fwd_pair" 0/1/2 = same-cell sample pairs in the forward kernel off /
- *            automatic / on; "fwd_interleave" column-interleaved slot order.
+ *   layout:  "tile1","tile2","tile3" bin shape in grid cells; "tileb1".."tileb3" bin shape of
+ *            the adjoint sort order; "chunk" max samples per forward work item; "order_b" 1 =
+ *            also build the adjoint sort order (3-D); "precomp_weights" 1 = plan-time
+ *            interpolation weights (0 = table lookups in the kernels, the table staged in
+ *            shared memory); "fwd_pair" 0/1/2 = same-cell sample pairs in the forward kernel
+ *            off / automatic / on; "fwd_interleave" column-interleaved slot order.
  *   launch:  "force_generic" 1 = one-thread-per-sample kernels only; "use_tma" 0 = cooperative
  *            tile loads; "fwd_pitch" shared-memory row pitch of the forward tile (0 = auto);
- *            "adj_kernel" 3 register window (default) / 2 shared-memory tile + TMA reduce / 1
- *            first-generation sliding window; "slide_pts" samples per warp of the window
- *            kernels; "win_lanes" 8/16/32 lanes per sample; "win_ring" 0..3 window shift
- *            variants (3 = last shift fused into the FMAs, default); "win_maxslide" longest
- *            slide in cells (0 = J-1); "win_facew" -1 auto / 0 off / 1,2 face-weight staging /
- *            3,4 plan-time window records (plain copy / cp.async double buffer);
- *            "pruned_fft" 1 = skip the all-zero planes of the padded FFT; "own_fft3" 1 = the
- *            axis-3 pass of the pruned FFT by the fused kernel of csrc/fft_axis3.cuh (zero
- *            padding, phase_before and crop inside the pass; break-even, off by default); "profile" 1 = CUDA
- *            events around the interpolation kernels; "sparse_mode" (set by the host for
- *            mode="sparse").
- *   read-only (b2n_plan_get_option): "last_fwd_kernel", "last_adj_kernel", "n_items",
- *            "n_slots", "lib_calls". */
+ *            "slide_pts" samples per warp of the register-window adjoint kernels;
+ *            "win_maxslide" longest window slide in cells (0 = J-1); "win_facew" -1 auto / 0
+ *            off / 1,2 face-weight staging of the 3-D window adjoint; "pruned_fft" 1 = skip
+ *            the all-zero planes of the padded FFT; "own_fft3" 1 = the axis-3 pass of the
+ *            pruned FFT by the fused kernel of csrc/fft_axis3.cuh (zero padding,
+ *            phase_before and crop inside the pass; break-even, off by default);
+ *            "profile" 1 = CUDA events around the interpolation kernels; "sparse_mode" (set
+ *            by the host for mode="sparse").
+ *   read-only (b2n_plan_get_option): "last_fwd_kernel" (0 one thread per sample, 1 tiled),
+ *            "last_adj_kernel" (0 one RED per tap, 3 3-D register window, 4 2-D register
+ *            window), "n_items", "n_slots", "lib_calls".
+ *
+ * Threading / streams: a plan is NOT re-entrant.  It owns one scratch grid and its cuFFT
+ * handles are re-pointed at the stream of each call, so transforms on one plan must be issued
+ * by one host thread at a time and on one stream (or be ordered by the caller with events).
+ * Plan-time arrays (sorted points, weights) are complete when set_points / set_tables return.
+ * Every entry point runs on the plan's device and restores the caller's current device. */
 int b2n_plan_set_option(b2n_plan *plan, const char *name, long value);
 long b2n_plan_get_option(b2n_plan *plan, const char *name);
 

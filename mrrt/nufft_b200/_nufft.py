@@ -189,6 +189,8 @@ class NufftBase(object):
             device = torch.device("cuda", torch.cuda.current_device())
         elif not isinstance(device, torch.device):
             device = torch.device("cuda", int(device))
+        elif device.index is None:          # torch.device("cuda"): the CURRENT device, not 0
+            device = torch.device("cuda", torch.cuda.current_device())
         self.device = device
 
         # ---- omega: validate, remember the caller's copy for the phase computation
@@ -239,7 +241,7 @@ class NufftBase(object):
         _lib.check(self._lib.b2n_plan_create(
             self.ndim, arr(self.Nd), arr(self.Kd), arr(self.Jd), int(Ld),
             _lib.B2N_SINGLE if precision == "single" else _lib.B2N_DOUBLE,
-            1 if phasing == "complex" else 0, self.device.index or 0, ctypes.byref(plan)))
+            1 if phasing == "complex" else 0, self.device.index, ctypes.byref(plan)))
         self._plan = plan
         for k, v in (options or {}).items():
             _lib.check(self._lib.b2n_plan_set_option(self._plan, k.encode(), int(v)))

@@ -74,7 +74,7 @@ class ToeplitzNorm(object):
             _lib.check(self._lib.b2n_plan_create(
                 self.ndim, arr(self.Nd), arr(N2), arr((1,) * self.ndim), 1,
                 _lib.B2N_SINGLE if A.precision == "single" else _lib.B2N_DOUBLE,
-                1, self.device.index or 0, ctypes.byref(plan)))
+                1, self.device.index, ctypes.byref(plan)))
             self._plan = plan
             sn_ptrs = (ctypes.c_void_p * 3)()
             self._ones = [np.ones(n, dtype=np.float64) for n in self.Nd]

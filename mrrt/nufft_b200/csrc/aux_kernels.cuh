@@ -32,7 +32,9 @@ __global__ void prep_points_kernel(Geom g, Gam<T> gam, int kind, const T* __rest
                 ok = ok && is_finite(t);
                 tm[(int64_t)d * M + i] = t;
                 int kw = 0;
-                if (ok) kw = wrap_index(window_origin<T>(t, g.J[d]), g.K[d]);
+                if (ok) kw = local_index(window_origin<T>(t, g.J[d]), g.Kg[d], g.korg[d]);
+                // slab plans: the whole window must lie inside the rows this plan holds
+                if (ok && g.Kg[d] != g.K[d] && kw + g.J[d] > g.K[d]) { atomicExch(nonfinite, 2); kw = 0; }
                 bin += (int64_t)(kw / g.tile[d]) * bstride;
                 cell += (int64_t)(kw % g.tile[d]) * cstride;
                 // adjoint order: its own (longer) bins, LAST axis fastest inside the bin
@@ -44,7 +46,7 @@ __global__ void prep_points_kernel(Geom g, Gam<T> gam, int kind, const T* __rest
                 cstride *= g.tile[d];
             }
         }
-        if (!ok) atomicExch(nonfinite, 1);
+        if (!ok) atomicMax(nonfinite, 3);
         keys[i] = (uint64_t)(bin * cstride + cell);
         if (keys_b != nullptr) keys_b[i] = (uint64_t)(bin_b * cstride_b + cell_b);
         bin_ids[i] = (int32_t)bin;
@@ -74,7 +76,7 @@ __global__ void point_windows_kernel(Geom g, const T* __restrict__ tm_s, int32_t
         for (int d = 0; d < g.ndim; d++) {
             const int ko = window_origin<T>(tm_s[(int64_t)d * M + i], g.J[d]);
             pt_ko[(int64_t)d * M + i] = ko;
-            pt_kw[(int64_t)d * M + i] = wrap_index(ko, g.K[d]);
+            pt_kw[(int64_t)d * M + i] = local_index(ko, g.Kg[d], g.korg[d]);
         }
     }
 }

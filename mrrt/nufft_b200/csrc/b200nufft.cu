@@ -44,6 +44,27 @@ static int fail(int code, const std::string& msg) {
             return fail(B2N_ECUDA, std::string(#call) + ": cufft error " + std::to_string((int)r_)); \
     } while (0)
 
+// Every entry point runs on the plan's device and restores the caller's current device on
+// return (a plan on cuda:1 must not switch a single-process multi-GPU program to cuda:1).
+struct DevGuard {
+    int prev = -1;
+    cudaError_t err = cudaSuccess;
+    explicit DevGuard(int device) {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != device) err = cudaSetDevice(device);
+        else if (err == cudaSuccess) prev = -1;      // nothing to restore
+    }
+    ~DevGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+    DevGuard(const DevGuard&) = delete;
+    DevGuard& operator=(const DevGuard&) = delete;
+};
+#define ON_DEVICE(p)                                                                  \
+    DevGuard dev_guard_((p)->device);                                                 \
+    if (dev_guard_.err != cudaSuccess)                                                \
+        return fail(B2N_ECUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(dev_guard_.err))
+
 // ---------------------------------------------------------------------------------
 // plan
 // ---------------------------------------------------------------------------------
@@ -58,21 +79,13 @@ struct b2n_plan {
     long opt_force_generic = 0;
     long opt_use_tma = 1;
     long opt_sparse_mode = 0;
-    long opt_slide_pts = 256;
-    // 0 generic, 1 sliding window + global REDs, 2 tiled sliding window (smem tile),
-    // 3 register window with lane-parallel batch weights and the adjoint sort order
-    long opt_adj_kernel = 3;
-    long opt_order_b = 1;        // build the adjoint sort order (adj_kernel 3)
+    long opt_slide_pts = 256;    // samples per warp of the register-window adjoint kernels
+    long opt_order_b = 1;        // build the adjoint sort order (3-D register-window adjoint)
     long opt_fwd_pitch = 0;      // shared-memory row pitch of the forward tile (0 = automatic)
-    long opt_win_lanes = 16;
     long opt_fwd_pair = 1;       // tiled forward: same-cell sample pairs share one window pass (1 = auto)
     long opt_fwd_interleave = 1; // ... and the slots of a bin are ordered column-interleaved
-    // register-window adjoint: 0 register shifts, 1 lane ring, 2 fixed ring with rotated
-    // weights, 3 last shift of a slide fused into the FMAs (default; fastest measured)
-    long opt_win_ring = 3;
     long opt_win_facew = -1;     // window adjoint: face-weight staging.  -1 = automatic: J <= 6 (measured at
-                                 // J = 4 and 6): float 2 (5 CTAs/SM), double 1; 0 = off; 3 = plan-time
-                                 // window records (tested option: no faster, 192 B/sample of plan memory)
+                                 // J = 4 and 6): float 2 (5 CTAs/SM), double 1; 0 = off
     long opt_win_maxslide = 0;   // longest window slide in cells before a new window is started (0 = J-1)
     bool tile_user_set = false;
     bool tile_b_user_set = false;
@@ -105,8 +118,6 @@ struct b2n_plan {
     // plan-time interpolation weights [sum(J)][M] for each sort order (real tables)
     void* d_wts = nullptr;
     void* d_wts_b = nullptr;
-    void* d_win_recs = nullptr;  // plan-time window records of the adjoint kernel (win_facew 3)
-    long win_recs_pts = -1, win_recs_slide = -1;
     long opt_precomp = 1;
     void* d_phase_s = nullptr;   // sorted sample phase or null
     int64_t nbins = 0;
@@ -144,7 +155,8 @@ struct b2n_plan {
     long opt_profile = 0;        // record CUDA events around the interpolation kernels
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_fwd, ev_adj;
     int last_fwd_kernel = -1;   // 0 generic, 1 tiled
-    int last_adj_kernel = -1;   // 0 generic, 1 sliding window, 2 tiled, 3 register window, 4 2-D multi-coil window
+    int last_adj_kernel = -1;   // 0 generic, 3 3-D register window, 4 2-D register window
+    std::map<void*, size_t> alloc_bytes;   // what dev_alloc handed out (device_bytes accounting)
 
     size_t real_size() const { return precision == B2N_SINGLE ? 4 : 8; }
     size_t cplx_size() const { return 2 * real_size(); }
@@ -154,10 +166,17 @@ static int dev_alloc(b2n_plan* p, void** ptr, size_t bytes) {
     if (bytes == 0) bytes = 16;
     CU(cudaMalloc(ptr, bytes));
     p->dev_bytes += (int64_t)bytes;
+    p->alloc_bytes[*ptr] = bytes;
     return B2N_OK;
 }
-static void dev_free(void* ptr) {
-    if (ptr) cudaFree(ptr);
+static void dev_free(b2n_plan* p, void* ptr) {
+    if (!ptr) return;
+    auto it = p->alloc_bytes.find(ptr);
+    if (it != p->alloc_bytes.end()) {
+        p->dev_bytes -= (int64_t)it->second;
+        p->alloc_bytes.erase(it);
+    }
+    cudaFree(ptr);
 }
 
 // plan-time scratch buffers: freed on every exit path
@@ -194,7 +213,8 @@ static void default_tiles(b2n_plan* p) {
         if (g.ndim == 3) { g.tile[0] = 16; g.tile[1] = 8; g.tile[2] = 8; }
     }
     if (!p->tile_b_user_set) {
-        g.tile_b[0] = 16; g.tile_b[1] = 16; g.tile_b[2] = 64;
+        // adjoint order: long bins along the LAST axis (the one the register windows slide along)
+        g.tile_b[0] = 16; g.tile_b[1] = g.ndim == 2 ? 64 : 16; g.tile_b[2] = 64;
     }
     for (int d = 0; d < 3; d++) {
         if (d >= g.ndim) g.tile_b[d] = 1;
@@ -223,7 +243,9 @@ extern "C" int b2n_plan_create(int ndim, const int* Nd, const int* Kd, const int
     int ndev = 0;
     CU(cudaGetDeviceCount(&ndev));
     if (device < 0 || device >= ndev) return fail(B2N_EINVAL, "bad device ordinal");
-    CU(cudaSetDevice(device));
+    DevGuard dev_guard_(device);
+    if (dev_guard_.err != cudaSuccess)
+        return fail(B2N_ECUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(dev_guard_.err));
     b2n_plan* p = new b2n_plan();
     p->precision = precision;
     p->cplx_table = table_is_complex ? 1 : 0;
@@ -257,21 +279,18 @@ extern "C" int b2n_plan_create(int ndim, const int* Nd, const int* Kd, const int
 }
 
 static void free_points(b2n_plan* p) {
-    dev_free(p->d_tm); dev_free(p->d_tm_s); dev_free(p->d_keys); dev_free(p->d_bin_ids);
-    dev_free(p->d_perm); dev_free(p->d_phase_s); dev_free(p->d_items);
-    dev_free(p->d_slots); dev_free(p->d_items_f);
-    dev_free(p->d_slot_kw); dev_free(p->d_slot_perm); dev_free(p->d_wts_f); dev_free(p->d_phase_f);
+    dev_free(p, p->d_tm); dev_free(p, p->d_tm_s); dev_free(p, p->d_keys); dev_free(p, p->d_bin_ids);
+    dev_free(p, p->d_perm); dev_free(p, p->d_phase_s); dev_free(p, p->d_items);
+    dev_free(p, p->d_slots); dev_free(p, p->d_items_f);
+    dev_free(p, p->d_slot_kw); dev_free(p, p->d_slot_perm); dev_free(p, p->d_phase_f);
     p->d_slots = nullptr; p->d_items_f = nullptr; p->n_items_f = 0; p->n_slots = 0;
     p->d_slot_kw = p->d_slot_perm = nullptr; p->d_wts_f = p->d_phase_f = nullptr;
-    dev_free(p->d_pt_ko); dev_free(p->d_pt_kw);
+    dev_free(p, p->d_pt_ko); dev_free(p, p->d_pt_kw);
     p->d_pt_ko = p->d_pt_kw = nullptr;
-    dev_free(p->d_tm_sb); dev_free(p->d_perm_b); dev_free(p->d_pt_ko_b); dev_free(p->d_pt_kw_b);
-    dev_free(p->d_phase_sb);
-    dev_free(p->d_wts); dev_free(p->d_wts_b); dev_free(p->d_wts_f);
+    dev_free(p, p->d_tm_sb); dev_free(p, p->d_perm_b); dev_free(p, p->d_pt_ko_b); dev_free(p, p->d_pt_kw_b);
+    dev_free(p, p->d_phase_sb);
+    dev_free(p, p->d_wts); dev_free(p, p->d_wts_b); dev_free(p, p->d_wts_f);
     p->d_wts = p->d_wts_b = p->d_wts_f = nullptr;
-    dev_free(p->d_win_recs);
-    p->d_win_recs = nullptr;
-    p->win_recs_pts = p->win_recs_slide = -1;
     p->d_tm_sb = p->d_phase_sb = nullptr;
     p->d_perm_b = p->d_pt_ko_b = p->d_pt_kw_b = nullptr;
     p->have_b = false;
@@ -282,21 +301,21 @@ static void free_points(b2n_plan* p) {
 
 extern "C" int b2n_plan_destroy(b2n_plan* p) {
     if (p == nullptr) return B2N_OK;
-    cudaSetDevice(p->device);
+    DevGuard dev_guard_(p->device);
     for (auto& kv : p->fft_plans) cufftDestroy(kv.second);
     if (p->fft_pruned_ready) { cufftDestroy(p->fft_2d); cufftDestroy(p->fft_1d); }
-    dev_free(p->d_tw3);
+    dev_free(p, p->d_tw3);
     free_points(p);
     for (int d = 0; d < 3; d++) {
         bool dup = false;
         for (int e = 0; e < d; e++) dup = dup || (p->d_tab[e] == p->d_tab[d]);
-        if (!dup) dev_free(p->d_tab[d]);
-        dev_free(p->d_sn[d]);
-        dev_free(p->d_pb[d]);
+        if (!dup) dev_free(p, p->d_tab[d]);
+        dev_free(p, p->d_sn[d]);
+        dev_free(p, p->d_pb[d]);
     }
-    dev_free(p->d_ell_vals);
-    dev_free(p->d_ell_cols);
-    dev_free(p->d_work);
+    dev_free(p, p->d_ell_vals);
+    dev_free(p, p->d_ell_cols);
+    dev_free(p, p->d_work);
     delete p;
     return B2N_OK;
 }
@@ -325,8 +344,6 @@ extern "C" int b2n_plan_set_option(b2n_plan* p, const char* name, long value) {
         p->opt_use_tma = value;
     } else if (n == "sparse_mode") {
         p->opt_sparse_mode = value;
-    } else if (n == "adj_kernel") {
-        p->opt_adj_kernel = value;
     } else if (n == "precomp_weights") {
         if (p->points_set) return fail(B2N_ESTATE, "precomp_weights must precede set_points");
         p->opt_precomp = value;
@@ -346,14 +363,8 @@ extern "C" int b2n_plan_set_option(b2n_plan* p, const char* name, long value) {
         if (value < 0 || value > 15) return fail(B2N_EINVAL, "win_maxslide must be in 0..15");
         p->opt_win_maxslide = value;
     } else if (n == "win_facew") {
-        if (value < -1 || value > 4) return fail(B2N_EINVAL, "win_facew must be -1 (auto) or 0..4");
+        if (value < -1 || value > 2) return fail(B2N_EINVAL, "win_facew must be -1 (auto) or 0..2");
         p->opt_win_facew = value;
-    } else if (n == "win_ring") {
-        if (value < 0 || value > 3) return fail(B2N_EINVAL, "win_ring must be in 0..3");
-        p->opt_win_ring = value;
-    } else if (n == "win_lanes") {
-        if (value != 8 && value != 16 && value != 32) return fail(B2N_EINVAL, "win_lanes must be 8, 16 or 32");
-        p->opt_win_lanes = value;
     } else if (n == "order_b") {
         if (p->points_set) return fail(B2N_ESTATE, "order_b must precede set_points");
         p->opt_order_b = value;
@@ -380,7 +391,6 @@ extern "C" long b2n_plan_get_option(b2n_plan* p, const char* name) {
     if (n == "sparse_mode") return p->opt_sparse_mode;
     if (n == "slide_pts") return p->opt_slide_pts;
     if (n == "profile") return p->opt_profile;
-    if (n == "adj_kernel") return p->opt_adj_kernel;
     if (n == "precomp_weights") return (p->d_wts != nullptr || p->d_wts_f != nullptr) ? 1 : 0;
     if (n == "lib_calls") return (long)p->lib_calls;
     if (n == "n_items") return (long)p->n_items;
@@ -388,8 +398,6 @@ extern "C" long b2n_plan_get_option(b2n_plan* p, const char* name) {
     if (n == "own_fft3") return (long)p->opt_own_fft3;
     if (n == "pruned_fft") return (long)p->opt_pruned_fft;
     if (n == "win_facew") return (long)p->opt_win_facew;
-    if (n == "win_ring") return (long)p->opt_win_ring;
-    if (n == "win_lanes") return (long)p->opt_win_lanes;
     if (n == "win_maxslide") return (long)p->opt_win_maxslide;
     if (n == "fwd_pair") return (long)p->opt_fwd_pair;
     if (n == "fwd_interleave") return (long)p->opt_fwd_interleave;
@@ -398,9 +406,11 @@ extern "C" long b2n_plan_get_option(b2n_plan* p, const char* name) {
     return -1;
 }
 
+static int ensure_weights(b2n_plan* p, cudaStream_t st);
+
 extern "C" int b2n_plan_set_tables(b2n_plan* p, const void* const* h_host) {
     if (p == nullptr || h_host == nullptr) return fail(B2N_EINVAL, "NULL argument");
-    CU(cudaSetDevice(p->device));
+    ON_DEVICE(p);
     const Geom& g = p->g;
     const size_t esz = p->cplx_table ? p->cplx_size() : p->real_size();
     for (int d = 0; d < g.ndim; d++)
@@ -423,8 +433,11 @@ extern "C" int b2n_plan_set_tables(b2n_plan* p, const void* const* h_host) {
         CU(cudaMemcpy(p->d_tab[d], h_host[d], esz * g.tlen[d], cudaMemcpyHostToDevice));
     }
     p->tables_set = true;
-    dev_free(p->d_wts); dev_free(p->d_wts_b); dev_free(p->d_wts_f);
+    dev_free(p, p->d_wts); dev_free(p, p->d_wts_b); dev_free(p, p->d_wts_f);
     p->d_wts = p->d_wts_b = p->d_wts_f = nullptr;
+    int rc = ensure_weights(p, (cudaStream_t)0);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize((cudaStream_t)0));
     return B2N_OK;
 }
 
@@ -432,7 +445,7 @@ extern "C" int b2n_plan_set_scaling(b2n_plan* p, const double* const* sn1d,
                                     const void* const* pb_angle, double fwd_scale,
                                     double adj_scale) {
     if (p == nullptr || sn1d == nullptr) return fail(B2N_EINVAL, "NULL argument");
-    CU(cudaSetDevice(p->device));
+    ON_DEVICE(p);
     const Geom& g = p->g;
     for (int d = 0; d < g.ndim; d++) {
         if (sn1d[d] == nullptr) return fail(B2N_EINVAL, "sn1d axis missing");
@@ -482,8 +495,8 @@ static int set_points_t(b2n_plan* p, const void* coords, int64_t M, int kind, cu
         return B2N_OK;
     }
     Scratch scratch;
-    // the adjoint order is only used by the 3-D register-window kernel
-    const bool want_b = g.ndim == 3 && !p->cplx_table && p->opt_adj_kernel == 3 && p->opt_order_b;
+    // the adjoint order is used by the 2-D and 3-D register-window kernels
+    const bool want_b = g.ndim >= 2 && !p->cplx_table && p->opt_order_b;
     uint64_t* keys_b = nullptr;
     if (want_b) {
         if ((rc = dev_alloc(p, &p->d_tm_sb, rs * M * g.ndim))) return rc;
@@ -695,22 +708,28 @@ extern "C" int b2n_plan_set_points(b2n_plan* p, const void* coords_dev, int64_t 
     if (M < 0 || M >= ((int64_t)1 << 31)) return fail(B2N_EINVAL, "need 0 <= M < 2^31");
     if (M > 0 && coords_dev == nullptr) return fail(B2N_EINVAL, "coords is NULL");
     if (kind != B2N_COORD_TM && kind != B2N_COORD_OMEGA) return fail(B2N_EINVAL, "bad coordinate kind");
-    CU(cudaSetDevice(p->device));
+    ON_DEVICE(p);
     free_points(p);
     p->sparse_set = false;
-    if (p->precision == B2N_SINGLE) return set_points_t<float>(p, coords_dev, M, kind, (cudaStream_t)stream);
-    return set_points_t<double>(p, coords_dev, M, kind, (cudaStream_t)stream);
+    int rc = p->precision == B2N_SINGLE ? set_points_t<float>(p, coords_dev, M, kind, (cudaStream_t)stream)
+                                        : set_points_t<double>(p, coords_dev, M, kind, (cudaStream_t)stream);
+    if (rc) return rc;
+    // plan-time weights are built here (or in set_tables, whichever comes last), not lazily by
+    // the first transform: later calls on other streams then only ever READ them
+    if ((rc = ensure_weights(p, (cudaStream_t)stream))) return rc;
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
+    return B2N_OK;
 }
 
 extern "C" int b2n_plan_set_sample_phase(b2n_plan* p, const void* phase_dev, void* stream) {
     if (p == nullptr) return fail(B2N_EINVAL, "NULL plan");
     if (!p->points_set) return fail(B2N_ESTATE, "set_points must precede set_sample_phase");
-    CU(cudaSetDevice(p->device));
+    ON_DEVICE(p);
     cudaStream_t st = (cudaStream_t)stream;
     if (phase_dev == nullptr) {
-        dev_free(p->d_phase_s);
-        dev_free(p->d_phase_sb);
-        dev_free(p->d_phase_f);
+        dev_free(p, p->d_phase_s);
+        dev_free(p, p->d_phase_sb);
+        dev_free(p, p->d_phase_f);
         p->d_phase_s = p->d_phase_sb = p->d_phase_f = nullptr;
         return B2N_OK;
     }
@@ -765,7 +784,7 @@ extern "C" int64_t b2n_plan_num_slots(b2n_plan* p) { return p && p->points_set ?
 extern "C" int b2n_plan_get_slots(b2n_plan* p, uint32_t* slots_dev, void* stream) {
     if (p == nullptr || slots_dev == nullptr) return fail(B2N_EINVAL, "NULL argument");
     if (!p->points_set) return fail(B2N_ESTATE, "points not set");
-    CU(cudaSetDevice(p->device));
+    ON_DEVICE(p);
     if (p->n_slots > 0)
         CU(cudaMemcpyAsync(slots_dev, p->d_slots, sizeof(uint32_t) * p->n_slots,
                            cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
@@ -778,7 +797,7 @@ extern "C" int64_t b2n_plan_launch_count(b2n_plan* p) { return p ? p->launches :
 // measured with CUDA events on the launching stream since the last call (option "profile")
 extern "C" int b2n_plan_get_timing(b2n_plan* p, double* out) {
     if (p == nullptr || out == nullptr) return fail(B2N_EINVAL, "NULL argument");
-    CU(cudaSetDevice(p->device));
+    ON_DEVICE(p);
     for (int k = 0; k < 2; k++) {
         auto& v = k == 0 ? p->ev_fwd : p->ev_adj;
         double tot = 0;
@@ -801,7 +820,7 @@ extern "C" int b2n_plan_get_points(b2n_plan* p, void* tm_dev, int32_t* bin_ids_d
                                    int64_t* keys_dev, int32_t* perm_dev, void* stream) {
     if (p == nullptr) return fail(B2N_EINVAL, "NULL plan");
     if (!p->points_set) return fail(B2N_ESTATE, "points not set");
-    CU(cudaSetDevice(p->device));
+    ON_DEVICE(p);
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t M = p->g.M;
     if (M == 0) return B2N_OK;
@@ -910,7 +929,9 @@ static int interp_fwd_impl(b2n_plan* p, const void* grid, void* samples, int nba
     prof_begin(p, true, st);
     if (!p->opt_force_generic && !p->cplx_table) {
         const void* ph = phase ? p->d_phase_s : nullptr;
-        const int fwd_flags = (int)((p->opt_use_tma ? 1 : 0) | (p->opt_fwd_pitch << 8));
+        FwdOpts fo;
+        fo.use_tma = p->opt_use_tma ? 1 : 0;
+        fo.pitch = (int)p->opt_fwd_pitch;
         const bool pairs = p->opt_fwd_pair && p->d_slots != nullptr;
         const int4* fit = pairs ? p->d_items_f : p->d_items;
         const int64_t nfit = pairs ? p->n_items_f : p->n_items;
@@ -926,9 +947,9 @@ static int interp_fwd_impl(b2n_plan* p, const void* grid, void* samples, int nba
         }
         int rc = p->precision == B2N_SINGLE
                      ? tiled_fwd_f32(p->g, p->tables_equal, table_ptrs(p), p->d_tm_s, p->d_wts, p->d_pt_ko, p->d_pt_kw, p->d_perm, fit,
-                                     nfit, sa, grid, samples, ph, nbatch, fwd_flags, st, &done)
+                                     nfit, sa, grid, samples, ph, nbatch, fo, st, &done)
                      : tiled_fwd_f64(p->g, p->tables_equal, table_ptrs(p), p->d_tm_s, p->d_wts, p->d_pt_ko, p->d_pt_kw, p->d_perm, fit,
-                                     nfit, sa, grid, samples, ph, nbatch, fwd_flags, st, &done);
+                                     nfit, sa, grid, samples, ph, nbatch, fo, st, &done);
         if (rc != 0) return fail(B2N_ECUDA, "tiled forward launch failed: " + std::string(cudaGetErrorString((cudaError_t)rc)));
     }
     if (!done) {
@@ -955,18 +976,21 @@ static int interp_adj_impl(b2n_plan* p, const void* samples, void* grid, int nba
     }
     bool done = false;
     prof_begin(p, false, st);
-    if (!p->opt_force_generic && !p->cplx_table && p->opt_adj_kernel >= 1 && p->g.ndim == 2) {
-        // 2-D multi-coil batches: register windows with the coil index as a window axis
-        const void* ph = phase ? p->d_phase_s : nullptr;
+    if (!p->opt_force_generic && !p->cplx_table && p->g.ndim == 2 && p->have_b) {
+        // 2-D: register windows sliding along axis 2 (adjoint sort order), lanes <-> (j1, coil)
+        const void* ph = phase ? p->d_phase_sb : nullptr;
+        WindowOpts wo;
+        wo.pts_per_warp = (int)p->opt_slide_pts;
+        wo.max_slide = (int)p->opt_win_maxslide;
         int rc = p->precision == B2N_SINGLE
-                     ? window2d_adj_f32(p->g, table_ptrs(p), p->d_tm_s, p->d_wts, p->d_pt_ko, p->d_pt_kw,
-                                        p->d_perm, samples, grid, ph, nbatch, (int)p->opt_slide_pts, st, &done)
-                     : window2d_adj_f64(p->g, table_ptrs(p), p->d_tm_s, p->d_wts, p->d_pt_ko, p->d_pt_kw,
-                                        p->d_perm, samples, grid, ph, nbatch, (int)p->opt_slide_pts, st, &done);
+                     ? window2d_adj_f32(p->g, table_ptrs(p), p->d_tm_sb, p->d_wts_b, p->d_pt_ko_b, p->d_pt_kw_b,
+                                        p->d_perm_b, samples, grid, ph, nbatch, wo, st, &done)
+                     : window2d_adj_f64(p->g, table_ptrs(p), p->d_tm_sb, p->d_wts_b, p->d_pt_ko_b, p->d_pt_kw_b,
+                                        p->d_perm_b, samples, grid, ph, nbatch, wo, st, &done);
         if (rc != 0) return fail(B2N_ECUDA, "2-D window adjoint launch failed: " + std::string(cudaGetErrorString((cudaError_t)rc)));
         if (done) p->last_adj_kernel = 4;
     }
-    if (!done && !p->opt_force_generic && !p->cplx_table && p->opt_adj_kernel == 3) {
+    if (!done && !p->opt_force_generic && !p->cplx_table && p->g.ndim == 3) {
         // register window, lane-parallel batch weights; adjoint sort order when built
         const bool ob = p->have_b;
         const void* ph = phase ? (ob ? p->d_phase_sb : p->d_phase_s) : nullptr;
@@ -975,72 +999,17 @@ static int interp_adj_impl(b2n_plan* p, const void* samples, void* grid, int nba
         const int32_t* ko = ob ? p->d_pt_ko_b : p->d_pt_ko;
         const int32_t* kw = ob ? p->d_pt_kw_b : p->d_pt_kw;
         const int32_t* pm = ob ? p->d_perm_b : p->d_perm;
-        long facew = p->opt_win_facew;
-        if (facew < 0) facew = p->g.J[0] <= 6 ? (p->precision == B2N_SINGLE ? 2 : 1) : 0;
-        // variant 3 (plan-time window records) needs the plan-time weights, 16 lanes per sample
-        // and the fused slide; the records follow the run partition and the longest slide
-        const bool rec_async = facew == 4;
-        if (facew == 4) facew = 3;
-        if (facew == 3 && (wts == nullptr || p->opt_win_lanes != 16 || p->opt_win_ring != 3 || nbatch > 65535))
-            facew = p->precision == B2N_SINGLE ? 2 : 1;
-        if (facew == 3) {
-            const size_t rs = p->precision == B2N_SINGLE ? window_record_bytes_f32(p->g.J[0])
-                                                         : window_record_bytes_f64(p->g.J[0]);
-            if (rs == 0) facew = 0;
-            else if (p->d_win_recs == nullptr || p->win_recs_pts != p->opt_slide_pts ||
-                     p->win_recs_slide != p->opt_win_maxslide) {
-                if (p->d_win_recs) {
-                    dev_free(p->d_win_recs);
-                    p->d_win_recs = nullptr;
-                }
-                int rcb = dev_alloc(p, &p->d_win_recs, rs * (size_t)p->g.M + 16);
-                if (rcb) return rcb;
-                const int sa = ob ? 2 : 0;
-                rcb = p->precision == B2N_SINGLE
-                          ? window_records_build_f32(p->g, sa, wts, kw, (int)p->opt_slide_pts,
-                                                     (int)p->opt_win_maxslide, p->d_win_recs, p->sm_count, st)
-                          : window_records_build_f64(p->g, sa, wts, kw, (int)p->opt_slide_pts,
-                                                     (int)p->opt_win_maxslide, p->d_win_recs, p->sm_count, st);
-                if (rcb != 0) return fail(B2N_ECUDA, "window record build failed: " + std::string(cudaGetErrorString((cudaError_t)rcb)));
-                p->win_recs_pts = p->opt_slide_pts;
-                p->win_recs_slide = p->opt_win_maxslide;
-                p->launches += 1;
-            }
-        }
-        if (facew == 3) wts = p->d_win_recs;
-        const int slide_axis = (ob ? 2 : 0) | (p->opt_win_ring == 1 ? 256 : 0) | (p->opt_win_ring == 2 ? 512 : 0) |
-                               (p->opt_win_ring == 3 ? 1024 : 0) | (facew ? 2048 : 0) | (facew == 2 ? (1 << 16) : 0) |
-                               (facew == 3 ? (1 << 17) : 0) | ((facew == 3 && rec_async) ? (1 << 18) : 0) |
-                               (int)((p->opt_win_maxslide & 15) << 12);
-        const int wpts = (int)(p->opt_win_lanes == 32 ? -p->opt_slide_pts
-                               : (p->opt_win_lanes == 8 ? p->opt_slide_pts + (1 << 20) : p->opt_slide_pts));
+        WindowOpts wo;
+        wo.slide_axis = ob ? 2 : 0;
+        wo.pts_per_warp = (int)p->opt_slide_pts;
+        wo.max_slide = (int)p->opt_win_maxslide;
+        wo.facew = (int)p->opt_win_facew;
+        if (wo.facew < 0) wo.facew = p->g.J[0] <= 6 ? (p->precision == B2N_SINGLE ? 2 : 1) : 0;
         int rc = p->precision == B2N_SINGLE
-                     ? window_adj_f32(p->g, table_ptrs(p), slide_axis, tms, wts, ko, kw, pm, samples, grid, ph,
-                                      nbatch, wpts, st, &done)
-                     : window_adj_f64(p->g, table_ptrs(p), slide_axis, tms, wts, ko, kw, pm, samples, grid, ph,
-                                      nbatch, wpts, st, &done);
+                     ? window_adj_f32(p->g, table_ptrs(p), wo, tms, wts, ko, kw, pm, samples, grid, ph, nbatch, st, &done)
+                     : window_adj_f64(p->g, table_ptrs(p), wo, tms, wts, ko, kw, pm, samples, grid, ph, nbatch, st, &done);
         if (rc != 0) return fail(B2N_ECUDA, "window adjoint launch failed: " + std::string(cudaGetErrorString((cudaError_t)rc)));
         if (done) p->last_adj_kernel = 3;
-    }
-    if (!done && !p->opt_force_generic && !p->cplx_table && p->opt_adj_kernel == 2) {
-        const void* ph = phase ? p->d_phase_s : nullptr;
-        int rc = p->precision == B2N_SINGLE
-                     ? tile_adj_f32(p->g, table_ptrs(p), p->d_tm_s, p->d_pt_ko, p->d_pt_kw, p->d_perm, p->d_items,
-                                    p->n_items, samples, grid, ph, nbatch, (int)p->opt_use_tma, st, &done)
-                     : tile_adj_f64(p->g, table_ptrs(p), p->d_tm_s, p->d_pt_ko, p->d_pt_kw, p->d_perm, p->d_items,
-                                    p->n_items, samples, grid, ph, nbatch, (int)p->opt_use_tma, st, &done);
-        if (rc != 0) return fail(B2N_ECUDA, "tiled adjoint launch failed: " + std::string(cudaGetErrorString((cudaError_t)rc)));
-        if (done) p->last_adj_kernel = 2;
-    }
-    if (!done && !p->opt_force_generic && !p->cplx_table && p->opt_adj_kernel >= 1) {
-        const void* ph = phase ? p->d_phase_s : nullptr;
-        int rc = p->precision == B2N_SINGLE
-                     ? slide_adj_f32(p->g, table_ptrs(p), p->d_tm_s, p->d_pt_ko, p->d_pt_kw, p->d_perm, samples, grid, ph, nbatch,
-                                     (int)p->opt_slide_pts, st, &done)
-                     : slide_adj_f64(p->g, table_ptrs(p), p->d_tm_s, p->d_pt_ko, p->d_pt_kw, p->d_perm, samples, grid, ph, nbatch,
-                                     (int)p->opt_slide_pts, st, &done);
-        if (rc != 0) return fail(B2N_ECUDA, "sliding adjoint launch failed: " + std::string(cudaGetErrorString((cudaError_t)rc)));
-        if (done) p->last_adj_kernel = 1;
     }
     if (!done) {
         int rc = run_generic(p, false, samples, grid, nbatch, phase, st);
@@ -1056,7 +1025,7 @@ extern "C" int b2n_interp_fwd(b2n_plan* p, const void* grid_dev, void* samples_d
                               int apply_phase, void* stream) {
     int rc = check_ready(p, grid_dev, samples_dev, nbatch);
     if (rc) return rc;
-    CU(cudaSetDevice(p->device));
+    ON_DEVICE(p);
     return interp_fwd_impl(p, grid_dev, samples_dev, nbatch, apply_phase && p->d_phase_s, (cudaStream_t)stream);
 }
 
@@ -1065,7 +1034,7 @@ extern "C" int b2n_interp_adj(b2n_plan* p, const void* samples_dev, void* grid_d
     int rc = check_ready(p, samples_dev, grid_dev, nbatch);
     if (rc) return rc;
     if (grid_dev == nullptr) return fail(B2N_EINVAL, "NULL array");
-    CU(cudaSetDevice(p->device));
+    ON_DEVICE(p);
     return interp_adj_impl(p, samples_dev, grid_dev, nbatch, (apply_phase & 1) && p->d_phase_s,
                            (cudaStream_t)stream, (apply_phase & 2) != 0);
 }
@@ -1079,14 +1048,14 @@ extern "C" int b2n_plan_set_sparse(b2n_plan* p, const void* const* coef,
     if (p == nullptr || coef == nullptr || kidx == nullptr) return fail(B2N_EINVAL, "NULL argument");
     if (!p->points_set) return fail(B2N_ESTATE, "set_points must precede set_sparse");
     if (M != p->g.M) return fail(B2N_EINVAL, "M does not match set_points");
-    CU(cudaSetDevice(p->device));
+    ON_DEVICE(p);
     cudaStream_t st = (cudaStream_t)stream;
     const Geom& g = p->g;
     int nnzr = 1;
     for (int d = 0; d < g.ndim; d++) nnzr *= g.J[d];
     const int64_t nnz = M * nnzr;
     const size_t vsz = p->cplx_table ? p->cplx_size() : p->real_size();
-    dev_free(p->d_ell_vals); dev_free(p->d_ell_cols);
+    dev_free(p, p->d_ell_vals); dev_free(p, p->d_ell_cols);
     p->d_ell_vals = nullptr; p->d_ell_cols = nullptr;
     int rc;
     if ((rc = dev_alloc(p, &p->d_ell_vals, vsz * nnz))) return rc;
@@ -1119,7 +1088,7 @@ extern "C" int64_t b2n_plan_sparse_nnz(b2n_plan* p) {
 extern "C" int b2n_plan_get_sparse(b2n_plan* p, void* vals_dev, int32_t* cols_dev, void* stream) {
     if (p == nullptr) return fail(B2N_EINVAL, "NULL plan");
     if (!p->sparse_set) return fail(B2N_ESTATE, "sparse matrix not set");
-    CU(cudaSetDevice(p->device));
+    ON_DEVICE(p);
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t nnz = p->g.M * p->nnzr;
     if (nnz == 0) return B2N_OK;
@@ -1172,7 +1141,7 @@ extern "C" int b2n_spmv_fwd(b2n_plan* p, const void* grid_dev, void* samples_dev
                             int apply_phase, void* stream) {
     int rc = check_ready(p, grid_dev, samples_dev, nbatch);
     if (rc) return rc;
-    CU(cudaSetDevice(p->device));
+    ON_DEVICE(p);
     return spmv_impl(p, true, grid_dev, samples_dev, nbatch, apply_phase && p->d_phase_s,
                      (cudaStream_t)stream);
 }
@@ -1182,7 +1151,7 @@ extern "C" int b2n_spmv_adj(b2n_plan* p, const void* samples_dev, void* grid_dev
     int rc = check_ready(p, samples_dev, grid_dev, nbatch);
     if (rc) return rc;
     if (grid_dev == nullptr) return fail(B2N_EINVAL, "NULL array");
-    CU(cudaSetDevice(p->device));
+    ON_DEVICE(p);
     return spmv_impl(p, false, samples_dev, grid_dev, nbatch, apply_phase && p->d_phase_s,
                      (cudaStream_t)stream);
 }
@@ -1197,13 +1166,14 @@ static int get_fft(b2n_plan* p, int nbatch, cufftHandle* out) {
         return B2N_OK;
     }
     const Geom& g = p->g;
-    int n[3];
+    long long n[3];
     for (int d = 0; d < g.ndim; d++) n[d] = g.K[g.ndim - 1 - d];   // slowest axis first
     cufftHandle h;
     FFT(cufftCreate(&h));
     size_t ws = 0;
-    FFT(cufftMakePlanMany(h, g.ndim, n, nullptr, 1, (int)g.PK, nullptr, 1, (int)g.PK,
-                          p->precision == B2N_SINGLE ? CUFFT_C2C : CUFFT_Z2Z, nbatch, &ws));
+    // 64-bit plan: prod(Kd) * nbatch may exceed 2^31 elements (384^3 with 38 coils)
+    FFT(cufftMakePlanMany64(h, g.ndim, n, nullptr, 1, (long long)g.PK, nullptr, 1, (long long)g.PK,
+                            p->precision == B2N_SINGLE ? CUFFT_C2C : CUFFT_Z2Z, (long long)nbatch, &ws));
     p->dev_bytes += (int64_t)ws;
     p->fft_plans[nbatch] = h;
     *out = h;
@@ -1334,8 +1304,7 @@ static int ensure_work(b2n_plan* p, int nbatch) {
     const size_t need = p->cplx_size() * (size_t)p->g.PK * nbatch;
     if (need <= p->work_bytes) return B2N_OK;
     if (p->d_work) {
-        cudaFree(p->d_work);
-        p->dev_bytes -= (int64_t)p->work_bytes;
+        dev_free(p, p->d_work);
         p->d_work = nullptr;
         p->work_bytes = 0;
     }
@@ -1426,7 +1395,7 @@ extern "C" int b2n_grid_fwd(b2n_plan* p, const void* image_dev, void* grid_dev, 
     if (nbatch < 1) return fail(B2N_EINVAL, "nbatch must be >= 1");
     if (image_dev == nullptr || grid_dev == nullptr) return fail(B2N_EINVAL, "NULL array");
     if (!p->scaling_set) return fail(B2N_ESTATE, "scaling not set");
-    CU(cudaSetDevice(p->device));
+    ON_DEVICE(p);
     return grid_fwd(p, image_dev, grid_dev, nbatch, (cudaStream_t)stream);
 }
 
@@ -1435,7 +1404,7 @@ extern "C" int b2n_grid_adj(b2n_plan* p, void* grid_dev, void* image_dev, int nb
     if (nbatch < 1) return fail(B2N_EINVAL, "nbatch must be >= 1");
     if (image_dev == nullptr || grid_dev == nullptr) return fail(B2N_EINVAL, "NULL array");
     if (!p->scaling_set) return fail(B2N_ESTATE, "scaling not set");
-    CU(cudaSetDevice(p->device));
+    ON_DEVICE(p);
     return grid_adj(p, grid_dev, image_dev, nbatch, (cudaStream_t)stream);
 }
 
@@ -1464,7 +1433,7 @@ extern "C" int b2n_nufft_fwd(b2n_plan* p, const void* image_dev, void* samples_d
     if (rc) return rc;
     if (image_dev == nullptr) return fail(B2N_EINVAL, "NULL array");
     if (!p->scaling_set) return fail(B2N_ESTATE, "scaling not set");
-    CU(cudaSetDevice(p->device));
+    ON_DEVICE(p);
     return nufft_fwd_impl(p, image_dev, samples_dev, nbatch, (cudaStream_t)stream);
 }
 
@@ -1474,7 +1443,7 @@ extern "C" int b2n_nufft_adj(b2n_plan* p, const void* samples_dev, void* image_d
     if (rc) return rc;
     if (image_dev == nullptr) return fail(B2N_EINVAL, "NULL array");
     if (!p->scaling_set) return fail(B2N_ESTATE, "scaling not set");
-    CU(cudaSetDevice(p->device));
+    ON_DEVICE(p);
     return nufft_adj_impl(p, samples_dev, image_dev, nbatch, (cudaStream_t)stream);
 }
 
@@ -1485,7 +1454,7 @@ extern "C" int b2n_sense_fwd(b2n_plan* p, const void* image_dev, const void* sma
     if (rc) return rc;
     if (image_dev == nullptr || smaps_dev == nullptr) return fail(B2N_EINVAL, "NULL array");
     if (!p->scaling_set) return fail(B2N_ESTATE, "scaling not set");
-    CU(cudaSetDevice(p->device));
+    ON_DEVICE(p);
     return nufft_fwd_impl(p, image_dev, samples_dev, ncoil, (cudaStream_t)stream, smaps_dev);
 }
 
@@ -1495,7 +1464,7 @@ extern "C" int b2n_sense_adj(b2n_plan* p, const void* samples_dev, const void* s
     if (rc) return rc;
     if (image_dev == nullptr || smaps_dev == nullptr) return fail(B2N_EINVAL, "NULL array");
     if (!p->scaling_set) return fail(B2N_ESTATE, "scaling not set");
-    CU(cudaSetDevice(p->device));
+    ON_DEVICE(p);
     return nufft_adj_impl(p, samples_dev, image_dev, ncoil, (cudaStream_t)stream, smaps_dev);
 }
 
@@ -1507,7 +1476,7 @@ extern "C" int b2n_grid_multiply(b2n_plan* p, void* grid_dev, const void* kernel
     if (p == nullptr) return fail(B2N_EINVAL, "NULL plan");
     if (nbatch < 1) return fail(B2N_EINVAL, "nbatch must be >= 1");
     if (grid_dev == nullptr || kernel_dev == nullptr) return fail(B2N_EINVAL, "NULL array");
-    CU(cudaSetDevice(p->device));
+    ON_DEVICE(p);
     cudaStream_t st = (cudaStream_t)stream;
     const Geom& g = p->g;
     const int nb = grid_for(g.PK * nbatch, 256, p->sm_count, 32);

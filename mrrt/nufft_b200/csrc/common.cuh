@@ -35,11 +35,20 @@ __device__ __forceinline__ int wrap_index(int k, int K) {
     return r < 0 ? r + K : r;
 }
 
+// grid index held by THIS plan of global index k: periodic wrap on the global grid, then the
+// offset of the plan's slab (Kg == K and korg == 0 for an ordinary plan: plain wrap)
+__device__ __forceinline__ int local_index(int k, int Kg, int korg) {
+    int r = wrap_index(k, Kg) - korg;
+    return r < 0 ? r + Kg : r;
+}
+
 // Device-side description of the transform geometry (passed by value to kernels)
 struct Geom {
     int ndim;
     int N[3];
-    int K[3];
+    int K[3];         // oversampled grid held by this plan (a slab plan: the LOCAL extent)
+    int Kg[3];        // global oversampled grid size: period of the coordinates (= K unless slab)
+    int korg[3];      // slab plans: global index of local row 0 along each axis (else 0)
     int J[3];
     int L;
     int ncenter[3];   // floor(J*L/2): centre of each table

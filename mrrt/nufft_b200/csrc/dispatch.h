@@ -25,47 +25,39 @@ struct SlotArgs {
     const void* phase2 = nullptr;      // [ns] pairs of sample phases, or nullptr
 };
 
-// each returns 0 or a cudaError_t
+// launch options of the tiled forward kernel
+struct FwdOpts {
+    int use_tma = 1;         // 0 = cooperative tile loads instead of the TMA box load
+    int pitch = 0;           // shared-memory row pitch of the tile in cells (0 = automatic)
+};
+
+// launch options of the register-window adjoint kernels (2-D and 3-D)
+struct WindowOpts {
+    int slide_axis = 0;      // 3-D: grid axis the window slides along (2 with the adjoint sort order, else 0)
+    int pts_per_warp = 256;  // samples per warp (two half-warp runs)
+    int max_slide = 0;       // longest slide in cells before a new window is started (0 = J - 1)
+    int facew = 0;           // 0 scalar staging records, 1 face-weight staging, 2 ... at 5 CTAs / SM
+};
+
+// each returns 0 or a cudaError_t; *done tells whether the kernel family took the call
 #define B2N_DECLARE(SUF)                                                                          \
     int generic_launch_##SUF(const Geom& g, int cplx_table, const TablePtrs& tabs, const void* tm_s, \
                              const int32_t* perm, bool fwd, const void* in, void* out,           \
                              const void* phase_s, int nbatch, int sm_count, cudaStream_t st);    \
     int tiled_fwd_##SUF(const Geom& g, bool tables_equal, const TablePtrs& tabs, const void* tm_s, \
-                        const void* wts, const int32_t* pt_ko, const int32_t* pt_kw, const int32_t* perm, const int4* items, int64_t n_items, const SlotArgs& sa, const void* grid, \
-                        void* out, const void* phase_s, int nbatch, int use_tma, cudaStream_t st, \
-                        bool* done);                                                             \
-    int slide_adj_##SUF(const Geom& g, const TablePtrs& tabs, const void* tm_s,                 \
-                        const int32_t* pt_ko, const int32_t* pt_kw, const int32_t* perm,        \
-                        const void* samples, void* grid, const void* phase_s, int nbatch,        \
-                        int pts_per_warp, cudaStream_t st, bool* done);
-#define B2N_DECLARE2(SUF)                                                                        \
-    int tile_adj_##SUF(const Geom& g, const TablePtrs& tabs, const void* tm_s, const int32_t* pt_ko, \
-                       const int32_t* pt_kw, const int32_t* perm, const int4* items,             \
-                       int64_t n_items, const void* samples, void* grid, const void* phase_s,    \
-                       int nbatch, int use_tma, cudaStream_t st, bool* done);
-#define B2N_DECLARE3(SUF)                                                                        \
-    int window_adj_##SUF(const Geom& g, const TablePtrs& tabs, int slide_axis, const void* tm_s, \
-                         const void* wts, const int32_t* pt_ko, const int32_t* pt_kw, const int32_t* perm,        \
-                         const void* samples, void* grid, const void* phase_s, int nbatch,       \
-                         int pts_per_warp, cudaStream_t st, bool* done);                         \
-    size_t window_record_bytes_##SUF(int J);                                                     \
-    int window_records_build_##SUF(const Geom& g, int slide_axis, const void* wts,               \
-                                   const int32_t* pt_kw, int pts_per_warp, int max_slide,        \
-                                   void* recs, int sm_count, cudaStream_t st);
-#define B2N_DECLARE4(SUF)                                                                        \
+                        const void* wts, const int32_t* pt_ko, const int32_t* pt_kw,             \
+                        const int32_t* perm, const int4* items, int64_t n_items,                 \
+                        const SlotArgs& sa, const void* grid, void* out, const void* phase_s,    \
+                        int nbatch, const FwdOpts& fo, cudaStream_t st, bool* done);             \
+    int window_adj_##SUF(const Geom& g, const TablePtrs& tabs, const WindowOpts& wo,             \
+                         const void* tm_s, const void* wts, const int32_t* pt_ko,                \
+                         const int32_t* pt_kw, const int32_t* perm, const void* samples,         \
+                         void* grid, const void* phase_s, int nbatch, cudaStream_t st,           \
+                         bool* done);                                                            \
     int window2d_adj_##SUF(const Geom& g, const TablePtrs& tabs, const void* tm_s, const void* wts, \
                            const int32_t* pt_ko, const int32_t* pt_kw, const int32_t* perm,      \
                            const void* samples, void* grid, const void* phase_s, int nbatch,     \
-                           int pts_per_warp, cudaStream_t st, bool* done);
-B2N_DECLARE4(f32)
-B2N_DECLARE4(f64)
-#undef B2N_DECLARE4
-B2N_DECLARE3(f32)
-B2N_DECLARE3(f64)
-#undef B2N_DECLARE3
-B2N_DECLARE2(f32)
-B2N_DECLARE2(f64)
-#undef B2N_DECLARE2
+                           const WindowOpts& wo, cudaStream_t st, bool* done);
 B2N_DECLARE(f32)
 B2N_DECLARE(f64)
 #undef B2N_DECLARE

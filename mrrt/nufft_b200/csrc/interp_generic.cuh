@@ -48,7 +48,7 @@ interp_fwd_generic(Geom g, TablePtrs tabs, const T* __restrict__ tm_s,
 #pragma unroll(JT > 0 ? JT : 1)
             for (int j = 0; j < J; j++) {
                 w[d][j] = load_tap<T, CT>(tabs.h[d], g.ncenter[d], g.tlen[d], t, koff + j, g.L);
-                off[d][j] = wrap_index(koff + j, g.K[d]) * stride;
+                off[d][j] = local_index(koff + j, g.Kg[d], g.korg[d]) * stride;
             }
             stride *= g.K[d];
         }
@@ -121,7 +121,7 @@ interp_adj_generic(Geom g, TablePtrs tabs, const T* __restrict__ tm_s,
 #pragma unroll(JT > 0 ? JT : 1)
             for (int j = 0; j < J; j++) {
                 w[d][j] = load_tap<T, CT>(tabs.h[d], g.ncenter[d], g.tlen[d], t, koff + j, g.L);
-                off[d][j] = wrap_index(koff + j, g.K[d]) * stride;
+                off[d][j] = local_index(koff + j, g.Kg[d], g.korg[d]) * stride;
             }
             stride *= g.K[d];
         }

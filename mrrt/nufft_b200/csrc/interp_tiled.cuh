@@ -304,12 +304,11 @@ template <typename T, int NDIM, int J>
 static int launch_fwd_tiled(const Geom& g, const TablePtrs& tabs, const void* tm_s,
                             const void* wts, const int32_t* pt_ko, const int32_t* pt_kw, const int32_t* perm, const int4* items, int64_t n_items,
                             const SlotArgs& sa, const void* grid, void* out, const void* phase_s, int nbatch,
-                            int use_tma, cudaStream_t st, bool* done) {
+                            const FwdOpts& fo, cudaStream_t st, bool* done) {
     using C = cplx_t<T>;
     *done = false;
-    // use_tma carries the requested row pitch in its upper bits (0 = automatic)
-    const int fwd_pitch = use_tma >> 8;
-    use_tma &= 0xff;
+    const int fwd_pitch = fo.pitch;
+    const int use_tma = fo.use_tma;
     TileShape ts;
     ts.E1 = g.tile[0] + J - 1;
     ts.E2 = NDIM > 1 ? g.tile[1] + J - 1 : 1;
@@ -372,7 +371,7 @@ static int launch_fwd_tiled(const Geom& g, const TablePtrs& tabs, const void* tm
 template <typename T>
 static int tiled_fwd_t(const Geom& g, bool tables_equal, const TablePtrs& tabs, const void* tm_s,
                        const void* wts, const int32_t* pt_ko, const int32_t* pt_kw, const int32_t* perm, const int4* items, int64_t n_items, const SlotArgs& sa, const void* grid,
-                       void* out, const void* phase_s, int nbatch, int use_tma, cudaStream_t st,
+                       void* out, const void* phase_s, int nbatch, const FwdOpts& fo, cudaStream_t st,
                        bool* done) {
     *done = false;
     if (g.ndim < 2 || (!tables_equal && wts == nullptr && !sa.packed) || n_items == 0 || n_items > 0x7fffffff ||
@@ -382,7 +381,7 @@ static int tiled_fwd_t(const Geom& g, bool tables_equal, const TablePtrs& tabs, 
         if (g.J[d] != g.J[0]) return 0;
 #define B2N_TILED(ND, JJ)                                                                      \
     return launch_fwd_tiled<T, ND, JJ>(g, tabs, tm_s, wts, pt_ko, pt_kw, perm, items, n_items, sa, grid, out, phase_s, \
-                                       nbatch, use_tma, st, done)
+                                       nbatch, fo, st, done)
     if (g.ndim == 2) {
         switch (g.J[0]) {
             case 4: B2N_TILED(2, 4);

@@ -1,22 +1,28 @@
-// Register-window adjoint gridding, second generation (3-D, real table, uniform J).
+// Register-window adjoint gridding (3-D, real table, uniform J).
 //
-// Each warp walks a contiguous run of cell-sorted samples and keeps the current sample's
-// J x J x J window of partial sums in registers: lane <-> one (b, c) position of the
-// window face, J accumulators along the SLIDE axis a.  Consecutive samples of the sorted
-// order sit in the same or the next cell along a, so the window slides and only the
+// Each half-warp walks a contiguous run of cell-sorted samples and keeps the current
+// sample's J x J x J window of partial sums in registers: lane <-> one (b, c) position of
+// the window face, J accumulators along the SLIDE axis a.  Consecutive samples of the
+// sorted order sit in the same or the next cell along a, so the window slides and only the
 // retiring J x J face is sent to L2 (vector REDs).  Axis roles are a run-time
 // permutation: with the adjoint sort order (cells ordered axis-3-fastest inside a bin)
 // a = axis 3 and the lane face is (axis 1, axis 2), so that the lanes of one retiring
 // face write runs of J CONSECUTIVE grid cells -- 2-3 sectors per run instead of one
 // sector per lane (profiles/r01_notes.md: strided REDs were the L1TEX bottleneck).
 //
-// Per 32-sample batch the weights are evaluated LANE-PARALLEL (lane = sample: 3J table
-// taps each, table staged in shared memory) together with a window action code
-// (slide distance or "new window") and written to a per-warp staging record; the
-// per-sample loop then only does broadcast shared-memory reads and FMAs.
+// Per 16-sample batch the weights are prepared LANE-PARALLEL (lane = sample) together
+// with a window action code (slide distance or "new window") and written to a per-warp
+// staging record; the per-sample loop then only does broadcast shared-memory reads and
+// packed FMAs.  The last cell of a slide is folded into the FMAs of the sliding sample
+// (destination j, addend j + 1): no register moves.
 //
 // Arithmetic per sample follows c/nufft_table.template.c:1122-1163:
 // v3 = coef3*f, v2 = coef2*v3, ck += coef1*v2 (the same products, grouped by axis role).
+//
+// Variants measured and dropped in round 2 (lane-ring and fixed-ring windows, 8 / 32 lanes
+// per sample, plan-time window records with and without cp.async, the shared-memory tile
+// adjoint and the first sliding-window generation) are described in profiles/r01_notes.md;
+// their code is in the history up to commit 4d956cd.
 #pragma once
 #include "common.cuh"
 #include "dispatch.h"
@@ -29,9 +35,11 @@ struct WindowAxes {
     int stride[3];      // grid stride (cells) along (a, b, c)
 };
 
-// Staging of one 32-sample batch: per sample a record of kW values (3J weights, fx, fy)
-// with an ODD pitch in elements, so that the 32 lanes' scalar stores (lane = sample)
-// fall in 32 different banks, plus a separate int4 (kA, kB, kC, action) per sample.
+constexpr int kWinLanes = 16;   // lanes per sample: two register windows per warp
+
+// Staging of one batch (16 samples per half-warp): per sample a record of kW values (3J
+// weights, fx, fy) with an ODD pitch in elements, so that the lanes' scalar stores (lane =
+// sample) fall in different banks, plus a separate int4 (kA, kB, kC, action) per sample.
 template <typename T, int J, bool FW = false> struct WinRec {
     static constexpr int kW = 3 * J + 2;                         // weights + fx, fy
     // odd pitch in units of sizeof(T): float records spread over all 32 banks, double
@@ -47,7 +55,7 @@ template <typename T, int J, bool FW = false> struct WinRec {
 // fy, (kA, kB, kC, action)} written by the batch phase with 16-byte vector stores and read
 // by the sample loop with 16-byte broadcast loads (3 for float J=6 instead of 9 scalar
 // ones), and a FACE record of the J*J products wb[jb]*wc[jc] in face order r = jb + J*jc,
-// so a lane fetches its face weights from ONE lane-dependent base (+G per slot) instead
+// so a lane fetches its face weights from ONE lane-dependent base (+16 per slot) instead
 // of two table-indexed reads and one multiply per slot.  Head pitch = 16 bytes x odd: the
 // 8 lanes of a quarter-warp store phase then cover all 32 banks exactly once.
 template <typename T, int J> struct WinRec<T, J, true> {
@@ -75,85 +83,12 @@ __device__ __forceinline__ void load16(const void* src, double* v) {
     v[0] = t.x; v[1] = t.y;
 }
 
-// Plan-time window RECORDS (FWV = 3): everything the staging area holds except the sample
-// value is a function of the trajectory only, so it is laid out once, in the adjoint order,
-// exactly as the sample loop wants it in shared memory:
-//   [wA[J] | fx fy (filled per launch) | pad | kA kB kC action | face J*J products | pad]
-// and the batch phase becomes a coalesced 16-byte-chunk copy global -> shared plus the
-// sample fetch.  The action code (slide distance or -1 = new window) depends on the run
-// partition (samples per lane group) and on the longest allowed slide: the records are
-// rebuilt when those options change.
-template <typename T, int J> struct WinRecG {
-    static constexpr int kF = J * (int)sizeof(T);                                   // offset of fx, fy
-    static constexpr int kInt = (((J + 2) * (int)sizeof(T) + 15) / 16) * 16;        // offset of the int4
-    static constexpr int kFace = kInt + 16;                                         // offset of the face
-    static constexpr int kSize = ((kFace + J * J * (int)sizeof(T) + 15) / 16) * 16; // record bytes
-    static constexpr int kBytes = 32 * kSize + 64 * (int)sizeof(T);                 // per warp (+ overread pad)
-};
-
-template <typename T, int J>
-__global__ void window_records_kernel(int64_t M, int aA, int aB, int aC, int per_group, int max_slide,
-                                      const T* __restrict__ wts, const int32_t* __restrict__ pt_kw,
-                                      unsigned char* __restrict__ recs) {
-    using RG = WinRecG<T, J>;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < M;
-         i += (int64_t)gridDim.x * blockDim.x) {
-        unsigned char* r = recs + i * RG::kSize;
-        T wA[J], wB[J], wC[J];
-#pragma unroll
-        for (int j = 0; j < J; j++) {
-            wA[j] = wts[(int64_t)(aA * J + j) * M + i];
-            wB[j] = wts[(int64_t)(aB * J + j) * M + i];
-            wC[j] = wts[(int64_t)(aC * J + j) * M + i];
-        }
-        const int kA = pt_kw[(int64_t)aA * M + i], kB = pt_kw[(int64_t)aB * M + i],
-                  kC = pt_kw[(int64_t)aC * M + i];
-        int act = -1;
-        if (i % per_group != 0) {   // the first sample of a lane group's run starts a window
-            const int qA = pt_kw[(int64_t)aA * M + i - 1], qB = pt_kw[(int64_t)aB * M + i - 1],
-                      qC = pt_kw[(int64_t)aC * M + i - 1];
-            const int d = kA - qA;
-            if (kB == qB && kC == qC && d >= 0 && d <= max_slide) act = d;
-        }
-        T* w = (T*)r;
-#pragma unroll
-        for (int j = 0; j < J; j++) w[j] = wA[j];
-#pragma unroll
-        for (int e = J; e < RG::kInt / (int)sizeof(T); e++) w[e] = (T)0;
-        *(int4*)(r + RG::kInt) = make_int4(kA, kB, kC, act);
-        T* f = (T*)(r + RG::kFace);
-#pragma unroll
-        for (int jc = 0; jc < J; jc++)
-#pragma unroll
-            for (int jb = 0; jb < J; jb++) f[jb + J * jc] = wB[jb] * wC[jc];
-#pragma unroll
-        for (int e = J * J; e < (RG::kSize - RG::kFace) / (int)sizeof(T); e++) f[e] = (T)0;
-    }
-}
-
 // TAB: 0 table in global memory, 1 table staged in shared memory, 2 plan-time weights.
-// G:   lanes per sample (32 or 16).  With G = 16 every half-warp walks its OWN run of
-//      samples with its own register window: the per-sample instructions (operand loads,
-//      packed FMAs, loop control) are issued once for two samples, and the J*J = 36 face
-//      positions fill 16 lanes x 3 slots at 75 % instead of 32 lanes x 2 slots at 56 %.
-// RING: 0 = the J accumulators of a lane run along the slide axis and are shifted when
-//       the window slides; 1 = the slide axis is laid out ACROSS LANES (lane <-> (column,
-//       jb), registers <-> jc): sliding only advances a phase counter, the lanes that hold
-//       the retiring column flush it, nothing moves; 2 = fixed register ring: accumulator
-//       r of a lane always holds the cell with (cell mod J) == r along the slide axis, the
-//       batch phase stores each sample's slide-axis weights in that rotated order, and a
-//       slide only flushes and clears the retiring register (no register shifts).
-// ring slot of the cell j cells past a window whose origin sits in slot m (= origin mod J)
-template <int J>
-__device__ __forceinline__ int rot_slot(int m, int j) {
-    const int r = m + j;
-    return r >= J ? r - J : r;
-}
-
-// FWV: 0 = scalar staging records; 1 = face-weight staging (below); 2 = the same compiled for
-//      5 CTAs per SM (float J=6: 96 registers with a 48-byte spill instead of 110).
-template <typename T, int J, int TAB, int G, int RING, int FWV = 0>
-__global__ void __launch_bounds__(128, (FWV == 2 || (FWV >= 3 && sizeof(T) == 4 && J <= 6)) ? 5 : 1)
+// FWV: 0 = scalar staging records; 1 = face-weight staging (plan-time weights only);
+//      2 = the same compiled for 5 CTAs per SM (float J<=6: 96 registers with a 48-byte
+//      spill instead of 110).
+template <typename T, int J, int TAB, int FWV = 0>
+__global__ void __launch_bounds__(128, FWV == 2 ? 5 : 1)
 spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T* __restrict__ h2,
                        const T* __restrict__ h3, const T* __restrict__ tm_s,
                        const T* __restrict__ wts,
@@ -162,20 +97,17 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
                        cplx_t<T>* __restrict__ grid, const cplx_t<T>* __restrict__ phase_s,
                        int pts_per_warp, int max_slide) {
     using C = cplx_t<T>;
+    constexpr int G = kWinLanes;
     constexpr bool FW = FWV != 0;
     constexpr int R = J * J;
     constexpr int RPL = (R + G - 1) / G;
     constexpr int NG = 32 / G;                                    // sample groups per warp
-    static_assert(!FW || (TAB == 2 && RING != 1 && RING != 2), "face weights: plan-time weights, shift/fuse windows");
+    static_assert(!FW || TAB == 2, "face-weight staging needs the plan-time weights");
     constexpr int RB = WinRec<T, J, false>::kPitch;               // (not used with FW)
-    constexpr bool ASY = FWV == 4;                                // records copied with cp.async, double-buffered
-    constexpr bool REC = FWV == 3 || ASY;                         // plan-time records (WinRecG)
-    constexpr int BSZ = ASY ? 8 : G;                              // samples per lane group and batch
-    constexpr int WB = REC ? WinRecG<T, J>::kBytes : WinRec<T, J, FW>::kBytes;
-    constexpr int HP = REC ? WinRecG<T, J>::kSize : WinRec<T, J, true>::kHead;     // FW: head pitch (bytes)
-    constexpr int HI = REC ? WinRecG<T, J>::kInt : WinRec<T, J, true>::kHeadInt;   // FW: offset of (kA, kB, kC, act)
-    constexpr int FP = REC ? WinRecG<T, J>::kSize / (int)sizeof(T)
-                           : WinRec<T, J, true>::kFaceElems;      // FW: face pitch (elements)
+    constexpr int WB = WinRec<T, J, FW>::kBytes;
+    constexpr int HP = WinRec<T, J, true>::kHead;                 // FW: head pitch (bytes)
+    constexpr int HI = WinRec<T, J, true>::kHeadInt;              // FW: offset of (kA, kB, kC, act)
+    constexpr int FP = WinRec<T, J, true>::kFaceElems;            // FW: face pitch (elements)
     constexpr int HV = HI / (int)sizeof(T);                       // FW: head values incl. padding
     constexpr int VPC = 16 / (int)sizeof(T);                      // values per 16-byte chunk
     constexpr unsigned FULL = 0xffffffffu;
@@ -185,8 +117,7 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
     const int wib = threadIdx.x >> 5;
     unsigned char* stage = dyn_smem + wib * WB;                   // this warp's records
     int4* actions = (int4*)(stage + WinRec<T, J, false>::kRecBytes);  // this warp's action codes (not FW)
-    T* face = REC ? (T*)(stage + WinRecG<T, J>::kFace)            // FW: this warp's face records
-                  : (T*)(stage + 32 * HP);
+    T* face = (T*)(stage + 32 * HP);                              // FW: this warp's face records
     const int64_t M = g.M;
     constexpr bool TAB_SMEM = TAB == 1;
     if (TAB_SMEM) {
@@ -236,110 +167,23 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
 #pragma unroll
         for (int j = 0; j < J; j++) acc[s][j] = make_c<T>(0, 0);
     }
-    constexpr bool ROT = RING == 2;
-    constexpr bool FUSE = RING == 3;  // shift by one fused into the FMAs of the sliding sample
     int WA = 0;             // wrapped window origin along the slide axis
-    int mA = 0;             // ROT: WA mod J = ring slot that holds the window's first cell
-    int ph = 0;             // RING: physical column that holds logical column 0
-    int jlog[RPL];          // RING: logical column of each lane slot
-    int offC[J];            // RING: grid offsets of the J register positions (axis c)
-#pragma unroll
-    for (int s = 0; s < RPL; s++) jlog[s] = rjc[s];
-#pragma unroll
-    for (int j = 0; j < J; j++) offC[j] = 0;
-    (void)ph;
     bool have = false;
     int pkA = -1 << 30, pkB = -1, pkC = -1;   // previous sample's wrapped origin
 
-    // ASY: a warp's staging area holds two buffers of NG * BSZ records; while the sample loop
-    // works on one, the next batch's records arrive in the other (cp.async, no registers) and
-    // the next batch's sample values are fetched into two registers
-    [[maybe_unused]] C fnext = make_c<T>(0, 0);
-    [[maybe_unused]] int buf = 0;
-    if constexpr (ASY) {
-        static_assert(G == 16, "ASY: 16 lanes per sample");
-        constexpr int CPR = HP / 16;
-        const int cnt0 = (int)(begin >= end ? 0 : (end - begin < BSZ ? end - begin : BSZ));
-        const unsigned char* gsrc = (const unsigned char*)wts + begin * HP;
-        const unsigned sdst = (unsigned)__cvta_generic_to_shared(stage + (grp * BSZ) * HP);
-#pragma unroll
-        for (int c = 0; c < (BSZ * CPR + G - 1) / G; c++) {
-            const int e = lg + G * c;
-            if (e < cnt0 * CPR)
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst + 16 * e), "l"(gsrc + 16 * e));
-        }
-        asm volatile("cp.async.commit_group;");
-        if (lg < cnt0) {
-            fnext = sb[perm[begin + lg]];
-            if (phase_s != nullptr) fnext = cmul_conj(fnext, phase_s[begin + lg]);
-        }
-    }
-    for (int it = 0; it < per_group; it += BSZ) {
+    for (int it = 0; it < per_group; it += G) {
         // (uniform trip count for the whole warp; groups past their end idle)
         const int64_t base = begin + it;
-        const int cnt = (int)(base >= end ? 0 : (end - base < BSZ ? end - base : BSZ));
+        const int cnt = (int)(base >= end ? 0 : (end - base < G ? end - base : G));
         __syncwarp();
-        if constexpr (ASY) {
-            constexpr int CPR = HP / 16;
-            constexpr int BUFB = NG * BSZ * HP;                   // bytes per buffer
-            const C fcur = fnext;
-            // next batch: records into the other buffer, sample values into registers
-            const int64_t nbase = base + BSZ;
-            const int ncnt = (it + BSZ >= per_group || nbase >= end) ? 0
-                             : (int)(end - nbase < BSZ ? end - nbase : BSZ);
-            {
-                const unsigned char* gsrc = (const unsigned char*)wts + nbase * HP;
-                const unsigned sdst = (unsigned)__cvta_generic_to_shared(
-                    stage + (buf ^ 1) * BUFB + (grp * BSZ) * HP);
-#pragma unroll
-                for (int c = 0; c < (BSZ * CPR + G - 1) / G; c++) {
-                    const int e = lg + G * c;
-                    if (e < ncnt * CPR)
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst + 16 * e), "l"(gsrc + 16 * e));
-                }
-                asm volatile("cp.async.commit_group;");
-                if (lg < ncnt) {
-                    fnext = sb[perm[nbase + lg]];
-                    if (phase_s != nullptr) fnext = cmul_conj(fnext, phase_s[nbase + lg]);
-                }
-            }
-            asm volatile("cp.async.wait_group 1;" ::: "memory");  // this batch's records have landed
-            __syncwarp();
-            if (lg < cnt) *(C*)(stage + buf * BUFB + (grp * BSZ + lg) * HP + J * sizeof(T)) = fcur;
-            __syncwarp();
-        } else
-        if constexpr (REC) {
-            // ---- batch phase with plan-time records: fetch this lane's sample, copy the lane
-            // group's cnt records (16-byte chunks, coalesced), then drop the sample value in
-            C f = make_c<T>(0, 0);
-            if (lg < cnt) {
-                const int64_t i = base + lg;
-                f = sb[perm[i]];
-                if (phase_s != nullptr) f = cmul_conj(f, phase_s[i]);
-            }
-            constexpr int CPR = HP / 16;                          // chunks per record
-            const int4* __restrict__ gsrc = (const int4*)((const unsigned char*)wts + base * HP);
-            int4* sdst = (int4*)(stage + (grp * G) * HP);
-            const int nch = cnt * CPR;
-#pragma unroll
-            for (int c = 0; c < CPR; c++) {
-                const int e = lg + G * c;
-                if (e < nch) sdst[e] = __ldg(gsrc + e);
-            }
-            __syncwarp();
-            if (lg < cnt) *(C*)(stage + lane * HP + J * sizeof(T)) = f;
-            __syncwarp();
-        }
         // ---- batch phase: lane = sample (record index = lane)
         int kA = 0, kB = 0, kC = 0;
-        if (!REC && lg < cnt) {
+        if (lg < cnt) {
             const int64_t i = base + lg;
             T* w = (T*)(stage + lane * RB);
             kA = pt_kw[(int64_t)aA * M + i];
             kB = pt_kw[(int64_t)aB * M + i];
             kC = pt_kw[(int64_t)aC * M + i];
-            // ROT: the slide-axis weight of cell kA + j goes to ring slot (kA + j) mod J
-            const int mrot = ROT ? kA % J : 0;
             if constexpr (FW) {
                 T hv[HV], wB[J], wC[J];
 #pragma unroll
@@ -365,7 +209,7 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
             } else if (TAB == 2) {
 #pragma unroll
                 for (int j = 0; j < J; j++) {
-                    w[rot_slot<J>(mrot, j)] = wts[(int64_t)(aA * J + j) * M + i];
+                    w[j] = wts[(int64_t)(aA * J + j) * M + i];
                     w[J + j] = wts[(int64_t)(aB * J + j) * M + i];
                     w[2 * J + j] = wts[(int64_t)(aC * J + j) * M + i];
                 }
@@ -376,7 +220,7 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
                           oC = pt_ko[(int64_t)aC * M + i];
 #pragma unroll
                 for (int j = 0; j < J; j++) {
-                    w[rot_slot<J>(mrot, j)] = tap_real<T>(tabA, ncA, tlA, tA, oA + j, g.L);
+                    w[j] = tap_real<T>(tabA, ncA, tlA, tA, oA + j, g.L);
                     w[J + j] = tap_real<T>(tabB, ncB, tlB, tB, oB + j, g.L);
                     w[2 * J + j] = tap_real<T>(tabC, ncC, tlC, tC, oC + j, g.L);
                 }
@@ -389,7 +233,7 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
             }
         }
         // window action: slide distance along a, or -1 = new window
-        if constexpr (!REC) {
+        {
             int qA = __shfl_up_sync(FULL, kA, 1, G), qB = __shfl_up_sync(FULL, kB, 1, G),
                 qC = __shfl_up_sync(FULL, kC, 1, G);
             if (lg == 0) { qA = pkA; qB = pkB; qC = pkC; }
@@ -411,95 +255,10 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
         // FW: only the action code is prefetched (one register); the origin (kA, kB, kC) is read
         // by the new-window path itself, and the record pointers advance by a constant
         int4 kk_next = make_int4(0, 0, 0, 0);
-        const unsigned char* recf = stage + (ASY ? buf * (NG * BSZ * HP) : 0) + (grp * BSZ) * HP;
-        const T* wff = (REC ? (const T*)(recf + WinRecG<T, J>::kFace) : face + (grp * G) * FP) + lg;
+        const unsigned char* recf = stage + (grp * G) * HP;
+        const T* wff = face + (grp * G) * FP + lg;
         if constexpr (FW) kk_next.w = *(const int*)(recf + HI + 12);
         else kk_next = actions[grp * G];
-        if constexpr (ASY) buf ^= 1;
-        if constexpr (RING == 1) {
-            for (int q = 0; q < cnt; q++) {
-                const unsigned char* rec = stage + (grp * G + q) * RB;
-                const int4 kk = kk_next;
-                if (q + 1 < cnt) kk_next = actions[grp * G + q + 1];
-                const T* w = (const T*)rec;
-                // operands first (their latency overlaps the window update).  The logical
-                // column of this lane AFTER the update is known from the action code.
-                T wC[J];
-#pragma unroll
-                for (int j = 0; j < J; j++) wC[j] = w[2 * J + j];
-                const C f = make_c<T>(w[3 * J], w[3 * J + 1]);
-                int jl[RPL];
-                T wab[RPL];
-#pragma unroll
-                for (int s = 0; s < RPL; s++) {
-                    int t = jlog[s] - kk.w;
-                    if (t < 0) t += J;
-                    jl[s] = kk.w < 0 ? rjc[s] : t;      // rjc = physical column id of the slot
-                    wab[s] = w[jl[s]] * w[J + rjb[s]];
-                }
-                if (kk.w != 0) {
-                    if (kk.w < 0) {
-                        if (have) {
-                            // retire every column
-#pragma unroll
-                            for (int s = 0; s < RPL; s++) {
-                                if (rvalid[s]) {
-                                    int ka = WA + jlog[s];
-                                    if (ka >= KA) ka -= KA;
-                                    C* pcol = faceptr[s] + (int64_t)ka * sA;
-#pragma unroll
-                                    for (int j = 0; j < J; j++) atomic_add_c(pcol + offC[j], acc[s][j]);
-                                }
-#pragma unroll
-                                for (int j = 0; j < J; j++) acc[s][j] = make_c<T>(0, 0);
-                            }
-                        }
-                        have = true;
-                        WA = kk.x;
-                        ph = 0;
-#pragma unroll
-                        for (int s = 0; s < RPL; s++) {
-                            int kb = kk.y + rjb[s]; if (kb >= KB) kb -= KB;
-                            faceptr[s] = gb + (int64_t)kb * sB;
-                        }
-#pragma unroll
-                        for (int j = 0; j < J; j++) {
-                            int kc = kk.z + j; if (kc >= KC) kc -= KC;
-                            offC[j] = kc * sC;
-                        }
-                    } else {
-#pragma unroll 1
-                        for (int sft = 0; sft < kk.w; sft++) {
-                            // retire the column that holds logical position 0
-                            const int64_t offA = (int64_t)WA * sA;
-#pragma unroll
-                            for (int s = 0; s < RPL; s++) {
-                                if (rvalid[s] && rjc[s] == ph) {
-                                    C* pcol = faceptr[s] + offA;
-#pragma unroll
-                                    for (int j = 0; j < J; j++) {
-                                        atomic_add_c(pcol + offC[j], acc[s][j]);
-                                        acc[s][j] = make_c<T>(0, 0);
-                                    }
-                                }
-                            }
-                            ph = ph + 1 == J ? 0 : ph + 1;
-                            WA++;   // stays < KA: it ends at this sample's wrapped origin
-                        }
-                    }
-                }
-#pragma unroll
-                for (int s = 0; s < RPL; s++) {
-                    jlog[s] = jl[s];
-                    if (rvalid[s]) {
-                        const C v = mul_w(wab[s], f);
-#pragma unroll
-                        for (int j = 0; j < J; j++) acc[s][j] = fma_w(wC[j], v, acc[s][j]);
-                    }
-                }
-            }
-            continue;
-        }
         for (int q = 0; q < cnt; q++, recf += HP, wff += FP) {
             const unsigned char* rec = FW ? recf : stage + (grp * G + q) * RB;
             const int4 kk = kk_next;
@@ -548,10 +307,7 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
                 if (have) {
 #pragma unroll
                     for (int j = 0; j < J; j++) {
-                        // ROT: register j is ring slot j = cell WA + ((j - mA) mod J)
-                        int jl = j;
-                        if (ROT) { jl = j - mA; if (jl < 0) jl += J; }
-                        int ka = WA + jl;
+                        int ka = WA + j;
                         if (ka >= KA) ka -= KA;
 #pragma unroll
                         for (int s = 0; s < RPL; s++) {
@@ -563,7 +319,6 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
                 have = true;
                 const int4 ko = FW ? *(const int4*)(rec + HI) : kk;     // this sample's origin
                 WA = ko.x;
-                if (ROT) mA = WA % J;
 #pragma unroll
                 for (int s = 0; s < RPL; s++) {
                     int kb = ko.y + rjb[s]; if (kb >= KB) kb -= KB;
@@ -572,55 +327,36 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
                 }
             } else {
 #pragma unroll 1
-                for (int sft = 0; sft < (FUSE ? kk.w - 1 : kk.w); sft++) {
-                    if constexpr (ROT) {
-                        // fixed ring: retire the slot of cell WA; nothing moves (the weights
-                        // were rotated into ring order by the batch phase)
-                        const int64_t offA = (int64_t)WA * sA;
+                for (int sft = 0; sft < kk.w - 1; sft++) {
 #pragma unroll
-                        for (int r = 0; r < J; r++) {
-                            if (mA == r) {
+                    for (int s = 0; s < RPL; s++) {
+                        if (rvalid[s]) atomic_add_c(faceptr[s] + (int64_t)WA * sA, acc[s][0]);
 #pragma unroll
-                                for (int s = 0; s < RPL; s++) {
-                                    if (rvalid[s]) atomic_add_c(faceptr[s] + offA, acc[s][r]);
-                                    acc[s][r] = make_c<T>(0, 0);
-                                }
-                            }
-                        }
-                        mA = mA + 1 == J ? 0 : mA + 1;
-                    } else {
-#pragma unroll
-                        for (int s = 0; s < RPL; s++) {
-                            if (rvalid[s]) atomic_add_c(faceptr[s] + (int64_t)WA * sA, acc[s][0]);
-#pragma unroll
-                            for (int j = 0; j + 1 < J; j++) acc[s][j] = acc[s][j + 1];
-                            acc[s][J - 1] = make_c<T>(0, 0);
-                        }
+                        for (int j = 0; j + 1 < J; j++) acc[s][j] = acc[s][j + 1];
+                        acc[s][J - 1] = make_c<T>(0, 0);
                     }
                     WA++;   // stays < KA: it ends at this sample's wrapped origin
                 }
-                if constexpr (FUSE) {
-                    if (kk.w > 0) {
-                        // last cell of the slide: flush register 0 and let the FMAs themselves
-                        // do the shift (destination j, addend j + 1) -- no register moves.
-                        // (Fusing slides by 2..J-1 cells the same way was measured: 124
-                        // registers and 5.25 ms instead of 4.79 ms: more divergence between the two
-                        // half-warps and one CTA per SM fewer.)
+                if (kk.w > 0) {
+                    // last cell of the slide: flush register 0 and let the FMAs themselves
+                    // do the shift (destination j, addend j + 1) -- no register moves.
+                    // (Fusing slides by 2..J-1 cells the same way was measured: 124
+                    // registers and 5.25 ms instead of 4.79 ms: more divergence between the two
+                    // half-warps and one CTA per SM fewer.)
 #pragma unroll
-                        for (int s = 0; s < RPL; s++) {
-                            if (rvalid[s]) {
-                                atomic_add_c(faceptr[s] + (int64_t)WA * sA, acc[s][0]);
-                                const C v2 = FW ? mul_w(wb[s], make_c<T>(fx, fy))
-                                                : mul_w(wb[s], mul_w(wc[s], make_c<T>(fx, fy)));
+                    for (int s = 0; s < RPL; s++) {
+                        if (rvalid[s]) {
+                            atomic_add_c(faceptr[s] + (int64_t)WA * sA, acc[s][0]);
+                            const C v2 = FW ? mul_w(wb[s], make_c<T>(fx, fy))
+                                            : mul_w(wb[s], mul_w(wc[s], make_c<T>(fx, fy)));
 #pragma unroll
-                                for (int j = 0; j + 1 < J; j++)
-                                    acc[s][j] = fma_w(wA[j], v2, acc[s][j + 1]);
-                                acc[s][J - 1] = fma_w(wA[J - 1], v2, make_c<T>(0, 0));
-                            }
+                            for (int j = 0; j + 1 < J; j++)
+                                acc[s][j] = fma_w(wA[j], v2, acc[s][j + 1]);
+                            acc[s][J - 1] = fma_w(wA[J - 1], v2, make_c<T>(0, 0));
                         }
-                        WA++;
-                        continue;
                     }
+                    WA++;
+                    continue;
                 }
             }
 #pragma unroll
@@ -635,27 +371,10 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
             }
         }
     }
-    if constexpr (RING == 1) {
-        if (have) {
-#pragma unroll
-            for (int s = 0; s < RPL; s++) {
-                if (rvalid[s]) {
-                    int ka = WA + jlog[s];
-                    if (ka >= KA) ka -= KA;
-                    C* pcol = faceptr[s] + (int64_t)ka * sA;
-#pragma unroll
-                    for (int j = 0; j < J; j++) atomic_add_c(pcol + offC[j], acc[s][j]);
-                }
-            }
-        }
-        return;
-    }
     if (have) {
 #pragma unroll
         for (int j = 0; j < J; j++) {
-            int jl = j;
-            if (ROT) { jl = j - mA; if (jl < 0) jl += J; }
-            int ka = WA + jl;
+            int ka = WA + j;
             if (ka >= KA) ka -= KA;
 #pragma unroll
             for (int s = 0; s < RPL; s++)
@@ -665,105 +384,29 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
 }
 
 template <typename T, int J>
-static int launch_window(const Geom& g, const TablePtrs& tabs, int slide_axis, const void* tm_s,
+static int launch_window(const Geom& g, const TablePtrs& tabs, const WindowOpts& wo, const void* tm_s,
                          const void* wts, const int32_t* pt_ko, const int32_t* pt_kw, const int32_t* perm,
                          const void* samples, void* grid, const void* phase_s, int nbatch,
-                         int pts_per_warp, cudaStream_t st, bool* done) {
-    // negative pts_per_warp selects 32 lanes per sample (one window per warp)
-    // pts_per_warp encodes the lane-group width: < 0 -> 32 lanes, >= 2^20 -> 8 lanes
-    int lanes_per_sample = 16;
-    if (pts_per_warp < 0) { lanes_per_sample = 32; pts_per_warp = -pts_per_warp; }
-    if (pts_per_warp >= (1 << 20)) { lanes_per_sample = 8; pts_per_warp -= (1 << 20); }
-    // slide_axis carries the RING flag in bit 8
-    const bool ring = (slide_axis & 256) != 0;
-    const bool rot = (slide_axis & 512) != 0;     // bit 9: fixed ring with rotated weights
-    const bool fuse = (slide_axis & 1024) != 0;   // bit 10: last shift fused into the FMAs
-    const bool facew = (slide_axis & 2048) != 0;  // bit 11: face-weight staging
-    const bool facew5 = (slide_axis & (1 << 16)) != 0;  // bit 16: ... compiled for 5 CTAs per SM
-    const bool facerec = (slide_axis & (1 << 17)) != 0; // bit 17: `wts` holds plan-time window records
-    const bool faceasy = (slide_axis & (1 << 18)) != 0; // bit 18: ... copied with cp.async, double-buffered
-    int max_slide = (slide_axis >> 12) & 15;      // bits 12-15: longest slide (0 = J - 1)
+                         cudaStream_t st, bool* done) {
+    int max_slide = wo.max_slide;
     if (max_slide <= 0 || max_slide > J - 1) max_slide = J - 1;
-    slide_axis &= 255;
-    pts_per_warp = (pts_per_warp + 31) / 32 * 32;
+    const int pts_per_warp = (wo.pts_per_warp + 31) / 32 * 32;
     using C = cplx_t<T>;
     const int64_t nwarps = (g.M + pts_per_warp - 1) / pts_per_warp;
     const int64_t nblocks = (nwarps + 3) / 4;
     if (nblocks > 0x7fffffff || nbatch > 65535) return 0;
     WindowAxes wa;
-    if (slide_axis == 2) { wa.ax[0] = 2; wa.ax[1] = 0; wa.ax[2] = 1; }
+    if (wo.slide_axis == 2) { wa.ax[0] = 2; wa.ax[1] = 0; wa.ax[2] = 1; }
     else { wa.ax[0] = 0; wa.ax[1] = 1; wa.ax[2] = 2; }
     const int strides[3] = {1, g.K[0], g.K[0] * g.K[1]};
     for (int r = 0; r < 3; r++) { wa.K[r] = g.K[wa.ax[r]]; wa.stride[r] = strides[wa.ax[r]]; }
     dim3 gd((unsigned)nblocks, (unsigned)nbatch);
     const bool tab_smem = tabs.h[0] == tabs.h[1] && tabs.h[1] == tabs.h[2] &&
                           (size_t)g.tlen[0] * sizeof(T) <= 56 * 1024;
-    const size_t stage_bytes = (size_t)4 * WinRec<T, J>::kBytes;
     cudaError_t e;
-    if (wts != nullptr && lanes_per_sample == 16 && fuse && facew) {
-        const size_t smem = (size_t)4 * (facerec ? WinRecG<T, J>::kBytes : WinRec<T, J, true>::kBytes);
-#define B2N_LAUNCH_FW(FWV)                                                                         \
-        {                                                                                          \
-            auto k = spread_window3d_kernel<T, J, 2, 16, 3, FWV>;                                  \
-            e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
-            if (e != cudaSuccess) return (int)e;                                                   \
-            k<<<gd, 128, smem, st>>>(g, wa, (const T*)tabs.h[0], (const T*)tabs.h[1],              \
-                                     (const T*)tabs.h[2], (const T*)tm_s, (const T*)wts, pt_ko,    \
-                                     pt_kw, perm, (const C*)samples, (C*)grid, (const C*)phase_s,  \
-                                     pts_per_warp, max_slide);                                     \
-        }
-        if (facerec && faceasy) B2N_LAUNCH_FW(4)
-        else if (facerec) B2N_LAUNCH_FW(3)
-        else if (facew5 && sizeof(T) == 4 && J <= 6) B2N_LAUNCH_FW(2) else B2N_LAUNCH_FW(1)
-#undef B2N_LAUNCH_FW
-        e = cudaGetLastError();
-        if (e != cudaSuccess) return (int)e;
-        *done = true;
-        return 0;
-    }
-#define B2N_LAUNCH_WIN(TABV, SMEM)                                                                 \
-    if (lanes_per_sample == 8) {                                                                   \
-        auto k = spread_window3d_kernel<T, J, TABV, 8, 0>;                                            \
-        e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM));     \
-        if (e != cudaSuccess) return (int)e;                                                       \
-        k<<<gd, 128, (SMEM), st>>>(g, wa, (const T*)tabs.h[0], (const T*)tabs.h[1],                \
-                                   (const T*)tabs.h[2], (const T*)tm_s, (const T*)wts, pt_ko, pt_kw, \
-                                   perm, (const C*)samples, (C*)grid, (const C*)phase_s,           \
-                                   pts_per_warp, max_slide);                                       \
-    } else if (lanes_per_sample == 16 && fuse) {                                                   \
-        auto k = spread_window3d_kernel<T, J, TABV, 16, 3>;                                        \
-        e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM));     \
-        if (e != cudaSuccess) return (int)e;                                                       \
-        k<<<gd, 128, (SMEM), st>>>(g, wa, (const T*)tabs.h[0], (const T*)tabs.h[1],                \
-                                   (const T*)tabs.h[2], (const T*)tm_s, (const T*)wts, pt_ko, pt_kw, \
-                                   perm, (const C*)samples, (C*)grid, (const C*)phase_s,           \
-                                   pts_per_warp, max_slide);                                       \
-    } else if (lanes_per_sample == 16 && rot) {                                                    \
-        auto k = spread_window3d_kernel<T, J, TABV, 16, 2>;                                        \
-        e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM));     \
-        if (e != cudaSuccess) return (int)e;                                                       \
-        k<<<gd, 128, (SMEM), st>>>(g, wa, (const T*)tabs.h[0], (const T*)tabs.h[1],                \
-                                   (const T*)tabs.h[2], (const T*)tm_s, (const T*)wts, pt_ko, pt_kw, \
-                                   perm, (const C*)samples, (C*)grid, (const C*)phase_s,           \
-                                   pts_per_warp, max_slide);                                       \
-    } else if (lanes_per_sample == 16 && ring) {                                                   \
-        auto k = spread_window3d_kernel<T, J, TABV, 16, 1>;                                        \
-        e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM));     \
-        if (e != cudaSuccess) return (int)e;                                                       \
-        k<<<gd, 128, (SMEM), st>>>(g, wa, (const T*)tabs.h[0], (const T*)tabs.h[1],                \
-                                   (const T*)tabs.h[2], (const T*)tm_s, (const T*)wts, pt_ko, pt_kw, \
-                                   perm, (const C*)samples, (C*)grid, (const C*)phase_s,           \
-                                   pts_per_warp, max_slide);                                       \
-    } else if (lanes_per_sample == 16) {                                                           \
-        auto k = spread_window3d_kernel<T, J, TABV, 16, 0>;                                           \
-        e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM));     \
-        if (e != cudaSuccess) return (int)e;                                                       \
-        k<<<gd, 128, (SMEM), st>>>(g, wa, (const T*)tabs.h[0], (const T*)tabs.h[1],                \
-                                   (const T*)tabs.h[2], (const T*)tm_s, (const T*)wts, pt_ko, pt_kw, \
-                                   perm, (const C*)samples, (C*)grid, (const C*)phase_s,           \
-                                   pts_per_warp, max_slide);                                       \
-    } else {                                                                                       \
-        auto k = spread_window3d_kernel<T, J, TABV, 32, 0>;                                           \
+#define B2N_LAUNCH_WIN(TABV, FWV, SMEM)                                                            \
+    {                                                                                              \
+        auto k = spread_window3d_kernel<T, J, TABV, FWV>;                                          \
         e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM));     \
         if (e != cudaSuccess) return (int)e;                                                       \
         k<<<gd, 128, (SMEM), st>>>(g, wa, (const T*)tabs.h[0], (const T*)tabs.h[1],                \
@@ -771,9 +414,13 @@ static int launch_window(const Geom& g, const TablePtrs& tabs, int slide_axis, c
                                    perm, (const C*)samples, (C*)grid, (const C*)phase_s,           \
                                    pts_per_warp, max_slide);                                       \
     }
-    if (wts != nullptr) B2N_LAUNCH_WIN(2, stage_bytes)
-    else if (tab_smem) B2N_LAUNCH_WIN(1, stage_bytes + (size_t)g.tlen[0] * sizeof(T))
-    else B2N_LAUNCH_WIN(0, stage_bytes)
+    const size_t stage_bytes = (size_t)4 * WinRec<T, J>::kBytes;
+    const size_t stage_fw = (size_t)4 * WinRec<T, J, true>::kBytes;
+    if (wts != nullptr && wo.facew == 2 && sizeof(T) == 4 && J <= 6) B2N_LAUNCH_WIN(2, 2, stage_fw)
+    else if (wts != nullptr && wo.facew != 0) B2N_LAUNCH_WIN(2, 1, stage_fw)
+    else if (wts != nullptr) B2N_LAUNCH_WIN(2, 0, stage_bytes)
+    else if (tab_smem) B2N_LAUNCH_WIN(1, 0, stage_bytes + (size_t)g.tlen[0] * sizeof(T))
+    else B2N_LAUNCH_WIN(0, 0, stage_bytes)
 #undef B2N_LAUNCH_WIN
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
@@ -781,61 +428,18 @@ static int launch_window(const Geom& g, const TablePtrs& tabs, int slide_axis, c
     return 0;
 }
 
-// bytes per plan-time window record (0 = this J has no record variant)
 template <typename T>
-static size_t window_record_bytes_t(int J) {
-    switch (J) {
-        case 4: return WinRecG<T, 4>::kSize;
-        case 5: return WinRecG<T, 5>::kSize;
-        case 6: return WinRecG<T, 6>::kSize;
-        case 7: return WinRecG<T, 7>::kSize;
-        case 8: return WinRecG<T, 8>::kSize;
-        default: return 0;
-    }
-}
-
-// builds recs[M] (adjoint order) from the plan-time weights [3J][M] and wrapped origins
-template <typename T>
-static int window_records_build_t(const Geom& g, int slide_axis, const void* wts, const int32_t* pt_kw,
-                                  int pts_per_warp, int max_slide, void* recs, int sm_count,
-                                  cudaStream_t st) {
-    const int J = g.J[0];
-    if (max_slide <= 0 || max_slide > J - 1) max_slide = J - 1;
-    pts_per_warp = (pts_per_warp + 31) / 32 * 32;
-    const int per_group = pts_per_warp / 2;                    // 16 lanes per sample
-    int aA = 0, aB = 1, aC = 2;
-    if ((slide_axis & 255) == 2) { aA = 2; aB = 0; aC = 1; }
-    int64_t nb = (g.M + 127) / 128;
-    const int64_t cap = (int64_t)sm_count * 32;
-    if (nb > cap) nb = cap;
-    if (nb < 1) nb = 1;
-#define B2N_REC(JJ)                                                                                 \
-    window_records_kernel<T, JJ><<<(unsigned)nb, 128, 0, st>>>(g.M, aA, aB, aC, per_group, max_slide, \
-                                                               (const T*)wts, pt_kw, (unsigned char*)recs)
-    switch (J) {
-        case 4: B2N_REC(4); break;
-        case 5: B2N_REC(5); break;
-        case 6: B2N_REC(6); break;
-        case 7: B2N_REC(7); break;
-        case 8: B2N_REC(8); break;
-        default: return (int)cudaErrorInvalidValue;
-    }
-#undef B2N_REC
-    return (int)cudaGetLastError();
-}
-
-template <typename T>
-static int window_adj_t(const Geom& g, const TablePtrs& tabs, int slide_axis, const void* tm_s,
+static int window_adj_t(const Geom& g, const TablePtrs& tabs, const WindowOpts& wo, const void* tm_s,
                         const void* wts, const int32_t* pt_ko, const int32_t* pt_kw, const int32_t* perm,
                         const void* samples, void* grid, const void* phase_s, int nbatch,
-                        int pts_per_warp, cudaStream_t st, bool* done) {
+                        cudaStream_t st, bool* done) {
     *done = false;
     if (g.ndim != 3) return 0;
     if (g.J[1] != g.J[0] || g.J[2] != g.J[0]) return 0;
     if (g.K[0] < g.J[0] || g.K[1] < g.J[0] || g.K[2] < g.J[0]) return 0;
 #define B2N_WIN(JJ)                                                                          \
-    return launch_window<T, JJ>(g, tabs, slide_axis, tm_s, wts, pt_ko, pt_kw, perm, samples, grid, \
-                                phase_s, nbatch, pts_per_warp, st, done)
+    return launch_window<T, JJ>(g, tabs, wo, tm_s, wts, pt_ko, pt_kw, perm, samples, grid,  \
+                                phase_s, nbatch, st, done)
     switch (g.J[0]) {
         case 4: B2N_WIN(4);
         case 5: B2N_WIN(5);

