@@ -10,15 +10,17 @@ Jd = 6 Kaiser-Bessel table (L = 1024), complex64, one coil.  A step is one forwa
 = 2 * M / (t_fwd + t_adj).  Synthetic data (seeded normal), trajectory cast to float32
 before the operator is built.
 
-N > 1 (launched by torch.distributed.run, one rank per GPU).  Default `--sharding coils`:
-an N-coil acquisition of the same volume, one coil per GPU, plan replicated, NO data-path
-collective (weak scaling; value counts point-coils per second over all ranks).
-`--sharding samples`: one coil, the spokes sharded over the ranks and the adjoint images
-combined with one NCCL all-reduce per step (strong scaling; total work fixed).
+N > 1 (launched by torch.distributed.run, one rank per GPU) measures configs[4] itself: ONE
+coil, the sample set sharded over the ranks (strong scaling, total work fixed).  Default
+`--sharding slab` (SlabShardedNufft): image sharded by planes, oversampled grid and samples by
+grid rows, one NCCL all-to-all per transform, halo rows summed by the receiver.
+`--sharding samples` (SampleShardedNufft): spokes sharded, grid stage replicated, one NCCL
+all-reduce of the adjoint image per step.  `--sharding coils`: an N-coil acquisition, one coil
+per GPU, no collective (weak scaling); also reported as the secondary key `coil_replicas`.
 
 `--impl reference` times the reference's own CPU implementation of the same path (its C
 interpolators compiled unmodified into oracle/_ref, driven by the NumPy restatement of
-its Python pipeline) on a bounded spoke subsample, on the host cores.
+its Python pipeline) on bounded spoke subsamples, on the host cores.
 """
 import argparse
 import json
@@ -34,6 +36,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "non-uniform pts/s fwd+adj at 3D 256^3 Jd=6"
+WORKLOAD = ("3D 256^3, 3-D radial 102944x512 (M=52707328), Kd=384^3, Jd=6, table mode L=1024, "
+            "complex64, 1 coil, fwd+adj per step")
 UNIT = "points/s"
 ND = (256, 256, 256)
 KD = (384, 384, 384)
@@ -118,62 +122,87 @@ class ClockSampler(object):
 
 
 # --------------------------------------------------------------------------- CPU arm
-class CpuReference(object):
-    """The reference CPU path on a 1/frac spoke subsample (evenly strided spokes, so the
-    sampling density pattern is preserved).  `step()` = one fft + one adj."""
+def _set_omp_threads(n):
+    try:
+        import ctypes
 
-    def __init__(self, frac=128):
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(int(n))
+    except OSError:  # pragma: no cover
+        pass
+
+
+def spoke_subsample(frac):
+    idx = np.arange(0, SPOKES, frac)
+    return np.concatenate([radial3d(SPOKES, NREAD, int(s), int(s) + 1) for s in idx], 0)
+
+
+class CpuReference(object):
+    """The reference CPU path of the bench workload on bounded spoke subsamples (evenly strided
+    spokes: the sampling density pattern is preserved).
+
+    `step()` = one fft + one adj on 1/frac_step of the spokes (the 384^3 FFTs are done in
+    full).  The interpolation stages alone are timed on the larger 1/frac_interp subsample
+    (1/16) and their cost, linear in M, is scaled to the full M; the
+    FFT + scaling part is the measured remainder of a step."""
+
+    def __init__(self, frac_step=256, frac_interp=16):
         from oracle import nufft_oracle as orc
 
+        self.orc = orc
         self.engine = "reference" if orc.have_reference_engine() else "port"
-        self.frac = frac
+        self.frac_step, self.frac_interp = frac_step, frac_interp
         # all the host threads this process may use, whatever OMP_NUM_THREADS says (torchrun
         # sets it to 1 for every rank): the reference's forward interpolator is OpenMP-parallel
         self.cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-        try:
-            import ctypes
-
-            ctypes.CDLL("libgomp.so.1").omp_set_num_threads(int(self.cores))
-        except OSError:  # pragma: no cover
-            pass
-        idx = np.arange(0, SPOKES, frac)
-        om = np.concatenate([radial3d(SPOKES, NREAD, int(s), int(s) + 1) for s in idx], 0)
-        t0 = time.perf_counter()
+        _set_omp_threads(self.cores)
+        om = spoke_subsample(frac_step)
         self.O = orc.OracleNufft(Nd=ND, omega=om, Jd=JD, Kd=KD, precision="single",
                                  mode="table", engine=self.engine)
-        self.t_plan = time.perf_counter() - t0
         self.x = image()
         self.Ms = om.shape[0]
         self.y = None
-        self.t_if = self.t_ia = None
 
     def step(self):
         t0 = time.perf_counter(); self.y = self.O.fft(self.x); t_fwd = time.perf_counter() - t0
         t0 = time.perf_counter(); self.O.adj(self.y); t_adj = time.perf_counter() - t0
         return t_fwd, t_adj
 
-    def interp_only(self):
-        """Interpolation stages alone (grid_only), to extrapolate to the full M."""
+    def _interp(self, O, threads):
+        _set_omp_threads(threads)
         rs = np.random.RandomState(1)
         g = (rs.standard_normal(int(np.prod(KD))).astype(np.float32) + 0j).astype(np.complex64)
-        t0 = time.perf_counter(); self.O.fft(g, grid_only=True); self.t_if = time.perf_counter() - t0
-        t0 = time.perf_counter(); self.O.adj(self.y, grid_only=True); self.t_ia = time.perf_counter() - t0
+        ys = (rs.standard_normal(O.M).astype(np.float32) + 0j).astype(np.complex64)
+        t0 = time.perf_counter(); O.fft(g, grid_only=True); t_f = time.perf_counter() - t0
+        t0 = time.perf_counter(); O.adj(ys, grid_only=True); t_a = time.perf_counter() - t0
+        _set_omp_threads(self.cores)
+        return t_f, t_a
 
-    def summary(self, t_fwd, t_adj):
+    def model(self, t_fwd, t_adj):
+        """Full-workload step time from the measured pieces (see the class docstring)."""
         M = SPOKES * NREAD
-        fixed = max(t_fwd - self.t_if, 0.0) + max(t_adj - self.t_ia, 0.0)
-        t_full = fixed + (self.t_if + self.t_ia) * (M / self.Ms)
+        tf_s, ta_s = self._interp(self.O, self.cores)            # interpolation share of a step
+        fixed = max(t_fwd - tf_s, 0.0) + max(t_adj - ta_s, 0.0)  # FFTs, scaling, phases
+        Ob = self.orc.OracleNufft(Nd=ND, omega=spoke_subsample(self.frac_interp), Jd=JD, Kd=KD,
+                                  precision="single", mode="table", engine=self.engine)
+        tf_b, ta_b = self._interp(Ob, self.cores)
+        tf_1, _ = self._interp(self.O, 1)                        # forward with ONE thread
+        scale_b, scale_s = M / Ob.M, M / self.Ms
+        t_full = fixed + (tf_b + ta_b) * scale_b
+        t_full_1 = fixed + tf_1 * scale_s + ta_b * scale_b
         return {
             "kind": "reference" if self.engine == "reference" else "port",
-            "pts_per_s_sample": 2 * self.Ms / (t_fwd + t_adj),
-            "pts_per_s_full": 2 * M / t_full,
             "cores": self.cores,
-            "sample": ("1/%d of the spokes (evenly strided, M=%d): fwd %.2fs (interp %.2fs, OpenMP over "
-                       "samples) adj %.2fs (interp %.2fs, one thread per coil as in the reference), "
-                       "numpy.fft for the 384^3 FFT; value = 2*M_full/(FFT+scaling time + interp time"
-                       " * M_full/M_sample); on the sample itself %.3g points/s"
-                       % (self.frac, self.Ms, t_fwd, self.t_if, t_adj, self.t_ia,
-                          2 * self.Ms / (t_fwd + t_adj))),
+            "t_full_s": t_full,
+            "value": 2 * M / t_full,
+            "value_one_thread": 2 * M / t_full_1,
+            "value_on_step_sample": 2 * self.Ms / (t_fwd + t_adj),
+            "sample": ("step = fft+adj on 1/%d of the spokes (evenly strided, M=%d): fwd %.2fs adj %.2fs "
+                       "incl. the full 384^3 numpy.fft; interpolation alone on 1/%d of the spokes "
+                       "(M=%d): fwd %.2fs (OpenMP over samples, %d threads; %.2fs with 1 thread on the "
+                       "step sample) adj %.2fs (one thread per coil, as the reference); value = "
+                       "2*M_full / (FFT+scaling %.2fs + interpolation * M_full/M_sample)"
+                       % (self.frac_step, self.Ms, t_fwd, t_adj, self.frac_interp, Ob.M, tf_b,
+                          self.cores, tf_1, ta_b, fixed)),
         }
 
 
@@ -182,31 +211,31 @@ def run_reference_arm(args):
     if rank != 0:
         return
     t_all = time.perf_counter()
-    ref = CpuReference(frac=args.cpu_frac)
+    ref = CpuReference(frac_step=args.cpu_frac, frac_interp=args.cpu_frac_interp)
     times = []
     for i in range(args.warmup + args.steps):
         tf, ta = ref.step()
         if i >= args.warmup:
             times.append((tf, ta))
-    ref.interp_only()
     tf = float(np.mean([t[0] for t in times]))
     ta = float(np.mean([t[1] for t in times]))
-    r = ref.summary(tf, ta)
-    value = r["pts_per_s_full"]
+    r = ref.model(tf, ta)
+    # value and ms_per_step are the SAME quantity (full workload, modelled from the measured
+    # pieces); what a timed step actually ran is reported next to them
     out = {
-        "metric": METRIC, "value": value, "unit": UNIT, "impl": "reference",
+        "metric": METRIC, "value": r["value"], "unit": UNIT, "impl": "reference",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1000 * (tf + ta),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic",
-        "config": {"workload": "3D 256^3, 3-D radial 102944x512 (M=52707328), Kd=384^3, Jd=6, "
-                               "table mode L=1024, complex64, 1 coil per GPU, fwd+adj per step (the "
-                               "CPU transforms the coils one after another, so its points/s does "
-                               "not depend on --gpus); each CPU step "
-                               "runs a 1/%d spoke subsample" % args.cpu_frac},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
-                         "sample": r["sample"]},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "ms_per_step": 1000 * r["t_full_s"], "extrapolated": True,
+        "sample_ms_per_step": 1000 * (tf + ta), "value_on_step_sample": r["value_on_step_sample"],
+        "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD,
+                   "sample": "each timed CPU step runs 1/%d of the spokes; see cpu_baseline.sample"
+                             % args.cpu_frac},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+                         "sample": r["sample"],
+                         "one_thread": {"value": r["value_one_thread"], "cores": 1}},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "wall_s": time.perf_counter() - t_all,
     }
@@ -214,6 +243,43 @@ def run_reference_arm(args):
 
 
 # --------------------------------------------------------------------------- GPU arm
+def csrc_sha():
+    """Hash of the kernel sources: ncu-derived numbers under profiles/ are only quoted for the
+    sources they were measured on."""
+    import glob
+    import hashlib
+
+    h = hashlib.sha256()
+    for f in sorted(glob.glob(os.path.join(ROOT, "mrrt", "nufft_b200", "csrc", "*.cu*")) +
+                    glob.glob(os.path.join(ROOT, "mrrt", "nufft_b200", "csrc", "*.h"))):
+        h.update(os.path.basename(f).encode())
+        h.update(open(f, "rb").read())
+    return h.hexdigest()[:16]
+
+
+def measured_traffic():
+    """dram bytes per launch of the two interpolation kernels from the committed ncu capture
+    (profiles/traffic.json, written by scripts/make_traffic.py), or None when the capture is of
+    other kernel sources than the ones being benchmarked."""
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        t = json.load(open(tp))
+    except Exception:
+        return None, None, "no capture"
+    if t.get("csrc_sha") != csrc_sha():
+        return None, None, "capture is of other kernel sources (csrc_sha %s)" % t.get("csrc_sha")
+    return (t.get("adj_kernel_dram_bytes_per_launch"), t.get("fwd_kernel_dram_bytes_per_launch"),
+            t.get("source", "ncu --set full"))
+
+
+def _pin(t):
+    import torch
+
+    out = torch.empty_strided(t.shape, t.stride(), dtype=t.dtype, pin_memory=True)
+    out.copy_(t)
+    return out
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -225,35 +291,42 @@ def run_gpu_arm(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    from mrrt.nufft_b200 import NufftBase, SampleShardedNufft, shard_range
+    from mrrt.nufft_b200 import NufftBase, SlabShardedNufft, shard_range
 
     M = SPOKES * NREAD
-    by_coil = world > 1 and args.sharding == "coils"
-    if by_coil:
-        s_lo, s_hi = 0, SPOKES                          # every rank: one whole coil of the volume
-    else:
-        s_lo, s_hi = shard_range(SPOKES, world, rank)   # shard whole spokes
-    om_local = radial3d(SPOKES, NREAD, s_lo, s_hi)
+    sharding = "none" if world == 1 else args.sharding
+    x_np = image(seed=rank if sharding == "coils" else 0)
     t0 = time.perf_counter()
-    A = NufftBase(Nd=ND, omega=om_local, Jd=JD, Kd=KD, precision="single", mode="table",
-                  on_gpu=True, device=dev, host_chunks=args.host_chunks)
+    S = A = None
+    if sharding == "slab":
+        S = SlabShardedNufft(ND, radial3d(SPOKES, NREAD), Jd=JD, Kd=KD, precision="single", device=dev)
+        M_local = S.M
+        slab_rows = S.nrows
+        prof = S.k
+    else:
+        s_lo, s_hi = (0, SPOKES) if sharding in ("none", "coils") else shard_range(SPOKES, world, rank)
+        A = NufftBase(Nd=ND, omega=radial3d(SPOKES, NREAD, s_lo, s_hi), Jd=JD, Kd=KD,
+                      precision="single", mode="table", on_gpu=True, device=dev,
+                      host_chunks=args.host_chunks)
+        M_local = A.M
+        prof = A
     torch.cuda.synchronize()
     t_plan = time.perf_counter() - t0
-    M_local = A.M
 
-    def all_reduce_img(x):
-        if world > 1 and not by_coil:
-            mem = x.permute(2, 1, 0)
-            dist.all_reduce(torch.view_as_real(mem), op=dist.ReduceOp.SUM)
-        return x
+    # ---- device-resident step
+    if sharding == "slab":
+        xp_dev = torch.from_numpy(np.ascontiguousarray(x_np[:, :, S.z0:S.z1])).to(dev)
 
-    x_np = image(seed=rank if by_coil else 0)
-    x_dev = torch.from_numpy(x_np).to(dev)              # F-ordered: consumed without a copy
+        def step_dev():
+            return S.adj(S.fft(xp_dev, planes=True), planes=True)    # image stays sharded by planes
+    else:
+        x_dev = torch.from_numpy(x_np).to(dev)                       # F-ordered: consumed without a copy
 
-    def step_dev():
-        y = A.fft(x_dev)
-        xa = A.adj(y)
-        return all_reduce_img(xa)
+        def step_dev():
+            xa = A.adj(A.fft(x_dev))
+            if sharding == "samples":
+                dist.all_reduce(torch.view_as_real(xa.permute(2, 1, 0)), op=dist.ReduceOp.SUM)
+            return xa
 
     for _ in range(args.warmup):
         step_dev()
@@ -263,9 +336,12 @@ def run_gpu_arm(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    A.set_option("profile", 1)
-    A.kernel_timing()
-    launches0 = A.launch_count
+    if S is not None:
+        S.k.set_profile(1)
+    else:
+        A.set_option("profile", 1)
+    prof.kernel_timing()
+    launches0 = prof.launch_count
     torch.cuda.synchronize()
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
@@ -277,48 +353,21 @@ def run_gpu_arm(args):
     if world > 1:
         dist.barrier()
     ms_total = e0.elapsed_time(e1)
-    kt = A.kernel_timing()
-    A.set_option("profile", 0)
-    launches = A.launch_count - launches0
+    kt = prof.kernel_timing()
+    if S is not None:
+        S.k.set_profile(0)
+    else:
+        A.set_option("profile", 0)
+    launches = prof.launch_count - launches0
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
-    ms_step = ms_total / args.steps
-    n_units = world if by_coil else 1                   # coils transformed per step, whole job
+    ms_step = float(t.item()) / args.steps
+    n_units = world if sharding == "coils" else 1                   # coils transformed per step, whole job
     value = 2.0 * M * n_units / (ms_step / 1000.0)
 
     # ---- end to end through the public API with pinned HOST buffers
-    x_host = torch.from_numpy(x_np).pin_memory()
-    x_host = x_host if x_host.stride() == torch.from_numpy(x_np).stride() else \
-        torch.empty_strided(x_np.shape, torch.from_numpy(x_np).stride(), dtype=torch.complex64,
-                            pin_memory=True).copy_(torch.from_numpy(x_np))
-
-    def step_e2e_blocking():
-        y_h = A.fft(x_host)                 # H2D image, transform, D2H samples
-        if world == 1 or by_coil:
-            return A.adj(y_h)               # H2D samples, transform, D2H image
-        xa_d = all_reduce_img(A.adj(y_h.to(dev, non_blocking=True)))   # H2D samples, reduce
-        out = torch.empty_strided(xa_d.shape, xa_d.stride(), dtype=xa_d.dtype, pin_memory=True)
-        out.copy_(xa_d)                     # D2H image
-        return out
-
-    overlapped = (world == 1 or by_coil) and args.host_chunks > 1
-    k_host = A.fft(x_host) if overlapped else None      # pinned samples: the adjoint's host input
-
-    def step_e2e():
-        """One fft and one adj from pinned HOST buffers; results back in pinned host memory.
-        Both calls are issued non-blocking (like torch's .to(non_blocking=True)) and the step
-        ends with ONE synchronize, so the samples of the fft travel device->host while the
-        adjoint's samples travel host->device (the two link directions are independent)."""
-        if not overlapped:
-            return step_e2e_blocking()
-        y_h = A.fft(x_host, non_blocking=True)
-        xa_h = A.adj(k_host, non_blocking=True)
-        A.synchronize()
-        return y_h, xa_h
-
     def time_e2e(fn, n):
         for _ in range(2):
             fn()
@@ -329,25 +378,93 @@ def run_gpu_arm(args):
         for _ in range(n):
             fn()
         torch.cuda.synchronize()
-        t = (time.perf_counter() - t0) / n
-        tt = torch.tensor([t], device=dev, dtype=torch.float64)
+        tt = torch.tensor([(time.perf_counter() - t0) / n], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         return float(tt.item())
 
     n_e2e = max(2, min(args.steps, 10))
-    t_e2e_blocking = time_e2e(step_e2e_blocking, n_e2e)
-    t_e2e = time_e2e(step_e2e, n_e2e) if overlapped else t_e2e_blocking
     img_bytes = int(np.prod(ND)) * 8
-    smp_bytes = M_local * 8
+    if sharding == "slab":
+        xp_host = _pin(torch.from_numpy(np.ascontiguousarray(x_np[:, :, S.z0:S.z1])))
+        k_host = _pin(S.fft(xp_dev, planes=True).cpu())
+        y_out = torch.empty(S.M, dtype=torch.complex64, pin_memory=True)
+        x_out = torch.empty_strided(xp_host.shape, xp_host.stride(), dtype=torch.complex64, pin_memory=True)
+
+        def step_e2e():
+            """This rank's image planes up, its samples down; its samples up, its planes down."""
+            y = S.fft(xp_host.to(dev, non_blocking=True), planes=True)
+            y_out.copy_(y, non_blocking=True)
+            xa = S.adj(k_host.to(dev, non_blocking=True), planes=True)
+            x_out.copy_(xa, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+        t_e2e = t_e2e_blocking = time_e2e(step_e2e, n_e2e)
+        h2d = d2h = img_bytes * (S.z1 - S.z0) // ND[2] + S.M * 8
+        mode = ("per rank: fft(planes_host) / adj(samples_host) with pinned host buffers in and out; "
+                "bytes are this rank's (image planes + its samples), every rank on its own PCIe link")
+    else:
+        x_host = _pin(torch.from_numpy(x_np))
+
+        def step_e2e_blocking():
+            y_h = A.fft(x_host)                 # H2D image, transform, D2H samples
+            if sharding != "samples":
+                return A.adj(y_h)               # H2D samples, transform, D2H image
+            xa_d = A.adj(y_h.to(dev, non_blocking=True))
+            dist.all_reduce(torch.view_as_real(xa_d.permute(2, 1, 0)), op=dist.ReduceOp.SUM)
+            return _pin(xa_d)
+
+        overlapped = sharding != "samples" and args.host_chunks > 1
+        k_host = A.fft(x_host) if overlapped else None      # pinned samples: the adjoint's host input
+
+        def step_e2e():
+            """One fft and one adj from pinned HOST buffers; results back in pinned host memory.
+            Both calls are issued non-blocking (like torch's .to(non_blocking=True)) and the step
+            ends with ONE synchronize, so the samples of the fft travel device->host while the
+            adjoint's samples travel host->device (the two link directions are independent)."""
+            if not overlapped:
+                return step_e2e_blocking()
+            y_h = A.fft(x_host, non_blocking=True)
+            xa_h = A.adj(k_host, non_blocking=True)
+            A.synchronize()
+            return y_h, xa_h
+
+        t_e2e_blocking = time_e2e(step_e2e_blocking, n_e2e)
+        t_e2e = time_e2e(step_e2e, n_e2e) if overlapped else t_e2e_blocking
+        h2d = d2h = img_bytes + M_local * 8
+        mode = ("fft(x_host, non_blocking=True); adj(k_host, non_blocking=True); synchronize() "
+                "-- pinned host buffers in and out, one synchronize per step, the two calls' "
+                "copies overlap in opposite link directions" if overlapped else "blocking calls")
     e2e = {"value": 2.0 * M * n_units / t_e2e, "unit": UNIT, "ms_per_step": 1000 * t_e2e,
-           "h2d_bytes_per_step": img_bytes + smp_bytes, "d2h_bytes_per_step": smp_bytes + img_bytes,
-           "steps": n_e2e,
-           "mode": ("fft(x_host, non_blocking=True); adj(k_host, non_blocking=True); synchronize() "
-                    "-- pinned host buffers in and out, one synchronize per step, the two calls' "
-                    "copies overlap in opposite link directions" if overlapped else
-                    "blocking calls"),
-           "blocking_ms_per_step": 1000 * t_e2e_blocking}
+           "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+           "h2d_gbs": h2d / t_e2e / 1e9, "d2h_gbs": d2h / t_e2e / 1e9,
+           "steps": n_e2e, "mode": mode, "blocking_ms_per_step": 1000 * t_e2e_blocking}
+
+    # ---- secondary (N > 1): the communication-free coil-replica number (weak scaling)
+    secondary = None
+    if world > 1 and sharding != "coils" and not args.no_secondary:
+        S = A = prof = None
+        torch.cuda.empty_cache()
+        Ac = NufftBase(Nd=ND, omega=radial3d(SPOKES, NREAD), Jd=JD, Kd=KD, precision="single",
+                       mode="table", on_gpu=True, device=dev)
+        xc = torch.from_numpy(image(seed=rank)).to(dev)
+        for _ in range(3):
+            Ac.adj(Ac.fft(xc))
+        torch.cuda.synchronize()
+        dist.barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(5):
+            Ac.adj(Ac.fft(xc))
+        c1.record()
+        torch.cuda.synchronize()
+        tc = torch.tensor([c0.elapsed_time(c1) / 5], device=dev, dtype=torch.float64)
+        dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+        secondary = {"coil_replicas": {"ms_per_step": float(tc.item()), "scaling": "weak",
+                                       "value": 2.0 * M * world / (float(tc.item()) / 1000.0),
+                                       "note": "%d-coil acquisition, one coil per rank, plan replicated, "
+                                               "no data-path collective; value counts point-coils" % world}}
+        del Ac
 
     if rank != 0:
         if world > 1:
@@ -361,56 +478,59 @@ def run_gpu_arm(args):
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    PK = int(np.prod(KD))
     fwd_ms = kt[0] / max(kt[1], 1)
     adj_ms = kt[2] / max(kt[3], 1)
-    # algorithmic bytes per launch: samples in (coords + value) and the
-    # grid written once / read once
-    adj_bytes = M_local * (3 * 4 + 8) + PK * 8
-    fwd_bytes = PK * 8 + M_local * (3 * 4 + 8)
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):
-        try:
-            traffic = json.load(open(tp)).get("adj_kernel_dram_bytes_per_launch")
-        except Exception:
-            traffic = None
+    # algorithmic bytes per launch, SURVEY 8(d): adjoint M(ndim r + c) + 2 P_K c (zero-fill and
+    # final write; the timed interval covers the zero-fill), forward P_K c + M(ndim r + c); for a
+    # slab P_K is this rank's slab
+    grid_cells = int(np.prod(KD)) if sharding != "slab" else KD[0] * KD[2] * slab_rows
+    adj_bytes = M_local * (3 * 4 + 8) + 2 * grid_cells * 8
+    fwd_bytes = grid_cells * 8 + M_local * (3 * 4 + 8)
+    tr_adj, tr_fwd, tr_src = measured_traffic() if world == 1 else (None, None, "single-GPU capture only")
     adj_gbs = adj_bytes / (adj_ms * 1e-3) / 1e9 if adj_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "spread_window3d_kernel<float,6> (adjoint gridding)",
+    roofline = {"bound": "hbm", "kernel": "spread_window3d_kernel<float,6> + zero-fill (adjoint gridding)",
                 "achieved": adj_gbs, "peak": peak, "unit": "GB/s", "frac": adj_gbs / peak,
-                "traffic": traffic, "peak_source": peak_src,
+                "traffic": tr_adj, "traffic_source": tr_src, "peak_source": peak_src,
                 "kernel_ms": adj_ms, "algorithmic_bytes": adj_bytes,
                 "forward_kernel": {"kernel": "interp_fwd_tiled_kernel<float,3,6>", "kernel_ms": fwd_ms,
                                    "achieved": fwd_bytes / (fwd_ms * 1e-3) / 1e9 if fwd_ms > 0 else 0.0,
-                                   "algorithmic_bytes": fwd_bytes},
-                "whole_step": {"algorithmic_bytes": 6.00e9 if world == 1 else None,
-                               "achieved": 6.00e9 / (ms_step * 1e-3) / 1e9 if world == 1 else None,
-                               "frac": 6.00e9 / (ms_step * 1e-3) / 1e9 / peak if world == 1 else None},
+                                   "algorithmic_bytes": fwd_bytes, "traffic": tr_fwd},
+                "whole_step": {"algorithmic_bytes": 6.00e9,
+                               "achieved": 6.00e9 / (ms_step * 1e-3) / 1e9,
+                               "frac": 6.00e9 / (ms_step * 1e-3) / 1e9 / (peak * world),
+                               "note": "SURVEY 8(d) pair bytes / step time / (peak x n_gpus)"},
                 "note": "on-chip bound, not HBM bound: see DESIGN.md section 5"}
+    if sharding == "slab":
+        roofline["note"] += "; kernel figures are rank 0's (its slab of the grid and its samples)"
 
+    shard_txt = {
+        "none": "none",
+        "slab": "slab: image sharded by planes, grid + samples by grid rows over %d ranks, one NCCL "
+                "all-to-all per transform (SlabShardedNufft); image stays sharded between steps" % world,
+        "samples": "samples: spokes sharded over %d ranks, grid stage replicated, NCCL all-reduce of "
+                   "the adjoint image" % world,
+        "coils": "coils: %d-coil acquisition, one coil per rank, no data-path collective; value "
+                 "counts point-coils" % world}[sharding]
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-        "scaling": "weak" if (by_coil or world == 1) else "strong", "vs_baseline": None,
+        "scaling": "weak" if sharding in ("none", "coils") else "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "3D 256^3, 3-D radial 102944x512 (M=52707328), Kd=384^3, Jd=6, "
-                               "table mode L=1024, complex64, 1 coil per GPU, fwd+adj per step",
-                   "sharding": "none" if world == 1 else (
-                       "coils: %d-coil acquisition, one coil per rank, no data-path collective; "
-                       "value counts point-coils" % world if by_coil else
-                       "samples sharded over %d ranks, NCCL all-reduce of the adjoint image" % world),
+        "config": {"workload": WORKLOAD, "sharding": shard_txt,
                    "l2": "inputs exceed L2 (grid 453 MB, samples 422 MB > 126 MB L2); no flush needed",
                    "plan_s": t_plan},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
     }
+    if secondary:
+        out["secondary"] = secondary
     if world == 1 and not args.no_cpu:
         try:
-            ref = CpuReference(frac=args.cpu_frac)
+            ref = CpuReference(frac_step=args.cpu_frac, frac_interp=args.cpu_frac_interp)
             tf, ta = ref.step()
-            ref.interp_only()
-            r = ref.summary(tf, ta)
-            out["cpu_baseline"] = {"value": r["pts_per_s_full"], "unit": UNIT, "cores": r["cores"],
-                                   "kind": r["kind"], "sample": r["sample"]}
+            r = ref.model(tf, ta)
+            out["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"],
+                                   "kind": r["kind"], "sample": r["sample"], "extrapolated": True,
+                                   "one_thread": {"value": r["value_one_thread"], "cores": 1}}
         except Exception as e:  # pragma: no cover
             out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(),
                                    "kind": "reference", "sample": "failed: %r" % (e,)}
@@ -485,15 +605,20 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-frac", type=int, default=256,
-                    help="CPU legs use 1/frac of the spokes")
+                    help="a timed CPU step runs 1/frac of the spokes")
+    ap.add_argument("--cpu-frac-interp", type=int, default=16,
+                    help="the CPU interpolation stages are timed on 1/frac of the spokes")
+    ap.add_argument("--no-secondary", action="store_true",
+                    help="N>1: skip the coil-replica secondary measurement")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--workload", default="c5", choices=["c5", "coils"],
                     help="c5 = BASELINE configs[4] (the contract bench, default); coils = "
                          "configs[3], the 32-coil 2-D batch sharded by coil")
-    ap.add_argument("--sharding", default="coils", choices=["coils", "samples"],
-                    help="N>1, c5 workload: coils = one coil of the volume per GPU, no collective "
-                         "(weak scaling, default); samples = one coil, spokes sharded, NCCL "
-                         "all-reduce of the adjoint image (strong scaling)")
+    ap.add_argument("--sharding", default="slab", choices=["slab", "samples", "coils"],
+                    help="N>1, c5 workload: slab (default) = one coil, image by planes / grid and "
+                         "samples by rows, NCCL all-to-all (strong scaling); samples = one coil, "
+                         "spokes sharded, NCCL all-reduce of the adjoint image (strong scaling); "
+                         "coils = one coil of the volume per GPU, no collective (weak scaling)")
     ap.add_argument("--host-chunks", type=int, default=4,
                     help="sample ranges pipelined against host<->device copies in the e2e leg")
     args = ap.parse_args()

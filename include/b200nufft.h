@@ -208,6 +208,30 @@ int b2n_spmv_fwd(b2n_plan *plan, const void *grid_dev, void *samples_dev, int nb
 int b2n_spmv_adj(b2n_plan *plan, const void *samples_dev, void *grid_dev, int nbatch,
                  int apply_phase, void *stream);
 
+/* Staged 3-D transforms for slab-distributed operation (no
+ * reference counterpart: the reference is single-device, _nufft.py:1333-1369, :1526-1559).
+ * The oversampled FFT of b2n_grid_fwd / b2n_grid_adj is split so that an all-to-all can sit
+ * between its in-plane part and its axis-3 part:
+ *   b2n_planes_fwd   image planes [z0, z0+nz) (complex[Nd[0]*Nd[1]*nz]) -> x*sn, zero-pad to
+ *                    Kd[0] x Kd[1] per plane, batched 2-D FFT -> planes_dev complex[Kd[0]*Kd[1]*nz]
+ *   b2n_axis3_fwd    grid_dev complex[prod(Kd)] whose planes >= Nd[2] are zero: FFT along axis 3
+ *                    (all Kd[0]*Kd[1] columns), then phase_before
+ *   b2n_axis3_adj    conj(phase_before), unnormalised inverse FFT along axis 3
+ *   b2n_planes_adj   planes_dev (overwritten): batched inverse 2-D FFT, crop, adj_scale * conj(sn)
+ *                    -> image planes [z0, z0+nz)
+ * The axis-3 calls run on a SLAB plan: a plan created with the slab's local Kd[1] and the
+ * options "slab_kglobal2" (global Kd[1]) / "slab_origin2" (global index of local row 0) set
+ * before b2n_plan_set_points; its coordinates, tables and window origins stay global (weights
+ * are bit-identical to the single-device plan's), only grid rows are addressed locally, and
+ * its pb_angle[1] holds the angles of the rows it owns.  b2n_plan_set_points rejects samples
+ * whose window leaves those rows. */
+int b2n_planes_fwd(b2n_plan *plan, const void *image_planes_dev, int z0, int nz,
+                   void *planes_dev, void *stream);
+int b2n_planes_adj(b2n_plan *plan, void *planes_dev, int z0, int nz, void *image_planes_dev,
+                   void *stream);
+int b2n_axis3_fwd(b2n_plan *plan, void *grid_dev, void *stream);
+int b2n_axis3_adj(b2n_plan *plan, void *grid_dev, void *stream);
+
 /* bytes of device memory owned by the plan */
 int64_t b2n_plan_device_bytes(b2n_plan *plan);
 /* number of OUR kernel launches issued so far (cuFFT executions and memsets are counted

@@ -7,6 +7,7 @@ from ._nufft import NufftBase, nufft_adj, nufft_forward
 from ._sense import SenseNufft
 from ._toeplitz import ToeplitzNorm
 from ._sharded import CoilShardedNufft, SampleShardedNufft, shard_range
+from ._slab import SlabShardedNufft
 
 __all__ = [
     "NufftBase",
@@ -17,6 +18,7 @@ __all__ = [
     "kaiser_bessel",
     "kaiser_bessel_ft",
     "SampleShardedNufft",
+    "SlabShardedNufft",
     "CoilShardedNufft",
     "shard_range",
     "SenseNufft",

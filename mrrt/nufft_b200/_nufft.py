@@ -85,10 +85,14 @@ class _ArrayKind(object):
             out = torch.empty_strided(t.shape, t.stride(), dtype=t.dtype, pin_memory=self.pinned)
             out.copy_(t, non_blocking=False)
             return out
-        if self.kind == "dlpack" and self.module == "cupy":
-            import cupy
+        if self.kind == "dlpack":
+            if self.module == "cupy":
+                import cupy
 
-            return cupy.from_dlpack(t)
+                return cupy.from_dlpack(t)
+            # any other DLPack producer: the result stays on the device as a torch tensor,
+            # itself a DLPack producer the caller's library can consume without a copy
+            return t
         return t.cpu().numpy()
 
 

@@ -39,7 +39,12 @@ def _all_reduce_sum(x, group):
     if isinstance(x, np.ndarray):
         buf = np.ascontiguousarray(x.T)            # F-ordered result -> C-contiguous view
         t = torch.view_as_real(torch.from_numpy(buf))
-        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        if dist.get_backend(group) == "nccl":      # NCCL reduces device tensors only
+            td = t.cuda()
+            dist.all_reduce(td, op=dist.ReduceOp.SUM, group=group)
+            t.copy_(td)
+        else:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
         return buf.T
     mem = x.permute(*reversed(range(x.dim())))      # the operator returns F-ordered views
     if not mem.is_contiguous():

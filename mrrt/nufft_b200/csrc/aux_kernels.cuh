@@ -13,7 +13,7 @@ namespace b2n {
 template <typename T> struct Gam { T g[3]; };
 
 template <typename T>
-__global__ void prep_points_kernel(Geom g, Gam<T> gam, int kind, const T* __restrict__ coords,
+__global__ void prep_points_kernel(Geom g, Gam<T> gam, int kind, int jmax, const T* __restrict__ coords,
                                    T* __restrict__ tm, uint64_t* __restrict__ keys,
                                    uint64_t* __restrict__ keys_b, int32_t* __restrict__ bin_ids,
                                    int32_t* __restrict__ iota, int* __restrict__ nonfinite) {
@@ -34,7 +34,7 @@ __global__ void prep_points_kernel(Geom g, Gam<T> gam, int kind, const T* __rest
                 int kw = 0;
                 if (ok) kw = local_index(window_origin<T>(t, g.J[d]), g.Kg[d], g.korg[d]);
                 // slab plans: the whole window must lie inside the rows this plan holds
-                if (ok && g.Kg[d] != g.K[d] && kw + g.J[d] > g.K[d]) { atomicExch(nonfinite, 2); kw = 0; }
+                if (ok && g.Kg[d] != g.K[d] && kw + jmax > g.K[d]) { atomicExch(nonfinite, 2); kw = 0; }
                 bin += (int64_t)(kw / g.tile[d]) * bstride;
                 cell += (int64_t)(kw % g.tile[d]) * cstride;
                 // adjoint order: its own (longer) bins, LAST axis fastest inside the bin
@@ -90,8 +90,11 @@ struct TabArgs {
 // bit-identical -- and the hot kernels stream the weights instead of gathering from the
 // table (a shared-memory gather costs several bank-conflict wavefronts per tap and the
 // forward kernel is shared-memory-bandwidth bound).  Layout [sum(J)][M], sample fastest.
+// Jk: kernel width the hot kernels are compiled for (>= every J[d]); an axis with J[d] < Jk gets
+// Jk - J[d] trailing taps of weight ZERO, so unequal / odd widths run on the equal-width kernels
+// (the extra taps multiply grid cells by 0 in the forward and add 0 in the adjoint).
 template <typename T>
-__global__ void point_weights_kernel(Geom g, TabArgs tabs, const T* __restrict__ tm_s,
+__global__ void point_weights_kernel(Geom g, TabArgs tabs, int Jk, const T* __restrict__ tm_s,
                                      const int32_t* __restrict__ pt_ko, T* __restrict__ wts) {
     const int64_t M = g.M;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < M;
@@ -100,9 +103,10 @@ __global__ void point_weights_kernel(Geom g, TabArgs tabs, const T* __restrict__
         for (int d = 0; d < g.ndim; d++) {
             const T t = tm_s[(int64_t)d * M + i];
             const int ko = pt_ko[(int64_t)d * M + i];
-            for (int j = 0; j < g.J[d]; j++, row++)
+            for (int j = 0; j < Jk; j++, row++)
                 wts[(int64_t)row * M + i] =
-                    tap_real<T>((const T*)tabs.h[d], g.ncenter[d], g.tlen[d], t, ko + j, g.L);
+                    j < g.J[d] ? tap_real<T>((const T*)tabs.h[d], g.ncenter[d], g.tlen[d], t, ko + j, g.L)
+                               : (T)0;
         }
     }
 }
@@ -221,7 +225,7 @@ __global__ void slot_phase_kernel(int64_t ns, const uint32_t* __restrict__ slots
 }
 // (weight, partner's weight or 0) per slot, same expression as point_weights_kernel
 template <typename T>
-__global__ void slot_weights_kernel(Geom g, TabArgs tabs, int64_t ns, const uint32_t* __restrict__ slots,
+__global__ void slot_weights_kernel(Geom g, TabArgs tabs, int Jk, int64_t ns, const uint32_t* __restrict__ slots,
                                     const T* __restrict__ tm_s, const int32_t* __restrict__ pt_ko,
                                     typename Cplx<T>::type* __restrict__ wts2) {
     const int64_t M = g.M;
@@ -237,11 +241,12 @@ __global__ void slot_weights_kernel(Geom g, TabArgs tabs, int64_t ns, const uint
             const int ko = pt_ko[(int64_t)d * M + i];
             // same wrapped cell, but the partner may sit whole periods away: its own origin
             const int koq = pt_ko[(int64_t)d * M + (pair ? i + 1 : i)];
-            for (int j = 0; j < g.J[d]; j++, row++) {
+            for (int j = 0; j < Jk; j++, row++) {
                 typename Cplx<T>::type ww;
-                ww.x = tap_real<T>((const T*)tabs.h[d], g.ncenter[d], g.tlen[d], t, ko + j, g.L);
-                ww.y = pair ? tap_real<T>((const T*)tabs.h[d], g.ncenter[d], g.tlen[d], tq, koq + j, g.L)
-                            : (T)0;
+                ww.x = j < g.J[d] ? tap_real<T>((const T*)tabs.h[d], g.ncenter[d], g.tlen[d], t, ko + j, g.L) : (T)0;
+                ww.y = (pair && j < g.J[d])
+                           ? tap_real<T>((const T*)tabs.h[d], g.ncenter[d], g.tlen[d], tq, koq + j, g.L)
+                           : (T)0;
                 wts2[(int64_t)row * ns + s] = ww;
             }
         }

@@ -5,6 +5,7 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -142,6 +143,9 @@ struct b2n_plan {
     std::map<int, cufftHandle> fft_plans;
     bool fft_pruned_ready = false;
     cufftHandle fft_2d = 0, fft_1d = 0;
+    std::map<int, cufftHandle> fft_planes;   // staged transforms: batched 2-D plans keyed by plane count
+    bool fft_ax3_ready = false;              // ... and the strided 1-D plan along axis 3
+    cufftHandle fft_ax3 = 0;
     long opt_pruned_fft = 1;
     long opt_own_fft3 = 0;       // pruned FFT: own axis-3 pass fused with the zero-padding, phase_before and the crop
     Axis3Plan ax3{};             // its radix schedule, and the K3-entry twiddle table (precision dtype)
@@ -154,6 +158,10 @@ struct b2n_plan {
     int64_t lib_calls = 0;       // cuFFT executions and memsets
     long opt_profile = 0;        // record CUDA events around the interpolation kernels
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_fwd, ev_adj;
+    // window width the tiled forward / register-window adjoint kernels run at: J itself when
+    // all axes share a width the kernels are compiled for, else the next such width (the extra
+    // taps get zero plan-time weights); 0 = no such kernel (1-D, complex table, J > 8)
+    int jk_fwd = 0, jk_adj = 0;
     int last_fwd_kernel = -1;   // 0 generic, 1 tiled
     int last_adj_kernel = -1;   // 0 generic, 3 3-D register window, 4 2-D register window
     std::map<void*, size_t> alloc_bytes;   // what dev_alloc handed out (device_bytes accounting)
@@ -260,6 +268,8 @@ extern "C" int b2n_plan_create(int ndim, const int* Nd, const int* Kd, const int
         g.N[d] = d < ndim ? Nd[d] : 1;
         g.K[d] = d < ndim ? Kd[d] : 1;
         g.J[d] = d < ndim ? Jd[d] : 1;
+        g.Kg[d] = g.K[d];
+        g.korg[d] = 0;
         if (g.N[d] < 1 || g.K[d] < g.N[d] || g.J[d] < 1 || g.J[d] > kMaxJ) {
             delete p;
             return fail(B2N_EINVAL, "need 1 <= N <= K and 1 <= J <= 16 on every axis");
@@ -274,6 +284,22 @@ extern "C" int b2n_plan_create(int ndim, const int* Nd, const int* Kd, const int
         return fail(B2N_EINVAL, "prod(Kd) must be < 2^31");
     }
     default_tiles(p);
+    if (ndim >= 2 && !p->cplx_table) {
+        int jmax = 0;
+        bool equal = true;
+        for (int d = 0; d < ndim; d++) {
+            jmax = g.J[d] > jmax ? g.J[d] : jmax;
+            equal = equal && g.J[d] == g.J[0];
+        }
+        const int even = jmax <= 4 ? 4 : (jmax + 1) / 2 * 2;       // forward, 2-D adjoint: 4, 6, 8
+        p->jk_fwd = jmax <= 8 ? even : 0;
+        // 3-D adjoint windows exist for every width 4..8
+        p->jk_adj = ndim == 3 ? (jmax <= 8 ? (jmax < 4 ? 4 : (equal ? jmax : even)) : 0) : p->jk_fwd;
+        for (int d = 0; d < ndim; d++) {
+            if (g.K[d] < p->jk_fwd) p->jk_fwd = 0;
+            if (g.K[d] < p->jk_adj) p->jk_adj = 0;
+        }
+    }
     *out = p;
     return B2N_OK;
 }
@@ -304,6 +330,8 @@ extern "C" int b2n_plan_destroy(b2n_plan* p) {
     DevGuard dev_guard_(p->device);
     for (auto& kv : p->fft_plans) cufftDestroy(kv.second);
     if (p->fft_pruned_ready) { cufftDestroy(p->fft_2d); cufftDestroy(p->fft_1d); }
+    for (auto& kv : p->fft_planes) cufftDestroy(kv.second);
+    if (p->fft_ax3_ready) cufftDestroy(p->fft_ax3);
     dev_free(p, p->d_tw3);
     free_points(p);
     for (int d = 0; d < 3; d++) {
@@ -335,6 +363,18 @@ extern "C" int b2n_plan_set_option(b2n_plan* p, const char* name, long value) {
         p->g.tile_b[n[5] - '1'] = (int)value;
         p->tile_b_user_set = true;
         default_tiles(p);
+    } else if (n == "slab_kglobal2" || n == "slab_origin2") {
+        // slab plan (SlabShardedNufft): this plan holds rows [origin, origin + Kd[1]) (mod the
+        // global size) of axis 2 of a larger periodic grid; coordinates stay global
+        if (p->points_set) return fail(B2N_ESTATE, "slab options must precede set_points");
+        if (p->g.ndim != 3) return fail(B2N_EINVAL, "slab plans are 3-D");
+        if (n == "slab_kglobal2") {
+            if (value < p->g.K[1]) return fail(B2N_EINVAL, "slab_kglobal2 must be >= Kd[1]");
+            p->g.Kg[1] = (int)value;
+        } else {
+            if (value < 0 || value >= p->g.Kg[1]) return fail(B2N_EINVAL, "slab_origin2 must be in [0, slab_kglobal2)");
+            p->g.korg[1] = (int)value;
+        }
     } else if (n == "chunk") {
         if (value < 32) return fail(B2N_EINVAL, "chunk must be >= 32");
         p->opt_chunk = value;
@@ -386,6 +426,8 @@ extern "C" long b2n_plan_get_option(b2n_plan* p, const char* name) {
     if (n == "tile2") return p->g.tile[1];
     if (n == "tile3") return p->g.tile[2];
     if (n == "chunk") return p->opt_chunk;
+    if (n == "slab_kglobal2") return p->g.Kg[1];
+    if (n == "slab_origin2") return p->g.korg[1];
     if (n == "force_generic") return p->opt_force_generic;
     if (n == "use_tma") return p->opt_use_tma;
     if (n == "sparse_mode") return p->opt_sparse_mode;
@@ -515,9 +557,12 @@ static int set_points_t(b2n_plan* p, const void* coords, int64_t M, int kind, cu
     CU(scratch.alloc(&flag, sizeof(int)));
     CU(cudaMemsetAsync(flag, 0, sizeof(int), st));
     Gam<T> gam;
-    for (int d = 0; d < 3; d++) gam.g[d] = (T)(2.0 * M_PI / (double)g.K[d]);
+    for (int d = 0; d < 3; d++) gam.g[d] = (T)(2.0 * M_PI / (double)g.Kg[d]);
+    int jmax = 1;          // slab plans: widest window any kernel will run over these samples
+    for (int d = 0; d < g.ndim; d++) jmax = g.J[d] > jmax ? g.J[d] : jmax;
+    if (p->opt_precomp) jmax = std::max(jmax, std::max(p->jk_fwd, p->jk_adj));
     prep_points_kernel<T><<<grid_for(M, 256, p->sm_count), 256, 0, st>>>(
-        g, gam, kind, (const T*)coords, (T*)p->d_tm, p->d_keys, keys_b, p->d_bin_ids, iota, flag);
+        g, gam, kind, jmax, (const T*)coords, (T*)p->d_tm, p->d_keys, keys_b, p->d_bin_ids, iota, flag);
     CU(cudaGetLastError());
     // stable LSD radix sort over just the significant key bits
     uint64_t maxkey = (uint64_t)p->nbins * (uint64_t)g.cells_per_tile;
@@ -568,6 +613,7 @@ static int set_points_t(b2n_plan* p, const void* coords, int64_t M, int kind, cu
     CU(cudaStreamSynchronize(st));
     if (hflag) {
         free_points(p);
+        if (hflag == 2) return fail(B2N_EINVAL, "a sample's window leaves the rows held by this slab plan");
         return fail(B2N_ENONFINITE, "omega contains NaN or Inf");
     }
     std::vector<int4> items;
@@ -601,7 +647,7 @@ static int set_points_t(b2n_plan* p, const void* coords, int64_t M, int kind, cu
     const bool want_pairs = g.ndim >= 2 && !p->cplx_table &&
                             (p->opt_fwd_pair == 2 ||
                              (p->opt_fwd_pair == 1 && g.ndim == 3 && p->precision == B2N_SINGLE &&
-                              g.J[0] >= 6));
+                              p->jk_fwd >= 6));
     if (want_pairs) {
         int32_t *head = nullptr, *isslot = nullptr, *slotidx = nullptr, *bss = nullptr;
         CU(scratch.alloc(&head, sizeof(int32_t) * M));
@@ -856,41 +902,44 @@ static int run_generic(b2n_plan* p, bool fwd, const void* in, void* out, int nba
 template <typename T>
 static int build_weights_t(b2n_plan* p, cudaStream_t st) {
     const Geom& g = p->g;
-    int rows = 0;
-    for (int d = 0; d < g.ndim; d++) rows += g.J[d];
     TabArgs tabs{{p->d_tab[0], p->d_tab[1], p->d_tab[2]}};
     int rc;
-    const bool packed = p->opt_fwd_pair && p->d_slots != nullptr;
+    // forward arrays at the forward kernels' width, the adjoint order at the adjoint kernels';
+    // without an adjoint order the adjoint reads the forward arrays (at the forward width)
+    const int jf = p->jk_fwd, ja = p->jk_adj;
+    const bool packed = p->opt_fwd_pair && p->d_slots != nullptr && jf > 0;
     if (packed) {
         // forward weights in slot order: (weight, partner's weight) pairs
-        if ((rc = dev_alloc(p, &p->d_wts_f, 2 * sizeof(T) * (size_t)rows * p->n_slots))) return rc;
+        if ((rc = dev_alloc(p, &p->d_wts_f, 2 * sizeof(T) * (size_t)g.ndim * jf * p->n_slots))) return rc;
         slot_weights_kernel<T><<<grid_for(p->n_slots, 256, p->sm_count), 256, 0, st>>>(
-            g, tabs, p->n_slots, p->d_slots, (const T*)p->d_tm_s, p->d_pt_ko,
+            g, tabs, jf, p->n_slots, p->d_slots, (const T*)p->d_tm_s, p->d_pt_ko,
             (typename Cplx<T>::type*)p->d_wts_f);
         CU(cudaGetLastError());
         p->launches++;
     }
-    // the sample-ordered weights of sort order A are read by the unpaired forward, the 2-D
-    // adjoint and the 3-D adjoint when it has no order of its own
-    if (!packed || g.ndim == 2 || !p->have_b) {
-        if ((rc = dev_alloc(p, &p->d_wts, sizeof(T) * (size_t)rows * g.M))) return rc;
+    // the sample-ordered weights of sort order A are read by the unpaired forward and by the
+    // adjoint when it has no order of its own
+    if (jf > 0 && (!packed || !p->have_b)) {
+        if ((rc = dev_alloc(p, &p->d_wts, sizeof(T) * (size_t)g.ndim * jf * g.M))) return rc;
         point_weights_kernel<T><<<grid_for(g.M, 256, p->sm_count), 256, 0, st>>>(
-            g, tabs, (const T*)p->d_tm_s, p->d_pt_ko, (T*)p->d_wts);
+            g, tabs, jf, (const T*)p->d_tm_s, p->d_pt_ko, (T*)p->d_wts);
         CU(cudaGetLastError());
+        p->launches++;
     }
-    if (p->have_b) {
-        if ((rc = dev_alloc(p, &p->d_wts_b, sizeof(T) * (size_t)rows * g.M))) return rc;
+    if (p->have_b && ja > 0) {
+        if ((rc = dev_alloc(p, &p->d_wts_b, sizeof(T) * (size_t)g.ndim * ja * g.M))) return rc;
         point_weights_kernel<T><<<grid_for(g.M, 256, p->sm_count), 256, 0, st>>>(
-            g, tabs, (const T*)p->d_tm_sb, p->d_pt_ko_b, (T*)p->d_wts_b);
+            g, tabs, ja, (const T*)p->d_tm_sb, p->d_pt_ko_b, (T*)p->d_wts_b);
         CU(cudaGetLastError());
+        p->launches++;
     }
-    p->launches += p->have_b ? 2 : 1;
     return B2N_OK;
 }
 
 static int ensure_weights(b2n_plan* p, cudaStream_t st) {
     if (!p->opt_precomp || p->cplx_table || p->g.ndim < 2 || p->d_wts != nullptr ||
-        p->d_wts_f != nullptr || p->g.M == 0)
+        p->d_wts_f != nullptr || p->d_wts_b != nullptr || p->g.M == 0 ||
+        (p->jk_fwd == 0 && p->jk_adj == 0))
         return B2N_OK;
     if (!p->tables_set || !p->points_set) return B2N_OK;
     return p->precision == B2N_SINGLE ? build_weights_t<float>(p, st) : build_weights_t<double>(p, st);
@@ -927,7 +976,7 @@ static int interp_fwd_impl(b2n_plan* p, const void* grid, void* samples, int nba
     }
     bool done = false;
     prof_begin(p, true, st);
-    if (!p->opt_force_generic && !p->cplx_table) {
+    if (!p->opt_force_generic && !p->cplx_table && p->jk_fwd > 0) {
         const void* ph = phase ? p->d_phase_s : nullptr;
         FwdOpts fo;
         fo.use_tma = p->opt_use_tma ? 1 : 0;
@@ -946,9 +995,9 @@ static int interp_fwd_impl(b2n_plan* p, const void* grid, void* samples, int nba
             sa.phase2 = phase ? p->d_phase_f : nullptr;
         }
         int rc = p->precision == B2N_SINGLE
-                     ? tiled_fwd_f32(p->g, p->tables_equal, table_ptrs(p), p->d_tm_s, p->d_wts, p->d_pt_ko, p->d_pt_kw, p->d_perm, fit,
+                     ? tiled_fwd_f32(p->g, p->jk_fwd, p->tables_equal, table_ptrs(p), p->d_tm_s, p->d_wts, p->d_pt_ko, p->d_pt_kw, p->d_perm, fit,
                                      nfit, sa, grid, samples, ph, nbatch, fo, st, &done)
-                     : tiled_fwd_f64(p->g, p->tables_equal, table_ptrs(p), p->d_tm_s, p->d_wts, p->d_pt_ko, p->d_pt_kw, p->d_perm, fit,
+                     : tiled_fwd_f64(p->g, p->jk_fwd, p->tables_equal, table_ptrs(p), p->d_tm_s, p->d_wts, p->d_pt_ko, p->d_pt_kw, p->d_perm, fit,
                                      nfit, sa, grid, samples, ph, nbatch, fo, st, &done);
         if (rc != 0) return fail(B2N_ECUDA, "tiled forward launch failed: " + std::string(cudaGetErrorString((cudaError_t)rc)));
     }
@@ -965,6 +1014,9 @@ static int interp_fwd_impl(b2n_plan* p, const void* grid, void* samples, int nba
 static int interp_adj_impl(b2n_plan* p, const void* samples, void* grid, int nbatch, bool phase,
                            cudaStream_t st, bool accumulate = false) {
     if (!p->tables_set) return fail(B2N_ESTATE, "tables not set");
+    // the profiled interval covers the zero-fill too: SURVEY 8(d) counts it in the adjoint's bytes
+    const bool prof = p->g.M > 0;
+    if (prof) prof_begin(p, false, st);
     if (!accumulate) {
         CU(cudaMemsetAsync(grid, 0, p->cplx_size() * p->g.PK * nbatch, st));
         p->lib_calls++;
@@ -975,24 +1027,25 @@ static int interp_adj_impl(b2n_plan* p, const void* samples, void* grid, int nba
         if (rc) return rc;
     }
     bool done = false;
-    prof_begin(p, false, st);
-    if (!p->opt_force_generic && !p->cplx_table && p->g.ndim == 2 && p->have_b) {
+    if (!p->opt_force_generic && !p->cplx_table && p->g.ndim == 2 && p->have_b && p->jk_adj > 0) {
         // 2-D: register windows sliding along axis 2 (adjoint sort order), lanes <-> (j1, coil)
         const void* ph = phase ? p->d_phase_sb : nullptr;
         WindowOpts wo;
         wo.pts_per_warp = (int)p->opt_slide_pts;
         wo.max_slide = (int)p->opt_win_maxslide;
         int rc = p->precision == B2N_SINGLE
-                     ? window2d_adj_f32(p->g, table_ptrs(p), p->d_tm_sb, p->d_wts_b, p->d_pt_ko_b, p->d_pt_kw_b,
+                     ? window2d_adj_f32(p->g, p->jk_adj, table_ptrs(p), p->d_tm_sb, p->d_wts_b, p->d_pt_ko_b, p->d_pt_kw_b,
                                         p->d_perm_b, samples, grid, ph, nbatch, wo, st, &done)
-                     : window2d_adj_f64(p->g, table_ptrs(p), p->d_tm_sb, p->d_wts_b, p->d_pt_ko_b, p->d_pt_kw_b,
+                     : window2d_adj_f64(p->g, p->jk_adj, table_ptrs(p), p->d_tm_sb, p->d_wts_b, p->d_pt_ko_b, p->d_pt_kw_b,
                                         p->d_perm_b, samples, grid, ph, nbatch, wo, st, &done);
         if (rc != 0) return fail(B2N_ECUDA, "2-D window adjoint launch failed: " + std::string(cudaGetErrorString((cudaError_t)rc)));
         if (done) p->last_adj_kernel = 4;
     }
-    if (!done && !p->opt_force_generic && !p->cplx_table && p->g.ndim == 3) {
+    if (!done && !p->opt_force_generic && !p->cplx_table && p->g.ndim == 3 &&
+        (p->have_b ? p->jk_adj : p->jk_fwd) > 0) {
         // register window, lane-parallel batch weights; adjoint sort order when built
         const bool ob = p->have_b;
+        const int jk = ob ? p->jk_adj : p->jk_fwd;
         const void* ph = phase ? (ob ? p->d_phase_sb : p->d_phase_s) : nullptr;
         const void* tms = ob ? p->d_tm_sb : p->d_tm_s;
         const void* wts = ob ? p->d_wts_b : p->d_wts;
@@ -1004,10 +1057,10 @@ static int interp_adj_impl(b2n_plan* p, const void* samples, void* grid, int nba
         wo.pts_per_warp = (int)p->opt_slide_pts;
         wo.max_slide = (int)p->opt_win_maxslide;
         wo.facew = (int)p->opt_win_facew;
-        if (wo.facew < 0) wo.facew = p->g.J[0] <= 6 ? (p->precision == B2N_SINGLE ? 2 : 1) : 0;
+        if (wo.facew < 0) wo.facew = jk <= 6 ? (p->precision == B2N_SINGLE ? 2 : 1) : 0;
         int rc = p->precision == B2N_SINGLE
-                     ? window_adj_f32(p->g, table_ptrs(p), wo, tms, wts, ko, kw, pm, samples, grid, ph, nbatch, st, &done)
-                     : window_adj_f64(p->g, table_ptrs(p), wo, tms, wts, ko, kw, pm, samples, grid, ph, nbatch, st, &done);
+                     ? window_adj_f32(p->g, jk, table_ptrs(p), wo, tms, wts, ko, kw, pm, samples, grid, ph, nbatch, st, &done)
+                     : window_adj_f64(p->g, jk, table_ptrs(p), wo, tms, wts, ko, kw, pm, samples, grid, ph, nbatch, st, &done);
         if (rc != 0) return fail(B2N_ECUDA, "window adjoint launch failed: " + std::string(cudaGetErrorString((cudaError_t)rc)));
         if (done) p->last_adj_kernel = 3;
     }
@@ -1048,6 +1101,7 @@ extern "C" int b2n_plan_set_sparse(b2n_plan* p, const void* const* coef,
     if (p == nullptr || coef == nullptr || kidx == nullptr) return fail(B2N_EINVAL, "NULL argument");
     if (!p->points_set) return fail(B2N_ESTATE, "set_points must precede set_sparse");
     if (M != p->g.M) return fail(B2N_EINVAL, "M does not match set_points");
+    if (p->g.Kg[1] != p->g.K[1]) return fail(B2N_EINVAL, "sparse mode is not available on slab plans");
     ON_DEVICE(p);
     cudaStream_t st = (cudaStream_t)stream;
     const Geom& g = p->g;
@@ -1489,4 +1543,163 @@ extern "C" int b2n_grid_multiply(b2n_plan* p, void* grid_dev, const void* kernel
     CU(cudaGetLastError());
     p->launches += 1;
     return B2N_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// Staged 3-D transforms for slab-distributed operation: the oversampled
+// FFT split into its in-plane part on a range of image planes and its axis-3 part on a slab of
+// grid rows, with an all-to-all between them (done by the host: SlabShardedNufft).  The
+// arithmetic per element is that of b2n_grid_fwd / b2n_grid_adj.
+// ---------------------------------------------------------------------------------
+static int get_planes_fft(b2n_plan* p, int nz, cufftHandle* out) {
+    auto it = p->fft_planes.find(nz);
+    if (it != p->fft_planes.end()) {
+        *out = it->second;
+        return B2N_OK;
+    }
+    const Geom& g = p->g;
+    int n2[2] = {g.K[1], g.K[0]};
+    cufftHandle h;
+    FFT(cufftCreate(&h));
+    size_t ws = 0;
+    FFT(cufftMakePlanMany(h, 2, n2, nullptr, 1, g.K[0] * g.K[1], nullptr, 1, g.K[0] * g.K[1],
+                          p->precision == B2N_SINGLE ? CUFFT_C2C : CUFFT_Z2Z, nz, &ws));
+    p->dev_bytes += (int64_t)ws;
+    p->fft_planes[nz] = h;
+    *out = h;
+    return B2N_OK;
+}
+
+static int get_axis3_fft(b2n_plan* p, cufftHandle* out) {
+    if (!p->fft_ax3_ready) {
+        const Geom& g = p->g;
+        int n1[1] = {g.K[2]};
+        int embed[1] = {g.K[2]};
+        size_t ws = 0;
+        FFT(cufftCreate(&p->fft_ax3));
+        FFT(cufftMakePlanMany(p->fft_ax3, 1, n1, embed, g.K[0] * g.K[1], 1, embed, g.K[0] * g.K[1], 1,
+                              p->precision == B2N_SINGLE ? CUFFT_C2C : CUFFT_Z2Z, g.K[0] * g.K[1], &ws));
+        p->dev_bytes += (int64_t)ws;
+        p->fft_ax3_ready = true;
+    }
+    *out = p->fft_ax3;
+    return B2N_OK;
+}
+
+static int check_planes(b2n_plan* p, const void* a, const void* b, int z0, int nz) {
+    if (p == nullptr) return fail(B2N_EINVAL, "NULL plan");
+    if (a == nullptr || b == nullptr) return fail(B2N_EINVAL, "NULL array");
+    if (p->g.ndim != 3) return fail(B2N_EINVAL, "staged transforms are 3-D");
+    if (!p->scaling_set) return fail(B2N_ESTATE, "scaling not set");
+    if (z0 < 0 || nz < 1 || z0 + nz > p->g.N[2]) return fail(B2N_EINVAL, "plane range outside [0, Nd[2])");
+    return B2N_OK;
+}
+
+template <typename T>
+static int planes_fwd_t(b2n_plan* p, const void* image, int z0, int nz, void* planes, cudaStream_t st) {
+    using C = cplx_t<T>;
+    Geom g2 = p->g;                       // the planes [z0, z0 + nz) as a volume of their own
+    g2.K[2] = nz; g2.N[2] = nz;
+    g2.PK = (int64_t)g2.K[0] * g2.K[1] * nz;
+    g2.PN = (int64_t)g2.N[0] * g2.N[1] * nz;
+    AxisPtrs ax = axis_ptrs(p);
+    ax.sn[2] += z0;
+    constexpr int VEC = 32 / (int)sizeof(C);
+    pre_scale_pad_kernel<T, VEC><<<grid_for(g2.PK / VEC + 1, 256, p->sm_count, 32), 256, 0, st>>>(
+        g2, ax, (T)p->fwd_scale, p->fwd_scale != 1.0, (const C*)image, (C*)planes, 1);
+    CU(cudaGetLastError());
+    cufftHandle h;
+    int rc = get_planes_fft(p, nz, &h);
+    if (rc) return rc;
+    FFT(cufftSetStream(h, st));
+    if ((rc = exec_fft<T>(h, planes, CUFFT_FORWARD))) return rc;
+    p->launches += 1;
+    p->lib_calls += 1;
+    return B2N_OK;
+}
+
+template <typename T>
+static int planes_adj_t(b2n_plan* p, void* planes, int z0, int nz, void* image, cudaStream_t st) {
+    using C = cplx_t<T>;
+    Geom g2 = p->g;
+    g2.K[2] = nz; g2.N[2] = nz;
+    g2.PK = (int64_t)g2.K[0] * g2.K[1] * nz;
+    g2.PN = (int64_t)g2.N[0] * g2.N[1] * nz;
+    AxisPtrs ax = axis_ptrs(p);
+    ax.sn[2] += z0;
+    cufftHandle h;
+    int rc = get_planes_fft(p, nz, &h);
+    if (rc) return rc;
+    FFT(cufftSetStream(h, st));
+    if ((rc = exec_fft<T>(h, planes, CUFFT_INVERSE))) return rc;
+    post_crop_scale_kernel<T><<<grid_for(g2.PN, 256, p->sm_count, 32), 256, 0, st>>>(
+        g2, ax, (T)p->adj_scale, p->adj_scale != 1.0, (const C*)planes, (C*)image, 1);
+    CU(cudaGetLastError());
+    p->launches += 1;
+    p->lib_calls += 1;
+    return B2N_OK;
+}
+
+extern "C" int b2n_planes_fwd(b2n_plan* p, const void* image_planes_dev, int z0, int nz,
+                              void* planes_dev, void* stream) {
+    int rc = check_planes(p, image_planes_dev, planes_dev, z0, nz);
+    if (rc) return rc;
+    ON_DEVICE(p);
+    return p->precision == B2N_SINGLE
+               ? planes_fwd_t<float>(p, image_planes_dev, z0, nz, planes_dev, (cudaStream_t)stream)
+               : planes_fwd_t<double>(p, image_planes_dev, z0, nz, planes_dev, (cudaStream_t)stream);
+}
+
+extern "C" int b2n_planes_adj(b2n_plan* p, void* planes_dev, int z0, int nz, void* image_planes_dev,
+                              void* stream) {
+    int rc = check_planes(p, planes_dev, image_planes_dev, z0, nz);
+    if (rc) return rc;
+    ON_DEVICE(p);
+    return p->precision == B2N_SINGLE
+               ? planes_adj_t<float>(p, planes_dev, z0, nz, image_planes_dev, (cudaStream_t)stream)
+               : planes_adj_t<double>(p, planes_dev, z0, nz, image_planes_dev, (cudaStream_t)stream);
+}
+
+template <typename T>
+static int axis3_t(b2n_plan* p, void* grid, bool inverse, cudaStream_t st) {
+    using C = cplx_t<T>;
+    const Geom& g = p->g;
+    AxisPtrs ax = axis_ptrs(p);
+    constexpr int VEC = 32 / (int)sizeof(C);
+    cufftHandle h;
+    int rc = get_axis3_fft(p, &h);
+    if (rc) return rc;
+    FFT(cufftSetStream(h, st));
+    if (inverse && p->have_pb) {
+        phase_before_kernel<T, VEC><<<grid_for(g.PK / VEC + 1, 256, p->sm_count, 32), 256, 0, st>>>(
+            g, ax, 1, (C*)grid, 1);
+        CU(cudaGetLastError());
+        p->launches++;
+    }
+    if ((rc = exec_fft<T>(h, grid, inverse ? CUFFT_INVERSE : CUFFT_FORWARD))) return rc;
+    p->lib_calls += 1;
+    if (!inverse && p->have_pb) {
+        phase_before_kernel<T, VEC><<<grid_for(g.PK / VEC + 1, 256, p->sm_count, 32), 256, 0, st>>>(
+            g, ax, 0, (C*)grid, 1);
+        CU(cudaGetLastError());
+        p->launches++;
+    }
+    return B2N_OK;
+}
+
+static int axis3_entry(b2n_plan* p, void* grid, bool inverse, void* stream) {
+    if (p == nullptr) return fail(B2N_EINVAL, "NULL plan");
+    if (grid == nullptr) return fail(B2N_EINVAL, "NULL array");
+    if (p->g.ndim != 3) return fail(B2N_EINVAL, "staged transforms are 3-D");
+    if (!p->scaling_set) return fail(B2N_ESTATE, "scaling not set");
+    ON_DEVICE(p);
+    return p->precision == B2N_SINGLE ? axis3_t<float>(p, grid, inverse, (cudaStream_t)stream)
+                                      : axis3_t<double>(p, grid, inverse, (cudaStream_t)stream);
+}
+
+extern "C" int b2n_axis3_fwd(b2n_plan* p, void* grid_dev, void* stream) {
+    return axis3_entry(p, grid_dev, false, stream);
+}
+extern "C" int b2n_axis3_adj(b2n_plan* p, void* grid_dev, void* stream) {
+    return axis3_entry(p, grid_dev, true, stream);
 }

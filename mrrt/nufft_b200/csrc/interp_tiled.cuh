@@ -369,7 +369,7 @@ static int launch_fwd_tiled(const Geom& g, const TablePtrs& tabs, const void* tm
 
 // returns 0 or a cudaError_t; *done tells whether the tiled kernel took the call
 template <typename T>
-static int tiled_fwd_t(const Geom& g, bool tables_equal, const TablePtrs& tabs, const void* tm_s,
+static int tiled_fwd_t(const Geom& g, int Jk, bool tables_equal, const TablePtrs& tabs, const void* tm_s,
                        const void* wts, const int32_t* pt_ko, const int32_t* pt_kw, const int32_t* perm, const int4* items, int64_t n_items, const SlotArgs& sa, const void* grid,
                        void* out, const void* phase_s, int nbatch, const FwdOpts& fo, cudaStream_t st,
                        bool* done) {
@@ -377,20 +377,23 @@ static int tiled_fwd_t(const Geom& g, bool tables_equal, const TablePtrs& tabs, 
     if (g.ndim < 2 || (!tables_equal && wts == nullptr && !sa.packed) || n_items == 0 || n_items > 0x7fffffff ||
         nbatch > 65535)
         return 0;
-    for (int d = 1; d < g.ndim; d++)
-        if (g.J[d] != g.J[0]) return 0;
+    // a window wider than an axis' own J needs the zero-padded plan-time weights
+    for (int d = 0; d < g.ndim; d++) {
+        if (g.J[d] != Jk && wts == nullptr && !sa.packed) return 0;
+        if (g.K[d] < Jk) return 0;
+    }
 #define B2N_TILED(ND, JJ)                                                                      \
     return launch_fwd_tiled<T, ND, JJ>(g, tabs, tm_s, wts, pt_ko, pt_kw, perm, items, n_items, sa, grid, out, phase_s, \
                                        nbatch, fo, st, done)
     if (g.ndim == 2) {
-        switch (g.J[0]) {
+        switch (Jk) {
             case 4: B2N_TILED(2, 4);
             case 6: B2N_TILED(2, 6);
             case 8: B2N_TILED(2, 8);
             default: return 0;
         }
     }
-    switch (g.J[0]) {
+    switch (Jk) {
         case 4: B2N_TILED(3, 4);
         case 6: B2N_TILED(3, 6);
         case 8: B2N_TILED(3, 8);

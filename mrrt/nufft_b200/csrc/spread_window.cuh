@@ -429,18 +429,20 @@ static int launch_window(const Geom& g, const TablePtrs& tabs, const WindowOpts&
 }
 
 template <typename T>
-static int window_adj_t(const Geom& g, const TablePtrs& tabs, const WindowOpts& wo, const void* tm_s,
+static int window_adj_t(const Geom& g, int Jk, const TablePtrs& tabs, const WindowOpts& wo, const void* tm_s,
                         const void* wts, const int32_t* pt_ko, const int32_t* pt_kw, const int32_t* perm,
                         const void* samples, void* grid, const void* phase_s, int nbatch,
                         cudaStream_t st, bool* done) {
     *done = false;
     if (g.ndim != 3) return 0;
-    if (g.J[1] != g.J[0] || g.J[2] != g.J[0]) return 0;
-    if (g.K[0] < g.J[0] || g.K[1] < g.J[0] || g.K[2] < g.J[0]) return 0;
+    for (int d = 0; d < 3; d++) {
+        if (g.J[d] != Jk && wts == nullptr) return 0;   // padded windows need the plan-time weights
+        if (g.K[d] < Jk) return 0;
+    }
 #define B2N_WIN(JJ)                                                                          \
     return launch_window<T, JJ>(g, tabs, wo, tm_s, wts, pt_ko, pt_kw, perm, samples, grid,  \
                                 phase_s, nbatch, st, done)
-    switch (g.J[0]) {
+    switch (Jk) {
         case 4: B2N_WIN(4);
         case 5: B2N_WIN(5);
         case 6: B2N_WIN(6);

@@ -253,13 +253,16 @@ static int launch_window2d(const Geom& g, const TablePtrs& tabs, const void* tm_
 
 // the sample arrays must be in the ADJOINT sort order (axis 2 fastest inside a bin)
 template <typename T>
-static int window2d_adj_t(const Geom& g, const TablePtrs& tabs, const void* tm_s, const void* wts,
+static int window2d_adj_t(const Geom& g, int Jk, const TablePtrs& tabs, const void* tm_s, const void* wts,
                           const int32_t* pt_ko, const int32_t* pt_kw, const int32_t* perm,
                           const void* samples, void* grid, const void* phase_s, int nbatch,
                           const WindowOpts& wo, cudaStream_t st, bool* done) {
     *done = false;
-    if (g.ndim != 2 || g.J[1] != g.J[0]) return 0;
-    if (g.K[0] < g.J[0] || g.K[1] < g.J[0]) return 0;
+    if (g.ndim != 2) return 0;
+    for (int d = 0; d < 2; d++) {
+        if (g.J[d] != Jk && wts == nullptr) return 0;   // padded windows need the plan-time weights
+        if (g.K[d] < Jk) return 0;
+    }
 #define B2N_W2D(JJ, GG, RR)                                                                      \
     return launch_window2d<T, JJ, GG, RR>(g, tabs, tm_s, wts, pt_ko, pt_kw, perm, samples, grid, \
                                           phase_s, nbatch, wo, st, done)
@@ -272,7 +275,7 @@ static int window2d_adj_t(const Geom& g, const TablePtrs& tabs, const void* tm_s
         if (nbatch * JJ <= 96) B2N_W2D(JJ, 32, 3);                      \
         B2N_W2D(JJ, 32, 6);                                             \
     }
-    switch (g.J[0]) {
+    switch (Jk) {
         case 4: B2N_W2D_J(4)
         case 6: B2N_W2D_J(6)
         case 8: B2N_W2D_J(8)
