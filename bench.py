@@ -440,6 +440,19 @@ def run_gpu_arm(args):
            "h2d_gbs": h2d / t_e2e / 1e9, "d2h_gbs": d2h / t_e2e / 1e9,
            "steps": n_e2e, "mode": mode, "blocking_ms_per_step": 1000 * t_e2e_blocking}
 
+    # ---- per-stage times of the slab operator (rank 0's, CUDA events between stages)
+    stages = None
+    if sharding == "slab":
+        S.profile_stages(True)
+        for _ in range(5):
+            step_dev()
+        stages = S.stage_times()
+        S.profile_stages(False)
+        stages["rows"] = [int(S.slabs[r][1]) for r in range(world)]
+        counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+        dist.all_gather(counts, torch.tensor([S.M], dtype=torch.int64, device=dev))
+        stages["samples"] = [int(c.item()) for c in counts]
+
     # ---- secondary (N > 1): the communication-free coil-replica number (weak scaling)
     secondary = None
     if world > 1 and sharding != "coils" and not args.no_secondary:
@@ -523,6 +536,8 @@ def run_gpu_arm(args):
     }
     if secondary:
         out["secondary"] = secondary
+    if stages:
+        out["slab_stages_ms"] = stages
     if world == 1 and not args.no_cpu:
         try:
             ref = CpuReference(frac_step=args.cpu_frac, frac_interp=args.cpu_frac_interp)

@@ -80,9 +80,9 @@ int b2n_plan_destroy(b2n_plan *plan);
  *            "slide_pts" samples per warp of the register-window adjoint kernels;
  *            "win_maxslide" longest window slide in cells (0 = J-1); "win_facew" -1 auto / 0
  *            off / 1,2 face-weight staging of the 3-D window adjoint; "pruned_fft" 1 = skip
- *            the all-zero planes of the padded FFT; "own_fft3" 1 = the axis-3 pass of the
- *            pruned FFT by the fused kernel of csrc/fft_axis3.cuh (zero padding,
- *            phase_before and crop inside the pass; break-even, off by default);
+ *            the all-zero planes of the padded FFT; "own_fft3" 1 (default) = the axis-3 pass of
+ *            the pruned FFT by the fused kernel of csrc/fft_axis3.cuh (zero padding,
+ *            phase_before and crop inside the pass), 0 = cuFFT strided pass + phase kernel;
  *            "profile" 1 = CUDA events around the interpolation kernels; "sparse_mode" (set
  *            by the host for mode="sparse").
  *   read-only (b2n_plan_get_option): "last_fwd_kernel" (0 one thread per sample, 1 tiled),

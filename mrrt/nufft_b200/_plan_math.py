@@ -109,8 +109,35 @@ def dense_phase_before(angles, cdt):
     return np.exp(1j * phase).astype(cdt, copy=False)
 
 
+def _phase_after_block(omega, shift, cdt):
+    return np.exp(1j * np.dot(omega, shift)).astype(cdt, copy=False)
+
+
 def phase_after(omega, mids, n_shift, rdt, cdt):
-    """``exp(i omega.(n_shift - n_mid))`` (_nufft.py:717-724)."""
+    """``exp(i omega.(n_shift - n_mid))`` (_nufft.py:717-724).
+
+    Stays on the HOST on purpose: in single precision the angle is a float32 dot product whose
+    rounding (~3e-5 rad at |angle| ~ 500) is part of what the reference computes, and only the
+    same NumPy expression on the same host reproduces it bit for bit (a device evaluation would
+    differ by an ulp of the angle, i.e. by more than the 1e-5 parity budget).  Large sample sets
+    are evaluated in row blocks on a thread pool (NumPy releases the GIL inside the loops; every
+    row's result is independent of the blocking)."""
     shift_vec = [(s - m) for s, m in zip(n_shift, mids)]
-    phase = np.exp(1j * np.dot(omega, np.asarray(shift_vec, dtype=rdt)))
-    return phase.astype(cdt, copy=False)
+    shift = np.asarray(shift_vec, dtype=rdt)
+    M = omega.shape[0]
+    nblk = min(32, M // (1 << 18))
+    if nblk < 2:
+        return _phase_after_block(omega, shift, cdt)
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+
+    out = np.empty(M, dtype=cdt)
+    edges = np.linspace(0, M, nblk + 1).astype(np.int64)
+
+    def run(b):
+        out[edges[b]:edges[b + 1]] = _phase_after_block(omega[edges[b]:edges[b + 1]], shift, cdt)
+
+    nthr = min(nblk, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else 4)
+    with ThreadPoolExecutor(max_workers=max(1, nthr)) as ex:
+        list(ex.map(run, range(nblk)))
+    return out

@@ -305,6 +305,30 @@ class SlabShardedNufft(object):
         self._fwd_in = [nz_me * self.slabs[s][1] * K1 for s in range(G)]
         self._fwd_out = [(self.planes[r][1] - self.planes[r][0]) * self.nrows * K1 for r in range(G)]
 
+    # ------------------------------------------------------------------ stage timing
+    def profile_stages(self, on=True):
+        """Record CUDA events between the stages of every transform (CUDA back end only)."""
+        self._stage_ev = [] if on and self.device.type == "cuda" else None
+
+    def _mark(self, name):
+        if getattr(self, "_stage_ev", None) is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(torch.cuda.current_stream(self.device))
+            self._stage_ev.append((name, ev))
+
+    def stage_times(self):
+        """Mean milliseconds per stage since ``profile_stages()`` (synchronises)."""
+        evs = getattr(self, "_stage_ev", None) or []
+        torch.cuda.synchronize(self.device)
+        tot, cnt = {}, {}
+        for (n0, e0), (n1, e1) in zip(evs[:-1], evs[1:]):
+            if n1 == "begin":
+                continue
+            tot[n1] = tot.get(n1, 0.0) + e0.elapsed_time(e1)
+            cnt[n1] = cnt.get(n1, 0) + 1
+        self._stage_ev = []
+        return {k: tot[k] / cnt[k] for k in tot}
+
     # ------------------------------------------------------------------ helpers
     def _a2a(self, out, inp, out_splits, in_splits):
         if self.world == 1:
@@ -345,7 +369,9 @@ class SlabShardedNufft(object):
     def _fft_dev(self, xp):
         K1, K2, K3 = self.Kd
         N3 = self.Nd[2]
+        self._mark("begin")
         A = self.k.planes_fwd(xp, self.z0)                        # [nz, K2, K1]
+        self._mark("fwd_planes")
         nz = A.shape[0]
         send = self.k.empty((sum(self._fwd_in),))
         off = 0
@@ -357,9 +383,14 @@ class SlabShardedNufft(object):
             off += nz * nrows * K1
         grid = self.k.empty((K3, self.nrows, K1))
         grid[N3:].zero_()
+        self._mark("fwd_pack")
         self._a2a(grid[:N3].view(-1), send, self._fwd_out, self._fwd_in)
+        self._mark("fwd_all_to_all")
         self.k.axis3_fwd(grid)
-        return self.k.interp_fwd(grid)
+        self._mark("fwd_axis3")
+        y = self.k.interp_fwd(grid)
+        self._mark("fwd_interp")
+        return y
 
     def adj(self, k_local, planes=False):
         """Adjoint transform of this rank's samples (see the class docstring)."""
@@ -376,12 +407,16 @@ class SlabShardedNufft(object):
     def _adj_dev(self, kt):
         K1, K2, K3 = self.Kd
         N3 = self.Nd[2]
+        self._mark("begin")
         grid = self.k.empty((K3, self.nrows, K1))
         self.k.interp_adj(kt, grid)
+        self._mark("adj_interp")
         self.k.axis3_adj(grid)
+        self._mark("adj_axis3")
         nz = self.z1 - self.z0
         recv = self.k.empty((sum(self._fwd_in),))
         self._a2a(recv, grid[:N3].view(-1), self._fwd_in, self._fwd_out)
+        self._mark("adj_all_to_all")
         # every grid row is the ORIGIN row of exactly one slab: those parts are copied (no
         # zero-fill pass), then the halo rows of the neighbouring slabs are added
         B = self.k.empty((nz, K2, K1))
@@ -398,7 +433,10 @@ class SlabShardedNufft(object):
             if nrows > own:
                 for glo, llo, n in _pieces((row0 + own) % K2, nrows - own, K2):
                     B[:, glo:glo + n] += views[s][:, own + llo:own + llo + n]
-        return self.k.planes_adj(B, self.z0)
+        self._mark("adj_unpack")
+        out = self.k.planes_adj(B, self.z0)
+        self._mark("adj_planes")
+        return out
 
     def _all_gather_padded(self, t, counts):
         """All-gather of per-rank 1-D complex tensors of (possibly) different lengths: every

@@ -93,9 +93,11 @@ struct TabArgs {
 // Jk: kernel width the hot kernels are compiled for (>= every J[d]); an axis with J[d] < Jk gets
 // Jk - J[d] trailing taps of weight ZERO, so unequal / odd widths run on the equal-width kernels
 // (the extra taps multiply grid cells by 0 in the forward and add 0 in the adjoint).
-template <typename T>
+// CT: complex table (phasing="complex"): the weights are complex (template.c:97-143, :623-709)
+template <typename T, bool CT = false>
 __global__ void point_weights_kernel(Geom g, TabArgs tabs, int Jk, const T* __restrict__ tm_s,
-                                     const int32_t* __restrict__ pt_ko, T* __restrict__ wts) {
+                                     const int32_t* __restrict__ pt_ko,
+                                     typename WeightT<T, CT>::type* __restrict__ wts) {
     const int64_t M = g.M;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < M;
          i += (int64_t)gridDim.x * blockDim.x) {
@@ -103,10 +105,17 @@ __global__ void point_weights_kernel(Geom g, TabArgs tabs, int Jk, const T* __re
         for (int d = 0; d < g.ndim; d++) {
             const T t = tm_s[(int64_t)d * M + i];
             const int ko = pt_ko[(int64_t)d * M + i];
-            for (int j = 0; j < Jk; j++, row++)
-                wts[(int64_t)row * M + i] =
-                    j < g.J[d] ? tap_real<T>((const T*)tabs.h[d], g.ncenter[d], g.tlen[d], t, ko + j, g.L)
-                               : (T)0;
+            for (int j = 0; j < Jk; j++, row++) {
+                if constexpr (CT) {
+                    wts[(int64_t)row * M + i] =
+                        j < g.J[d] ? tap_cplx<T>((const cplx_t<T>*)tabs.h[d], g.ncenter[d], g.tlen[d], t, ko + j, g.L)
+                                   : make_c<T>(0, 0);
+                } else {
+                    wts[(int64_t)row * M + i] =
+                        j < g.J[d] ? tap_real<T>((const T*)tabs.h[d], g.ncenter[d], g.tlen[d], t, ko + j, g.L)
+                                   : (T)0;
+                }
+            }
         }
     }
 }

@@ -147,7 +147,7 @@ struct b2n_plan {
     bool fft_ax3_ready = false;              // ... and the strided 1-D plan along axis 3
     cufftHandle fft_ax3 = 0;
     long opt_pruned_fft = 1;
-    long opt_own_fft3 = 0;       // pruned FFT: own axis-3 pass fused with the zero-padding, phase_before and the crop
+    long opt_own_fft3 = 1;       // pruned FFT: own axis-3 pass fused with the zero-padding, phase_before and the crop
     Axis3Plan ax3{};             // its radix schedule, and the K3-entry twiddle table (precision dtype)
     int ax3_state = 0;           // 0 = not prepared, 1 = ready, -1 = K3 not supported
     void* d_tw3 = nullptr;
@@ -284,7 +284,7 @@ extern "C" int b2n_plan_create(int ndim, const int* Nd, const int* Kd, const int
         return fail(B2N_EINVAL, "prod(Kd) must be < 2^31");
     }
     default_tiles(p);
-    if (ndim >= 2 && !p->cplx_table) {
+    if (ndim >= 2) {
         int jmax = 0;
         bool equal = true;
         for (int d = 0; d < ndim; d++) {
@@ -538,7 +538,7 @@ static int set_points_t(b2n_plan* p, const void* coords, int64_t M, int kind, cu
     }
     Scratch scratch;
     // the adjoint order is used by the 2-D and 3-D register-window kernels
-    const bool want_b = g.ndim >= 2 && !p->cplx_table && p->opt_order_b;
+    const bool want_b = g.ndim >= 2 && p->opt_order_b && (!p->cplx_table || p->opt_precomp);
     uint64_t* keys_b = nullptr;
     if (want_b) {
         if ((rc = dev_alloc(p, &p->d_tm_sb, rs * M * g.ndim))) return rc;
@@ -919,17 +919,27 @@ static int build_weights_t(b2n_plan* p, cudaStream_t st) {
     }
     // the sample-ordered weights of sort order A are read by the unpaired forward and by the
     // adjoint when it has no order of its own
+    const size_t wsz = p->cplx_table ? 2 * sizeof(T) : sizeof(T);      // complex tables: complex weights
+    using CW = typename Cplx<T>::type;
     if (jf > 0 && (!packed || !p->have_b)) {
-        if ((rc = dev_alloc(p, &p->d_wts, sizeof(T) * (size_t)g.ndim * jf * g.M))) return rc;
-        point_weights_kernel<T><<<grid_for(g.M, 256, p->sm_count), 256, 0, st>>>(
-            g, tabs, jf, (const T*)p->d_tm_s, p->d_pt_ko, (T*)p->d_wts);
+        if ((rc = dev_alloc(p, &p->d_wts, wsz * (size_t)g.ndim * jf * g.M))) return rc;
+        if (p->cplx_table)
+            point_weights_kernel<T, true><<<grid_for(g.M, 256, p->sm_count), 256, 0, st>>>(
+                g, tabs, jf, (const T*)p->d_tm_s, p->d_pt_ko, (CW*)p->d_wts);
+        else
+            point_weights_kernel<T><<<grid_for(g.M, 256, p->sm_count), 256, 0, st>>>(
+                g, tabs, jf, (const T*)p->d_tm_s, p->d_pt_ko, (T*)p->d_wts);
         CU(cudaGetLastError());
         p->launches++;
     }
     if (p->have_b && ja > 0) {
-        if ((rc = dev_alloc(p, &p->d_wts_b, sizeof(T) * (size_t)g.ndim * ja * g.M))) return rc;
-        point_weights_kernel<T><<<grid_for(g.M, 256, p->sm_count), 256, 0, st>>>(
-            g, tabs, ja, (const T*)p->d_tm_sb, p->d_pt_ko_b, (T*)p->d_wts_b);
+        if ((rc = dev_alloc(p, &p->d_wts_b, wsz * (size_t)g.ndim * ja * g.M))) return rc;
+        if (p->cplx_table)
+            point_weights_kernel<T, true><<<grid_for(g.M, 256, p->sm_count), 256, 0, st>>>(
+                g, tabs, ja, (const T*)p->d_tm_sb, p->d_pt_ko_b, (CW*)p->d_wts_b);
+        else
+            point_weights_kernel<T><<<grid_for(g.M, 256, p->sm_count), 256, 0, st>>>(
+                g, tabs, ja, (const T*)p->d_tm_sb, p->d_pt_ko_b, (T*)p->d_wts_b);
         CU(cudaGetLastError());
         p->launches++;
     }
@@ -937,7 +947,7 @@ static int build_weights_t(b2n_plan* p, cudaStream_t st) {
 }
 
 static int ensure_weights(b2n_plan* p, cudaStream_t st) {
-    if (!p->opt_precomp || p->cplx_table || p->g.ndim < 2 || p->d_wts != nullptr ||
+    if (!p->opt_precomp || p->g.ndim < 2 || p->d_wts != nullptr ||
         p->d_wts_f != nullptr || p->d_wts_b != nullptr || p->g.M == 0 ||
         (p->jk_fwd == 0 && p->jk_adj == 0))
         return B2N_OK;
@@ -976,7 +986,7 @@ static int interp_fwd_impl(b2n_plan* p, const void* grid, void* samples, int nba
     }
     bool done = false;
     prof_begin(p, true, st);
-    if (!p->opt_force_generic && !p->cplx_table && p->jk_fwd > 0) {
+    if (!p->opt_force_generic && p->jk_fwd > 0 && (!p->cplx_table || p->d_wts != nullptr)) {
         const void* ph = phase ? p->d_phase_s : nullptr;
         FwdOpts fo;
         fo.use_tma = p->opt_use_tma ? 1 : 0;
@@ -995,9 +1005,9 @@ static int interp_fwd_impl(b2n_plan* p, const void* grid, void* samples, int nba
             sa.phase2 = phase ? p->d_phase_f : nullptr;
         }
         int rc = p->precision == B2N_SINGLE
-                     ? tiled_fwd_f32(p->g, p->jk_fwd, p->tables_equal, table_ptrs(p), p->d_tm_s, p->d_wts, p->d_pt_ko, p->d_pt_kw, p->d_perm, fit,
+                     ? tiled_fwd_f32(p->g, p->jk_fwd, p->cplx_table != 0, p->tables_equal, table_ptrs(p), p->d_tm_s, p->d_wts, p->d_pt_ko, p->d_pt_kw, p->d_perm, fit,
                                      nfit, sa, grid, samples, ph, nbatch, fo, st, &done)
-                     : tiled_fwd_f64(p->g, p->jk_fwd, p->tables_equal, table_ptrs(p), p->d_tm_s, p->d_wts, p->d_pt_ko, p->d_pt_kw, p->d_perm, fit,
+                     : tiled_fwd_f64(p->g, p->jk_fwd, p->cplx_table != 0, p->tables_equal, table_ptrs(p), p->d_tm_s, p->d_wts, p->d_pt_ko, p->d_pt_kw, p->d_perm, fit,
                                      nfit, sa, grid, samples, ph, nbatch, fo, st, &done);
         if (rc != 0) return fail(B2N_ECUDA, "tiled forward launch failed: " + std::string(cudaGetErrorString((cudaError_t)rc)));
     }
@@ -1027,22 +1037,23 @@ static int interp_adj_impl(b2n_plan* p, const void* samples, void* grid, int nba
         if (rc) return rc;
     }
     bool done = false;
-    if (!p->opt_force_generic && !p->cplx_table && p->g.ndim == 2 && p->have_b && p->jk_adj > 0) {
+    if (!p->opt_force_generic && p->g.ndim == 2 && p->have_b && p->jk_adj > 0 &&
+        (!p->cplx_table || p->d_wts_b != nullptr)) {
         // 2-D: register windows sliding along axis 2 (adjoint sort order), lanes <-> (j1, coil)
         const void* ph = phase ? p->d_phase_sb : nullptr;
         WindowOpts wo;
         wo.pts_per_warp = (int)p->opt_slide_pts;
         wo.max_slide = (int)p->opt_win_maxslide;
         int rc = p->precision == B2N_SINGLE
-                     ? window2d_adj_f32(p->g, p->jk_adj, table_ptrs(p), p->d_tm_sb, p->d_wts_b, p->d_pt_ko_b, p->d_pt_kw_b,
+                     ? window2d_adj_f32(p->g, p->jk_adj, p->cplx_table != 0, table_ptrs(p), p->d_tm_sb, p->d_wts_b, p->d_pt_ko_b, p->d_pt_kw_b,
                                         p->d_perm_b, samples, grid, ph, nbatch, wo, st, &done)
-                     : window2d_adj_f64(p->g, p->jk_adj, table_ptrs(p), p->d_tm_sb, p->d_wts_b, p->d_pt_ko_b, p->d_pt_kw_b,
+                     : window2d_adj_f64(p->g, p->jk_adj, p->cplx_table != 0, table_ptrs(p), p->d_tm_sb, p->d_wts_b, p->d_pt_ko_b, p->d_pt_kw_b,
                                         p->d_perm_b, samples, grid, ph, nbatch, wo, st, &done);
         if (rc != 0) return fail(B2N_ECUDA, "2-D window adjoint launch failed: " + std::string(cudaGetErrorString((cudaError_t)rc)));
         if (done) p->last_adj_kernel = 4;
     }
-    if (!done && !p->opt_force_generic && !p->cplx_table && p->g.ndim == 3 &&
-        (p->have_b ? p->jk_adj : p->jk_fwd) > 0) {
+    if (!done && !p->opt_force_generic && p->g.ndim == 3 && (p->have_b ? p->jk_adj : p->jk_fwd) > 0 &&
+        (!p->cplx_table || (p->have_b ? p->d_wts_b : p->d_wts) != nullptr)) {
         // register window, lane-parallel batch weights; adjoint sort order when built
         const bool ob = p->have_b;
         const int jk = ob ? p->jk_adj : p->jk_fwd;
@@ -1059,8 +1070,8 @@ static int interp_adj_impl(b2n_plan* p, const void* samples, void* grid, int nba
         wo.facew = (int)p->opt_win_facew;
         if (wo.facew < 0) wo.facew = jk <= 6 ? (p->precision == B2N_SINGLE ? 2 : 1) : 0;
         int rc = p->precision == B2N_SINGLE
-                     ? window_adj_f32(p->g, jk, table_ptrs(p), wo, tms, wts, ko, kw, pm, samples, grid, ph, nbatch, st, &done)
-                     : window_adj_f64(p->g, jk, table_ptrs(p), wo, tms, wts, ko, kw, pm, samples, grid, ph, nbatch, st, &done);
+                     ? window_adj_f32(p->g, jk, p->cplx_table != 0, table_ptrs(p), wo, tms, wts, ko, kw, pm, samples, grid, ph, nbatch, st, &done)
+                     : window_adj_f64(p->g, jk, p->cplx_table != 0, table_ptrs(p), wo, tms, wts, ko, kw, pm, samples, grid, ph, nbatch, st, &done);
         if (rc != 0) return fail(B2N_ECUDA, "window adjoint launch failed: " + std::string(cudaGetErrorString((cudaError_t)rc)));
         if (done) p->last_adj_kernel = 3;
     }
@@ -1275,7 +1286,7 @@ static int prepare_axis3(b2n_plan* p) {
     const int L = p->g.K[2];
     int max_smem = 0;
     CU(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, p->device));
-    if (!axis3_factor(L, &p->ax3) || Axis3Cfg<T>::smem(L) > (size_t)max_smem) {
+    if (!axis3_factor(L, &p->ax3) || Axis3Cfg<T>::smem(L) > (size_t)max_smem || !Axis3Cfg<T>::fits(L)) {
         p->ax3_state = -1;
         return B2N_OK;
     }
@@ -1325,10 +1336,10 @@ static int run_fft(b2n_plan* p, void* data, int nbatch, int dir, cudaStream_t st
             const void* a1 = p->have_pb ? p->d_pb[0] : nullptr;
             if (dir == CUFFT_FORWARD) {
                 if ((rc = exec_fft<T>(h2, data, dir))) return rc;
-                rc = fft_axis3_launch<T>(p->ax3, p->g, false, p->d_tw3, a1, p->d_pb[1], p->d_pb[2], data, st);
+                rc = fft_axis3_launch<T>(p->ax3, p->g, false, p->d_tw3, a1, p->d_pb[1], p->d_pb[2], data, p->sm_count, st);
                 if (rc != 0) return fail(B2N_ECUDA, "axis-3 FFT launch failed: " + std::string(cudaGetErrorString((cudaError_t)rc)));
             } else {
-                rc = fft_axis3_launch<T>(p->ax3, p->g, true, p->d_tw3, a1, p->d_pb[1], p->d_pb[2], data, st);
+                rc = fft_axis3_launch<T>(p->ax3, p->g, true, p->d_tw3, a1, p->d_pb[1], p->d_pb[2], data, p->sm_count, st);
                 if (rc != 0) return fail(B2N_ECUDA, "axis-3 FFT launch failed: " + std::string(cudaGetErrorString((cudaError_t)rc)));
                 if ((rc = exec_fft<T>(h2, data, dir))) return rc;
             }
@@ -1666,8 +1677,18 @@ static int axis3_t(b2n_plan* p, void* grid, bool inverse, cudaStream_t st) {
     const Geom& g = p->g;
     AxisPtrs ax = axis_ptrs(p);
     constexpr int VEC = 32 / (int)sizeof(C);
+    int rc;
+    if (p->opt_own_fft3 && p->g.N[2] <= g.K[2] && (rc = prepare_axis3<T>(p)) == B2N_OK && p->ax3_state == 1) {
+        // the fused pass: planes >= Nd[2] are treated as zero on input (forward) and not
+        // written (adjoint); phase_before rides along
+        const void* a1 = p->have_pb ? p->d_pb[0] : nullptr;
+        rc = fft_axis3_launch<T>(p->ax3, g, inverse, p->d_tw3, a1, p->d_pb[1], p->d_pb[2], grid, p->sm_count, st);
+        if (rc != 0) return fail(B2N_ECUDA, "axis-3 FFT launch failed: " + std::string(cudaGetErrorString((cudaError_t)rc)));
+        p->launches += 1;
+        return B2N_OK;
+    }
     cufftHandle h;
-    int rc = get_axis3_fft(p, &h);
+    rc = get_axis3_fft(p, &h);
     if (rc) return rc;
     FFT(cufftSetStream(h, st));
     if (inverse && p->have_pb) {

@@ -149,6 +149,23 @@ __device__ __forceinline__ float2 w_mul(float w, float2 v) { return make_float2(
 __device__ __forceinline__ double2 w_mul(double w, double2 v) { return make_double2(w * v.x, w * v.y); }
 __device__ __forceinline__ float2 w_mul(float2 w, float2 v) { return cmul(w, v); }
 __device__ __forceinline__ double2 w_mul(double2 w, double2 v) { return cmul(w, v); }
+// acc + w * v (forward) and acc + conj(w) * v (adjoint) for real or complex weights
+__device__ __forceinline__ float2 wfma(float w, float2 v, float2 acc) { return fma_w(w, v, acc); }
+__device__ __forceinline__ double2 wfma(double w, double2 v, double2 acc) { return fma_w(w, v, acc); }
+__device__ __forceinline__ float2 wfma(float2 w, float2 v, float2 acc) {
+    return make_float2(fmaf(w.x, v.x, fmaf(-w.y, v.y, acc.x)), fmaf(w.x, v.y, fmaf(w.y, v.x, acc.y)));
+}
+__device__ __forceinline__ double2 wfma(double2 w, double2 v, double2 acc) {
+    return make_double2(fma(w.x, v.x, fma(-w.y, v.y, acc.x)), fma(w.x, v.y, fma(w.y, v.x, acc.y)));
+}
+__device__ __forceinline__ float2 wfma_conj(float w, float2 v, float2 acc) { return fma_w(w, v, acc); }
+__device__ __forceinline__ double2 wfma_conj(double w, double2 v, double2 acc) { return fma_w(w, v, acc); }
+__device__ __forceinline__ float2 wfma_conj(float2 w, float2 v, float2 acc) {
+    return make_float2(fmaf(w.x, v.x, fmaf(w.y, v.y, acc.x)), fmaf(w.x, v.y, fmaf(-w.y, v.x, acc.y)));
+}
+__device__ __forceinline__ double2 wfma_conj(double2 w, double2 v, double2 acc) {
+    return make_double2(fma(w.x, v.x, fma(w.y, v.y, acc.x)), fma(w.x, v.y, fma(-w.y, v.x, acc.y)));
+}
 // conj(w) * v
 __device__ __forceinline__ float2 w_mul_conj(float w, float2 v) { return make_float2(w * v.x, w * v.y); }
 __device__ __forceinline__ double2 w_mul_conj(double w, double2 v) { return make_double2(w * v.x, w * v.y); }

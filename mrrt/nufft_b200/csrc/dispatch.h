@@ -46,17 +46,17 @@ struct WindowOpts {
     int generic_launch_##SUF(const Geom& g, int cplx_table, const TablePtrs& tabs, const void* tm_s, \
                              const int32_t* perm, bool fwd, const void* in, void* out,           \
                              const void* phase_s, int nbatch, int sm_count, cudaStream_t st);    \
-    int tiled_fwd_##SUF(const Geom& g, int Jk, bool tables_equal, const TablePtrs& tabs, const void* tm_s, \
+    int tiled_fwd_##SUF(const Geom& g, int Jk, bool cplx, bool tables_equal, const TablePtrs& tabs, const void* tm_s, \
                         const void* wts, const int32_t* pt_ko, const int32_t* pt_kw,             \
                         const int32_t* perm, const int4* items, int64_t n_items,                 \
                         const SlotArgs& sa, const void* grid, void* out, const void* phase_s,    \
                         int nbatch, const FwdOpts& fo, cudaStream_t st, bool* done);             \
-    int window_adj_##SUF(const Geom& g, int Jk, const TablePtrs& tabs, const WindowOpts& wo,             \
+    int window_adj_##SUF(const Geom& g, int Jk, bool cplx, const TablePtrs& tabs, const WindowOpts& wo,             \
                          const void* tm_s, const void* wts, const int32_t* pt_ko,                \
                          const int32_t* pt_kw, const int32_t* perm, const void* samples,         \
                          void* grid, const void* phase_s, int nbatch, cudaStream_t st,           \
                          bool* done);                                                            \
-    int window2d_adj_##SUF(const Geom& g, int Jk, const TablePtrs& tabs, const void* tm_s, const void* wts, \
+    int window2d_adj_##SUF(const Geom& g, int Jk, bool cplx, const TablePtrs& tabs, const void* tm_s, const void* wts, \
                            const int32_t* pt_ko, const int32_t* pt_kw, const int32_t* perm,      \
                            const void* samples, void* grid, const void* phase_s, int nbatch,     \
                            const WindowOpts& wo, cudaStream_t st, bool* done);

@@ -27,16 +27,24 @@ struct Axis3Plan {
     int radix[12];
 };
 
-// radices 4.., 2, 3..; returns false when L has another prime factor
+// radices 8.., 4.., 2.., 3.. with one (2, 3) pair merged into a radix-6 pass (384 = 8 * 8 * 6:
+// three passes instead of four); returns false when L has another prime factor
 static inline bool axis3_factor(int L, Axis3Plan* ap) {
     ap->L = L;
     ap->npass = 0;
     if (L < 2) return false;
+    int n2 = 0, n3 = 0;
     while (L % 8 == 0) { ap->radix[ap->npass++] = 8; L /= 8; }
     while (L % 4 == 0) { ap->radix[ap->npass++] = 4; L /= 4; }
-    while (L % 2 == 0) { ap->radix[ap->npass++] = 2; L /= 2; }
-    while (L % 3 == 0) { ap->radix[ap->npass++] = 3; L /= 3; }
-    return L == 1 && ap->npass <= 12;
+    while (L % 2 == 0) { n2++; L /= 2; }
+    while (L % 3 == 0) { n3++; L /= 3; }
+    if (L != 1) return false;
+    const bool six = n2 > 0 && n3 > 0;
+    if (six) { n2--; n3--; }
+    while (n2-- > 0 && ap->npass < 12) ap->radix[ap->npass++] = 2;
+    while (n3-- > 0 && ap->npass < 12) ap->radix[ap->npass++] = 3;
+    if (six && ap->npass < 12) ap->radix[ap->npass++] = 6;
+    return ap->npass <= 11;
 }
 
 template <typename T>
@@ -100,6 +108,28 @@ __device__ __forceinline__ void axis3_pass(const cplx_t<T>* __restrict__ in, cpl
             v[2] = csub<T>(m, rr);
         } else if (R == 4) {
             dft4<T, INV>(v[0], v[1], v[2], v[3]);
+        } else if (R == 6) {
+            // two length-3 DFTs (even / odd inputs) + one radix-2 stage with w6^q
+            const T hs = (T)0.86602540378443864676 * (INV ? (T)1 : (T)-1);
+            C e[3], o[3];
+            {
+                const C s12 = cadd<T>(v[2], v[4]), d12 = csub<T>(v[2], v[4]);
+                const C m = make_c<T>(v[0].x - (T)0.5 * s12.x, v[0].y - (T)0.5 * s12.y);
+                const C rr = make_c<T>(-hs * d12.y, hs * d12.x);
+                e[0] = cadd<T>(v[0], s12); e[1] = cadd<T>(m, rr); e[2] = csub<T>(m, rr);
+            }
+            {
+                const C s12 = cadd<T>(v[3], v[5]), d12 = csub<T>(v[3], v[5]);
+                const C m = make_c<T>(v[1].x - (T)0.5 * s12.x, v[1].y - (T)0.5 * s12.y);
+                const C rr = make_c<T>(-hs * d12.y, hs * d12.x);
+                o[0] = cadd<T>(v[1], s12); o[1] = cadd<T>(m, rr); o[2] = csub<T>(m, rr);
+            }
+            // w6 = exp(-+ 2 pi i / 6) = (1/2, -+ sqrt(3)/2), w6^2 = (-1/2, -+ sqrt(3)/2)
+            const C t1 = make_c<T>((T)0.5 * o[1].x - hs * o[1].y, (T)0.5 * o[1].y + hs * o[1].x);
+            const C t2 = make_c<T>((T)-0.5 * o[2].x - hs * o[2].y, (T)-0.5 * o[2].y + hs * o[2].x);
+            v[0] = cadd<T>(e[0], o[0]); v[3] = csub<T>(e[0], o[0]);
+            v[1] = cadd<T>(e[1], t1);   v[4] = csub<T>(e[1], t1);
+            v[2] = cadd<T>(e[2], t2);   v[5] = csub<T>(e[2], t2);
         } else {                                     // R == 8: two length-4 DFTs + one radix-2 stage
             dft4<T, INV>(v[0], v[2], v[4], v[6]);
             dft4<T, INV>(v[1], v[3], v[5], v[7]);
@@ -124,9 +154,13 @@ __device__ __forceinline__ void axis3_pass(const cplx_t<T>* __restrict__ in, cpl
 }
 
 // INV = false: exp(-i...) (cuFFT forward); INV = true: exp(+i...)
-template <typename T, bool INV, int COLS, int NT>
-__global__ void __launch_bounds__(NT)
-fft_axis3_kernel(Axis3Plan ap, int64_t plane, int K1, int NZ, const cplx_t<T>* __restrict__ tw,
+// Persistent CTAs: a CTA walks tiles of COLS columns; the global loads of the NEXT tile are
+// issued into registers (PF values per thread) before the passes of the current one, so that
+// their latency overlaps the shared-memory passes instead of idling the SM.
+template <typename T, bool INV, int COLS, int NT, int PF>
+__global__ void __launch_bounds__(NT, sizeof(T) == 4 ? 3 : 2)
+fft_axis3_kernel(Axis3Plan ap, int64_t plane, int K1, int NZ, int64_t ntiles,
+                 const cplx_t<T>* __restrict__ tw,
                  const T* __restrict__ a1, const T* __restrict__ a2, const T* __restrict__ a3,
                  cplx_t<T>* __restrict__ data) {
     using C = cplx_t<T>;
@@ -136,103 +170,137 @@ fft_axis3_kernel(Axis3Plan ap, int64_t plane, int K1, int NZ, const cplx_t<T>* _
     C* bufB = bufA + (size_t)L * COLS;
     C* twS = bufB + (size_t)L * COLS;
     const int tid = threadIdx.x;
-    const int64_t col0 = (int64_t)blockIdx.x * COLS;
     const bool phase = a1 != nullptr;
+    constexpr int RL = NT / COLS;                    // rows per load round
 
     for (int e = tid; e < L; e += NT) {
         C w = tw[e];
         if (INV) w.y = -w.y;
         twS[e] = w;
     }
-    // this thread's column (fixed: NT % COLS == 0) and its in-plane phase angle
+    // this thread's column inside a tile (fixed: NT % COLS == 0) and its first row
     const int c = tid % COLS;
-    const int64_t col = col0 + c;
-    const bool col_ok = col < plane;
-    T a12 = (T)0;
-    if (phase && col_ok) {
-        const int k1 = (int)(col % K1), k2 = (int)(col / K1);
-        a12 = a1[k1] + a2[k2];                       // the reference's summation order
+    const int r0 = tid / COLS;
+    const int rows_in = INV ? L : NZ;                // forward: only the non-zero planes are read
+    const int rows_out = INV ? NZ : L;               // adjoint: only the planes that survive the crop
+    C pf[PF];
+    int64_t tile = blockIdx.x;
+    if (tile < ntiles) {
+        const int64_t col = tile * COLS + c;
+#pragma unroll
+        for (int i = 0; i < PF; i++) {
+            const int k3 = r0 + i * RL;
+            pf[i] = make_c<T>(0, 0);
+            if (k3 < rows_in && col < plane) pf[i] = data[(int64_t)k3 * plane + col];
+        }
     }
-    // ---- load (forward: only the non-zero planes; the rest of the column is padding)
-    const int rows_in = INV ? L : NZ;
-    for (int k3 = tid / COLS; k3 < L; k3 += NT / COLS) {
-        C v = make_c<T>(0, 0);
-        if (k3 < rows_in && col_ok) {
-            v = data[(int64_t)k3 * plane + col];
-            if (INV && phase) {
-                T s, co;
-                sincos_t(a12 + a3[k3], &s, &co);
-                v = make_c<T>(v.x * co + v.y * s, v.y * co - v.x * s);      // * conj(phase)
+    for (; tile < ntiles; tile += gridDim.x) {
+        const int64_t col = tile * COLS + c;
+        const bool col_ok = col < plane;
+        T a12 = (T)0;
+        if (phase && col_ok) {
+            const int k1 = (int)(col % K1), k2 = (int)(col / K1);
+            a12 = a1[k1] + a2[k2];                   // the reference's summation order
+        }
+        // ---- registers -> shared memory (the rest of a forward column is zero padding)
+#pragma unroll
+        for (int i = 0; i < PF; i++) {
+            const int k3 = r0 + i * RL;
+            if (k3 < L) {
+                C v = pf[i];
+                if (INV && phase && k3 < rows_in) {
+                    T sn, co;
+                    sincos_t(a12 + a3[k3], &sn, &co);
+                    v = make_c<T>(v.x * co + v.y * sn, v.y * co - v.x * sn);      // * conj(phase)
+                }
+                bufA[k3 * COLS + c] = v;
             }
         }
-        bufA[k3 * COLS + c] = v;
-    }
-    __syncthreads();
-    // ---- Stockham passes (radix dispatch is uniform; Ns is a power of two until the first
-    // radix-3 pass, so the index split is a shift and a mask there)
-    C* in = bufA;
-    C* out = bufB;
-    int Ns = 1;
-    for (int p = 0; p < ap.npass; p++) {
-        const int R = ap.radix[p];
-        const bool pow2 = (Ns & (Ns - 1)) == 0;
-        const int sh = 31 - __clz(Ns);
-        if (R == 8) axis3_pass<T, INV, COLS, 8, NT>(in, out, twS, L, Ns, sh, pow2, tid);
-        else if (R == 4) axis3_pass<T, INV, COLS, 4, NT>(in, out, twS, L, Ns, sh, pow2, tid);
-        else if (R == 2) axis3_pass<T, INV, COLS, 2, NT>(in, out, twS, L, Ns, sh, pow2, tid);
-        else axis3_pass<T, INV, COLS, 3, NT>(in, out, twS, L, Ns, sh, pow2, tid);
         __syncthreads();
-        C* t = in; in = out; out = t;
-        Ns *= R;
-    }
-    // ---- store (adjoint: only the planes that survive the crop)
-    if (!col_ok) return;
-    const int rows_out = INV ? NZ : L;
-    for (int k3 = tid / COLS; k3 < rows_out; k3 += NT / COLS) {
-        C v = in[k3 * COLS + c];
-        if (!INV && phase) {
-            T s, co;
-            sincos_t(a12 + a3[k3], &s, &co);
-            v = make_c<T>(v.x * co - v.y * s, v.x * s + v.y * co);          // * phase
+        // ---- next tile's loads go out now; they land while this tile is transformed
+        {
+            const int64_t nt = tile + gridDim.x;
+            const int64_t ncol = nt * COLS + c;
+            if (nt < ntiles) {
+#pragma unroll
+                for (int i = 0; i < PF; i++) {
+                    const int k3 = r0 + i * RL;
+                    pf[i] = make_c<T>(0, 0);
+                    if (k3 < rows_in && ncol < plane) pf[i] = data[(int64_t)k3 * plane + ncol];
+                }
+            }
         }
-        data[(int64_t)k3 * plane + col] = v;
+        // ---- Stockham passes (radix dispatch is uniform; Ns is a power of two until the first
+        // pass with a factor 3, so the index split is a shift and a mask there)
+        C* in = bufA;
+        C* out = bufB;
+        int Ns = 1;
+        for (int p = 0; p < ap.npass; p++) {
+            const int R = ap.radix[p];
+            const bool pow2 = (Ns & (Ns - 1)) == 0;
+            const int sh = 31 - __clz(Ns);
+            if (R == 8) axis3_pass<T, INV, COLS, 8, NT>(in, out, twS, L, Ns, sh, pow2, tid);
+            else if (R == 6) axis3_pass<T, INV, COLS, 6, NT>(in, out, twS, L, Ns, sh, pow2, tid);
+            else if (R == 4) axis3_pass<T, INV, COLS, 4, NT>(in, out, twS, L, Ns, sh, pow2, tid);
+            else if (R == 2) axis3_pass<T, INV, COLS, 2, NT>(in, out, twS, L, Ns, sh, pow2, tid);
+            else axis3_pass<T, INV, COLS, 3, NT>(in, out, twS, L, Ns, sh, pow2, tid);
+            __syncthreads();
+            C* t = in; in = out; out = t;
+            Ns *= R;
+        }
+        // ---- store
+        if (col_ok) {
+            for (int k3 = r0; k3 < rows_out; k3 += RL) {
+                C v = in[k3 * COLS + c];
+                if (!INV && phase) {
+                    T sn, co;
+                    sincos_t(a12 + a3[k3], &sn, &co);
+                    v = make_c<T>(v.x * co - v.y * sn, v.x * sn + v.y * co);      // * phase
+                }
+                data[(int64_t)k3 * plane + col] = v;
+            }
+        }
+        __syncthreads();                             // the buffers are rewritten by the next tile
     }
 }
 
 template <typename T> struct Axis3Cfg {
-    // 8 (4) columns = 64-byte runs per global access, 256 threads; at K3 = 384 the two buffers
-    // take 48 KB: 4 CTAs = 32 warps per SM.  Measured on the bench workload against cuFFT's
-    // strided pass + the phase kernel (fft / adj, ms): 16 columns x 256 threads +0.10 / +0.33,
-    // 16 x 512 -0.03 / +0.08, 8 x 256 -0.06 / +0.02 -- break-even, so the option stays off.
+    // 8 (4) columns = 64-byte runs per global access, 256 threads, up to PF values per thread
+    // prefetched in registers; at K3 = 384 the two buffers take 48 KB: 3 CTAs per SM.
     static constexpr int COLS = sizeof(T) == 4 ? 8 : 4;
     static constexpr int NT = 256;
+    static constexpr int PF = sizeof(T) == 4 ? 16 : 8;
     static size_t smem(int L) { return (size_t)(2 * L * COLS + L) * 2 * sizeof(T); }
+    static bool fits(int L) { return (L * COLS + NT - 1) / NT <= PF; }
 };
 
 // returns 0 or a cudaError_t
 template <typename T>
 static int fft_axis3_launch(const Axis3Plan& ap, const Geom& g, bool inverse, const void* tw,
                             const void* a1, const void* a2, const void* a3, void* data,
-                            cudaStream_t st) {
+                            int sm_count, cudaStream_t st) {
     using C = cplx_t<T>;
     constexpr int COLS = Axis3Cfg<T>::COLS;
     constexpr int NT = Axis3Cfg<T>::NT;
+    constexpr int PF = Axis3Cfg<T>::PF;
     const int64_t plane = (int64_t)g.K[0] * g.K[1];
     const size_t smem = Axis3Cfg<T>::smem(ap.L);
-    const unsigned nb = (unsigned)((plane + COLS - 1) / COLS);
+    const int64_t ntiles = (plane + COLS - 1) / COLS;
+    int64_t nb = (int64_t)sm_count * (sizeof(T) == 4 ? 3 : 2);   // persistent: resident CTAs only
+    if (nb > ntiles) nb = ntiles;
     cudaError_t e;
     if (inverse) {
-        auto k = fft_axis3_kernel<T, true, COLS, NT>;
+        auto k = fft_axis3_kernel<T, true, COLS, NT, PF>;
         e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        k<<<nb, NT, smem, st>>>(ap, plane, g.K[0], g.N[2], (const C*)tw, (const T*)a1, (const T*)a2,
-                                 (const T*)a3, (C*)data);
+        k<<<(unsigned)nb, NT, smem, st>>>(ap, plane, g.K[0], g.N[2], ntiles, (const C*)tw, (const T*)a1,
+                                          (const T*)a2, (const T*)a3, (C*)data);
     } else {
-        auto k = fft_axis3_kernel<T, false, COLS, NT>;
+        auto k = fft_axis3_kernel<T, false, COLS, NT, PF>;
         e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        k<<<nb, NT, smem, st>>>(ap, plane, g.K[0], g.N[2], (const C*)tw, (const T*)a1, (const T*)a2,
-                                 (const T*)a3, (C*)data);
+        k<<<(unsigned)nb, NT, smem, st>>>(ap, plane, g.K[0], g.N[2], ntiles, (const C*)tw, (const T*)a1,
+                                          (const T*)a2, (const T*)a3, (C*)data);
     }
     return (int)cudaGetLastError();
 }

@@ -78,7 +78,9 @@ struct TileShape {
 //       sample-ordered arrays through slots[]; PAIR 2 (plan-time weights only) reads
 //       slot-ordered copies (weights of both samples as one vector load), which stay
 //       coalesced when the slots of a bin are stored column-interleaved.
-template <typename T, int NDIM, int J, int TAB, int PAIR>
+// CT:   complex table (phasing="complex"): complex plan-time weights (TAB 2, no pairs);
+//       arithmetic of template.c:623-709 / :710-821 (full complex products).
+template <typename T, int NDIM, int J, int TAB, int PAIR, bool CT = false>
 __global__ void __launch_bounds__(256)
 interp_fwd_tiled_kernel(const __grid_constant__ CUtensorMap tmap, Geom g, TileShape ts, int use_tma,
                         const T* __restrict__ tab, const T* __restrict__ wts,
@@ -89,6 +91,8 @@ interp_fwd_tiled_kernel(const __grid_constant__ CUtensorMap tmap, Geom g, TileSh
                         const cplx_t<T>* __restrict__ grid, cplx_t<T>* __restrict__ out,
                         const cplx_t<T>* __restrict__ phase_s) {
     using C = cplx_t<T>;
+    using W = typename WeightT<T, CT>::type;
+    static_assert(!CT || (TAB == 2 && PAIR == 0), "complex tables: plan-time weights, no pairs");
     constexpr bool TAB_SMEM = TAB == 1;
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t mbar;
@@ -155,13 +159,13 @@ interp_fwd_tiled_kernel(const __grid_constant__ CUtensorMap tmap, Geom g, TileSh
             pa = __ldg(sa.perm + sidx);
             pb = __ldg(sa.perm + ns + sidx);
         }
-        T w[NDIM][J];
+        W w[NDIM][J];
         T wq[PAIR ? NDIM : 1][PAIR ? J : 1];   // partner's weights (zero when there is none)
         int c[NDIM];
 #pragma unroll
         for (int d = 0; d < NDIM; d++) {
             const int od = d == 0 ? o1 : (d == 1 ? o2 : o3);
-            if (PAIR == 2) {
+            if constexpr (PAIR == 2) {
                 c[d] = __ldg(sa.kw + (int64_t)d * ns + sidx) - od;
 #pragma unroll
                 for (int j = 0; j < J; j++) {
@@ -172,7 +176,10 @@ interp_fwd_tiled_kernel(const __grid_constant__ CUtensorMap tmap, Geom g, TileSh
                 continue;
             }
             c[d] = pt_kw[(int64_t)d * M + i] - od;           // wrapped origin inside the tile
-            if (TAB == 2) {
+            if constexpr (CT) {
+#pragma unroll
+                for (int j = 0; j < J; j++) w[d][j] = ((const W*)wts)[(int64_t)(d * J + j) * M + i];
+            } else if (TAB == 2) {
 #pragma unroll
                 for (int j = 0; j < J; j++) w[d][j] = wts[(int64_t)(d * J + j) * M + i];
                 if (PAIR) {
@@ -180,7 +187,7 @@ interp_fwd_tiled_kernel(const __grid_constant__ CUtensorMap tmap, Geom g, TileSh
                     for (int j = 0; j < J; j++)
                         wq[d][j] = pair ? wts[(int64_t)(d * J + j) * M + i + 1] : (T)0;
                 }
-            } else {
+            } else if constexpr (!CT) {
                 const T t = tm_s[(int64_t)d * M + i];
                 const int koff = pt_ko[(int64_t)d * M + i];  // 1 + floor(t - J/2.), plan time
 #pragma unroll
@@ -211,14 +218,14 @@ interp_fwd_tiled_kernel(const __grid_constant__ CUtensorMap tmap, Geom g, TileSh
 #pragma unroll
                 for (int j1 = 0; j1 < J; j1++) {
                     const C v = pr[j1];
-                    s1 = fma_w(w[0][j1], v, s1);                       // FFMA2
+                    s1 = wfma(w[0][j1], v, s1);                        // FFMA2 (real weights)
                     if (PAIR) q1 = fma_w(wq[0][j1], v, q1);
                 }
-                s2 = fma_w(w[NDIM > 1 ? 1 : 0][j2], s1, s2);
+                s2 = wfma(w[NDIM > 1 ? 1 : 0][j2], s1, s2);
                 if (PAIR) q2 = fma_w(wq[NDIM > 1 ? 1 : 0][j2], q1, q2);
             }
             if (NDIM > 2) {
-                s3 = fma_w(w[NDIM > 2 ? 2 : 0][j3], s2, s3);
+                s3 = wfma(w[NDIM > 2 ? 2 : 0][j3], s2, s3);
                 if (PAIR) q3 = fma_w(wq[NDIM > 2 ? 2 : 0][j3], q2, q3);
             } else {
                 s3 = s2;
@@ -301,7 +308,7 @@ static bool make_grid_tmap(CUtensorMap* map, const Geom& g, const TileShape& ts,
 }
 
 template <typename T, int NDIM, int J>
-static int launch_fwd_tiled(const Geom& g, const TablePtrs& tabs, const void* tm_s,
+static int launch_fwd_tiled(const Geom& g, bool cplx, const TablePtrs& tabs, const void* tm_s,
                             const void* wts, const int32_t* pt_ko, const int32_t* pt_kw, const int32_t* perm, const int4* items, int64_t n_items,
                             const SlotArgs& sa, const void* grid, void* out, const void* phase_s, int nbatch,
                             const FwdOpts& fo, cudaStream_t st, bool* done) {
@@ -350,6 +357,20 @@ static int launch_fwd_tiled(const Geom& g, const TablePtrs& tabs, const void* tm
                                       (const T*)wts, (const T*)tm_s, pt_ko, pt_kw, perm, items,    \
                                       sa, (const C*)grid, (C*)out, (const C*)phase_s);             \
     }
+    if (cplx) {
+        // complex table: plan-time complex weights only
+        if (wts == nullptr) return 0;
+        auto k = interp_fwd_tiled_kernel<T, NDIM, J, 2, 0, true>;
+        e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        k<<<gridDim, 256, smem, st>>>(map, g, ts, tma_ok ? 1 : 0, (const T*)tabs.h[0], (const T*)wts,
+                                      (const T*)tm_s, pt_ko, pt_kw, perm, items, sa, (const C*)grid,
+                                      (C*)out, (const C*)phase_s);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return (int)e;
+        *done = true;
+        return 0;
+    }
     const int pairv = sa.slots == nullptr ? 0 : (sa.packed ? 2 : 1);
 #define B2N_LAUNCH_FWD(TABV)                                                                       \
     {                                                                                              \
@@ -369,7 +390,7 @@ static int launch_fwd_tiled(const Geom& g, const TablePtrs& tabs, const void* tm
 
 // returns 0 or a cudaError_t; *done tells whether the tiled kernel took the call
 template <typename T>
-static int tiled_fwd_t(const Geom& g, int Jk, bool tables_equal, const TablePtrs& tabs, const void* tm_s,
+static int tiled_fwd_t(const Geom& g, int Jk, bool cplx, bool tables_equal, const TablePtrs& tabs, const void* tm_s,
                        const void* wts, const int32_t* pt_ko, const int32_t* pt_kw, const int32_t* perm, const int4* items, int64_t n_items, const SlotArgs& sa, const void* grid,
                        void* out, const void* phase_s, int nbatch, const FwdOpts& fo, cudaStream_t st,
                        bool* done) {
@@ -383,7 +404,7 @@ static int tiled_fwd_t(const Geom& g, int Jk, bool tables_equal, const TablePtrs
         if (g.K[d] < Jk) return 0;
     }
 #define B2N_TILED(ND, JJ)                                                                      \
-    return launch_fwd_tiled<T, ND, JJ>(g, tabs, tm_s, wts, pt_ko, pt_kw, perm, items, n_items, sa, grid, out, phase_s, \
+    return launch_fwd_tiled<T, ND, JJ>(g, cplx, tabs, tm_s, wts, pt_ko, pt_kw, perm, items, n_items, sa, grid, out, phase_s, \
                                        nbatch, fo, st, done)
     if (g.ndim == 2) {
         switch (Jk) {

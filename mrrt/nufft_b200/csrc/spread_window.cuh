@@ -40,8 +40,8 @@ constexpr int kWinLanes = 16;   // lanes per sample: two register windows per wa
 // Staging of one batch (16 samples per half-warp): per sample a record of kW values (3J
 // weights, fx, fy) with an ODD pitch in elements, so that the lanes' scalar stores (lane =
 // sample) fall in different banks, plus a separate int4 (kA, kB, kC, action) per sample.
-template <typename T, int J, bool FW = false> struct WinRec {
-    static constexpr int kW = 3 * J + 2;                         // weights + fx, fy
+template <typename T, int J, bool FW = false, bool CT = false> struct WinRec {
+    static constexpr int kW = (CT ? 6 : 3) * J + 2;              // weights (complex: re, im) + fx, fy
     // odd pitch in units of sizeof(T): float records spread over all 32 banks, double
     // records over all 16 bank pairs, and every element stays naturally aligned
     static constexpr int kPitchElems = kW % 2 == 1 ? kW : kW + 1;
@@ -58,7 +58,7 @@ template <typename T, int J, bool FW = false> struct WinRec {
 // so a lane fetches its face weights from ONE lane-dependent base (+16 per slot) instead
 // of two table-indexed reads and one multiply per slot.  Head pitch = 16 bytes x odd: the
 // 8 lanes of a quarter-warp store phase then cover all 32 banks exactly once.
-template <typename T, int J> struct WinRec<T, J, true> {
+template <typename T, int J> struct WinRec<T, J, true, false> {
     static constexpr int kHeadInt = (((J + 2) * (int)sizeof(T) + 15) / 16) * 16;   // offset of the int4
     static constexpr int kHeadMin = kHeadInt + 16;
     static constexpr int kHead = (kHeadMin / 16) % 2 == 1 ? kHeadMin : kHeadMin + 16;
@@ -83,11 +83,22 @@ __device__ __forceinline__ void load16(const void* src, double* v) {
     v[0] = t.x; v[1] = t.y;
 }
 
+// conj(coef_b) * (conj(coef_c) * f): the face value every slide-axis tap is multiplied with
+// (face-weight staging: wb already holds the product coef_b * coef_c)
+template <typename T, bool FW, bool CT, typename WT>
+__device__ __forceinline__ cplx_t<T> face_value(WT wb, WT wc, T fx, T fy) {
+    if constexpr (CT) return w_mul_conj(wb, w_mul_conj(wc, make_c<T>(fx, fy)));
+    else if constexpr (FW) return mul_w(wb, make_c<T>(fx, fy));
+    else return mul_w(wb, mul_w(wc, make_c<T>(fx, fy)));
+}
+
 // TAB: 0 table in global memory, 1 table staged in shared memory, 2 plan-time weights.
 // FWV: 0 = scalar staging records; 1 = face-weight staging (plan-time weights only);
 //      2 = the same compiled for 5 CTAs per SM (float J<=6: 96 registers with a 48-byte
 //      spill instead of 110).
-template <typename T, int J, int TAB, int FWV = 0>
+// CT:  complex table (phasing="complex"): complex plan-time weights in the scalar records,
+//      conjugated products (template.c:1021-1022); TAB 2, FWV 0 only.
+template <typename T, int J, int TAB, int FWV = 0, bool CT = false>
 __global__ void __launch_bounds__(128, FWV == 2 ? 5 : 1)
 spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T* __restrict__ h2,
                        const T* __restrict__ h3, const T* __restrict__ tm_s,
@@ -103,8 +114,10 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
     constexpr int RPL = (R + G - 1) / G;
     constexpr int NG = 32 / G;                                    // sample groups per warp
     static_assert(!FW || TAB == 2, "face-weight staging needs the plan-time weights");
-    constexpr int RB = WinRec<T, J, false>::kPitch;               // (not used with FW)
-    constexpr int WB = WinRec<T, J, FW>::kBytes;
+    static_assert(!CT || (TAB == 2 && !FW), "complex tables: plan-time weights, scalar records");
+    using W = typename WeightT<T, CT>::type;
+    constexpr int RB = WinRec<T, J, false, CT>::kPitch;           // (not used with FW)
+    constexpr int WB = FW ? WinRec<T, J, true, false>::kBytes : WinRec<T, J, false, CT>::kBytes;
     constexpr int HP = WinRec<T, J, true>::kHead;                 // FW: head pitch (bytes)
     constexpr int HI = WinRec<T, J, true>::kHeadInt;              // FW: offset of (kA, kB, kC, act)
     constexpr int FP = WinRec<T, J, true>::kFaceElems;            // FW: face pitch (elements)
@@ -116,7 +129,7 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     unsigned char* stage = dyn_smem + wib * WB;                   // this warp's records
-    int4* actions = (int4*)(stage + WinRec<T, J, false>::kRecBytes);  // this warp's action codes (not FW)
+    int4* actions = (int4*)(stage + WinRec<T, J, false, CT>::kRecBytes);  // this warp's action codes (not FW)
     T* face = (T*)(stage + 32 * HP);                              // FW: this warp's face records
     const int64_t M = g.M;
     constexpr bool TAB_SMEM = TAB == 1;
@@ -206,6 +219,16 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
                 for (int jc = 0; jc < J; jc++)
 #pragma unroll
                     for (int jb = 0; jb < J; jb++) fr[jb + J * jc] = wB[jb] * wC[jc];
+            } else if constexpr (CT) {
+                const W* __restrict__ wc_ = (const W*)wts;
+#pragma unroll
+                for (int j = 0; j < J; j++) {
+                    const W a = wc_[(int64_t)(aA * J + j) * M + i], bq = wc_[(int64_t)(aB * J + j) * M + i],
+                            cq = wc_[(int64_t)(aC * J + j) * M + i];
+                    w[2 * j] = a.x; w[2 * j + 1] = a.y;
+                    w[2 * (J + j)] = bq.x; w[2 * (J + j) + 1] = bq.y;
+                    w[2 * (2 * J + j)] = cq.x; w[2 * (2 * J + j) + 1] = cq.y;
+                }
             } else if (TAB == 2) {
 #pragma unroll
                 for (int j = 0; j < J; j++) {
@@ -213,7 +236,7 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
                     w[J + j] = wts[(int64_t)(aB * J + j) * M + i];
                     w[2 * J + j] = wts[(int64_t)(aC * J + j) * M + i];
                 }
-            } else {
+            } else if constexpr (!CT) {
                 const T tA = tm_s[(int64_t)aA * M + i], tB = tm_s[(int64_t)aB * M + i],
                         tC = tm_s[(int64_t)aC * M + i];
                 const int oA = pt_ko[(int64_t)aA * M + i], oB = pt_ko[(int64_t)aB * M + i],
@@ -228,8 +251,8 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
             if constexpr (!FW) {
                 C f = sb[perm[i]];
                 if (phase_s != nullptr) f = cmul_conj(f, phase_s[i]);
-                w[3 * J] = f.x;
-                w[3 * J + 1] = f.y;
+                w[(CT ? 6 : 3) * J] = f.x;
+                w[(CT ? 6 : 3) * J + 1] = f.y;
             }
         }
         // window action: slide distance along a, or -1 = new window
@@ -269,9 +292,20 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
             // operands of this sample are fetched before the window update so that their
             // shared-memory latency overlaps it
             const T* w = (const T*)rec;
-            T wA[J], fx, fy;
-            T wb[RPL], wc[RPL];
-            if constexpr (FW) {
+            W wA[J];
+            T fx, fy;
+            W wb[RPL], wc[RPL];
+            if constexpr (CT) {
+#pragma unroll
+                for (int j = 0; j < J; j++) wA[j] = make_c<T>(w[2 * j], w[2 * j + 1]);
+                fx = w[6 * J];
+                fy = w[6 * J + 1];
+#pragma unroll
+                for (int s = 0; s < RPL; s++) {
+                    wb[s] = make_c<T>(w[2 * (J + rjb[s])], w[2 * (J + rjb[s]) + 1]);
+                    wc[s] = make_c<T>(w[2 * (2 * J + rjc[s])], w[2 * (2 * J + rjc[s]) + 1]);
+                }
+            } else if constexpr (FW) {
                 T hv[HV];
 #pragma unroll
                 for (int c = 0; c < HV / VPC; c++) load16(rec + 16 * c, hv + VPC * c);
@@ -286,7 +320,7 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
 #pragma unroll
                 for (int s = 0; s < RPL; s++) {
                     wb[s] = wf[G * s];
-                    wc[s] = (T)1;
+                    wc[s] = wb[s];
                 }
             } else {
 #pragma unroll
@@ -347,12 +381,11 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
                     for (int s = 0; s < RPL; s++) {
                         if (rvalid[s]) {
                             atomic_add_c(faceptr[s] + (int64_t)WA * sA, acc[s][0]);
-                            const C v2 = FW ? mul_w(wb[s], make_c<T>(fx, fy))
-                                            : mul_w(wb[s], mul_w(wc[s], make_c<T>(fx, fy)));
+                            const C v2 = face_value<T, FW, CT>(wb[s], wc[s], fx, fy);
 #pragma unroll
                             for (int j = 0; j + 1 < J; j++)
-                                acc[s][j] = fma_w(wA[j], v2, acc[s][j + 1]);
-                            acc[s][J - 1] = fma_w(wA[J - 1], v2, make_c<T>(0, 0));
+                                acc[s][j] = wfma_conj(wA[j], v2, acc[s][j + 1]);
+                            acc[s][J - 1] = wfma_conj(wA[J - 1], v2, make_c<T>(0, 0));
                         }
                     }
                     WA++;
@@ -363,10 +396,9 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
             for (int s = 0; s < RPL; s++) {
                 if (rvalid[s]) {
                     // (coef_c * f) * coef_b, then * coef_a per cell; packed re/im arithmetic
-                    const C v2 = FW ? mul_w(wb[s], make_c<T>(fx, fy))
-                                    : mul_w(wb[s], mul_w(wc[s], make_c<T>(fx, fy)));
+                    const C v2 = face_value<T, FW, CT>(wb[s], wc[s], fx, fy);
 #pragma unroll
-                    for (int j = 0; j < J; j++) acc[s][j] = fma_w(wA[j], v2, acc[s][j]);
+                    for (int j = 0; j < J; j++) acc[s][j] = wfma_conj(wA[j], v2, acc[s][j]);
                 }
             }
         }
@@ -384,7 +416,7 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
 }
 
 template <typename T, int J>
-static int launch_window(const Geom& g, const TablePtrs& tabs, const WindowOpts& wo, const void* tm_s,
+static int launch_window(const Geom& g, bool cplx, const TablePtrs& tabs, const WindowOpts& wo, const void* tm_s,
                          const void* wts, const int32_t* pt_ko, const int32_t* pt_kw, const int32_t* perm,
                          const void* samples, void* grid, const void* phase_s, int nbatch,
                          cudaStream_t st, bool* done) {
@@ -416,6 +448,16 @@ static int launch_window(const Geom& g, const TablePtrs& tabs, const WindowOpts&
     }
     const size_t stage_bytes = (size_t)4 * WinRec<T, J>::kBytes;
     const size_t stage_fw = (size_t)4 * WinRec<T, J, true>::kBytes;
+    if (cplx) {
+        if (wts == nullptr) return 0;                 // complex tables: plan-time weights only
+        const size_t smem_c = (size_t)4 * WinRec<T, J, false, true>::kBytes;
+        auto k = spread_window3d_kernel<T, J, 2, 0, true>;
+        e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c);
+        if (e != cudaSuccess) return (int)e;
+        k<<<gd, 128, smem_c, st>>>(g, wa, (const T*)tabs.h[0], (const T*)tabs.h[1], (const T*)tabs.h[2],
+                                   (const T*)tm_s, (const T*)wts, pt_ko, pt_kw, perm, (const C*)samples,
+                                   (C*)grid, (const C*)phase_s, pts_per_warp, max_slide);
+    } else
     if (wts != nullptr && wo.facew == 2 && sizeof(T) == 4 && J <= 6) B2N_LAUNCH_WIN(2, 2, stage_fw)
     else if (wts != nullptr && wo.facew != 0) B2N_LAUNCH_WIN(2, 1, stage_fw)
     else if (wts != nullptr) B2N_LAUNCH_WIN(2, 0, stage_bytes)
@@ -429,7 +471,7 @@ static int launch_window(const Geom& g, const TablePtrs& tabs, const WindowOpts&
 }
 
 template <typename T>
-static int window_adj_t(const Geom& g, int Jk, const TablePtrs& tabs, const WindowOpts& wo, const void* tm_s,
+static int window_adj_t(const Geom& g, int Jk, bool cplx, const TablePtrs& tabs, const WindowOpts& wo, const void* tm_s,
                         const void* wts, const int32_t* pt_ko, const int32_t* pt_kw, const int32_t* perm,
                         const void* samples, void* grid, const void* phase_s, int nbatch,
                         cudaStream_t st, bool* done) {
@@ -440,7 +482,7 @@ static int window_adj_t(const Geom& g, int Jk, const TablePtrs& tabs, const Wind
         if (g.K[d] < Jk) return 0;
     }
 #define B2N_WIN(JJ)                                                                          \
-    return launch_window<T, JJ>(g, tabs, wo, tm_s, wts, pt_ko, pt_kw, perm, samples, grid,  \
+    return launch_window<T, JJ>(g, cplx, tabs, wo, tm_s, wts, pt_ko, pt_kw, perm, samples, grid,  \
                                 phase_s, nbatch, st, done)
     switch (Jk) {
         case 4: B2N_WIN(4);

@@ -23,7 +23,9 @@
 namespace b2n {
 
 // G: lanes per sample; RPL: slots per lane; coils per group = G*RPL / J
-template <typename T, int J, int G, int RPL, bool HAVE_WTS>
+// CT: complex table (phasing="complex"): complex plan-time weights, conjugated products
+//     (template.c:490-491); HAVE_WTS only.
+template <typename T, int J, int G, int RPL, bool HAVE_WTS, bool CT = false>
 __global__ void __launch_bounds__(128)
 spread_window2d_kernel(Geom g, const T* __restrict__ h1, const T* __restrict__ h2,
                        const T* __restrict__ tm_s, const T* __restrict__ wts,
@@ -34,10 +36,13 @@ spread_window2d_kernel(Geom g, const T* __restrict__ h1, const T* __restrict__ h
     using C = cplx_t<T>;
     constexpr int NG = 32 / G;                        // sample runs per warp
     constexpr int NCG = G * RPL / J;                  // coils per group
-    constexpr int NW = 2 * J + 2 * NCG;               // values per staging record
+    constexpr int WV = CT ? 2 : 1;                    // values per weight
+    constexpr int NW = 2 * J * WV + 2 * NCG;          // values per staging record
     constexpr int PITCH = NW % 2 == 1 ? NW : NW + 1;  // odd pitch (elements of T)
     constexpr unsigned FULL = 0xffffffffu;
+    using W = typename WeightT<T, CT>::type;
     static_assert(NCG >= 1, "a lane group must hold at least one coil's row");
+    static_assert(!CT || HAVE_WTS, "complex tables: plan-time weights");
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
@@ -87,7 +92,15 @@ spread_window2d_kernel(Geom g, const T* __restrict__ h1, const T* __restrict__ h
             T* w = stage + lane * PITCH;
             k1 = pt_kw[i];
             k2 = pt_kw[M + i];
-            if (HAVE_WTS) {
+            if constexpr (CT) {
+                const W* __restrict__ wc_ = (const W*)wts;
+#pragma unroll
+                for (int j = 0; j < J; j++) {
+                    const W a = wc_[(int64_t)(J + j) * M + i], bq = wc_[(int64_t)j * M + i];
+                    w[2 * j] = a.x; w[2 * j + 1] = a.y;
+                    w[2 * (J + j)] = bq.x; w[2 * (J + j) + 1] = bq.y;
+                }
+            } else if (HAVE_WTS) {
 #pragma unroll
                 for (int j = 0; j < J; j++) {
                     w[j] = wts[(int64_t)(J + j) * M + i];      // axis 2: along the registers
@@ -112,8 +125,8 @@ spread_window2d_kernel(Geom g, const T* __restrict__ h1, const T* __restrict__ h
                     f = samples[(int64_t)(coil0 + c) * M + src];
                     if (phase_s != nullptr) f = cmul_conj(f, ph);
                 }
-                w[2 * J + 2 * c] = f.x;
-                w[2 * J + 2 * c + 1] = f.y;
+                w[2 * J * WV + 2 * c] = f.x;
+                w[2 * J * WV + 2 * c + 1] = f.y;
             }
         }
         {
@@ -133,15 +146,26 @@ spread_window2d_kernel(Geom g, const T* __restrict__ h1, const T* __restrict__ h
             const T* w = stage + (grp * G + q) * PITCH;
             const int4 kk = kk_next;
             if (q + 1 < cnt) kk_next = actions[grp * G + q + 1];
-            T w2[J];
-#pragma unroll
-            for (int j = 0; j < J; j++) w2[j] = w[j];
+            W w2[J];
             C v[RPL];
+            if constexpr (CT) {
 #pragma unroll
-            for (int s = 0; s < RPL; s++) {
-                const T w1 = w[J + rj1[s]];
-                const C f = make_c<T>(w[2 * J + 2 * rc[s]], w[2 * J + 2 * rc[s] + 1]);
-                v[s] = mul_w(w1, f);
+                for (int j = 0; j < J; j++) w2[j] = make_c<T>(w[2 * j], w[2 * j + 1]);
+#pragma unroll
+                for (int s = 0; s < RPL; s++) {
+                    const W w1 = make_c<T>(w[2 * (J + rj1[s])], w[2 * (J + rj1[s]) + 1]);
+                    const C f = make_c<T>(w[4 * J + 2 * rc[s]], w[4 * J + 2 * rc[s] + 1]);
+                    v[s] = w_mul_conj(w1, f);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < J; j++) w2[j] = w[j];
+#pragma unroll
+                for (int s = 0; s < RPL; s++) {
+                    const T w1 = w[J + rj1[s]];
+                    const C f = make_c<T>(w[2 * J + 2 * rc[s]], w[2 * J + 2 * rc[s] + 1]);
+                    v[s] = mul_w(w1, f);
+                }
             }
             if (kk.w < 0) {
                 if (have) {
@@ -181,8 +205,8 @@ spread_window2d_kernel(Geom g, const T* __restrict__ h1, const T* __restrict__ h
                     if (rvalid[s]) {
                         atomic_add_c(colptr[s] + (int64_t)W2 * K1, acc[s][0]);
 #pragma unroll
-                        for (int j = 0; j + 1 < J; j++) acc[s][j] = fma_w(w2[j], v[s], acc[s][j + 1]);
-                        acc[s][J - 1] = fma_w(w2[J - 1], v[s], make_c<T>(0, 0));
+                        for (int j = 0; j + 1 < J; j++) acc[s][j] = wfma_conj(w2[j], v[s], acc[s][j + 1]);
+                        acc[s][J - 1] = wfma_conj(w2[J - 1], v[s], make_c<T>(0, 0));
                     }
                 }
                 W2++;
@@ -192,7 +216,7 @@ spread_window2d_kernel(Geom g, const T* __restrict__ h1, const T* __restrict__ h
             for (int s = 0; s < RPL; s++) {
                 if (rvalid[s]) {
 #pragma unroll
-                    for (int j = 0; j < J; j++) acc[s][j] = fma_w(w2[j], v[s], acc[s][j]);
+                    for (int j = 0; j < J; j++) acc[s][j] = wfma_conj(w2[j], v[s], acc[s][j]);
                 }
             }
         }
@@ -210,14 +234,14 @@ spread_window2d_kernel(Geom g, const T* __restrict__ h1, const T* __restrict__ h
 }
 
 template <typename T, int J, int G, int RPL>
-static int launch_window2d(const Geom& g, const TablePtrs& tabs, const void* tm_s, const void* wts,
+static int launch_window2d(const Geom& g, bool cplx, const TablePtrs& tabs, const void* tm_s, const void* wts,
                            const int32_t* pt_ko, const int32_t* pt_kw, const int32_t* perm,
                            const void* samples, void* grid, const void* phase_s, int nbatch,
                            const WindowOpts& wo, cudaStream_t st, bool* done) {
     using C = cplx_t<T>;
     constexpr int NCG = G * RPL / J;
-    constexpr int NW = 2 * J + 2 * NCG;
-    constexpr int PITCH = NW % 2 == 1 ? NW : NW + 1;
+    const int NW = 2 * J * (cplx ? 2 : 1) + 2 * NCG;
+    const int PITCH = NW % 2 == 1 ? NW : NW + 1;
     int max_slide = wo.max_slide;
     if (max_slide <= 0 || max_slide > J - 1) max_slide = J - 1;
     const int pts_per_warp = (wo.pts_per_warp + 31) / 32 * 32;
@@ -230,7 +254,15 @@ static int launch_window2d(const Geom& g, const TablePtrs& tabs, const void* tm_
     const size_t smem = rec_bytes + (size_t)4 * 32 * sizeof(int4) + 16;
     dim3 gd((unsigned)nblocks, (unsigned)ngroups);
     cudaError_t e;
-    if (wts != nullptr) {
+    if (cplx) {
+        if (wts == nullptr) return 0;                 // complex tables: plan-time weights only
+        auto k = spread_window2d_kernel<T, J, G, RPL, true, true>;
+        e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        k<<<gd, 128, smem, st>>>(g, (const T*)tabs.h[0], (const T*)tabs.h[1], (const T*)tm_s,
+                                 (const T*)wts, pt_ko, pt_kw, perm, (const C*)samples, (C*)grid,
+                                 (const C*)phase_s, pts_per_warp, nbatch, max_slide);
+    } else if (wts != nullptr) {
         auto k = spread_window2d_kernel<T, J, G, RPL, true>;
         e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
@@ -253,7 +285,7 @@ static int launch_window2d(const Geom& g, const TablePtrs& tabs, const void* tm_
 
 // the sample arrays must be in the ADJOINT sort order (axis 2 fastest inside a bin)
 template <typename T>
-static int window2d_adj_t(const Geom& g, int Jk, const TablePtrs& tabs, const void* tm_s, const void* wts,
+static int window2d_adj_t(const Geom& g, int Jk, bool cplx, const TablePtrs& tabs, const void* tm_s, const void* wts,
                           const int32_t* pt_ko, const int32_t* pt_kw, const int32_t* perm,
                           const void* samples, void* grid, const void* phase_s, int nbatch,
                           const WindowOpts& wo, cudaStream_t st, bool* done) {
@@ -264,7 +296,7 @@ static int window2d_adj_t(const Geom& g, int Jk, const TablePtrs& tabs, const vo
         if (g.K[d] < Jk) return 0;
     }
 #define B2N_W2D(JJ, GG, RR)                                                                      \
-    return launch_window2d<T, JJ, GG, RR>(g, tabs, tm_s, wts, pt_ko, pt_kw, perm, samples, grid, \
+    return launch_window2d<T, JJ, GG, RR>(g, cplx, tabs, tm_s, wts, pt_ko, pt_kw, perm, samples, grid, \
                                           phase_s, nbatch, wo, st, done)
 #define B2N_W2D_J(JJ)                                                   \
     {                                                                   \

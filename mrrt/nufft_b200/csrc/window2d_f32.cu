@@ -1,11 +1,11 @@
 // 2-D register-window adjoint gridding, float instantiations
 #include "spread_window2d.cuh"
 namespace b2n {
-int window2d_adj_f32(const Geom& g, int Jk, const TablePtrs& tabs, const void* tm_s, const void* wts,
+int window2d_adj_f32(const Geom& g, int Jk, bool cplx, const TablePtrs& tabs, const void* tm_s, const void* wts,
                      const int32_t* pt_ko, const int32_t* pt_kw, const int32_t* perm,
                      const void* samples, void* grid, const void* phase_s, int nbatch,
                      const WindowOpts& wo, cudaStream_t st, bool* done) {
-    return window2d_adj_t<float>(g, Jk, tabs, tm_s, wts, pt_ko, pt_kw, perm, samples, grid, phase_s,
+    return window2d_adj_t<float>(g, Jk, cplx, tabs, tm_s, wts, pt_ko, pt_kw, perm, samples, grid, phase_s,
                               nbatch, wo, st, done);
 }
 }  // namespace b2n

@@ -694,15 +694,32 @@ def dtft_adj(xk, omega, shape, n_shift=None):
 # no counterpart (it calls numpy.fft / cuFFT, _nufft.py:1331, :1335-1369).
 # ---------------------------------------------------------------------------------------
 def axis3_radices(L):
-    """Radix schedule of ``axis3_factor``: 8s, 4s, 2s, then 3s; None if L has another factor."""
+    """Radix schedule of ``axis3_factor``: 8s, 4s, 2s, then 3s, with one (2, 3) pair merged into
+    a final radix-6 pass; None if L has another factor."""
     if L < 2:
         return None
     out = []
-    for r in (8, 4, 2, 3):
-        while L % r == 0:
-            out.append(r)
-            L //= r
-    return out if L == 1 else None
+    while L % 8 == 0:
+        out.append(8)
+        L //= 8
+    while L % 4 == 0:
+        out.append(4)
+        L //= 4
+    n2 = n3 = 0
+    while L % 2 == 0:
+        n2 += 1
+        L //= 2
+    while L % 3 == 0:
+        n3 += 1
+        L //= 3
+    if L != 1:
+        return None
+    six = n2 > 0 and n3 > 0
+    if six:
+        n2 -= 1
+        n3 -= 1
+    out += [2] * n2 + [3] * n3 + ([6] if six else [])
+    return out
 
 
 def axis3_stockham(x, inverse=False):

@@ -48,11 +48,10 @@ def test_golden(name, variant):
     assert rel_l2(out, z["interp_out"]) <= tol
     out = nufft_adj(A, ysamp, grid_only=True).cpu().numpy()
     assert rel_l2(out, z["grid_out"]) <= tol
-    if variant == "auto" and cfg["mode"] == "table" and cfg["phasing"] == "real" and A.ndim >= 2 \
-            and max(A.Jd) <= 8:
-        # 2-D / 3-D real tables of any width up to 8 (equal or not, odd or even: narrower axes
-        # run zero-padded at the compiled width) take the tiled forward and the register-window
-        # adjoint, provided the grid is at least one window wide
+    if variant == "auto" and cfg["mode"] == "table" and A.ndim >= 2 and max(A.Jd) <= 8:
+        # 2-D / 3-D tables, real or complex, of any width up to 8 (equal or not, odd or even:
+        # narrower axes run zero-padded at the compiled width) take the tiled forward and the
+        # register-window adjoint, provided the grid is at least one window wide
         jk = max(4, (max(A.Jd) + 1) // 2 * 2)
         if min(A.Kd) >= jk:
             assert A.option("last_fwd_kernel") == 1   # tiled TMA kernel really ran
@@ -581,15 +580,16 @@ def test_toeplitz_norm_vs_exact_gram(case):
 
 @pytest.mark.parametrize("name", [n for n in case_names() if n.startswith("d3_")])
 def test_own_axis3_fft_golden(name):
-    """Option own_fft3: the axis-3 pass of the pruned FFT done by the fused kernel (zero
-    padding in shared memory, phase_before on store / conj(phase_before) on load, cropped
-    store) instead of cuFFT + the phase kernel -- every 3-D golden case of the reference."""
+    """Option own_fft3 (default on): the axis-3 pass of the pruned FFT done by the fused kernel
+    (zero padding in shared memory, phase_before on store / conj(phase_before) on load, cropped
+    store) against cuFFT + the phase kernel (own_fft3 = 0) -- every 3-D golden case of the
+    reference."""
     cfg, z = load_case(name)
     tol = TOL[cfg["precision"]]
     A = _op(cfg, z["omega"], options={"own_fft3": 1})
     assert rel_l2(A.fft(z["x"]), z["y"]) <= tol
     assert rel_l2(A.adj(z["y"]), z["x_adj"]) <= tol
-    B = _op(cfg, z["omega"])
+    B = _op(cfg, z["omega"], options={"own_fft3": 0})       # cuFFT strided pass + phase kernel
     assert rel_l2(A.fft(z["x"]), B.fft(z["x"])) <= tol / 4
     assert rel_l2(A.adj(z["y"]), B.adj(z["y"])) <= tol / 4
 

@@ -129,4 +129,4 @@ def test_axis3_stockham_schedule(L):
     x = rs.standard_normal((3, L)) + 1j * rs.standard_normal((3, L))
     assert np.allclose(orc.axis3_stockham(x), np.fft.fft(x, axis=-1), rtol=0, atol=1e-11)
     assert np.allclose(orc.axis3_stockham(x, inverse=True), np.fft.ifft(x, axis=-1) * L, rtol=0, atol=1e-11)
-    assert orc.axis3_radices(35) is None and orc.axis3_radices(384) == [8, 8, 2, 3]
+    assert orc.axis3_radices(35) is None and orc.axis3_radices(384) == [8, 8, 6]
