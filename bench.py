@@ -299,9 +299,11 @@ def run_gpu_arm(args):
     t0 = time.perf_counter()
     S = A = None
     if sharding == "slab":
-        S = SlabShardedNufft(ND, radial3d(SPOKES, NREAD), Jd=JD, Kd=KD, precision="single", device=dev)
+        S = SlabShardedNufft(ND, radial3d(SPOKES, NREAD), Jd=JD, Kd=KD, precision="single", device=dev,
+                             exchange=args.exchange)
         M_local = S.M
         slab_rows = S.nrows
+        slab_exchange = S.exchange
         prof = S.k
     else:
         s_lo, s_hi = (0, SPOKES) if sharding in ("none", "coils") else shard_range(SPOKES, world, rank)
@@ -391,7 +393,7 @@ def run_gpu_arm(args):
         y_out = torch.empty(S.M, dtype=torch.complex64, pin_memory=True)
         x_out = torch.empty_strided(xp_host.shape, xp_host.stride(), dtype=torch.complex64, pin_memory=True)
 
-        def step_e2e():
+        def step_e2e_blocking():
             """This rank's image planes up, its samples down; its samples up, its planes down."""
             y = S.fft(xp_host.to(dev, non_blocking=True), planes=True)
             y_out.copy_(y, non_blocking=True)
@@ -399,10 +401,45 @@ def run_gpu_arm(args):
             x_out.copy_(xa, non_blocking=True)
             torch.cuda.current_stream().synchronize()
 
-        t_e2e = t_e2e_blocking = time_e2e(step_e2e, n_e2e)
+        s_h2d, s_d2h = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+        def step_e2e():
+            """The same four transfers on two copy streams (one per link direction) around the
+            two transforms on the compute stream: the adjoint's samples travel up while the
+            forward runs, the forward's samples travel down while the adjoint runs."""
+            main = torch.cuda.current_stream()
+            ev_x, ev_k, ev_y, ev_a = (torch.cuda.Event() for _ in range(4))
+            with torch.cuda.stream(s_h2d):
+                xd = xp_host.to(dev, non_blocking=True)
+                ev_x.record(s_h2d)
+                kd = k_host.to(dev, non_blocking=True)
+                ev_k.record(s_h2d)
+            xd.record_stream(main)
+            kd.record_stream(main)
+            main.wait_event(ev_x)
+            y = S.fft(xd, planes=True)
+            ev_y.record(main)
+            y.record_stream(s_d2h)
+            with torch.cuda.stream(s_d2h):
+                s_d2h.wait_event(ev_y)
+                y_out.copy_(y, non_blocking=True)
+            main.wait_event(ev_k)
+            xa = S.adj(kd, planes=True)
+            ev_a.record(main)
+            xa.record_stream(s_d2h)
+            with torch.cuda.stream(s_d2h):
+                s_d2h.wait_event(ev_a)
+                x_out.copy_(xa, non_blocking=True)
+            s_d2h.synchronize()
+            main.synchronize()
+
+        t_e2e_blocking = time_e2e(step_e2e_blocking, n_e2e)
+        t_e2e = time_e2e(step_e2e, n_e2e)
         h2d = d2h = img_bytes * (S.z1 - S.z0) // ND[2] + S.M * 8
-        mode = ("per rank: fft(planes_host) / adj(samples_host) with pinned host buffers in and out; "
-                "bytes are this rank's (image planes + its samples), every rank on its own PCIe link")
+        mode = ("per rank: fft(planes) / adj(samples) from pinned host buffers, results back in pinned "
+                "host buffers; host->device and device->host copies on their own streams around the "
+                "transforms, one synchronize per step; bytes are this rank's (its image planes + its "
+                "samples), every rank on its own PCIe link")
     else:
         x_host = _pin(torch.from_numpy(x_np))
 
@@ -446,12 +483,17 @@ def run_gpu_arm(args):
         S.profile_stages(True)
         for _ in range(5):
             step_dev()
-        stages = S.stage_times()
+        mine = S.stage_times()
         S.profile_stages(False)
-        stages["rows"] = [int(S.slabs[r][1]) for r in range(world)]
-        counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
-        dist.all_gather(counts, torch.tensor([S.M], dtype=torch.int64, device=dev))
-        stages["samples"] = [int(c.item()) for c in counts]
+        mine["samples"] = int(S.M)
+        every = [None] * world
+        dist.all_gather_object(every, mine)
+        stages = {"rank0": {k: v for k, v in mine.items() if k != "samples"},
+                  "rows": [int(S.slabs[r][1]) for r in range(world)],
+                  "samples": [e["samples"] for e in every],
+                  "interp_ms_per_rank": [e["fwd_interp"] + e["adj_interp"] for e in every],
+                  "axis3_ms_per_rank": [e["fwd_axis3"] + e["adj_axis3"] for e in every],
+                  "all_to_all_ms_per_rank": [e["fwd_all_to_all"] + e["adj_all_to_all"] for e in every]}
 
     # ---- secondary (N > 1): the communication-free coil-replica number (weak scaling)
     secondary = None
@@ -518,8 +560,10 @@ def run_gpu_arm(args):
 
     shard_txt = {
         "none": "none",
-        "slab": "slab: image sharded by planes, grid + samples by grid rows over %d ranks, one NCCL "
-                "all-to-all per transform (SlabShardedNufft); image stays sharded between steps" % world,
+        "slab": "slab: image sharded by planes, grid + samples by grid rows over %d ranks, one "
+                "exchange per transform (%s; SlabShardedNufft); image stays sharded between steps"
+                % (world, "NCCL all-to-all" if sharding != "slab" or slab_exchange == "nccl" else
+                   "direct stores/loads on peer memory over NVLink, device-side barriers"),
         "samples": "samples: spokes sharded over %d ranks, grid stage replicated, NCCL all-reduce of "
                    "the adjoint image" % world,
         "coils": "coils: %d-coil acquisition, one coil per rank, no data-path collective; value "
@@ -634,6 +678,9 @@ def main():
                          "samples by rows, NCCL all-to-all (strong scaling); samples = one coil, "
                          "spokes sharded, NCCL all-reduce of the adjoint image (strong scaling); "
                          "coils = one coil of the volume per GPU, no collective (weak scaling)")
+    ap.add_argument("--exchange", default="auto", choices=["nccl", "p2p", "auto"],
+                    help="slab sharding: how grid rows travel between the plane stage and the axis-3 "
+                         "stage: NCCL all-to-all, or direct stores / loads on peer (symmetric) memory")
     ap.add_argument("--host-chunks", type=int, default=4,
                     help="sample ranges pipelined against host<->device copies in the e2e leg")
     args = ap.parse_args()

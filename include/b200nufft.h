@@ -87,7 +87,9 @@ int b2n_plan_destroy(b2n_plan *plan);
  *            by the host for mode="sparse").
  *   read-only (b2n_plan_get_option): "last_fwd_kernel" (0 one thread per sample, 1 tiled),
  *            "last_adj_kernel" (0 one RED per tap, 3 3-D register window, 4 2-D register
- *            window), "n_items", "n_slots", "lib_calls".
+ *            window), "n_items", "n_slots", "lib_calls", "axis3_fused" (1 when the fused
+ *            axis-3 kernel serves this plan: b2n_axis3_fwd then ignores the planes >= Nd[2]
+ *            of its input instead of requiring them to be zero).
  *
  * Threading / streams: a plan is NOT re-entrant.  It owns one scratch grid and its cuFFT
  * handles are re-pointed at the stream of each call, so transforms on one plan must be issued
@@ -231,6 +233,23 @@ int b2n_planes_adj(b2n_plan *plan, void *planes_dev, int z0, int nz, void *image
                    void *stream);
 int b2n_axis3_fwd(b2n_plan *plan, void *grid_dev, void *stream);
 int b2n_axis3_adj(b2n_plan *plan, void *grid_dev, void *stream);
+
+/* Exchange of grid rows between the plane stage and the axis-3 stage over PEER memory (one
+ * process per GPU; every rank's slab grid mapped into every rank's address space, e.g. with
+ * torch.distributed._symmetric_memory): the all-to-all, its pack / unpack passes and the halo
+ * summation in one kernel each (csrc/slab_exchange.cuh).  `plan` is the plan with the GLOBAL
+ * geometry; slab s holds rows (row0[s] + arange(nrows[s])) mod Kd[1] as complex
+ * [Kd[2]][nrows[s]][Kd[0]] at peer_grids[s] (pointers valid on THIS device).
+ *   b2n_slab_scatter  forward: rows of this rank's planes [z0, z0+nz) (planes_dev, complex
+ *                     [nz][Kd[1]][Kd[0]]) stored into planes z0.. of every slab that holds them
+ *   b2n_slab_gather   adjoint: planes_dev[z][k2][:] = sum over the slabs holding row k2 of their
+ *                     plane z0+z (the halo rows of neighbouring slabs add up), fixed order
+ * The caller orders the phases across ranks (barriers).  Needs Kd[0]*sizeof(complex) % 16 == 0
+ * and at most 16 ranks. */
+int b2n_slab_scatter(b2n_plan *plan, const void *planes_dev, int nz, int z0, int world,
+                     void *const *peer_grids, const int *row0, const int *nrows, void *stream);
+int b2n_slab_gather(b2n_plan *plan, void *planes_dev, int nz, int z0, int world,
+                    void *const *peer_grids, const int *row0, const int *nrows, void *stream);
 
 /* bytes of device memory owned by the plan */
 int64_t b2n_plan_device_bytes(b2n_plan *plan);

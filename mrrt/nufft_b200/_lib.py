@@ -58,6 +58,8 @@ SIGNATURES = {
     "b2n_planes_adj": (c_int, [c_vp, c_vp, c_int, c_int, c_vp, c_vp]),
     "b2n_axis3_fwd": (c_int, [c_vp, c_vp, c_vp]),
     "b2n_axis3_adj": (c_int, [c_vp, c_vp, c_vp]),
+    "b2n_slab_scatter": (c_int, [c_vp, c_vp, c_int, c_int, c_int, PP, PI, PI, c_vp]),
+    "b2n_slab_gather": (c_int, [c_vp, c_vp, c_int, c_int, c_int, PP, PI, PI, c_vp]),
     "b2n_plan_device_bytes": (c_i64, [c_vp]),
     "b2n_plan_launch_count": (c_i64, [c_vp]),
     "b2n_plan_get_timing": (c_int, [c_vp, ctypes.POINTER(c_dbl)]),

@@ -58,17 +58,57 @@ def window_rows(omega2, J, K, rdt):
     return np.mod(koff, K).astype(np.int64)
 
 
-def slab_boundaries(rows, K, world, row_cost):
-    """Boundaries ``b[0] = 0 < b[1] < ... < b[world] = K`` of the origin-row ranges, balancing
-    ``samples + row_cost * rows`` per rank (every range has at least one row)."""
+def row_statistics(omega, Jd, Kd, rdt, device):
+    """Per grid row of axis 2: ``rows`` (int64 [M], the row of every sample's window origin),
+    ``n`` (samples per row) and ``cells`` (distinct window-origin cells per row).  Evaluated
+    with torch on ``device`` (the GPU for the CUDA back end: a 52.7 M-sample trajectory takes
+    ~0.1 s there instead of ~10 s of NumPy sorting on every rank)."""
+    tdt = torch.float32 if rdt == np.float32 else torch.float64
+    om = torch.from_numpy(np.ascontiguousarray(omega)).to(device=device, dtype=tdt)
+    kw = []
+    for d in range(3):
+        # (T)(2 pi / K) as a one-element DEVICE tensor: with a 0-dim (scalar) divisor PyTorch
+        # multiplies by the reciprocal instead of dividing, which differs from the IEEE division
+        # the library (and the reference) performs by an ulp for some coordinates
+        gam = torch.full((1,), 2 * np.pi / Kd[d], dtype=torch.float64).to(tdt).to(device)
+        tm = torch.div(om[:, d], gam)
+        koff = torch.floor(tm.to(torch.float64) - Jd[d] / 2.0).to(torch.int64) + 1
+        kw.append(torch.remainder(koff, Kd[d]))
+    rows = kw[1]
+    K1, K2, K3 = Kd
+    n = torch.bincount(rows, minlength=K2)
+    key = (rows * K1 + kw[0]) * K3 + kw[2]
+    key, _ = torch.sort(key)
+    first = torch.ones_like(key, dtype=torch.bool)
+    first[1:] = key[1:] != key[:-1]
+    cells = torch.bincount(torch.div(key[first], K1 * K3, rounding_mode="floor"), minlength=K2)
+    return rows.cpu().numpy(), n.cpu().numpy().astype(np.float64), cells.cpu().numpy().astype(np.float64)
+
+
+# Cost of one origin row in units of "one sample in a dense region", fitted to the per-rank
+# stage times of the 8-GPU bench run (profiles/r02_slab_cost_fit.md): the interpolation
+# kernels cost 9.5e-8 ms per sample plus 1.3e-7 ms per occupied cell (a new cell means a window
+# slide in the adjoint and one forward slot more), the axis-3 pass 1.9e-3 ms per row of
+# K1*K3 = 384^2 cells.
+CELL_COST = 1.38
+ROW_COST_PER_CELL = 19900.0 / (384.0 * 384.0)
+
+
+def slab_boundaries(cost, world):
+    """Boundaries ``b[0] = 0 < b[1] < ... < b[world] = K`` of the origin-row ranges that
+    balance ``cost`` (one value per row) over the ranks; every range has at least one row."""
+    cost = np.asarray(cost, dtype=np.float64)
+    K = cost.shape[0]
     if world > K:
         raise ValueError("more ranks than grid rows")
-    cost = np.bincount(rows, minlength=K).astype(np.float64) + float(row_cost)
     cum = np.concatenate([[0.0], np.cumsum(cost)])
     b = [0]
     for s in range(1, world):
         target = cum[-1] * s / world
         k = int(np.searchsorted(cum, target, side="left"))
+        # the boundary whose cumulative cost is closest to the target
+        if k > 0 and abs(cum[k - 1] - target) < abs(cum[k] - target):
+            k -= 1
         k = max(k, b[-1] + 1)
         k = min(k, K - (world - s))
         b.append(k)
@@ -140,12 +180,15 @@ class CudaSlabKernels(object):
         (``omega_local`` as handed in by the caller, any float dtype)."""
         K1, K2, K3 = self.Kd
         rows = (row0 + np.arange(nrows)) % K2
-        ones = [np.ones(1)] * 3
+        # the slab plan never runs the image stages: unit deapodization; Nd[2] tells the fused
+        # axis-3 pass how many planes are non-zero (forward) / survive the crop (adjoint)
+        ones = [np.ones(1), np.ones(1), np.ones(self.Nd[2])]
         pb = [self._pb[0], np.ascontiguousarray(self._pb[1][rows]), self._pb[2]]
         opts = dict(self.options)
         if nrows != K2:
             opts.update({"slab_kglobal2": K2, "slab_origin2": row0})
-        self.lplan = self._create((1, 1, 1), (K1, nrows, K3), ones, pb, opts)
+        self.lplan = self._create((1, 1, self.Nd[2]), (K1, nrows, K3), ones, pb, opts)
+        self.axis3_fused = bool(self.lib.b2n_plan_get_option(self.lplan, b"axis3_fused") == 1)
         self._keep = (ones, pb)
         om = np.asarray(omega_local)
         self.M = om.shape[0]
@@ -250,7 +293,8 @@ class SlabShardedNufft(object):
 
     def __init__(self, Nd, omega, Jd=4, Kd=None, precision="single", Ld=1024, ortho=False,
                  n_shift=None, adjoint_scalefactor=1.0, group=None, device=None, options=None,
-                 kernels=None, row_cost=None, mode="table", phasing="real", on_gpu=True):
+                 kernels=None, row_cost=None, mode="table", phasing="real", on_gpu=True,
+                 exchange="auto"):
         if mode != "table" or phasing != "real":
             raise ValueError("SlabShardedNufft supports mode='table' with phasing='real'")
         self.group = group
@@ -274,13 +318,17 @@ class SlabShardedNufft(object):
         K1, K2, K3 = self.Kd
         J2 = self.Jd[1]
         G = self.world
-        # ---- grid rows of the window origins -> slab boundaries -> this rank's samples
-        rows = window_rows(omega[:, 1], J2, K2, self.rdt)
+        # ---- grid rows of the window origins -> per-row cost -> slab boundaries -> samples
+        stat_dev = torch.device("cpu") if kernels is not None and getattr(kernels, "device", None) in (
+            None, torch.device("cpu")) else (device if device is not None else torch.device(
+                "cuda", torch.cuda.current_device()))
+        if not isinstance(stat_dev, torch.device):
+            stat_dev = torch.device("cuda", int(stat_dev))
+        rows, n_row, cells_row = row_statistics(omega, self.Jd, self.Kd, self.rdt, stat_dev)
         if row_cost is None:
-            # one grid row costs about as much as 12 000 samples at K1*K3 = 384^2 (axis-3 FFT +
-            # phase pass over the row vs. interpolating a sample both ways)
-            row_cost = 12000.0 * (K1 * K3) / (384.0 * 384.0)
-        self.bounds = slab_boundaries(rows, K2, G, row_cost) if G > 1 else [0, K2]
+            row_cost = ROW_COST_PER_CELL * (K1 * K3)
+        self.row_cost_model = n_row + CELL_COST * cells_row + float(row_cost)
+        self.bounds = slab_boundaries(self.row_cost_model, G) if G > 1 else [0, K2]
         halo = J2 - 1 if G > 1 else 0
         self.slabs = []                                  # per rank: (row0, nrows)
         for s in range(G):
@@ -300,6 +348,11 @@ class SlabShardedNufft(object):
         self.k = kernels
         self.k.make_local(omega[self.index], self.row0, self.nrows)
         self.device = getattr(self.k, "device", torch.device("cpu"))
+        self.exchange = "nccl"
+        if exchange not in ("nccl", "p2p", "auto"):
+            raise ValueError("exchange must be 'nccl', 'p2p' or 'auto'")
+        if exchange != "nccl" and G > 1 and self.device.type == "cuda":
+            self._setup_p2p(strict=exchange == "p2p")
         # all-to-all split sizes (complex elements)
         nz_me = self.z1 - self.z0
         self._fwd_in = [nz_me * self.slabs[s][1] * K1 for s in range(G)]
@@ -328,6 +381,97 @@ class SlabShardedNufft(object):
             cnt[n1] = cnt.get(n1, 0) + 1
         self._stage_ev = []
         return {k: tot[k] / cnt[k] for k in tot}
+
+    # ------------------------------------------------------------------ peer-memory exchange
+    def _setup_p2p(self, strict):
+        """Slab grids in SYMMETRIC memory (torch.distributed._symmetric_memory: every rank's
+        buffer is mapped into every other rank's address space over NVLink).  The exchange
+        between the plane stage and the axis-3 stage then needs no pack pass, no NCCL staging
+        and no unpack pass: in the forward transform each rank stores the rows of its planes
+        straight into the destination ranks' grids; in the adjoint each rank reads its planes
+        straight out of the source ranks' grids, adding the halo rows as it goes.  Device-side
+        barriers (signal pads) order the phases."""
+        ok = torch.ones(1, device=self.device)
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+
+            K1, K2, K3 = self.Kd
+            nmax = max(nrows for _, nrows in self.slabs)
+            tdt = _TORCH_C[self.cdt]
+            rdt = torch.float32 if tdt == torch.complex64 else torch.float64
+            grp = self.group if self.group is not None else dist.group.WORLD
+            self._sym = symm_mem.empty(K3 * nmax * K1 * 2, dtype=rdt, device=self.device)
+            self._hdl = symm_mem.rendezvous(self._sym, grp)
+            self._peer_grids = []
+            for r in range(self.world):
+                nr = self.slabs[r][1]
+                buf = self._hdl.get_buffer(r, (K3, nr, K1, 2), rdt, 0)
+                self._peer_grids.append(torch.view_as_complex(buf))
+        except Exception:
+            if strict:
+                raise
+            ok.zero_()
+        # every rank must take the same path
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        if ok.item() > 0:
+            self.exchange = "p2p"
+        elif strict:
+            raise RuntimeError("symmetric-memory exchange is not available on every rank")
+
+    def _barrier(self):
+        self._hdl.barrier(channel=0)
+
+    def _fft_dev_p2p(self, xp):
+        K1, K2, K3 = self.Kd
+        N3 = self.Nd[2]
+        self._mark("begin")
+        A = self.k.planes_fwd(xp, self.z0)                        # [nz, K2, K1]
+        self._mark("fwd_planes")
+        self._barrier()                                           # every rank is done with its grid
+        for d in range(self.world):
+            s = (self.rank + d) % self.world                      # spread the traffic over the peers
+            row0, nrows = self.slabs[s]
+            dst = self._peer_grids[s]
+            for glo, llo, n in _pieces(row0, nrows, K2):
+                dst[self.z0:self.z1, llo:llo + n].copy_(A[:, glo:glo + n])
+        grid = self._peer_grids[self.rank]
+        if not getattr(self.k, "axis3_fused", False):
+            grid[N3:].zero_()
+        self._barrier()                                           # all rows have landed
+        self._mark("fwd_all_to_all")
+        self.k.axis3_fwd(grid)
+        self._mark("fwd_axis3")
+        y = self.k.interp_fwd(grid)
+        self._mark("fwd_interp")
+        return y
+
+    def _adj_dev_p2p(self, kt):
+        K1, K2, K3 = self.Kd
+        self._mark("begin")
+        grid = self._peer_grids[self.rank]
+        self.k.interp_adj(kt, grid)
+        self._mark("adj_interp")
+        self.k.axis3_adj(grid)
+        self._mark("adj_axis3")
+        nz = self.z1 - self.z0
+        B = self.k.empty((nz, K2, K1))
+        self._barrier()                                           # every slab is gridded and transformed
+        order = [(self.rank + d) % self.world for d in range(self.world)]
+        for s in order:                                           # origin rows: plain copies
+            row0, _ = self.slabs[s]
+            own = self.bounds[s + 1] - self.bounds[s]
+            B[:, row0:row0 + own].copy_(self._peer_grids[s][self.z0:self.z1, :own])
+        for s in order:                                           # halo rows of the neighbours add up
+            row0, nrows = self.slabs[s]
+            own = self.bounds[s + 1] - self.bounds[s]
+            if nrows > own:
+                for glo, llo, n in _pieces((row0 + own) % K2, nrows - own, K2):
+                    B[:, glo:glo + n] += self._peer_grids[s][self.z0:self.z1, own + llo:own + llo + n]
+        self._barrier()                                           # the grids may be reused
+        self._mark("adj_all_to_all")
+        out = self.k.planes_adj(B, self.z0)
+        self._mark("adj_planes")
+        return out
 
     # ------------------------------------------------------------------ helpers
     def _a2a(self, out, inp, out_splits, in_splits):
@@ -367,6 +511,8 @@ class SlabShardedNufft(object):
         return y.cpu().numpy() if is_np else y
 
     def _fft_dev(self, xp):
+        if self.exchange == "p2p":
+            return self._fft_dev_p2p(xp)
         K1, K2, K3 = self.Kd
         N3 = self.Nd[2]
         self._mark("begin")
@@ -382,7 +528,8 @@ class SlabShardedNufft(object):
                 view[:, llo:llo + n].copy_(A[:, glo:glo + n])
             off += nz * nrows * K1
         grid = self.k.empty((K3, self.nrows, K1))
-        grid[N3:].zero_()
+        if not getattr(self.k, "axis3_fused", False):
+            grid[N3:].zero_()             # (the fused axis-3 pass creates the padding itself)
         self._mark("fwd_pack")
         self._a2a(grid[:N3].view(-1), send, self._fwd_out, self._fwd_in)
         self._mark("fwd_all_to_all")
@@ -405,6 +552,8 @@ class SlabShardedNufft(object):
         return out.cpu().numpy() if is_np else out
 
     def _adj_dev(self, kt):
+        if self.exchange == "p2p":
+            return self._adj_dev_p2p(kt)
         K1, K2, K3 = self.Kd
         N3 = self.Nd[2]
         self._mark("begin")

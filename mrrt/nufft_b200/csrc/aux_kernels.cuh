@@ -108,11 +108,11 @@ __global__ void point_weights_kernel(Geom g, TabArgs tabs, int Jk, const T* __re
             for (int j = 0; j < Jk; j++, row++) {
                 if constexpr (CT) {
                     wts[(int64_t)row * M + i] =
-                        j < g.J[d] ? tap_cplx<T>((const cplx_t<T>*)tabs.h[d], g.ncenter[d], g.tlen[d], t, ko + j, g.L)
+                        j < g.J[d] ? tap_cplx<T>((const cplx_t<T>*)tabs.h[d], g.ncenter[d], g.tlen[d], t, ko + j, g.L, g.order)
                                    : make_c<T>(0, 0);
                 } else {
                     wts[(int64_t)row * M + i] =
-                        j < g.J[d] ? tap_real<T>((const T*)tabs.h[d], g.ncenter[d], g.tlen[d], t, ko + j, g.L)
+                        j < g.J[d] ? tap_real<T>((const T*)tabs.h[d], g.ncenter[d], g.tlen[d], t, ko + j, g.L, g.order)
                                    : (T)0;
                 }
             }
@@ -252,9 +252,9 @@ __global__ void slot_weights_kernel(Geom g, TabArgs tabs, int Jk, int64_t ns, co
             const int koq = pt_ko[(int64_t)d * M + (pair ? i + 1 : i)];
             for (int j = 0; j < Jk; j++, row++) {
                 typename Cplx<T>::type ww;
-                ww.x = j < g.J[d] ? tap_real<T>((const T*)tabs.h[d], g.ncenter[d], g.tlen[d], t, ko + j, g.L) : (T)0;
+                ww.x = j < g.J[d] ? tap_real<T>((const T*)tabs.h[d], g.ncenter[d], g.tlen[d], t, ko + j, g.L, g.order) : (T)0;
                 ww.y = (pair && j < g.J[d])
-                           ? tap_real<T>((const T*)tabs.h[d], g.ncenter[d], g.tlen[d], tq, koq + j, g.L)
+                           ? tap_real<T>((const T*)tabs.h[d], g.ncenter[d], g.tlen[d], tq, koq + j, g.L, g.order)
                            : (T)0;
                 wts2[(int64_t)row * ns + s] = ww;
             }

@@ -16,6 +16,7 @@
 #include "../../../include/b200nufft.h"
 #include "aux_kernels.cuh"
 #include "fft_axis3.cuh"
+#include "slab_exchange.cuh"
 #include "common.cuh"
 #include "dispatch.h"
 
@@ -262,6 +263,7 @@ extern "C" int b2n_plan_create(int ndim, const int* Nd, const int* Kd, const int
     Geom& g = p->g;
     g.ndim = ndim;
     g.L = L;
+    g.order = 1;
     g.PK = 1;
     g.PN = 1;
     for (int d = 0; d < 3; d++) {
@@ -375,6 +377,11 @@ extern "C" int b2n_plan_set_option(b2n_plan* p, const char* name, long value) {
             if (value < 0 || value >= p->g.Kg[1]) return fail(B2N_EINVAL, "slab_origin2 must be in [0, slab_kglobal2)");
             p->g.korg[1] = (int)value;
         }
+    } else if (n == "table_order") {
+        // 1 = linear interpolation of the table (default), 0 = the entry at floor((t-k)*L)
+        if (value != 0 && value != 1) return fail(B2N_EINVAL, "table_order must be 0 or 1");
+        if (p->points_set) return fail(B2N_ESTATE, "table_order must precede set_points");
+        p->g.order = (int)value;
     } else if (n == "chunk") {
         if (value < 32) return fail(B2N_EINVAL, "chunk must be >= 32");
         p->opt_chunk = value;
@@ -419,13 +426,21 @@ extern "C" int b2n_plan_set_option(b2n_plan* p, const char* name, long value) {
     return B2N_OK;
 }
 
+template <typename T> static bool axis3_fused(b2n_plan* p, int nbatch);
+
 extern "C" long b2n_plan_get_option(b2n_plan* p, const char* name) {
     if (p == nullptr || name == nullptr) return -1;
     std::string n(name);
+    if (n == "axis3_fused") {       // 1 when the fused axis-3 kernel (not cuFFT) serves this plan
+        DevGuard dev_guard_(p->device);
+        return p->precision == B2N_SINGLE ? (axis3_fused<float>(p, 1) ? 1 : 0)
+                                          : (axis3_fused<double>(p, 1) ? 1 : 0);
+    }
     if (n == "tile1") return p->g.tile[0];
     if (n == "tile2") return p->g.tile[1];
     if (n == "tile3") return p->g.tile[2];
     if (n == "chunk") return p->opt_chunk;
+    if (n == "table_order") return p->g.order;
     if (n == "slab_kglobal2") return p->g.Kg[1];
     if (n == "slab_origin2") return p->g.korg[1];
     if (n == "force_generic") return p->opt_force_generic;
@@ -1304,8 +1319,6 @@ static int prepare_axis3(b2n_plan* p) {
 }
 
 // true when run_fft will apply phase_before / conj(phase_before) itself
-template <typename T>
-static bool axis3_fused(b2n_plan* p, int nbatch);
 
 template <typename T>
 static int exec_fft(cufftHandle h, void* data, int dir) {
@@ -1678,7 +1691,7 @@ static int axis3_t(b2n_plan* p, void* grid, bool inverse, cudaStream_t st) {
     AxisPtrs ax = axis_ptrs(p);
     constexpr int VEC = 32 / (int)sizeof(C);
     int rc;
-    if (p->opt_own_fft3 && p->g.N[2] <= g.K[2] && (rc = prepare_axis3<T>(p)) == B2N_OK && p->ax3_state == 1) {
+    if (axis3_fused<T>(p, 1)) {
         // the fused pass: planes >= Nd[2] are treated as zero on input (forward) and not
         // written (adjoint); phase_before rides along
         const void* a1 = p->have_pb ? p->d_pb[0] : nullptr;
@@ -1723,4 +1736,64 @@ extern "C" int b2n_axis3_fwd(b2n_plan* p, void* grid_dev, void* stream) {
 }
 extern "C" int b2n_axis3_adj(b2n_plan* p, void* grid_dev, void* stream) {
     return axis3_entry(p, grid_dev, true, stream);
+}
+
+// ---- peer-memory exchange of the slab-distributed transforms (slab_exchange.cuh)
+static int slab_peers(b2n_plan* p, int world, void* const* grids, const int* row0, const int* nrows,
+                      int nz, int z0, SlabPeers* out) {
+    if (p == nullptr) return fail(B2N_EINVAL, "NULL plan");
+    if (p->g.ndim != 3) return fail(B2N_EINVAL, "staged transforms are 3-D");
+    if (world < 1 || world > kMaxPeers) return fail(B2N_EINVAL, "1 <= world <= 16");
+    if (grids == nullptr || row0 == nullptr || nrows == nullptr) return fail(B2N_EINVAL, "NULL argument");
+    if (z0 < 0 || nz < 1 || z0 + nz > p->g.K[2]) return fail(B2N_EINVAL, "plane range outside the grid");
+    if ((p->g.K[0] * p->cplx_size()) % 16 != 0) return fail(B2N_EINVAL, "Kd[0] * sizeof(complex) must be a multiple of 16");
+    out->world = world;
+    for (int s = 0; s < world; s++) {
+        if (grids[s] == nullptr || nrows[s] < 1 || nrows[s] > p->g.K[1] || row0[s] < 0 || row0[s] >= p->g.K[1])
+            return fail(B2N_EINVAL, "bad slab description");
+        out->grid[s] = grids[s];
+        out->row0[s] = row0[s];
+        out->nrows[s] = nrows[s];
+    }
+    return B2N_OK;
+}
+
+extern "C" int b2n_slab_scatter(b2n_plan* p, const void* planes_dev, int nz, int z0, int world,
+                                void* const* peer_grids, const int* row0, const int* nrows,
+                                void* stream) {
+    SlabPeers P;
+    int rc = slab_peers(p, world, peer_grids, row0, nrows, nz, z0, &P);
+    if (rc) return rc;
+    if (planes_dev == nullptr) return fail(B2N_EINVAL, "NULL array");
+    ON_DEVICE(p);
+    const int vpr = (int)(p->g.K[0] * p->cplx_size() / 16);
+    int total = 0;
+    for (int s = 0; s < world; s++) total += nrows[s];
+    const int nb = grid_for((int64_t)nz * total * 32, 256, p->sm_count, 16);
+    if (p->precision == B2N_SINGLE)
+        slab_scatter_kernel<float4><<<nb, 256, 0, (cudaStream_t)stream>>>(P, (const float4*)planes_dev, nz, z0, p->g.K[1], vpr);
+    else
+        slab_scatter_kernel<double2><<<nb, 256, 0, (cudaStream_t)stream>>>(P, (const double2*)planes_dev, nz, z0, p->g.K[1], vpr);
+    CU(cudaGetLastError());
+    p->launches += 1;
+    return B2N_OK;
+}
+
+extern "C" int b2n_slab_gather(b2n_plan* p, void* planes_dev, int nz, int z0, int world,
+                               void* const* peer_grids, const int* row0, const int* nrows,
+                               void* stream) {
+    SlabPeers P;
+    int rc = slab_peers(p, world, peer_grids, row0, nrows, nz, z0, &P);
+    if (rc) return rc;
+    if (planes_dev == nullptr) return fail(B2N_EINVAL, "NULL array");
+    ON_DEVICE(p);
+    const int vpr = (int)(p->g.K[0] * p->cplx_size() / 16);
+    const int nb = grid_for((int64_t)nz * p->g.K[1] * 32, 256, p->sm_count, 16);
+    if (p->precision == B2N_SINGLE)
+        slab_gather_kernel<float4><<<nb, 256, 0, (cudaStream_t)stream>>>(P, (float4*)planes_dev, nz, z0, p->g.K[1], vpr);
+    else
+        slab_gather_kernel<double2><<<nb, 256, 0, (cudaStream_t)stream>>>(P, (double2*)planes_dev, nz, z0, p->g.K[1], vpr);
+    CU(cudaGetLastError());
+    p->launches += 1;
+    return B2N_OK;
 }

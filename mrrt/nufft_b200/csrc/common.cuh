@@ -51,6 +51,8 @@ struct Geom {
     int korg[3];      // slab plans: global index of local row 0 along each axis (else 0)
     int J[3];
     int L;
+    int order;        // table lookup: 1 linear interpolation between entries (the reference's only
+                      // CPU mode), 0 the entry at floor(p) ("order 0" of cuda/jinja/table_*.jinja)
     int ncenter[3];   // floor(J*L/2): centre of each table
     int tlen[3];      // J*L+1
     int tile[3];      // bin shape in grid cells
@@ -73,7 +75,8 @@ struct Geom {
 // p=-3072.000000000002): the reference reads h[-1] there (undefined behaviour, weight
 // 1-alf ~ 1e-12); that entry is taken as 0 here.
 template <typename T>
-__device__ __forceinline__ T tap_real(const T* __restrict__ h, int ncenter, int tlen, T t, int k, int L) {
+__device__ __forceinline__ T tap_real(const T* __restrict__ h, int ncenter, int tlen, T t, int k, int L,
+                                      int order = 1) {
     const T p = (t - (T)k) * (T)L;
     const T fl = floor(p);
     const int n = (int)fl;
@@ -81,11 +84,13 @@ __device__ __forceinline__ T tap_real(const T* __restrict__ h, int ncenter, int 
     const int i0 = ncenter + n;
     const int i1 = max(min(i0 + 1, tlen - 1), 0);
     const T h0 = i0 >= 0 ? h[i0] : (T)0;
+    if (order == 0) return h0;                       // table_2d_forward.jinja:61-67
     return ((T)1 - alf) * h0 + alf * h[i1];
 }
 
 template <typename T>
-__device__ __forceinline__ cplx_t<T> tap_cplx(const cplx_t<T>* __restrict__ h, int ncenter, int tlen, T t, int k, int L) {
+__device__ __forceinline__ cplx_t<T> tap_cplx(const cplx_t<T>* __restrict__ h, int ncenter, int tlen, T t, int k, int L,
+                                              int order = 1) {
     const T p = (t - (T)k) * (T)L;
     const T fl = floor(p);
     const int n = (int)fl;
@@ -93,6 +98,7 @@ __device__ __forceinline__ cplx_t<T> tap_cplx(const cplx_t<T>* __restrict__ h, i
     const int i0 = ncenter + n;
     const int i1 = max(min(i0 + 1, tlen - 1), 0);
     const cplx_t<T> a = i0 >= 0 ? h[i0] : make_c<T>(0, 0), b = h[i1];
+    if (order == 0) return a;
     return make_c<T>(((T)1 - alf) * a.x + alf * b.x, ((T)1 - alf) * a.y + alf * b.y);
 }
 

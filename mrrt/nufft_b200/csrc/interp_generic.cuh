@@ -13,11 +13,11 @@ namespace b2n {
 
 template <typename T, bool CT>
 __device__ __forceinline__ typename WeightT<T, CT>::type
-load_tap(const void* __restrict__ h, int ncenter, int tlen, T t, int k, int L) {
+load_tap(const void* __restrict__ h, int ncenter, int tlen, T t, int k, int L, int order) {
     if constexpr (CT) {
-        return tap_cplx<T>((const cplx_t<T>*)h, ncenter, tlen, t, k, L);
+        return tap_cplx<T>((const cplx_t<T>*)h, ncenter, tlen, t, k, L, order);
     } else {
-        return tap_real<T>((const T*)h, ncenter, tlen, t, k, L);
+        return tap_real<T>((const T*)h, ncenter, tlen, t, k, L, order);
     }
 }
 
@@ -47,7 +47,7 @@ interp_fwd_generic(Geom g, TablePtrs tabs, const T* __restrict__ tm_s,
             const int koff = window_origin<T>(t, J);
 #pragma unroll(JT > 0 ? JT : 1)
             for (int j = 0; j < J; j++) {
-                w[d][j] = load_tap<T, CT>(tabs.h[d], g.ncenter[d], g.tlen[d], t, koff + j, g.L);
+                w[d][j] = load_tap<T, CT>(tabs.h[d], g.ncenter[d], g.tlen[d], t, koff + j, g.L, g.order);
                 off[d][j] = local_index(koff + j, g.Kg[d], g.korg[d]) * stride;
             }
             stride *= g.K[d];
@@ -120,7 +120,7 @@ interp_adj_generic(Geom g, TablePtrs tabs, const T* __restrict__ tm_s,
             const int koff = window_origin<T>(t, J);
 #pragma unroll(JT > 0 ? JT : 1)
             for (int j = 0; j < J; j++) {
-                w[d][j] = load_tap<T, CT>(tabs.h[d], g.ncenter[d], g.tlen[d], t, koff + j, g.L);
+                w[d][j] = load_tap<T, CT>(tabs.h[d], g.ncenter[d], g.tlen[d], t, koff + j, g.L, g.order);
                 off[d][j] = local_index(koff + j, g.Kg[d], g.korg[d]) * stride;
             }
             stride *= g.K[d];

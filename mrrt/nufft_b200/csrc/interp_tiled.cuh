@@ -192,14 +192,14 @@ interp_fwd_tiled_kernel(const __grid_constant__ CUtensorMap tmap, Geom g, TileSh
                 const int koff = pt_ko[(int64_t)d * M + i];  // 1 + floor(t - J/2.), plan time
 #pragma unroll
                 for (int j = 0; j < J; j++)
-                    w[d][j] = tap_real<T>(h, g.ncenter[0], g.tlen[0], t, koff + j, g.L);
+                    w[d][j] = tap_real<T>(h, g.ncenter[0], g.tlen[0], t, koff + j, g.L, g.order);
                 if (PAIR) {
                     const T tq = tm_s[(int64_t)d * M + (pair ? i + 1 : i)];
                     // same wrapped cell, but possibly whole periods away: its own origin
                     const int koq = pt_ko[(int64_t)d * M + (pair ? i + 1 : i)];
 #pragma unroll
                     for (int j = 0; j < J; j++)
-                        wq[d][j] = pair ? tap_real<T>(h, g.ncenter[0], g.tlen[0], tq, koq + j, g.L)
+                        wq[d][j] = pair ? tap_real<T>(h, g.ncenter[0], g.tlen[0], tq, koq + j, g.L, g.order)
                                         : (T)0;
                 }
             }

@@ -243,9 +243,9 @@ spread_window3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ h1, const T*
                           oC = pt_ko[(int64_t)aC * M + i];
 #pragma unroll
                 for (int j = 0; j < J; j++) {
-                    w[j] = tap_real<T>(tabA, ncA, tlA, tA, oA + j, g.L);
-                    w[J + j] = tap_real<T>(tabB, ncB, tlB, tB, oB + j, g.L);
-                    w[2 * J + j] = tap_real<T>(tabC, ncC, tlC, tC, oC + j, g.L);
+                    w[j] = tap_real<T>(tabA, ncA, tlA, tA, oA + j, g.L, g.order);
+                    w[J + j] = tap_real<T>(tabB, ncB, tlB, tB, oB + j, g.L, g.order);
+                    w[2 * J + j] = tap_real<T>(tabC, ncC, tlC, tC, oC + j, g.L, g.order);
                 }
             }
             if constexpr (!FW) {

@@ -111,8 +111,8 @@ spread_window2d_kernel(Geom g, const T* __restrict__ h1, const T* __restrict__ h
                 const int o1 = pt_ko[i], o2 = pt_ko[M + i];
 #pragma unroll
                 for (int j = 0; j < J; j++) {
-                    w[j] = tap_real<T>(h2, g.ncenter[1], g.tlen[1], t2, o2 + j, g.L);
-                    w[J + j] = tap_real<T>(h1, g.ncenter[0], g.tlen[0], t1, o1 + j, g.L);
+                    w[j] = tap_real<T>(h2, g.ncenter[1], g.tlen[1], t2, o2 + j, g.L, g.order);
+                    w[J + j] = tap_real<T>(h1, g.ncenter[0], g.tlen[0], t1, o1 + j, g.L, g.order);
                 }
             }
             const int64_t src = perm[i];

@@ -24,6 +24,13 @@ static inline int NAME(wrap)(int k, int K)
     return r < 0 ? r + K : r;
 }
 
+/* Table lookup order: 1 = linear interpolation between entries (the only mode of the
+ * reference's C code), 0 = the entry at floor(p) -- "order 0" of the reference's GPU templates
+ * (cuda/jinja/table_1d_forward.jinja:40-47, table_2d_forward.jinja:61-67, :84-90 and the
+ * adjoint / 3-D siblings; cuda/cupy.py:96-98).  Process-wide switch set from Python. */
+static int NAME(g_order) = 1;
+void NAME(set_table_order)(int order) { NAME(g_order) = order; }
+
 /* coefficient for one tap: linear interpolation of the centred table.
  * The reference indexes h[n] and h[n+1] unguarded; n can be -1 (weight 1-alf ~ 1e-12,
  * when `t - J/2.` rounds up to an integer in the window-origin formula) and n+1 can be
@@ -37,6 +44,11 @@ static inline void NAME(coef)(const REAL *h, int h_cplx, int ncenter, int tlen, 
     const REAL alf = p - (REAL)n;
     const long i0 = (long)ncenter + n;
     const int ok0 = i0 >= 0 && i0 < tlen, ok1 = i0 + 1 >= 0 && i0 + 1 < tlen;
+    if (NAME(g_order) == 0) {
+        *cr = ok0 ? (h_cplx ? h[2 * i0] : h[i0]) : 0;
+        *ci = (ok0 && h_cplx) ? h[2 * i0 + 1] : 0;
+        return;
+    }
     if (h_cplx) {
         *cr = (1 - alf) * (ok0 ? h[2 * i0] : 0) + alf * (ok1 ? h[2 * (i0 + 1)] : 0);
         *ci = (1 - alf) * (ok0 ? h[2 * i0 + 1] : 0) + alf * (ok1 ? h[2 * (i0 + 1) + 1] : 0);

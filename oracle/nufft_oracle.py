@@ -240,6 +240,15 @@ def _ptr(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
 
+def set_table_order(order):
+    """Table lookup order of the C restatement ("port" engine only): 1 linear interpolation
+    (default, the reference's CPU behaviour), 0 the entry at floor(p) (the reference's GPU
+    templates with ``order=0``, cuda/cupy.py:96-98)."""
+    lib = _lib("port")
+    for pre in ("orc_f32_", "orc_f64_"):
+        getattr(lib, pre + "set_table_order")(ctypes.c_int(int(order)))
+
+
 def _interp_port(direction, Kd, Jd, L, h, tm, data):
     """Call our C restatement. data: [prod(Kd)] (fwd) or [M] (adj), complex."""
     ndim = len(Kd)

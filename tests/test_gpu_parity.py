@@ -639,3 +639,38 @@ def test_3d_window_kernels_other_J(J, precision):
     else:
         assert_single_parity(xa, O.adj(yo), orc.float64_twin(O).adj(yo.astype(np.complex128)),
                              "adj J=%d" % J)
+
+
+@pytest.mark.parametrize("precision", ["single", "double"])
+@pytest.mark.parametrize("case", ["2d", "3d", "3d_complex", "1d"])
+def test_table_order0_vs_oracle(case, precision):
+    """Plan option table_order=0: the table entry at floor((t-k)*L) instead of the linear
+    interpolation between entries -- ``order=0`` of the reference's GPU kernel templates
+    (cuda/cupy.py:96-98, cuda/jinja/table_2d_forward.jinja:61-67), which NufftBase never selects
+    and its C code does not have; checked against the oracle's restatement of those templates."""
+    from oracle import nufft_oracle as orc
+    from mrrt.nufft_b200 import NufftBase
+
+    spec = {"1d": dict(Nd=(32,), Kd=(64,), Jd=6), "2d": dict(Nd=(24, 20), Kd=(48, 40), Jd=6),
+            "3d": dict(Nd=(16, 14, 12), Kd=(24, 22, 18), Jd=(6, 5, 4)),
+            "3d_complex": dict(Nd=(16, 14, 12), Kd=(24, 22, 18), Jd=6, phasing="complex")}[case]
+    rs = np.random.RandomState(7)
+    rdt = np.float32 if precision == "single" else np.float64
+    nd = len(spec["Nd"])
+    om = ((rs.rand(4000, nd) * 2 - 1) * np.pi).astype(rdt)
+    A = NufftBase(omega=om, precision=precision, options={"table_order": 0}, **spec)
+    B = NufftBase(omega=om, precision=precision, **spec)
+    O = orc.OracleNufft(omega=om, precision=precision, engine="port", **spec)
+    x = (rs.standard_normal(spec["Nd"]) + 1j * rs.standard_normal(spec["Nd"])).astype(A._cplx_dtype)
+    y = (rs.standard_normal(4000) + 1j * rs.standard_normal(4000)).astype(A._cplx_dtype)
+    try:
+        orc.set_table_order(0)
+        yo, xo = O.fft(x), O.adj(y)
+    finally:
+        orc.set_table_order(1)
+    tol = TOL[precision]
+    ya = A.fft(x)
+    assert rel_l2(ya, yo) <= tol
+    assert rel_l2(A.adj(y), xo) <= tol
+    # it IS a different operator: the linear-interpolation result is 1e-4 .. 1e-3 away
+    assert rel_l2(B.fft(x), yo) > 10 * max(tol, 1e-7)

@@ -92,17 +92,24 @@ def test_slab_sharding_gloo(world):
 
 
 def test_slab_boundaries_balance():
-    from mrrt.nufft_b200._slab import slab_boundaries, window_rows, _pieces
+    import torch
+    from mrrt.nufft_b200._slab import _pieces, row_statistics, slab_boundaries, window_rows
 
     rs = np.random.RandomState(0)
-    K, J = 384, 6
-    om = np.clip(0.6 * rs.standard_normal(200000), -np.pi, np.pi - 1e-6)   # centre-heavy
-    rows = window_rows(om, J, K, np.dtype(np.float32))
-    assert rows.min() >= 0 and rows.max() < K
+    Kd, Jd = (24, 384, 20), (6, 6, 6)
+    om = np.clip(0.6 * rs.standard_normal((200000, 3)), -np.pi, np.pi - 1e-6).astype(np.float32)   # centre-heavy
+    rows, n, cells = row_statistics(om, Jd, Kd, np.dtype(np.float32), torch.device("cpu"))
+    assert np.array_equal(rows, window_rows(om[:, 1], 6, 384, np.dtype(np.float32)))
+    assert rows.min() >= 0 and rows.max() < 384 and n.sum() == 200000
+    # distinct origin cells per row, the slow way
+    tm = om / np.array([2 * np.pi / k for k in Kd], dtype=np.float32)
+    kw = np.mod(1 + np.floor(tm.astype(np.float64) - 3.0), Kd).astype(np.int64)
+    uniq = np.unique(kw, axis=0)
+    assert np.array_equal(cells, np.bincount(uniq[:, 1], minlength=384))
+    cost = n + 1.38 * cells + 50.0
     for world in (2, 4, 8):
-        b = slab_boundaries(rows, K, world, row_cost=50.0)
-        assert b[0] == 0 and b[-1] == K and all(b[i] < b[i + 1] for i in range(world))
-        cost = np.bincount(rows, minlength=K) + 50.0
+        b = slab_boundaries(cost, world)
+        assert b[0] == 0 and b[-1] == 384 and all(b[i] < b[i + 1] for i in range(world))
         per = [cost[b[i]:b[i + 1]].sum() for i in range(world)]
         assert max(per) <= 1.15 * (sum(per) / world)
     assert _pieces(380, 10, 384) == [(380, 0, 4), (0, 4, 6)]

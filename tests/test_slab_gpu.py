@@ -32,7 +32,7 @@ def test_slab_plans_one_gpu(G, precision):
     import torch
     from oracle import nufft_oracle as orc
     from mrrt.nufft_b200 import NufftBase
-    from mrrt.nufft_b200._slab import CudaSlabKernels, _pieces, slab_boundaries, window_rows
+    from mrrt.nufft_b200._slab import CudaSlabKernels, _pieces, row_statistics, slab_boundaries
 
     Nd, Kd, J = (32, 28, 24), (48, 44, 36), 6
     n_shift = (3.0, 0.0, 1.5)
@@ -49,8 +49,8 @@ def test_slab_plans_one_gpu(G, precision):
     y = (rs.standard_normal(M) + 1j * rs.standard_normal(M)).astype(cdt)
     K1, K2, K3 = Kd
     N3 = Nd[2]
-    rows = window_rows(om[:, 1], J, K2, rdt)
-    bounds = slab_boundaries(rows, K2, G, row_cost=20.0) if G > 1 else [0, K2]
+    rows, n_row, cells_row = row_statistics(om, (J, J, J), Kd, rdt, torch.device("cuda"))
+    bounds = slab_boundaries(n_row + 1.38 * cells_row + 20.0, G) if G > 1 else [0, K2]
     halo = J - 1 if G > 1 else 0
     ranks = []
     for s in range(G):
@@ -99,6 +99,24 @@ def test_slab_plans_one_gpu(G, precision):
         if (rows[far] - row0) % K2 + J > nrows:
             with pytest.raises(ValueError):
                 bad.make_local(om[[far]], row0, nrows)
+
+
+def test_row_statistics_on_device_match_host():
+    """The device-side row computation (torch) is bit-identical to the host formula and to the
+    plan's own window origins, also for coordinates within an ulp of a cell boundary."""
+    import torch
+    from mrrt.nufft_b200._slab import row_statistics, window_rows
+
+    rs = np.random.RandomState(5)
+    Kd, Jd = (384, 384, 384), (6, 6, 6)
+    om = ((rs.rand(2000000, 3) * 2 - 1) * np.pi).astype(np.float32)
+    k = rs.randint(-190, 190, 200000)                      # on cell boundaries, +- one ulp
+    edge = (k * np.float32(2 * np.pi / 384)).astype(np.float32)
+    om[:200000, 1] = np.nextafter(edge, np.float32(np.where(rs.rand(200000) < 0.5, -10, 10)))
+    om[200000:400000, 1] = edge
+    rows, n, cells = row_statistics(om, Jd, Kd, np.dtype(np.float32), torch.device("cuda"))
+    assert np.array_equal(rows, window_rows(om[:, 1], 6, 384, np.dtype(np.float32)))
+    assert n.sum() == om.shape[0]
 
 
 def _free_port():
@@ -174,3 +192,63 @@ def test_slab_sharded_nccl():
     for r in out:
         for key in ("fwd", "gather", "adj", "adj_planes", "sample_fwd", "sample_adj"):
             assert r[key] <= 2.5e-6, (key, r)
+
+
+def _p2p_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from mrrt.nufft_b200 import NufftBase, SlabShardedNufft
+
+        Nd, Kd, J = (48, 40, 32), (72, 60, 48), 6
+        om = _radial3d(3000, 96).astype(np.float32)
+        rs = np.random.RandomState(0)
+        x = (rs.standard_normal(Nd) + 1j * rs.standard_normal(Nd)).astype(np.complex64)
+        y = (rs.standard_normal(om.shape[0]) + 1j * rs.standard_normal(om.shape[0])).astype(np.complex64)
+        A = NufftBase(Nd=Nd, omega=om, Jd=J, Kd=Kd, precision="single")
+        S = SlabShardedNufft(Nd, om, Jd=J, Kd=Kd, precision="single", exchange="auto")
+        res = {"rank": rank, "exchange": S.exchange}
+        y1, x1 = A.fft(x), A.adj(y)
+        for rep in range(3):                      # repeated calls: the barriers protect grid reuse
+            res["fwd%d" % rep] = rel_l2(S.fft(x), y1[S.index])
+            res["adj%d" % rep] = rel_l2(S.adj(y[S.index]), x1)
+        res["fwd_twice"] = rel_l2(S.fft(x), y1[S.index]) + rel_l2(S.fft(x), y1[S.index])
+        q.put(res)
+    except Exception:
+        import traceback
+
+        q.put({"rank": rank, "error": traceback.format_exc()})
+    finally:
+        dist.destroy_process_group()
+
+
+def test_slab_sharded_peer_memory_exchange():
+    """exchange="auto": rows travel by direct stores / loads on symmetric (peer-mapped) memory
+    when torch's symmetric memory is available on the box, else over NCCL -- same results."""
+    import torch
+    import torch.multiprocessing as mp
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_p2p_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=120)
+    for r in out:
+        assert "error" not in r, r["error"]
+    print("exchange used:", [r["exchange"] for r in out])
+    assert out[0]["exchange"] == out[1]["exchange"]
+    for r in out:
+        for k, v in r.items():
+            if k.startswith(("fwd", "adj")):
+                assert v <= 5e-6, (k, r)
