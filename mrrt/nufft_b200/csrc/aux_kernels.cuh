@@ -39,7 +39,8 @@ __global__ void prep_points_kernel(Geom g, Gam<T> gam, int kind, int jmax, const
                 cell += (int64_t)(kw % g.tile[d]) * cstride;
                 // adjoint order: its own (longer) bins, LAST axis fastest inside the bin
                 bin_b += (int64_t)(kw / g.tile_b[d]) * bstride_b;
-                cell_b = cell_b * g.tile_b[d] + (kw % g.tile_b[d]);
+                if (g.colmode) cell_b += (int64_t)(kw % g.tile_b[d]) * cstride_b;   // last axis slowest
+                else cell_b = cell_b * g.tile_b[d] + (kw % g.tile_b[d]);
                 bstride_b *= g.nbin_b[d];
                 cstride_b *= g.tile_b[d];
                 bstride *= g.nbin[d];

@@ -81,7 +81,8 @@ struct b2n_plan {
     long opt_force_generic = 0;
     long opt_use_tma = 1;
     long opt_sparse_mode = 0;
-    long opt_slide_pts = 256;    // samples per warp of the register-window adjoint kernels
+    long opt_slide_pts = 0;      // samples per warp of the register-window adjoint kernels (0 = automatic:
+                                 // 256, column-group kernel 512)
     long opt_order_b = 1;        // build the adjoint sort order (3-D register-window adjoint)
     long opt_fwd_pitch = 0;      // shared-memory row pitch of the forward tile (0 = automatic)
     long opt_fwd_pair = 1;       // tiled forward: same-cell sample pairs share one window pass (1 = auto)
@@ -89,6 +90,7 @@ struct b2n_plan {
     long opt_win_facew = -1;     // window adjoint: face-weight staging.  -1 = automatic: J <= 6 (measured at
                                  // J = 4 and 6): float 2 (5 CTAs/SM), double 1; 0 = off
     long opt_win_maxslide = 0;   // longest window slide in cells before a new window is started (0 = J-1)
+    long opt_adj_column = 1;     // 3-D real-table adjoint: column sort order + column-group window kernel
     bool tile_user_set = false;
     bool tile_b_user_set = false;
     // tables
@@ -214,6 +216,36 @@ static int grid_for(int64_t n, int block, int sm_count, int per_sm = 16) {
 extern "C" int b2n_version(void) { return 100; }
 extern "C" const char* b2n_last_error(void) { return g_err.c_str(); }
 
+// window width the tiled forward / register-window adjoint kernels run at (see b2n_plan)
+static void choose_widths(b2n_plan* p) {
+    const Geom& g = p->g;
+    p->jk_fwd = p->jk_adj = 0;
+    if (g.ndim < 2) return;
+    int jmax = 0;
+    bool equal = true;
+    for (int d = 0; d < g.ndim; d++) {
+        jmax = g.J[d] > jmax ? g.J[d] : jmax;
+        equal = equal && g.J[d] == g.J[0];
+    }
+    const int even = jmax <= 4 ? 4 : (jmax + 1) / 2 * 2;       // forward, 2-D adjoint: 4, 6, 8
+    p->jk_fwd = jmax <= 8 ? even : 0;
+    // 3-D adjoint windows exist for every width 4..8
+    p->jk_adj = g.ndim == 3 ? (jmax <= 8 ? (jmax < 4 ? 4 : (equal ? jmax : even)) : 0) : p->jk_fwd;
+    for (int d = 0; d < g.ndim; d++) {
+        if (g.K[d] < p->jk_fwd) p->jk_fwd = 0;
+        if (g.K[d] < p->jk_adj) p->jk_adj = 0;
+    }
+}
+
+// whether the 3-D adjoint runs the column-group kernel (and the plan builds the column order)
+static bool column_mode(const b2n_plan* p, int* GB, int* GC) {
+    const Geom& g = p->g;
+    int FB = 0, FC = 0;
+    if (g.ndim != 3 || p->cplx_table || !p->opt_precomp || !p->opt_order_b || !p->opt_adj_column) return false;
+    if (!column_shape(p->jk_adj, &FB, &FC, GB, GC)) return false;
+    return g.K[0] >= FB && g.K[1] >= FC && g.K[2] >= p->jk_adj;
+}
+
 static void default_tiles(b2n_plan* p) {
     Geom& g = p->g;
     if (!p->tile_user_set) {
@@ -221,7 +253,12 @@ static void default_tiles(b2n_plan* p) {
         if (g.ndim == 2) { g.tile[0] = 32; g.tile[1] = 32; }
         if (g.ndim == 3) { g.tile[0] = 16; g.tile[1] = 8; g.tile[2] = 8; }
     }
-    if (!p->tile_b_user_set) {
+    int GB = 1, GC = 1;
+    g.colmode = column_mode(p, &GB, &GC) ? 1 : 0;
+    if (g.colmode) {
+        // column order: one bin per group of GB x GC grid columns, whole last axis
+        g.tile_b[0] = GB; g.tile_b[1] = GC; g.tile_b[2] = g.K[2];
+    } else if (!p->tile_b_user_set) {
         // adjoint order: long bins along the LAST axis (the one the register windows slide along)
         g.tile_b[0] = 16; g.tile_b[1] = g.ndim == 2 ? 64 : 16; g.tile_b[2] = 64;
     }
@@ -285,23 +322,8 @@ extern "C" int b2n_plan_create(int ndim, const int* Nd, const int* Kd, const int
         delete p;
         return fail(B2N_EINVAL, "prod(Kd) must be < 2^31");
     }
+    choose_widths(p);
     default_tiles(p);
-    if (ndim >= 2) {
-        int jmax = 0;
-        bool equal = true;
-        for (int d = 0; d < ndim; d++) {
-            jmax = g.J[d] > jmax ? g.J[d] : jmax;
-            equal = equal && g.J[d] == g.J[0];
-        }
-        const int even = jmax <= 4 ? 4 : (jmax + 1) / 2 * 2;       // forward, 2-D adjoint: 4, 6, 8
-        p->jk_fwd = jmax <= 8 ? even : 0;
-        // 3-D adjoint windows exist for every width 4..8
-        p->jk_adj = ndim == 3 ? (jmax <= 8 ? (jmax < 4 ? 4 : (equal ? jmax : even)) : 0) : p->jk_fwd;
-        for (int d = 0; d < ndim; d++) {
-            if (g.K[d] < p->jk_fwd) p->jk_fwd = 0;
-            if (g.K[d] < p->jk_adj) p->jk_adj = 0;
-        }
-    }
     *out = p;
     return B2N_OK;
 }
@@ -394,6 +416,7 @@ extern "C" int b2n_plan_set_option(b2n_plan* p, const char* name, long value) {
     } else if (n == "precomp_weights") {
         if (p->points_set) return fail(B2N_ESTATE, "precomp_weights must precede set_points");
         p->opt_precomp = value;
+        default_tiles(p);
     } else if (n == "fwd_pitch") {
         if (value < 0 || value > 127) return fail(B2N_EINVAL, "fwd_pitch must be in 0..127");
         p->opt_fwd_pitch = value;
@@ -415,10 +438,15 @@ extern "C" int b2n_plan_set_option(b2n_plan* p, const char* name, long value) {
     } else if (n == "order_b") {
         if (p->points_set) return fail(B2N_ESTATE, "order_b must precede set_points");
         p->opt_order_b = value;
+        default_tiles(p);
+    } else if (n == "adj_column") {
+        if (p->points_set) return fail(B2N_ESTATE, "adj_column must precede set_points");
+        p->opt_adj_column = value;
+        default_tiles(p);
     } else if (n == "profile") {
         p->opt_profile = value;
     } else if (n == "slide_pts") {
-        if (value < 32) return fail(B2N_EINVAL, "slide_pts must be >= 32");
+        if (value != 0 && value < 32) return fail(B2N_EINVAL, "slide_pts must be 0 (automatic) or >= 32");
         p->opt_slide_pts = value;
     } else {
         return fail(B2N_EINVAL, "unknown option " + n);
@@ -460,6 +488,7 @@ extern "C" long b2n_plan_get_option(b2n_plan* p, const char* name) {
     if (n == "fwd_interleave") return (long)p->opt_fwd_interleave;
     if (n == "last_fwd_kernel") return p->last_fwd_kernel;
     if (n == "last_adj_kernel") return p->last_adj_kernel;
+    if (n == "adj_column") return p->g.colmode;
     return -1;
 }
 
@@ -1057,7 +1086,7 @@ static int interp_adj_impl(b2n_plan* p, const void* samples, void* grid, int nba
         // 2-D: register windows sliding along axis 2 (adjoint sort order), lanes <-> (j1, coil)
         const void* ph = phase ? p->d_phase_sb : nullptr;
         WindowOpts wo;
-        wo.pts_per_warp = (int)p->opt_slide_pts;
+        wo.pts_per_warp = p->opt_slide_pts ? (int)p->opt_slide_pts : 256;
         wo.max_slide = (int)p->opt_win_maxslide;
         int rc = p->precision == B2N_SINGLE
                      ? window2d_adj_f32(p->g, p->jk_adj, p->cplx_table != 0, table_ptrs(p), p->d_tm_sb, p->d_wts_b, p->d_pt_ko_b, p->d_pt_kw_b,
@@ -1066,6 +1095,18 @@ static int interp_adj_impl(b2n_plan* p, const void* samples, void* grid, int nba
                                         p->d_perm_b, samples, grid, ph, nbatch, wo, st, &done);
         if (rc != 0) return fail(B2N_ECUDA, "2-D window adjoint launch failed: " + std::string(cudaGetErrorString((cudaError_t)rc)));
         if (done) p->last_adj_kernel = 4;
+    }
+    if (!done && !p->opt_force_generic && p->g.colmode && p->have_b && p->d_wts_b != nullptr) {
+        // 3-D, real table: column-group register window (one warp per group of grid columns)
+        WindowOpts wo;
+        wo.pts_per_warp = p->opt_slide_pts ? (int)p->opt_slide_pts : 512;
+        wo.max_slide = (int)p->opt_win_maxslide;
+        const void* ph = phase ? p->d_phase_sb : nullptr;
+        int rc = p->precision == B2N_SINGLE
+                     ? column_adj_f32(p->g, p->jk_adj, wo, p->d_wts_b, p->d_pt_kw_b, p->d_perm_b, samples, grid, ph, nbatch, st, &done)
+                     : column_adj_f64(p->g, p->jk_adj, wo, p->d_wts_b, p->d_pt_kw_b, p->d_perm_b, samples, grid, ph, nbatch, st, &done);
+        if (rc != 0) return fail(B2N_ECUDA, "column adjoint launch failed: " + std::string(cudaGetErrorString((cudaError_t)rc)));
+        if (done) p->last_adj_kernel = 5;
     }
     if (!done && !p->opt_force_generic && p->g.ndim == 3 && (p->have_b ? p->jk_adj : p->jk_fwd) > 0 &&
         (!p->cplx_table || (p->have_b ? p->d_wts_b : p->d_wts) != nullptr)) {
@@ -1080,7 +1121,7 @@ static int interp_adj_impl(b2n_plan* p, const void* samples, void* grid, int nba
         const int32_t* pm = ob ? p->d_perm_b : p->d_perm;
         WindowOpts wo;
         wo.slide_axis = ob ? 2 : 0;
-        wo.pts_per_warp = (int)p->opt_slide_pts;
+        wo.pts_per_warp = p->opt_slide_pts ? (int)p->opt_slide_pts : 256;
         wo.max_slide = (int)p->opt_win_maxslide;
         wo.facew = (int)p->opt_win_facew;
         if (wo.facew < 0) wo.facew = jk <= 6 ? (p->precision == B2N_SINGLE ? 2 : 1) : 0;

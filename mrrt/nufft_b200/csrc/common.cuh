@@ -59,6 +59,9 @@ struct Geom {
     int nbin[3];      // bins per axis
     int tile_b[3];    // bin shape of the adjoint sort order (long along the last axis)
     int nbin_b[3];
+    int colmode;      // adjoint sort order = COLUMN order (spread_column.cuh): bins of tile_b[0] x tile_b[1]
+                      // grid columns over the whole last axis, samples ordered by the origin along
+                      // the last axis inside a bin (else: cells last-axis-fastest inside the bin)
     int64_t PK;       // prod(K)
     int64_t PN;       // prod(N)
     int64_t M;        // samples

@@ -39,6 +39,18 @@ struct WindowOpts {
     int facew = 0;           // 0 scalar staging records, 1 face-weight staging, 2 ... at 5 CTAs / SM
 };
 
+// Face of the column-group adjoint kernel (spread_column.cuh: ColumnShape<J>) for window width J
+// in 4..8: FB x FC grid cells shared by the windows of GB x GC neighbouring grid columns.  The
+// plan builds its column sort order from GB, GC and checks that the grid is as large as the face.
+inline bool column_shape(int J, int* FB, int* FC, int* GB, int* GC) {
+    if (J < 4 || J > 8) return false;
+    *FB = 8;
+    *FC = 4 * ((J + 3) / 4);
+    *GB = *FB - J + 1;
+    *GC = *FC - J + 1;
+    return true;
+}
+
 // each returns 0 or a cudaError_t; *done tells whether the kernel family took the call.
 // Jk: compile-time window width to run (>= every g.J[d]; wider than g.J[d] only with plan-time
 // weights, whose extra taps are zero: aux_kernels.cuh:point_weights_kernel)
@@ -53,6 +65,10 @@ struct WindowOpts {
                         int nbatch, const FwdOpts& fo, cudaStream_t st, bool* done);             \
     int window_adj_##SUF(const Geom& g, int Jk, bool cplx, const TablePtrs& tabs, const WindowOpts& wo,             \
                          const void* tm_s, const void* wts, const int32_t* pt_ko,                \
+                         const int32_t* pt_kw, const int32_t* perm, const void* samples,         \
+                         void* grid, const void* phase_s, int nbatch, cudaStream_t st,           \
+                         bool* done);                                                            \
+    int column_adj_##SUF(const Geom& g, int Jk, const WindowOpts& wo, const void* wts,           \
                          const int32_t* pt_kw, const int32_t* perm, const void* samples,         \
                          void* grid, const void* phase_s, int nbatch, cudaStream_t st,           \
                          bool* done);                                                            \

@@ -99,3 +99,17 @@ def assert_single_parity(got, ref32, twin64, what=""):
     assert ok, ("%s: vs reference float32 %.3g; vs float64 twin: cuda %.3g, reference %.3g"
                 % (what, direct, e_cuda, e_ref))
     return direct, e_cuda, e_ref
+
+
+def expected_adj_kernel(A):
+    """``last_adj_kernel`` a table-mode plan with windows up to 8 wide must report: 4 = 2-D
+    register window, 5 = 3-D column-group window (real table, grid at least as large as the
+    8 x 4*ceil(J/4) face), 3 = 3-D per-cell register window (complex tables, small grids)."""
+    if A.ndim == 2:
+        return 4
+    jk = max(A.Jd) if len(set(A.Jd)) == 1 else (max(A.Jd) + 1) // 2 * 2
+    jk = max(jk, 4)
+    real = getattr(A, "phasing", "real") == "real"
+    if real and A.Kd[0] >= 8 and A.Kd[1] >= 4 * ((jk + 3) // 4) and A.Kd[2] >= jk:
+        return 5
+    return 3

@@ -3,7 +3,7 @@ reference and against the CPU oracle on seeded inputs.  Needs a B200."""
 import numpy as np
 import pytest
 
-from golden_util import (PSF_CASES, TOL, assert_single_parity, case_names, ctor_kwargs,
+from golden_util import (PSF_CASES, TOL, assert_single_parity, case_names, ctor_kwargs, expected_adj_kernel,
                          grid_only_inputs, load_case, psf_cases, rel_l2, table_key, tables)
 
 pytestmark = pytest.mark.gpu
@@ -55,7 +55,7 @@ def test_golden(name, variant):
         jk = max(4, (max(A.Jd) + 1) // 2 * 2)
         if min(A.Kd) >= jk:
             assert A.option("last_fwd_kernel") == 1   # tiled TMA kernel really ran
-            assert A.option("last_adj_kernel") == (3 if A.ndim == 3 else 4)
+            assert A.option("last_adj_kernel") == expected_adj_kernel(A)
 
 
 @pytest.mark.parametrize("name", PSF_CASES)
@@ -136,6 +136,7 @@ def _radial3d(S, n):
 
 @pytest.mark.parametrize("precision", ["single", "double"])
 @pytest.mark.parametrize("variant", ["auto", "generic", "no_tma", "window_a", "table_in_kernel",
+                                     "window_percell", "column_256",
                                      "window_scalar", "window_facew", "window_facew5", "pair_on",
                                      "pair_off", "pair_sorted", "pair_table"])
 def test_mid_3d_radial_vs_oracle(precision, variant):
@@ -149,6 +150,7 @@ def test_mid_3d_radial_vs_oracle(precision, variant):
     om = _radial3d(700, 64).astype(rdt)
     opts = {"generic": {"force_generic": 1}, "no_tma": {"use_tma": 0}, "auto": {},
             "window_a": {"order_b": 0}, "table_in_kernel": {"precomp_weights": 0},
+            "window_percell": {"adj_column": 0}, "column_256": {"slide_pts": 256, "win_maxslide": 2},
             "window_scalar": {"win_facew": 0}, "window_facew": {"win_facew": 1},
             "window_facew5": {"win_facew": 2}, "pair_on": {"fwd_pair": 2},
             "pair_off": {"fwd_pair": 0}, "pair_sorted": {"fwd_pair": 2, "fwd_interleave": 0},
@@ -633,7 +635,7 @@ def test_3d_window_kernels_other_J(J, precision):
     yo = O.fft(x)
     assert rel_l2(A.fft(x), yo) <= TOL[precision]
     xa = A.adj(yo)
-    assert A.option("last_adj_kernel") == 3
+    assert A.option("last_adj_kernel") == 5
     if precision == "double":
         assert rel_l2(xa, O.adj(yo)) <= TOL[precision]
     else:

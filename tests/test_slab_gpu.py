@@ -82,7 +82,7 @@ def test_slab_plans_one_gpu(G, precision):
         grid = k.empty((K3, nrows, K1))
         k.interp_adj(k.to_device(y[idx]), grid)
         if G > 1 and idx.size:
-            assert k.option("last_adj_kernel") == 3
+            assert k.option("last_adj_kernel") in (3, 5)
         k.axis3_adj(grid)
         for glo, llo, n in _pieces(row0, nrows, K2):
             B[:, glo:glo + n] += grid[:N3, llo:llo + n]
