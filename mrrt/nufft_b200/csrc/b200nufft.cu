@@ -122,6 +122,7 @@ struct b2n_plan {
     // plan-time interpolation weights [sum(J)][M] for each sort order (real tables)
     void* d_wts = nullptr;
     void* d_wts_b = nullptr;
+    void* d_col_rec = nullptr;   // column order: blocked plan-time records of the column-group adjoint kernel
     long opt_precomp = 1;
     void* d_phase_s = nullptr;   // sorted sample phase or null
     int64_t nbins = 0;
@@ -339,8 +340,8 @@ static void free_points(b2n_plan* p) {
     p->d_pt_ko = p->d_pt_kw = nullptr;
     dev_free(p, p->d_tm_sb); dev_free(p, p->d_perm_b); dev_free(p, p->d_pt_ko_b); dev_free(p, p->d_pt_kw_b);
     dev_free(p, p->d_phase_sb);
-    dev_free(p, p->d_wts); dev_free(p, p->d_wts_b); dev_free(p, p->d_wts_f);
-    p->d_wts = p->d_wts_b = p->d_wts_f = nullptr;
+    dev_free(p, p->d_wts); dev_free(p, p->d_wts_b); dev_free(p, p->d_wts_f); dev_free(p, p->d_col_rec);
+    p->d_wts = p->d_wts_b = p->d_wts_f = p->d_col_rec = nullptr;
     p->d_tm_sb = p->d_phase_sb = nullptr;
     p->d_perm_b = p->d_pt_ko_b = p->d_pt_kw_b = nullptr;
     p->have_b = false;
@@ -519,8 +520,8 @@ extern "C" int b2n_plan_set_tables(b2n_plan* p, const void* const* h_host) {
         CU(cudaMemcpy(p->d_tab[d], h_host[d], esz * g.tlen[d], cudaMemcpyHostToDevice));
     }
     p->tables_set = true;
-    dev_free(p, p->d_wts); dev_free(p, p->d_wts_b); dev_free(p, p->d_wts_f);
-    p->d_wts = p->d_wts_b = p->d_wts_f = nullptr;
+    dev_free(p, p->d_wts); dev_free(p, p->d_wts_b); dev_free(p, p->d_wts_f); dev_free(p, p->d_col_rec);
+    p->d_wts = p->d_wts_b = p->d_wts_f = p->d_col_rec = nullptr;
     int rc = ensure_weights(p, (cudaStream_t)0);
     if (rc) return rc;
     CU(cudaStreamSynchronize((cudaStream_t)0));
@@ -585,10 +586,14 @@ static int set_points_t(b2n_plan* p, const void* coords, int64_t M, int kind, cu
     const bool want_b = g.ndim >= 2 && p->opt_order_b && (!p->cplx_table || p->opt_precomp);
     uint64_t* keys_b = nullptr;
     if (want_b) {
-        if ((rc = dev_alloc(p, &p->d_tm_sb, rs * M * g.ndim))) return rc;
         if ((rc = dev_alloc(p, (void**)&p->d_perm_b, sizeof(int32_t) * M))) return rc;
-        if ((rc = dev_alloc(p, (void**)&p->d_pt_ko_b, sizeof(int32_t) * M * g.ndim))) return rc;
-        if ((rc = dev_alloc(p, (void**)&p->d_pt_kw_b, sizeof(int32_t) * M * g.ndim))) return rc;
+        if (!g.colmode) {
+            // (column order: the sorted coordinates and window origins are only needed while the
+            // column records are built; build_weights_t makes them in scratch memory)
+            if ((rc = dev_alloc(p, &p->d_tm_sb, rs * M * g.ndim))) return rc;
+            if ((rc = dev_alloc(p, (void**)&p->d_pt_ko_b, sizeof(int32_t) * M * g.ndim))) return rc;
+            if ((rc = dev_alloc(p, (void**)&p->d_pt_kw_b, sizeof(int32_t) * M * g.ndim))) return rc;
+        }
         CU(scratch.alloc(&keys_b, sizeof(uint64_t) * M));
     }
     uint64_t* keys_s = nullptr;
@@ -634,12 +639,14 @@ static int set_points_t(b2n_plan* p, const void* coords, int64_t M, int kind, cu
         CU(scratch.alloc(&keys_bs, sizeof(uint64_t) * M));
         CU(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys_b, keys_bs, iota, p->d_perm_b, M, 0,
                                            bits, st));
-        gather_points_kernel<T><<<grid_for(M, 256, p->sm_count), 256, 0, st>>>(
-            g.ndim, M, p->d_perm_b, (const T*)p->d_tm, (T*)p->d_tm_sb);
-        CU(cudaGetLastError());
-        point_windows_kernel<T><<<grid_for(M, 256, p->sm_count), 256, 0, st>>>(
-            g, (const T*)p->d_tm_sb, p->d_pt_ko_b, p->d_pt_kw_b);
-        CU(cudaGetLastError());
+        if (!g.colmode) {
+            gather_points_kernel<T><<<grid_for(M, 256, p->sm_count), 256, 0, st>>>(
+                g.ndim, M, p->d_perm_b, (const T*)p->d_tm, (T*)p->d_tm_sb);
+            CU(cudaGetLastError());
+            point_windows_kernel<T><<<grid_for(M, 256, p->sm_count), 256, 0, st>>>(
+                g, (const T*)p->d_tm_sb, p->d_pt_ko_b, p->d_pt_kw_b);
+            CU(cudaGetLastError());
+        }
         CU(cudaStreamSynchronize(st));
         p->have_b = true;
     }
@@ -976,7 +983,30 @@ static int build_weights_t(b2n_plan* p, cudaStream_t st) {
         CU(cudaGetLastError());
         p->launches++;
     }
-    if (p->have_b && ja > 0) {
+    if (p->have_b && ja > 0 && g.colmode) {
+        // column order: blocked records (weights, origins, acquisition index) of the column-group kernel
+        Scratch scratch;
+        T* tm_sb = nullptr;
+        int32_t *ko_b = nullptr, *kw_b = nullptr;
+        CU(scratch.alloc(&tm_sb, sizeof(T) * g.M * 3));
+        CU(scratch.alloc(&ko_b, sizeof(int32_t) * g.M * 3));
+        CU(scratch.alloc(&kw_b, sizeof(int32_t) * g.M * 3));
+        const int nb = grid_for(g.M, 256, p->sm_count);
+        gather_points_kernel<T><<<nb, 256, 0, st>>>(3, g.M, p->d_perm_b, (const T*)p->d_tm, tm_sb);
+        CU(cudaGetLastError());
+        point_windows_kernel<T><<<nb, 256, 0, st>>>(g, tm_sb, ko_b, kw_b);
+        CU(cudaGetLastError());
+        const bool f32 = sizeof(T) == 4;
+        const size_t bytes = f32 ? column_record_bytes_f32(ja, g.M) : column_record_bytes_f64(ja, g.M);
+        if ((rc = dev_alloc(p, &p->d_col_rec, bytes))) return rc;
+        CU(cudaMemsetAsync(p->d_col_rec, 0, bytes, st));
+        const TablePtrs tp{{p->d_tab[0], p->d_tab[1], p->d_tab[2]}};
+        const int e = f32 ? column_build_f32(g, ja, tp, tm_sb, ko_b, kw_b, p->d_perm_b, p->d_col_rec, nb, st)
+                          : column_build_f64(g, ja, tp, tm_sb, ko_b, kw_b, p->d_perm_b, p->d_col_rec, nb, st);
+        if (e != 0) return fail(B2N_ECUDA, std::string("column records: ") + cudaGetErrorString((cudaError_t)e));
+        CU(cudaStreamSynchronize(st));      // the scratch arrays are freed on return
+        p->launches += 3;
+    } else if (p->have_b && ja > 0) {
         if ((rc = dev_alloc(p, &p->d_wts_b, wsz * (size_t)g.ndim * ja * g.M))) return rc;
         if (p->cplx_table)
             point_weights_kernel<T, true><<<grid_for(g.M, 256, p->sm_count), 256, 0, st>>>(
@@ -992,7 +1022,7 @@ static int build_weights_t(b2n_plan* p, cudaStream_t st) {
 
 static int ensure_weights(b2n_plan* p, cudaStream_t st) {
     if (!p->opt_precomp || p->g.ndim < 2 || p->d_wts != nullptr ||
-        p->d_wts_f != nullptr || p->d_wts_b != nullptr || p->g.M == 0 ||
+        p->d_wts_f != nullptr || p->d_wts_b != nullptr || p->d_col_rec != nullptr || p->g.M == 0 ||
         (p->jk_fwd == 0 && p->jk_adj == 0))
         return B2N_OK;
     if (!p->tables_set || !p->points_set) return B2N_OK;
@@ -1096,19 +1126,19 @@ static int interp_adj_impl(b2n_plan* p, const void* samples, void* grid, int nba
         if (rc != 0) return fail(B2N_ECUDA, "2-D window adjoint launch failed: " + std::string(cudaGetErrorString((cudaError_t)rc)));
         if (done) p->last_adj_kernel = 4;
     }
-    if (!done && !p->opt_force_generic && p->g.colmode && p->have_b && p->d_wts_b != nullptr) {
+    if (!done && !p->opt_force_generic && p->g.colmode && p->d_col_rec != nullptr) {
         // 3-D, real table: column-group register window (one warp per group of grid columns)
         WindowOpts wo;
         wo.pts_per_warp = p->opt_slide_pts ? (int)p->opt_slide_pts : 512;
         wo.max_slide = (int)p->opt_win_maxslide;
         const void* ph = phase ? p->d_phase_sb : nullptr;
         int rc = p->precision == B2N_SINGLE
-                     ? column_adj_f32(p->g, p->jk_adj, wo, p->d_wts_b, p->d_pt_kw_b, p->d_perm_b, samples, grid, ph, nbatch, st, &done)
-                     : column_adj_f64(p->g, p->jk_adj, wo, p->d_wts_b, p->d_pt_kw_b, p->d_perm_b, samples, grid, ph, nbatch, st, &done);
+                     ? column_adj_f32(p->g, p->jk_adj, wo, p->d_col_rec, samples, grid, ph, nbatch, st, &done)
+                     : column_adj_f64(p->g, p->jk_adj, wo, p->d_col_rec, samples, grid, ph, nbatch, st, &done);
         if (rc != 0) return fail(B2N_ECUDA, "column adjoint launch failed: " + std::string(cudaGetErrorString((cudaError_t)rc)));
         if (done) p->last_adj_kernel = 5;
     }
-    if (!done && !p->opt_force_generic && p->g.ndim == 3 && (p->have_b ? p->jk_adj : p->jk_fwd) > 0 &&
+    if (!done && !p->opt_force_generic && p->g.ndim == 3 && !p->g.colmode && (p->have_b ? p->jk_adj : p->jk_fwd) > 0 &&
         (!p->cplx_table || (p->have_b ? p->d_wts_b : p->d_wts) != nullptr)) {
         // register window, lane-parallel batch weights; adjoint sort order when built
         const bool ob = p->have_b;

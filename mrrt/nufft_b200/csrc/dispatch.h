@@ -68,10 +68,13 @@ inline bool column_shape(int J, int* FB, int* FC, int* GB, int* GC) {
                          const int32_t* pt_kw, const int32_t* perm, const void* samples,         \
                          void* grid, const void* phase_s, int nbatch, cudaStream_t st,           \
                          bool* done);                                                            \
-    int column_adj_##SUF(const Geom& g, int Jk, const WindowOpts& wo, const void* wts,           \
-                         const int32_t* pt_kw, const int32_t* perm, const void* samples,         \
-                         void* grid, const void* phase_s, int nbatch, cudaStream_t st,           \
-                         bool* done);                                                            \
+    int column_adj_##SUF(const Geom& g, int Jk, const WindowOpts& wo, const void* records,       \
+                         const void* samples, void* grid, const void* phase_s, int nbatch,       \
+                         cudaStream_t st, bool* done);                                           \
+    size_t column_record_bytes_##SUF(int Jk, int64_t M);                                         \
+    int column_build_##SUF(const Geom& g, int Jk, const TablePtrs& tabs, const void* tm_s,       \
+                           const int32_t* pt_ko, const int32_t* pt_kw, const int32_t* perm,      \
+                           void* records, int nblocks, cudaStream_t st);                         \
     int window2d_adj_##SUF(const Geom& g, int Jk, bool cplx, const TablePtrs& tabs, const void* tm_s, const void* wts, \
                            const int32_t* pt_ko, const int32_t* pt_kw, const int32_t* perm,      \
                            const void* samples, void* grid, const void* phase_s, int nbatch,     \

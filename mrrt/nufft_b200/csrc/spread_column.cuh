@@ -47,16 +47,62 @@ template <typename T, int J> struct ColumnRec {
     static constexpr int kBytes = 32 * kHead + (32 * kFaceElems * (int)sizeof(T) + 15) / 16 * 16;   // per warp
 };
 
+// Plan-time COLUMN RECORDS (built by column_records_kernel below): everything the batch phase
+// reads per sample, blocked by 32 samples of the column order so that one lane-pass reads
+// rows of 32 consecutive values from ONE base address with immediate offsets (no per-load
+// address arithmetic, which was 2/3 of the batch phase):
+//   rows 0 .. 3J-1   weights along a (axis 3), b (axis 1), c (axis 2)     [32] x T each
+//   4 int rows       origin along a | face corner ab + (ob << 16) | ac + (oc << 16) | acquisition index
+template <typename T, int J> struct ColumnBlock {
+    static constexpr int kRow = 32 * (int)sizeof(T);
+    static constexpr int kInts = 3 * J * kRow;                 // byte offset of the int rows
+    static constexpr int kBytes = kInts + 4 * 128;             // per block of 32 samples
+};
+
+template <typename T, int J>
+__global__ void column_records_kernel(Geom g, const void* h0, const void* h1, const void* h2,
+                                      const T* __restrict__ tm_s, const int32_t* __restrict__ pt_ko,
+                                      const int32_t* __restrict__ pt_kw, const int32_t* __restrict__ perm,
+                                      unsigned char* __restrict__ rec) {
+    using S = ColumnShape<J>;
+    using B = ColumnBlock<T, J>;
+    const int64_t M = g.M;
+    const void* tabs[3] = {h0, h1, h2};
+    const int axes[3] = {2, 0, 1};                             // a, b, c
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < M;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        unsigned char* blk = rec + (i >> 5) * B::kBytes;
+        const int l = (int)(i & 31);
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            const int d = axes[r];
+            const T t = tm_s[(int64_t)d * M + i];
+            const int ko = pt_ko[(int64_t)d * M + i];
+#pragma unroll
+            for (int j = 0; j < J; j++)
+                ((T*)(blk + (r * J + j) * B::kRow))[l] =
+                    j < g.J[d] ? tap_real<T>((const T*)tabs[d], g.ncenter[d], g.tlen[d], t, ko + j, g.L, g.order) : (T)0;
+        }
+        const int kB = pt_kw[i], kC = pt_kw[M + i];
+        const int ab = kB / S::GB * S::GB, ac = kC / S::GC * S::GC;
+        int32_t* ir = (int32_t*)(blk + B::kInts);
+        ir[l] = pt_kw[2 * M + i];
+        ir[32 + l] = ab | ((kB - ab) << 16);
+        ir[64 + l] = ac | ((kC - ac) << 16);
+        ir[96 + l] = perm[i];
+    }
+}
+
 template <typename T, int J, int MINB>
 __global__ void __launch_bounds__(128, MINB)
-spread_column3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ wts,
-                       const int32_t* __restrict__ pt_kw, const int32_t* __restrict__ perm,
+spread_column3d_kernel(Geom g, WindowAxes wa, const unsigned char* __restrict__ records,
                        const cplx_t<T>* __restrict__ samples, cplx_t<T>* __restrict__ grid,
                        const cplx_t<T>* __restrict__ phase_s, int pts_per_warp, int max_slide) {
     using C = cplx_t<T>;
     using S = ColumnShape<J>;
     using R = ColumnRec<T, J>;
-    constexpr int RPL = S::RPL, FB = S::FB, FC = S::FC, GB = S::GB, GC = S::GC;
+    using B = ColumnBlock<T, J>;
+    constexpr int RPL = S::RPL, FB = S::FB, FC = S::FC;
     constexpr int HP = R::kHead, HI = R::kHeadInt, HV = R::HV, VPC = R::VPC, FP = R::kFaceElems;
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char dyn_smem[];
@@ -72,7 +118,6 @@ spread_column3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ wts,
     const int bt = blockIdx.y;
     const C* __restrict__ sb = samples + (int64_t)bt * M;
     C* __restrict__ gb = grid + (int64_t)bt * g.PK;
-    const int aA = wa.ax[0], aB = wa.ax[1], aC = wa.ax[2];
     const int KA = wa.K[0], KB = wa.K[1], KC = wa.K[2];
     const int sA = wa.stride[0], sB = wa.stride[1], sC = wa.stride[2];
     const int lb = lane & 7, lc0 = lane >> 3;
@@ -88,38 +133,43 @@ spread_column3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ wts,
     int WA = 0;
     bool have = false;
     int pkA = -1 << 30, pab = -1, pac = -1;   // previous sample: origin along a, face corner
+    // this lane's column of the current block of 32 records
+    const unsigned char* blk = records + (begin >> 5) * B::kBytes + lane * (int)sizeof(T);
+    const unsigned char* blki = records + (begin >> 5) * B::kBytes + B::kInts + lane * 4;
 
-    for (int64_t base = begin; base < end; base += 32) {
+    for (int64_t base = begin; base < end; base += 32, blk += B::kBytes, blki += B::kBytes) {
         const int cnt = (int)(end - base < 32 ? end - base : 32);
         __syncwarp();
         // ---- batch phase: lane = sample
         int kA = 0, ab = 0, ac = 0;
+        // the next block of this run on its way from HBM to L2 while this one is worked on
+        if (base + 32 < end && lane * 128 < B::kBytes)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(blk + B::kBytes + lane * (128 - (int)sizeof(T))));
         if (lane < cnt) {
-            const int64_t i = base + lane;
-            kA = pt_kw[(int64_t)aA * M + i];
-            const int kB = pt_kw[(int64_t)aB * M + i];
-            const int kC = pt_kw[(int64_t)aC * M + i];
-            ab = kB / GB * GB;
-            ac = kC / GC * GC;
-            const int ob = kB - ab, oc = kC - ac;
+            kA = *(const int*)blki;
+            const int pb = *(const int*)(blki + 128), pc = *(const int*)(blki + 256);
+            C f = sb[*(const int*)(blki + 384)];
+            ab = pb & 0xffff;
+            ac = pc & 0xffff;
+            const int ob = pb >> 16, oc = pc >> 16;
             T hv[HV];
 #pragma unroll
             for (int e = 0; e < HV; e++) hv[e] = (T)0;
 #pragma unroll
-            for (int j = 0; j < J; j++) hv[j] = wts[(int64_t)(aA * J + j) * M + i];
-            T* fr = faces + lane * FP;
+            for (int j = 0; j < J; j++) hv[j] = *(const T*)(blk + j * B::kRow);
+            T* frb = faces + lane * FP + ob;
+            T* frc = faces + lane * FP + FB + oc;
 #pragma unroll
             for (int j = 0; j < J; j++) {
-                fr[ob + j] = wts[(int64_t)(aB * J + j) * M + i];
-                fr[FB + oc + j] = wts[(int64_t)(aC * J + j) * M + i];
+                frb[j] = *(const T*)(blk + (J + j) * B::kRow);
+                frc[j] = *(const T*)(blk + (2 * J + j) * B::kRow);
             }
             // the face positions this sample's window does not reach
 #pragma unroll
-            for (int z = 0; z < FB - J; z++) fr[z < ob ? z : z + J] = (T)0;
+            for (int z = 0; z < FB - J; z++) frb[z < ob ? z - ob : z + J - ob] = (T)0;
 #pragma unroll
-            for (int z = 0; z < FC - J; z++) fr[FB + (z < oc ? z : z + J)] = (T)0;
-            C f = sb[perm[i]];
-            if (phase_s != nullptr) f = cmul_conj(f, phase_s[i]);
+            for (int z = 0; z < FC - J; z++) frc[z < oc ? z - oc : z + J - oc] = (T)0;
+            if (phase_s != nullptr) f = cmul_conj(f, phase_s[base + lane]);
             hv[J] = f.x;
             hv[J + 1] = f.y;
             unsigned char* hb = heads + lane * HP;
@@ -145,6 +195,7 @@ spread_column3d_kernel(Geom g, WindowAxes wa, const T* __restrict__ wts,
         const T* fwb = faces + lb;
         const T* fwc = faces + FB + lc0;
         int act_next = *(const int*)(rec + HI + 12);
+#pragma unroll 2
         for (; rec != rec_end; rec += HP, fwb += FP, fwc += FP) {
             const int act = act_next;
             act_next = *(const int*)(rec + HP + HI + 12);
@@ -220,11 +271,10 @@ template <int J> static bool column_fits(const Geom& g) {
 }
 
 template <typename T, int J>
-static int launch_column(const Geom& g, const WindowOpts& wo, const void* wts, const int32_t* pt_kw,
-                         const int32_t* perm, const void* samples, void* grid, const void* phase_s,
-                         int nbatch, cudaStream_t st, bool* done) {
+static int launch_column(const Geom& g, const WindowOpts& wo, const void* records, const void* samples,
+                         void* grid, const void* phase_s, int nbatch, cudaStream_t st, bool* done) {
     using C = cplx_t<T>;
-    if (!column_fits<J>(g) || wts == nullptr) return 0;
+    if (!column_fits<J>(g) || records == nullptr) return 0;
     int max_slide = wo.max_slide;
     if (max_slide <= 0 || max_slide > J - 1) max_slide = J - 1;
     const int pts_per_warp = (wo.pts_per_warp + 31) / 32 * 32;
@@ -241,7 +291,7 @@ static int launch_column(const Geom& g, const WindowOpts& wo, const void* wts, c
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     dim3 gd((unsigned)nblocks, (unsigned)nbatch);
-    k<<<gd, 128, smem, st>>>(g, wa, (const T*)wts, pt_kw, perm, (const C*)samples, (C*)grid,
+    k<<<gd, 128, smem, st>>>(g, wa, (const unsigned char*)records, (const C*)samples, (C*)grid,
                              (const C*)phase_s, pts_per_warp, max_slide);
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
@@ -249,14 +299,42 @@ static int launch_column(const Geom& g, const WindowOpts& wo, const void* wts, c
     return 0;
 }
 
+// bytes of the column records of M samples at width J (0: no column kernel at this width)
+template <typename T> static size_t column_record_bytes_t(int Jk, int64_t M) {
+    const size_t nblk = (size_t)((M + 31) / 32);
+    switch (Jk) {
+        case 4: return nblk * ColumnBlock<T, 4>::kBytes;
+        case 5: return nblk * ColumnBlock<T, 5>::kBytes;
+        case 6: return nblk * ColumnBlock<T, 6>::kBytes;
+        case 7: return nblk * ColumnBlock<T, 7>::kBytes;
+        case 8: return nblk * ColumnBlock<T, 8>::kBytes;
+        default: return 0;
+    }
+}
+
 template <typename T>
-static int column_adj_t(const Geom& g, int Jk, const WindowOpts& wo, const void* wts, const int32_t* pt_kw,
-                        const int32_t* perm, const void* samples, void* grid, const void* phase_s,
-                        int nbatch, cudaStream_t st, bool* done) {
+static int column_build_t(const Geom& g, int Jk, const TablePtrs& tabs, const void* tm_s, const int32_t* pt_ko,
+                          const int32_t* pt_kw, const int32_t* perm, void* records, int nblocks,
+                          cudaStream_t st) {
+#define B2N_COLB(JJ)                                                                              \
+    case JJ:                                                                                      \
+        column_records_kernel<T, JJ><<<nblocks, 256, 0, st>>>(g, tabs.h[0], tabs.h[1], tabs.h[2], \
+            (const T*)tm_s, pt_ko, pt_kw, perm, (unsigned char*)records);                         \
+        break;
+    switch (Jk) {
+        B2N_COLB(4) B2N_COLB(5) B2N_COLB(6) B2N_COLB(7) B2N_COLB(8)
+        default: return (int)cudaErrorInvalidValue;
+    }
+#undef B2N_COLB
+    return (int)cudaGetLastError();
+}
+
+template <typename T>
+static int column_adj_t(const Geom& g, int Jk, const WindowOpts& wo, const void* records, const void* samples,
+                        void* grid, const void* phase_s, int nbatch, cudaStream_t st, bool* done) {
     *done = false;
     if (g.ndim != 3) return 0;
-#define B2N_COL(JJ)                                                                               \
-    return launch_column<T, JJ>(g, wo, wts, pt_kw, perm, samples, grid, phase_s, nbatch, st, done)
+#define B2N_COL(JJ) return launch_column<T, JJ>(g, wo, records, samples, grid, phase_s, nbatch, st, done)
     switch (Jk) {
         case 4: B2N_COL(4);
         case 5: B2N_COL(5);
