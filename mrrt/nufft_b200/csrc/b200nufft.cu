@@ -156,6 +156,8 @@ struct b2n_plan {
     int ax3_state = 0;           // 0 = not prepared, 1 = ready, -1 = K3 not supported
     void* d_tw3 = nullptr;
     void* d_work = nullptr;
+    void* d_acc64 = nullptr;     // complex128 scratch grid of the float one-RED-per-tap adjoint
+    size_t acc64_bytes = 0;
     size_t work_bytes = 0;
     int64_t dev_bytes = 0;
     int64_t launches = 0;        // our own kernels
@@ -369,6 +371,7 @@ extern "C" int b2n_plan_destroy(b2n_plan* p) {
     dev_free(p, p->d_ell_vals);
     dev_free(p, p->d_ell_cols);
     dev_free(p, p->d_work);
+    dev_free(p, p->d_acc64);
     delete p;
     return B2N_OK;
 }
@@ -942,11 +945,30 @@ static int run_generic(b2n_plan* p, bool fwd, const void* in, void* out, int nba
                        cudaStream_t st) {
     const TablePtrs tabs = table_ptrs(p);
     const void* ph = phase ? p->d_phase_s : nullptr;
-    if (p->precision == B2N_SINGLE)
+    if (p->precision == B2N_SINGLE) {
+        // float adjoint: per-cell sums in a double scratch grid (kept by the plan, at most 1 GiB;
+        // above that the float atomics go straight to the output grid)
+        void* acc64 = nullptr;
+        const size_t need = sizeof(double2) * (size_t)p->g.PK * nbatch;
+        if (!fwd && need <= ((size_t)1 << 30)) {
+            if (p->acc64_bytes < need) {
+                dev_free(p, p->d_acc64);
+                p->d_acc64 = nullptr;
+                p->acc64_bytes = 0;
+                if (dev_alloc(p, &p->d_acc64, need) == B2N_OK) p->acc64_bytes = need;
+            }
+            if (p->d_acc64 != nullptr) {
+                if (cudaMemsetAsync(p->d_acc64, 0, need, st) != cudaSuccess) return (int)cudaGetLastError();
+                acc64 = p->d_acc64;
+                p->lib_calls++;
+                p->launches++;       // the add-back kernel
+            }
+        }
         return generic_launch_f32(p->g, p->cplx_table, tabs, p->d_tm_s, p->d_perm, fwd, in, out, ph,
-                                  nbatch, p->sm_count, st);
+                                  nbatch, p->sm_count, acc64, st);
+    }
     return generic_launch_f64(p->g, p->cplx_table, tabs, p->d_tm_s, p->d_perm, fwd, in, out, ph,
-                              nbatch, p->sm_count, st);
+                              nbatch, p->sm_count, nullptr, st);
 }
 
 // weights need both the points and the tables; built on first use
@@ -1001,8 +1023,8 @@ static int build_weights_t(b2n_plan* p, cudaStream_t st) {
         if ((rc = dev_alloc(p, &p->d_col_rec, bytes))) return rc;
         CU(cudaMemsetAsync(p->d_col_rec, 0, bytes, st));
         const TablePtrs tp{{p->d_tab[0], p->d_tab[1], p->d_tab[2]}};
-        const int e = f32 ? column_build_f32(g, ja, tp, tm_sb, ko_b, kw_b, p->d_perm_b, p->d_col_rec, nb, st)
-                          : column_build_f64(g, ja, tp, tm_sb, ko_b, kw_b, p->d_perm_b, p->d_col_rec, nb, st);
+        const int e = f32 ? column_build_f32(g, ja, tp, tm_sb, ko_b, kw_b, p->d_perm_b, (int)p->opt_win_maxslide, p->d_col_rec, nb, st)
+                          : column_build_f64(g, ja, tp, tm_sb, ko_b, kw_b, p->d_perm_b, (int)p->opt_win_maxslide, p->d_col_rec, nb, st);
         if (e != 0) return fail(B2N_ECUDA, std::string("column records: ") + cudaGetErrorString((cudaError_t)e));
         CU(cudaStreamSynchronize(st));      // the scratch arrays are freed on return
         p->launches += 3;

@@ -51,13 +51,16 @@ inline bool column_shape(int J, int* FB, int* FC, int* GB, int* GC) {
     return true;
 }
 
+// generic_launch: acc64 = zeroed complex128 scratch grid [nbatch][PK] for the float adjoint's
+// per-cell sums (nullptr: float atomics straight into `out`; ignored by the forward and by f64).
 // each returns 0 or a cudaError_t; *done tells whether the kernel family took the call.
 // Jk: compile-time window width to run (>= every g.J[d]; wider than g.J[d] only with plan-time
 // weights, whose extra taps are zero: aux_kernels.cuh:point_weights_kernel)
 #define B2N_DECLARE(SUF)                                                                          \
     int generic_launch_##SUF(const Geom& g, int cplx_table, const TablePtrs& tabs, const void* tm_s, \
                              const int32_t* perm, bool fwd, const void* in, void* out,           \
-                             const void* phase_s, int nbatch, int sm_count, cudaStream_t st);    \
+                             const void* phase_s, int nbatch, int sm_count, void* acc64,         \
+                             cudaStream_t st);                                                   \
     int tiled_fwd_##SUF(const Geom& g, int Jk, bool cplx, bool tables_equal, const TablePtrs& tabs, const void* tm_s, \
                         const void* wts, const int32_t* pt_ko, const int32_t* pt_kw,             \
                         const int32_t* perm, const int4* items, int64_t n_items,                 \
@@ -74,7 +77,7 @@ inline bool column_shape(int J, int* FB, int* FC, int* GB, int* GC) {
     size_t column_record_bytes_##SUF(int Jk, int64_t M);                                         \
     int column_build_##SUF(const Geom& g, int Jk, const TablePtrs& tabs, const void* tm_s,       \
                            const int32_t* pt_ko, const int32_t* pt_kw, const int32_t* perm,      \
-                           void* records, int nblocks, cudaStream_t st);                         \
+                           int max_slide, void* records, int nblocks, cudaStream_t st);          \
     int window2d_adj_##SUF(const Geom& g, int Jk, bool cplx, const TablePtrs& tabs, const void* tm_s, const void* wts, \
                            const int32_t* pt_ko, const int32_t* pt_kw, const int32_t* perm,      \
                            const void* samples, void* grid, const void* phase_s, int nbatch,     \

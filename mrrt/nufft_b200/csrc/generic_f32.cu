@@ -4,7 +4,7 @@
 namespace b2n {
 int generic_launch_f32(const Geom& g, int cplx_table, const TablePtrs& tabs, const void* tm_s,
                        const int32_t* perm, bool fwd, const void* in, void* out,
-                       const void* phase_s, int nbatch, int sm_count, cudaStream_t st) {
-    return generic_launch_t<float>(g, cplx_table, tabs, tm_s, perm, fwd, in, out, phase_s, nbatch, sm_count, st);
+                       const void* phase_s, int nbatch, int sm_count, void* acc64, cudaStream_t st) {
+    return generic_launch_t<float>(g, cplx_table, tabs, tm_s, perm, fwd, in, out, phase_s, nbatch, sm_count, acc64, st);
 }
 }  // namespace b2n

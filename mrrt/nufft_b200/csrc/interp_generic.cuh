@@ -96,11 +96,20 @@ interp_fwd_generic(Geom g, TablePtrs tabs, const T* __restrict__ tm_s,
     }
 }
 
-template <typename T, int NDIM, bool CT, int JT>
+// TA: type the grid accumulates in.  The float instantiation is launched with TA = double on a
+// scratch grid when the plan can afford one: the products are formed in float exactly as in
+// the reference (template.c:1122-1163), but the per-cell sums no longer depend on the order in
+// which L2 happens to apply the float atomics (measured on the mid-size 3-D test: 6.4e-6 ..
+// 9.7e-6 from the reference between launches with float sums, scripts/diag_generic_noise.py).
+__device__ __forceinline__ float2 to_acc(float2 v, float) { return v; }
+__device__ __forceinline__ double2 to_acc(double2 v, double) { return v; }
+__device__ __forceinline__ double2 to_acc(float2 v, double) { return make_double2((double)v.x, (double)v.y); }
+
+template <typename T, int NDIM, bool CT, int JT, typename TA = T>
 __global__ void __launch_bounds__(128)
 interp_adj_generic(Geom g, TablePtrs tabs, const T* __restrict__ tm_s,
                    const int32_t* __restrict__ perm, const cplx_t<T>* __restrict__ samples,
-                   cplx_t<T>* __restrict__ grid, const cplx_t<T>* __restrict__ phase_s,
+                   cplx_t<TA>* __restrict__ grid, const cplx_t<T>* __restrict__ phase_s,
                    int nbatch) {
     using C = cplx_t<T>;
     using W = typename WeightT<T, CT>::type;
@@ -129,7 +138,7 @@ interp_adj_generic(Geom g, TablePtrs tabs, const T* __restrict__ tm_s,
         C ph = make_c<T>(1, 0);
         if (phase_s != nullptr) ph = phase_s[i];
         for (int b = 0; b < nbatch; b++) {
-            C* __restrict__ gb = grid + (int64_t)b * g.PK;
+            cplx_t<TA>* __restrict__ gb = grid + (int64_t)b * g.PK;
             C f = samples[(int64_t)b * M + src];
             if (phase_s != nullptr) f = cmul_conj(f, ph);
 #pragma unroll(JT > 0 ? JT : 1)
@@ -145,7 +154,7 @@ interp_adj_generic(Geom g, TablePtrs tabs, const T* __restrict__ tm_s,
                     if (NDIM > 2) base += off[NDIM > 2 ? 2 : 0][j3];
 #pragma unroll(JT > 0 ? JT : 1)
                     for (int j1 = 0; j1 < Jd[0]; j1++) {
-                        atomic_add_c(gb + base + off[0][j1], w_mul_conj(w[0][j1], v2));
+                        atomic_add_c(gb + base + off[0][j1], to_acc(w_mul_conj(w[0][j1], v2), (TA)0));
                     }
                 }
             }
@@ -154,14 +163,38 @@ interp_adj_generic(Geom g, TablePtrs tabs, const T* __restrict__ tm_s,
 }
 
 #ifdef B2N_GENERIC_TU
+// out += acc (the double scratch grid of the float adjoint)
+static __global__ void add_acc64_kernel(int64_t n, const double2* __restrict__ acc, float2* __restrict__ out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const double2 a = acc[i];
+        float2 o = out[i];
+        o.x += (float)a.x;
+        o.y += (float)a.y;
+        out[i] = o;
+    }
+}
+
 template <typename T, int NDIM, bool CT, int JT>
 static void launch_generic(const Geom& g, const TablePtrs& tabs, const void* tm_s, const int32_t* perm,
                            bool fwd, const void* in, void* out, const void* phase_s, int nbatch,
-                           int sm_count, cudaStream_t st) {
+                           int sm_count, void* acc64, cudaStream_t st) {
     using C = cplx_t<T>;
     int64_t nb = (g.M + 127) / 128;
     if (nb > (int64_t)sm_count * 32) nb = (int64_t)sm_count * 32;
     const int grid = (int)(nb < 1 ? 1 : nb);
+    if constexpr (sizeof(T) == 4) {
+        if (!fwd && acc64 != nullptr) {
+            // float adjoint with per-cell sums in double (scratch grid, zeroed by the caller)
+            interp_adj_generic<T, NDIM, CT, JT, double><<<grid, 128, 0, st>>>(
+                g, tabs, (const T*)tm_s, perm, (const C*)in, (double2*)acc64, (const C*)phase_s, nbatch);
+            const int64_t n = g.PK * nbatch;
+            int64_t cb = (n + 255) / 256;
+            if (cb > (int64_t)sm_count * 16) cb = (int64_t)sm_count * 16;
+            add_acc64_kernel<<<(int)(cb < 1 ? 1 : cb), 256, 0, st>>>(n, (const double2*)acc64, (float2*)out);
+            return;
+        }
+    }
     if (fwd)
         interp_fwd_generic<T, NDIM, CT, JT><<<grid, 128, 0, st>>>(
             g, tabs, (const T*)tm_s, perm, (const C*)in, (C*)out, (const C*)phase_s, nbatch);
@@ -173,22 +206,22 @@ static void launch_generic(const Geom& g, const TablePtrs& tabs, const void* tm_
 template <typename T, int NDIM, bool CT>
 static void dispatch_generic_J(const Geom& g, const TablePtrs& tabs, const void* tm_s,
                                const int32_t* perm, bool fwd, const void* in, void* out,
-                               const void* phase_s, int nbatch, int sm_count, cudaStream_t st) {
+                               const void* phase_s, int nbatch, int sm_count, void* acc64, cudaStream_t st) {
     int J = g.J[0];
     for (int d = 1; d < g.ndim; d++)
         if (g.J[d] != g.J[0]) J = 0;
     switch (J) {
-        case 4: launch_generic<T, NDIM, CT, 4>(g, tabs, tm_s, perm, fwd, in, out, phase_s, nbatch, sm_count, st); break;
-        case 6: launch_generic<T, NDIM, CT, 6>(g, tabs, tm_s, perm, fwd, in, out, phase_s, nbatch, sm_count, st); break;
-        default: launch_generic<T, NDIM, CT, 0>(g, tabs, tm_s, perm, fwd, in, out, phase_s, nbatch, sm_count, st); break;
+        case 4: launch_generic<T, NDIM, CT, 4>(g, tabs, tm_s, perm, fwd, in, out, phase_s, nbatch, sm_count, acc64, st); break;
+        case 6: launch_generic<T, NDIM, CT, 6>(g, tabs, tm_s, perm, fwd, in, out, phase_s, nbatch, sm_count, acc64, st); break;
+        default: launch_generic<T, NDIM, CT, 0>(g, tabs, tm_s, perm, fwd, in, out, phase_s, nbatch, sm_count, acc64, st); break;
     }
 }
 
 template <typename T>
 static int generic_launch_t(const Geom& g, int cplx_table, const TablePtrs& tabs, const void* tm_s,
                             const int32_t* perm, bool fwd, const void* in, void* out,
-                            const void* phase_s, int nbatch, int sm_count, cudaStream_t st) {
-#define B2N_GO(ND, CTV) dispatch_generic_J<T, ND, CTV>(g, tabs, tm_s, perm, fwd, in, out, phase_s, nbatch, sm_count, st)
+                            const void* phase_s, int nbatch, int sm_count, void* acc64, cudaStream_t st) {
+#define B2N_GO(ND, CTV) dispatch_generic_J<T, ND, CTV>(g, tabs, tm_s, perm, fwd, in, out, phase_s, nbatch, sm_count, acc64, st)
     if (cplx_table) {
         if (g.ndim == 1) B2N_GO(1, true);
         if (g.ndim == 2) B2N_GO(2, true);
