@@ -543,7 +543,7 @@ def run_gpu_arm(args):
     fwd_bytes = grid_cells * 8 + M_local * (3 * 4 + 8)
     tr_adj, tr_fwd, tr_src = measured_traffic() if world == 1 else (None, None, "single-GPU capture only")
     adj_gbs = adj_bytes / (adj_ms * 1e-3) / 1e9 if adj_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "spread_window3d_kernel<float,6> + zero-fill (adjoint gridding)",
+    roofline = {"bound": "hbm", "kernel": "spread_column3d_kernel<float,6> + zero-fill (adjoint gridding)",
                 "achieved": adj_gbs, "peak": peak, "unit": "GB/s", "frac": adj_gbs / peak,
                 "traffic": tr_adj, "traffic_source": tr_src, "peak_source": peak_src,
                 "kernel_ms": adj_ms, "algorithmic_bytes": adj_bytes,

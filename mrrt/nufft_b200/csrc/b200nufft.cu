@@ -76,6 +76,7 @@ struct b2n_plan {
     int cplx_table = 0;
     int device = 0;
     int sm_count = 148;
+    int max_smem = 0;            // opt-in shared memory per block (queried on first use)
     // options
     long opt_chunk = 4096;
     long opt_force_generic = 0;
@@ -153,6 +154,7 @@ struct b2n_plan {
     long opt_pruned_fft = 1;
     long opt_own_fft3 = 1;       // pruned FFT: own axis-3 pass fused with the zero-padding, phase_before and the crop
     Axis3Plan ax3{};             // its radix schedule, and the K3-entry twiddle table (precision dtype)
+    bool ax3_general = false;    // the run-time-schedule kernel can serve K3 (else only the fixed-schedule one)
     int ax3_state = 0;           // 0 = not prepared, 1 = ready, -1 = K3 not supported
     void* d_tw3 = nullptr;
     void* d_work = nullptr;
@@ -1394,10 +1396,13 @@ static int prepare_axis3(b2n_plan* p) {
     const int L = p->g.K[2];
     int max_smem = 0;
     CU(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, p->device));
-    if (!axis3_factor(L, &p->ax3) || Axis3Cfg<T>::smem(L) > (size_t)max_smem || !Axis3Cfg<T>::fits(L)) {
+    const bool fixed = fixed_npass(L) > 0 && fft_axis3_fixed_smem<T>(L) <= (size_t)max_smem && p->opt_own_fft3 != 2;
+    const bool general = axis3_factor(L, &p->ax3) && Axis3Cfg<T>::smem(L) <= (size_t)max_smem && Axis3Cfg<T>::fits(L);
+    if (!fixed && !general) {
         p->ax3_state = -1;
         return B2N_OK;
     }
+    p->ax3_general = general;
     std::vector<T> tw(2 * (size_t)L);
     for (int t = 0; t < L; t++) {
         const double a = -2.0 * M_PI * (double)t / (double)L;
@@ -1418,6 +1423,21 @@ static int exec_fft(cufftHandle h, void* data, int dir) {
     if (sizeof(T) == 4) FFT(cufftExecC2C(h, (cufftComplex*)data, (cufftComplex*)data, dir));
     else FFT(cufftExecZ2Z(h, (cufftDoubleComplex*)data, (cufftDoubleComplex*)data, dir));
     return B2N_OK;
+}
+
+// the fused axis-3 pass: compile-time schedule when K3 has one (own_fft3 = 1), else / with
+// own_fft3 = 2 the run-time radix schedule.  Returns 0 or a cudaError_t.
+template <typename T>
+static int run_axis3(b2n_plan* p, bool inverse, const void* a1, void* data, cudaStream_t st) {
+    if (p->opt_own_fft3 != 2) {
+        if (p->max_smem == 0) cudaDeviceGetAttribute(&p->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, p->device);
+        bool done = false;
+        const int rc = fft_axis3_fixed_launch<T>(p->g, inverse, p->d_tw3, a1, p->d_pb[1], p->d_pb[2], data,
+                                                       p->sm_count, p->max_smem, st, &done);
+        if (rc != 0 || done) return rc;
+    }
+    if (!p->ax3_general) return (int)cudaErrorNotSupported;
+    return fft_axis3_launch<T>(p->ax3, p->g, inverse, p->d_tw3, a1, p->d_pb[1], p->d_pb[2], data, p->sm_count, st);
 }
 
 // forward: in-plane passes on the non-zero planes, then axis 3; inverse: the reverse
@@ -1442,10 +1462,10 @@ static int run_fft(b2n_plan* p, void* data, int nbatch, int dir, cudaStream_t st
             const void* a1 = p->have_pb ? p->d_pb[0] : nullptr;
             if (dir == CUFFT_FORWARD) {
                 if ((rc = exec_fft<T>(h2, data, dir))) return rc;
-                rc = fft_axis3_launch<T>(p->ax3, p->g, false, p->d_tw3, a1, p->d_pb[1], p->d_pb[2], data, p->sm_count, st);
+                rc = run_axis3<T>(p, false, a1, data, st);
                 if (rc != 0) return fail(B2N_ECUDA, "axis-3 FFT launch failed: " + std::string(cudaGetErrorString((cudaError_t)rc)));
             } else {
-                rc = fft_axis3_launch<T>(p->ax3, p->g, true, p->d_tw3, a1, p->d_pb[1], p->d_pb[2], data, p->sm_count, st);
+                rc = run_axis3<T>(p, true, a1, data, st);
                 if (rc != 0) return fail(B2N_ECUDA, "axis-3 FFT launch failed: " + std::string(cudaGetErrorString((cudaError_t)rc)));
                 if ((rc = exec_fft<T>(h2, data, dir))) return rc;
             }
@@ -1788,7 +1808,7 @@ static int axis3_t(b2n_plan* p, void* grid, bool inverse, cudaStream_t st) {
         // the fused pass: planes >= Nd[2] are treated as zero on input (forward) and not
         // written (adjoint); phase_before rides along
         const void* a1 = p->have_pb ? p->d_pb[0] : nullptr;
-        rc = fft_axis3_launch<T>(p->ax3, g, inverse, p->d_tw3, a1, p->d_pb[1], p->d_pb[2], grid, p->sm_count, st);
+        rc = run_axis3<T>(p, inverse, a1, grid, st);
         if (rc != 0) return fail(B2N_ECUDA, "axis-3 FFT launch failed: " + std::string(cudaGetErrorString((cudaError_t)rc)));
         p->launches += 1;
         return B2N_OK;

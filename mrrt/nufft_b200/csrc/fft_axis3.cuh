@@ -71,6 +71,67 @@ __device__ __forceinline__ void dft4(cplx_t<T>& a0, cplx_t<T>& a1, cplx_t<T>& a2
     a3 = csub<T>(d02, id13);
 }
 
+// length-R DFT of v[0..R-1] in place, R in {2, 3, 4, 6, 8}
+template <typename T, bool INV, int R>
+__device__ __forceinline__ void butterfly(cplx_t<T>* v) {
+    using C = cplx_t<T>;
+    if (R == 2) {
+        const C a = v[0];
+        v[0] = cadd<T>(a, v[1]);
+        v[1] = csub<T>(a, v[1]);
+    } else if (R == 3) {
+        // w = exp(-+ 2 pi i / 3) = (-1/2, -+ sqrt(3)/2)
+        const T hs = (T)0.86602540378443864676 * (INV ? (T)1 : (T)-1);
+        const C s12 = cadd<T>(v[1], v[2]), d12 = csub<T>(v[1], v[2]);
+        const C m = make_c<T>(v[0].x - (T)0.5 * s12.x, v[0].y - (T)0.5 * s12.y);
+        const C rr = make_c<T>(-hs * d12.y, hs * d12.x);                // i * hs * d12
+        v[0] = cadd<T>(v[0], s12);
+        v[1] = cadd<T>(m, rr);
+        v[2] = csub<T>(m, rr);
+    } else if (R == 4) {
+        dft4<T, INV>(v[0], v[1], v[2], v[3]);
+    } else if (R == 6) {
+        // two length-3 DFTs (even / odd inputs) + one radix-2 stage with w6^q
+        const T hs = (T)0.86602540378443864676 * (INV ? (T)1 : (T)-1);
+        C e[3], o[3];
+        {
+            const C s12 = cadd<T>(v[2], v[4]), d12 = csub<T>(v[2], v[4]);
+            const C m = make_c<T>(v[0].x - (T)0.5 * s12.x, v[0].y - (T)0.5 * s12.y);
+            const C rr = make_c<T>(-hs * d12.y, hs * d12.x);
+            e[0] = cadd<T>(v[0], s12); e[1] = cadd<T>(m, rr); e[2] = csub<T>(m, rr);
+        }
+        {
+            const C s12 = cadd<T>(v[3], v[5]), d12 = csub<T>(v[3], v[5]);
+            const C m = make_c<T>(v[1].x - (T)0.5 * s12.x, v[1].y - (T)0.5 * s12.y);
+            const C rr = make_c<T>(-hs * d12.y, hs * d12.x);
+            o[0] = cadd<T>(v[1], s12); o[1] = cadd<T>(m, rr); o[2] = csub<T>(m, rr);
+        }
+        // w6 = exp(-+ 2 pi i / 6) = (1/2, -+ sqrt(3)/2), w6^2 = (-1/2, -+ sqrt(3)/2)
+        const C t1 = make_c<T>((T)0.5 * o[1].x - hs * o[1].y, (T)0.5 * o[1].y + hs * o[1].x);
+        const C t2 = make_c<T>((T)-0.5 * o[2].x - hs * o[2].y, (T)-0.5 * o[2].y + hs * o[2].x);
+        v[0] = cadd<T>(e[0], o[0]); v[3] = csub<T>(e[0], o[0]);
+        v[1] = cadd<T>(e[1], t1);   v[4] = csub<T>(e[1], t1);
+        v[2] = cadd<T>(e[2], t2);   v[5] = csub<T>(e[2], t2);
+    } else {                                     // R == 8: two length-4 DFTs + one radix-2 stage
+        dft4<T, INV>(v[0], v[2], v[4], v[6]);
+        dft4<T, INV>(v[1], v[3], v[5], v[7]);
+        // odd half times w8^q, w8 = exp(-+ 2 pi i / 8)
+        const T h = (T)0.70710678118654752440;
+        const C b1 = v[3], b3 = v[7];
+        // w8^1 = (h, -+h), w8^2 = -+i, w8^3 = (-h, -+h)
+        const C t1 = INV ? make_c<T>(h * (b1.x - b1.y), h * (b1.x + b1.y))
+                         : make_c<T>(h * (b1.x + b1.y), h * (b1.y - b1.x));
+        const C t2 = rot90<T, INV>(v[5]);
+        const C t3 = INV ? make_c<T>(-h * (b3.x + b3.y), h * (b3.x - b3.y))
+                         : make_c<T>(h * (b3.y - b3.x), -h * (b3.x + b3.y));
+        const C e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6], o0 = v[1];
+        v[0] = cadd<T>(e0, o0); v[4] = csub<T>(e0, o0);
+        v[1] = cadd<T>(e1, t1); v[5] = csub<T>(e1, t1);
+        v[2] = cadd<T>(e2, t2); v[6] = csub<T>(e2, t2);
+        v[3] = cadd<T>(e3, t3); v[7] = csub<T>(e3, t3);
+    }
+}
+
 // One Stockham pass of radix R over the CTA's COLS columns: butterfly j reads rows
 // j + r*L/R, multiplies by the twiddles W^(r*k*L/(Ns*R)), k = j mod Ns, and writes rows
 // (j div Ns)*Ns*R + k + r*Ns.
@@ -93,61 +154,7 @@ __device__ __forceinline__ void axis3_pass(const cplx_t<T>* __restrict__ in, cpl
 #pragma unroll
             for (int r = 1; r < R; r++) v[r] = cmulc<T>(v[r], twS[r * k * tstep]);
         }
-        if (R == 2) {
-            const C a = v[0];
-            v[0] = cadd<T>(a, v[1]);
-            v[1] = csub<T>(a, v[1]);
-        } else if (R == 3) {
-            // w = exp(-+ 2 pi i / 3) = (-1/2, -+ sqrt(3)/2)
-            const T hs = (T)0.86602540378443864676 * (INV ? (T)1 : (T)-1);
-            const C s12 = cadd<T>(v[1], v[2]), d12 = csub<T>(v[1], v[2]);
-            const C m = make_c<T>(v[0].x - (T)0.5 * s12.x, v[0].y - (T)0.5 * s12.y);
-            const C rr = make_c<T>(-hs * d12.y, hs * d12.x);                // i * hs * d12
-            v[0] = cadd<T>(v[0], s12);
-            v[1] = cadd<T>(m, rr);
-            v[2] = csub<T>(m, rr);
-        } else if (R == 4) {
-            dft4<T, INV>(v[0], v[1], v[2], v[3]);
-        } else if (R == 6) {
-            // two length-3 DFTs (even / odd inputs) + one radix-2 stage with w6^q
-            const T hs = (T)0.86602540378443864676 * (INV ? (T)1 : (T)-1);
-            C e[3], o[3];
-            {
-                const C s12 = cadd<T>(v[2], v[4]), d12 = csub<T>(v[2], v[4]);
-                const C m = make_c<T>(v[0].x - (T)0.5 * s12.x, v[0].y - (T)0.5 * s12.y);
-                const C rr = make_c<T>(-hs * d12.y, hs * d12.x);
-                e[0] = cadd<T>(v[0], s12); e[1] = cadd<T>(m, rr); e[2] = csub<T>(m, rr);
-            }
-            {
-                const C s12 = cadd<T>(v[3], v[5]), d12 = csub<T>(v[3], v[5]);
-                const C m = make_c<T>(v[1].x - (T)0.5 * s12.x, v[1].y - (T)0.5 * s12.y);
-                const C rr = make_c<T>(-hs * d12.y, hs * d12.x);
-                o[0] = cadd<T>(v[1], s12); o[1] = cadd<T>(m, rr); o[2] = csub<T>(m, rr);
-            }
-            // w6 = exp(-+ 2 pi i / 6) = (1/2, -+ sqrt(3)/2), w6^2 = (-1/2, -+ sqrt(3)/2)
-            const C t1 = make_c<T>((T)0.5 * o[1].x - hs * o[1].y, (T)0.5 * o[1].y + hs * o[1].x);
-            const C t2 = make_c<T>((T)-0.5 * o[2].x - hs * o[2].y, (T)-0.5 * o[2].y + hs * o[2].x);
-            v[0] = cadd<T>(e[0], o[0]); v[3] = csub<T>(e[0], o[0]);
-            v[1] = cadd<T>(e[1], t1);   v[4] = csub<T>(e[1], t1);
-            v[2] = cadd<T>(e[2], t2);   v[5] = csub<T>(e[2], t2);
-        } else {                                     // R == 8: two length-4 DFTs + one radix-2 stage
-            dft4<T, INV>(v[0], v[2], v[4], v[6]);
-            dft4<T, INV>(v[1], v[3], v[5], v[7]);
-            // odd half times w8^q, w8 = exp(-+ 2 pi i / 8)
-            const T h = (T)0.70710678118654752440;
-            const C b1 = v[3], b3 = v[7];
-            // w8^1 = (h, -+h), w8^2 = -+i, w8^3 = (-h, -+h)
-            const C t1 = INV ? make_c<T>(h * (b1.x - b1.y), h * (b1.x + b1.y))
-                             : make_c<T>(h * (b1.x + b1.y), h * (b1.y - b1.x));
-            const C t2 = rot90<T, INV>(v[5]);
-            const C t3 = INV ? make_c<T>(-h * (b3.x + b3.y), h * (b3.x - b3.y))
-                             : make_c<T>(h * (b3.y - b3.x), -h * (b3.x + b3.y));
-            const C e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6], o0 = v[1];
-            v[0] = cadd<T>(e0, o0); v[4] = csub<T>(e0, o0);
-            v[1] = cadd<T>(e1, t1); v[5] = csub<T>(e1, t1);
-            v[2] = cadd<T>(e2, t2); v[6] = csub<T>(e2, t2);
-            v[3] = cadd<T>(e3, t3); v[7] = csub<T>(e3, t3);
-        }
+        butterfly<T, INV, R>(v);
 #pragma unroll
         for (int r = 0; r < R; r++) out[(j0 + r * Ns) * COLS + c] = v[r];
     }
@@ -261,6 +268,257 @@ fft_axis3_kernel(Axis3Plan ap, int64_t plane, int K1, int NZ, int64_t ntiles,
             }
         }
         __syncthreads();                             // the buffers are rewritten by the next tile
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fixed-schedule variant for the transform lengths oversampled MRI grids actually have
+// (K = 1.5 N or 2 N with N a power of two).  Same data flow as fft_axis3_kernel, but the length
+// and the radix schedule are template parameters, so every index split, twiddle stride and
+// loop bound of the passes is a compile-time constant (the run-time schedule spent 150 warp
+// instructions per output value, two thirds of them index arithmetic and sincosf), and
+// phase_before costs one accurate sincos per COLUMN and tile instead of one per value:
+//     exp(i * fl(a12 + a3[k])) = exp(i a12) * exp(i a3[k]) * exp(-i err),
+// with err the rounding error of the float sum, recovered exactly by TwoSum (|err| <= ulp/2 of
+// an angle of a few thousand radians, so exp(-i err) = 1 - err^2/2 - i err to 1e-13), and
+// exp(i a3[k]) from a table filled once per CTA.  The angle that is exponentiated is still the
+// reference's float32 sum (_nufft.py:703-715); only the evaluation is factored.
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ constexpr int fixed_npass(int L) {
+    return (L == 128 || L == 192 || L == 256 || L == 384 || L == 512) ? 3 : ((L == 768 || L == 1024) ? 4 : 0);
+}
+__host__ __device__ constexpr int fixed_radix(int L, int p) {
+    // 128 = 8 4 4, 192 = 8 8 3, 256 = 8 8 4, 384 = 8 8 6, 512 = 8 8 8, 768 = 8 8 4 3, 1024 = 8 8 4 4
+    if (p < 2) return (L == 128 && p == 1) ? 4 : 8;
+    if (p == 2) return L == 192 ? 3 : (L == 384 ? 6 : (L == 512 ? 8 : 4));
+    return L == 768 ? 3 : 4;
+}
+__host__ __device__ constexpr int fixed_ns(int L, int p) {          // product of the radices before pass p
+    int ns = 1;
+    for (int q = 0; q < p; q++) ns *= fixed_radix(L, q);
+    return ns;
+}
+
+template <typename T, bool INV, int L, int COLS, int SLOTS, int P>
+__device__ __forceinline__ void fixed_pass(const cplx_t<T>* __restrict__ in, cplx_t<T>* __restrict__ out,
+                                           const cplx_t<T>* __restrict__ twS, int slot, int c) {
+    using C = cplx_t<T>;
+    constexpr int R = fixed_radix(L, P);
+    constexpr int Ns = fixed_ns(L, P);
+    constexpr int Tn = L / R;
+    constexpr int tstep = Tn / Ns;
+    constexpr int ROUNDS = (Tn + SLOTS - 1) / SLOTS;
+#pragma unroll
+    for (int i = 0; i < ROUNDS; i++) {
+        const int j = slot + i * SLOTS;
+        if (Tn % SLOTS != 0 && j >= Tn) break;
+        const int k = j % Ns;
+        const int j0 = j * R - k * (R - 1);          // (j div Ns) * Ns * R + k
+        C v[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) v[r] = in[(j + r * Tn) * COLS + c];
+        if (Ns > 1) {
+#pragma unroll
+            for (int r = 1; r < R; r++) v[r] = cmulc<T>(v[r], twS[r * k * tstep]);
+        }
+        butterfly<T, INV, R>(v);
+#pragma unroll
+        for (int r = 0; r < R; r++) out[(j0 + r * Ns) * COLS + c] = v[r];
+    }
+}
+
+// v * exp(+-i * fl(a12 + a3k)) given e12 = exp(i a12) and e3k = exp(i a3k) (see above)
+template <typename T, bool CONJ>
+__device__ __forceinline__ cplx_t<T> phase_mul(cplx_t<T> v, T a12, cplx_t<T> e12, T a3k, cplx_t<T> e3k) {
+    const T s = a12 + a3k;
+    const T bb = s - a12;
+    const T err = (a12 - (s - bb)) + (a3k - bb);     // a12 + a3k = s + err exactly
+    const T d = -err;
+    const T h = (T)1 - (T)0.5 * d * d;
+    const cplx_t<T> c0 = cmulc<T>(e12, e3k);
+    const T cr = c0.x * h - d * c0.y;
+    T ci = c0.y * h + d * c0.x;
+    if (CONJ) ci = -ci;
+    return make_c<T>(v.x * cr - v.y * ci, v.x * ci + v.y * cr);
+}
+
+template <typename T, bool INV, int L, int COLS, int NT>
+__global__ void __launch_bounds__(NT)
+fft_axis3_fixed_kernel(int64_t plane, int K1, int NZ, int64_t ntiles, const cplx_t<T>* __restrict__ tw,
+                       const T* __restrict__ a1, const T* __restrict__ a2, const T* __restrict__ a3,
+                       cplx_t<T>* __restrict__ data) {
+    using C = cplx_t<T>;
+    constexpr int NP = fixed_npass(L);
+    constexpr int SLOTS = NT / COLS;                 // butterflies in flight per pass round = rows per load round
+    constexpr int PF = (L + SLOTS - 1) / SLOTS;      // values per thread and tile
+    extern __shared__ __align__(16) unsigned char fft3_smem[];
+    C* bufA = (C*)fft3_smem;
+    C* bufB = bufA + L * COLS;
+    C* twS = bufB + L * COLS;
+    C* e3S = twS + L;
+    T* a3S = (T*)(e3S + L);
+    const int tid = threadIdx.x;
+    const bool phase = a1 != nullptr;
+    for (int e = tid; e < L; e += NT) {
+        C w = tw[e];
+        if (INV) w.y = -w.y;
+        twS[e] = w;
+        if (phase) {
+            const T a = a3[e];
+            T sn, co;
+            sincos_t(a, &sn, &co);
+            a3S[e] = a;
+            e3S[e] = make_c<T>(co, sn);
+        }
+    }
+    __syncthreads();
+    const int c = tid % COLS;
+    const int r0 = tid / COLS;
+    const int rows_in = INV ? L : NZ;                // forward: only the non-zero planes are read
+    const int rows_out = INV ? NZ : L;               // adjoint: only the planes that survive the crop
+    C pf[PF];
+    int64_t tile = blockIdx.x;
+    const int64_t rstride = (int64_t)SLOTS * plane;  // elements between the rows of two load rounds
+    if (tile < ntiles) {
+        const int64_t col = tile * COLS + c;
+        const C* src = data + ((int64_t)r0 * plane + col);
+#pragma unroll
+        for (int i = 0; i < PF; i++, src += rstride) {
+            const int k3 = r0 + i * SLOTS;
+            pf[i] = make_c<T>(0, 0);
+            if (k3 < rows_in && col < plane) pf[i] = *src;
+        }
+    }
+    for (; tile < ntiles; tile += gridDim.x) {
+        const int64_t col = tile * COLS + c;
+        const bool col_ok = col < plane;
+        T a12 = (T)0;
+        C e12 = make_c<T>(1, 0);
+        if (phase && col_ok) {
+            const int k1 = (int)(col % K1), k2 = (int)(col / K1);
+            a12 = a1[k1] + a2[k2];                   // the reference's summation order
+            T sn, co;
+            sincos_t(a12, &sn, &co);
+            e12 = make_c<T>(co, sn);
+        }
+        // ---- registers -> shared memory (the rest of a forward column is zero padding)
+#pragma unroll
+        for (int i = 0; i < PF; i++) {
+            const int k3 = r0 + i * SLOTS;
+            if (L % SLOTS == 0 || k3 < L) {
+                C v = pf[i];
+                if (INV && phase) v = phase_mul<T, true>(v, a12, e12, a3S[k3], e3S[k3]);
+                bufA[k3 * COLS + c] = v;
+            }
+        }
+        __syncthreads();
+        // ---- next tile's loads go out now; they land while this tile is transformed
+        {
+            const int64_t nt = tile + gridDim.x;
+            const int64_t ncol = nt * COLS + c;
+            if (nt < ntiles) {
+                const C* src = data + ((int64_t)r0 * plane + ncol);
+#pragma unroll
+                for (int i = 0; i < PF; i++, src += rstride) {
+                    const int k3 = r0 + i * SLOTS;
+                    pf[i] = make_c<T>(0, 0);
+                    if (k3 < rows_in && ncol < plane) pf[i] = *src;
+                }
+            }
+        }
+        // ---- Stockham passes, schedule known at compile time
+        fixed_pass<T, INV, L, COLS, SLOTS, 0>(bufA, bufB, twS, r0, c);
+        __syncthreads();
+        fixed_pass<T, INV, L, COLS, SLOTS, 1>(bufB, bufA, twS, r0, c);
+        __syncthreads();
+        fixed_pass<T, INV, L, COLS, SLOTS, 2>(bufA, bufB, twS, r0, c);
+        __syncthreads();
+        if constexpr (NP == 4) {
+            fixed_pass<T, INV, L, COLS, SLOTS, 3>(bufB, bufA, twS, r0, c);
+            __syncthreads();
+        }
+        const C* res = NP == 4 ? bufA : bufB;
+        // ---- store
+        if (col_ok) {
+            C* dst = data + ((int64_t)r0 * plane + col);
+#pragma unroll 4
+            for (int k3 = r0; k3 < rows_out; k3 += SLOTS, dst += rstride) {
+                C v = res[k3 * COLS + c];
+                if (!INV && phase) v = phase_mul<T, false>(v, a12, e12, a3S[k3], e3S[k3]);
+                *dst = v;
+            }
+        }
+        __syncthreads();                             // the buffers are rewritten by the next tile
+    }
+}
+
+// Tile width: 128-byte runs per global access (16 float / 8 double columns, 256 threads: measured
+// 0.25 ms per pass on the bench grid against 0.29 ms with 64-byte runs and 0.36 ms with the
+// run-time schedule), 64-byte runs where two 128-byte buffers would not fit in shared memory
+template <typename T, int L> struct Axis3FixedCfg {
+    static constexpr size_t smem_for(int cols) {
+        return (size_t)(2 * L * cols + 2 * L) * 2 * sizeof(T) + (size_t)L * sizeof(T);
+    }
+    static constexpr bool WIDE = smem_for(128 / (2 * (int)sizeof(T))) <= 200 * 1024;
+    static constexpr int COLS = (WIDE ? 128 : 64) / (2 * (int)sizeof(T));
+    static constexpr int NT = (L >= 768 ? 256 : 128) * (WIDE ? 2 : 1);   // <= 24 values per thread
+    static constexpr size_t smem = smem_for(COLS);
+};
+
+template <typename T, bool INV, int L>
+static int fft_axis3_fixed_launch_L(const Geom& g, const void* tw, const void* a1, const void* a2,
+                                    const void* a3, void* data, int sm_count, int max_smem, cudaStream_t st,
+                                    bool* done) {
+    using C = cplx_t<T>;
+    constexpr int COLS = Axis3FixedCfg<T, L>::COLS;
+    constexpr int NT = Axis3FixedCfg<T, L>::NT;
+    const size_t smem = Axis3FixedCfg<T, L>::smem;
+    if (smem > (size_t)max_smem) return 0;
+    const int64_t plane = (int64_t)g.K[0] * g.K[1];
+    const int64_t ntiles = (plane + COLS - 1) / COLS;
+    auto k = fft_axis3_fixed_kernel<T, INV, L, COLS, NT>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    int per_sm = 1;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, NT, smem);
+    if (e != cudaSuccess) return (int)e;
+    int64_t nb = (int64_t)sm_count * (per_sm < 1 ? 1 : per_sm);      // persistent: resident CTAs only
+    if (nb > ntiles) nb = ntiles;
+    k<<<(unsigned)nb, NT, smem, st>>>(plane, g.K[0], g.N[2], ntiles, (const C*)tw, (const T*)a1,
+                                      (const T*)a2, (const T*)a3, (C*)data);
+    *done = true;
+    return (int)cudaGetLastError();
+}
+
+// returns 0 or a cudaError_t; *done = false when K3 has no fixed schedule (the caller then runs
+// fft_axis3_launch)
+template <typename T>
+static int fft_axis3_fixed_launch(const Geom& g, bool inverse, const void* tw, const void* a1, const void* a2,
+                                  const void* a3, void* data, int sm_count, int max_smem, cudaStream_t st,
+                                  bool* done) {
+    *done = false;
+#define B2N_AX3(LL)                                                                                          \
+    case LL:                                                                                                 \
+        return inverse ? fft_axis3_fixed_launch_L<T, true, LL>(g, tw, a1, a2, a3, data, sm_count, max_smem, st, done) \
+                       : fft_axis3_fixed_launch_L<T, false, LL>(g, tw, a1, a2, a3, data, sm_count, max_smem, st, done);
+    switch (g.K[2]) {
+        B2N_AX3(128) B2N_AX3(192) B2N_AX3(256) B2N_AX3(384) B2N_AX3(512) B2N_AX3(768) B2N_AX3(1024)
+        default: return 0;
+    }
+#undef B2N_AX3
+}
+
+// shared memory the fixed-schedule kernel needs for length L (0: no fixed schedule)
+template <typename T> static size_t fft_axis3_fixed_smem(int L) {
+    switch (L) {
+        case 128: return Axis3FixedCfg<T, 128>::smem;
+        case 192: return Axis3FixedCfg<T, 192>::smem;
+        case 256: return Axis3FixedCfg<T, 256>::smem;
+        case 384: return Axis3FixedCfg<T, 384>::smem;
+        case 512: return Axis3FixedCfg<T, 512>::smem;
+        case 768: return Axis3FixedCfg<T, 768>::smem;
+        case 1024: return Axis3FixedCfg<T, 1024>::smem;
+        default: return 0;
     }
 }
 

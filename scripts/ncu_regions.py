@@ -39,7 +39,11 @@ for i, h in enumerate(hdr):
         out.append("| %s | %s | %s |" % (h, vals[i], units[i]))
 
 src = page("source")
-shdr, data = src[1], src[2:]
+shdr, data = src[1], []
+for r in src[2:]:           # first kernel of the report only
+    if len(r) < len(shdr):
+        break
+    data.append(r)
 ia, isrc = shdr.index("Address"), shdr.index("Source")
 ist, iex = shdr.index("Warp Stall Sampling (All Samples)"), shdr.index("Instructions Executed")
 tot = sum(int(r[iex]) for r in data)

@@ -618,6 +618,37 @@ def test_own_axis3_fft_vs_oracle(precision, Kd):
 
 
 @pytest.mark.parametrize("precision", ["single", "double"])
+@pytest.mark.parametrize("K3,N3", [(128, 64), (192, 128), (256, 128), (384, 256), (512, 300), (768, 512),
+                                   (1024, 512)])
+def test_fixed_schedule_axis3_fft_vs_oracle(K3, N3, precision):
+    """The compile-time-schedule axis-3 kernel (fft_axis3_fixed_kernel: every length it is built
+    for, 3- and 4-pass schedules, zero padding, phase_before factored as exp(i a12) exp(i a3)
+    exp(-i err), cropped store) vs the oracle, vs cuFFT + the phase kernel (own_fft3 = 0) and vs
+    the run-time-schedule kernel (own_fft3 = 2)."""
+    from oracle import nufft_oracle as orc
+    from mrrt.nufft_b200 import NufftBase
+
+    Nd, Kd = (12, 10, N3), (20, 16, K3)
+    rs = np.random.RandomState(K3)
+    rdt = np.float32 if precision == "single" else np.float64
+    om = ((rs.rand(3000, 3) * 2 - 1) * np.pi).astype(rdt)
+    kw = dict(Nd=Nd, omega=om, Jd=4, Kd=Kd, precision=precision, n_shift=(1, 0, 5))
+    A = NufftBase(options={"own_fft3": 1}, **kw)
+    assert A.option("axis3_fused") == 1
+    O = orc.OracleNufft(**kw)
+    x = (rs.standard_normal(Nd) + 1j * rs.standard_normal(Nd)).astype(A._cplx_dtype)
+    tol = TOL[precision]
+    yo, ya = O.fft(x), A.fft(x)
+    assert rel_l2(ya, yo) <= tol
+    xo, xa = O.adj(yo), A.adj(yo)
+    assert rel_l2(xa, xo) <= tol
+    for other in (0, 2):
+        B = NufftBase(options={"own_fft3": other}, **kw)
+        assert rel_l2(ya, B.fft(x)) <= tol / 4
+        assert rel_l2(xa, B.adj(yo)) <= tol / 4
+
+
+@pytest.mark.parametrize("precision", ["single", "double"])
 @pytest.mark.parametrize("J", [5, 7, 8])
 def test_3d_window_kernels_other_J(J, precision):
     """3-D register-window adjoint / tiled forward at the kernel sizes the golden cases do not
