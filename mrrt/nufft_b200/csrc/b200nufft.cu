@@ -157,6 +157,10 @@ struct b2n_plan {
     bool ax3_general = false;    // the run-time-schedule kernel can serve K3 (else only the fixed-schedule one)
     int ax3_state = 0;           // 0 = not prepared, 1 = ready, -1 = K3 not supported
     void* d_tw3 = nullptr;
+    long opt_own_fft12 = 1;      // own in-plane passes with the scale/pad and crop/scale fused (needs own_fft3 = 1)
+    int inplane_state = 0;       // 0 = not prepared, 1 = ready, -1 = not available for this grid
+    void* d_tw12[2] = {nullptr, nullptr};   // twiddle tables of K1, K2 (may alias d_tw3 / each other)
+    bool tw12_owned[2] = {false, false};
     void* d_work = nullptr;
     void* d_acc64 = nullptr;     // complex128 scratch grid of the float one-RED-per-tap adjoint
     size_t acc64_bytes = 0;
@@ -362,6 +366,7 @@ extern "C" int b2n_plan_destroy(b2n_plan* p) {
     for (auto& kv : p->fft_planes) cufftDestroy(kv.second);
     if (p->fft_ax3_ready) cufftDestroy(p->fft_ax3);
     dev_free(p, p->d_tw3);
+    for (int d = 0; d < 2; d++) if (p->tw12_owned[d]) dev_free(p, p->d_tw12[d]);
     free_points(p);
     for (int d = 0; d < 3; d++) {
         bool dup = false;
@@ -428,6 +433,8 @@ extern "C" int b2n_plan_set_option(b2n_plan* p, const char* name, long value) {
         p->opt_fwd_pitch = value;
     } else if (n == "pruned_fft") {
         p->opt_pruned_fft = value;
+    } else if (n == "own_fft12") {
+        p->opt_own_fft12 = value;
     } else if (n == "own_fft3") {
         p->opt_own_fft3 = value;
     } else if (n == "fwd_pair") {
@@ -487,6 +494,8 @@ extern "C" long b2n_plan_get_option(b2n_plan* p, const char* name) {
     if (n == "n_items") return (long)p->n_items;
     if (n == "n_slots") return (long)p->n_slots;
     if (n == "own_fft3") return (long)p->opt_own_fft3;
+    if (n == "own_fft12") return (long)p->opt_own_fft12;
+    if (n == "inplane_own") return p->inplane_state == 1 ? 1 : 0;
     if (n == "pruned_fft") return (long)p->opt_pruned_fft;
     if (n == "win_facew") return (long)p->opt_win_facew;
     if (n == "win_maxslide") return (long)p->opt_win_maxslide;
@@ -1396,7 +1405,7 @@ static int prepare_axis3(b2n_plan* p) {
     const int L = p->g.K[2];
     int max_smem = 0;
     CU(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, p->device));
-    const bool fixed = fixed_npass(L) > 0 && fft_axis3_fixed_smem<T>(L) <= (size_t)max_smem && p->opt_own_fft3 != 2;
+    const bool fixed = fixed_npass(L) > 0 && fft_lines_smem<T, 0>(L) <= (size_t)max_smem && p->opt_own_fft3 != 2;
     const bool general = axis3_factor(L, &p->ax3) && Axis3Cfg<T>::smem(L) <= (size_t)max_smem && Axis3Cfg<T>::fits(L);
     if (!fixed && !general) {
         p->ax3_state = -1;
@@ -1431,9 +1440,21 @@ template <typename T>
 static int run_axis3(b2n_plan* p, bool inverse, const void* a1, void* data, cudaStream_t st) {
     if (p->opt_own_fft3 != 2) {
         if (p->max_smem == 0) cudaDeviceGetAttribute(&p->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, p->device);
+        const Geom& g = p->g;
+        LineArgs<T> la{};
+        la.data = (cplx_t<T>*)data;
+        la.tw = (const cplx_t<T>*)p->d_tw3;
+        la.nz = g.N[2];
+        la.ntiles = 1;                               // one outer block: the whole grid
+        la.row_stride = (int64_t)g.K[0] * g.K[1];
+        la.outer_stride = 0;
+        la.inner_extent = la.row_stride;
+        la.a1 = (const T*)a1;
+        la.a2 = (const T*)p->d_pb[1];
+        la.a3 = (const T*)p->d_pb[2];
+        la.K1 = g.K[0];
         bool done = false;
-        const int rc = fft_axis3_fixed_launch<T>(p->g, inverse, p->d_tw3, a1, p->d_pb[1], p->d_pb[2], data,
-                                                       p->sm_count, p->max_smem, st, &done);
+        const int rc = fft_lines_launch<T, 0>(g.K[2], inverse, la, p->sm_count, p->max_smem, st, &done);
         if (rc != 0 || done) return rc;
     }
     if (!p->ax3_general) return (int)cudaErrorNotSupported;
@@ -1446,6 +1467,84 @@ static bool axis3_fused(b2n_plan* p, int nbatch) {
     if (!p->opt_own_fft3 || !pruned_ok(p, nbatch)) return false;
     if (prepare_axis3<T>(p) != B2N_OK) return false;
     return p->ax3_state == 1;
+}
+
+// Own in-plane passes (option own_fft12, default on): axis 1 with the scale / zero-pad (forward)
+// or crop / scale (adjoint) fused, axis 2 on the N2 non-zero rows only -- instead of a scale/pad
+// sweep + cuFFT's two passes over the zero-padded planes.  Needs the fixed-schedule kernel for
+// K1 and K2 and the fused axis-3 pass; one volume, no coil maps.
+template <typename T>
+static bool inplane_own(b2n_plan* p, int nbatch) {
+    if (!p->opt_own_fft12 || p->opt_own_fft3 == 2 || !axis3_fused<T>(p, nbatch)) return false;
+    if (p->inplane_state != 0) return p->inplane_state == 1;
+    p->inplane_state = -1;
+    const Geom& g = p->g;
+    if (p->max_smem == 0) cudaDeviceGetAttribute(&p->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, p->device);
+    const size_t s1 = fft_lines_smem<T, 1>(g.K[0]), s2 = fft_lines_smem<T, 0>(g.K[1]);
+    if (s1 == 0 || s2 == 0 || s1 > (size_t)p->max_smem || s2 > (size_t)p->max_smem) return false;
+    if (fft_lines_smem<T, 0>(g.K[2]) == 0) return false;      // axis 3 on the run-time schedule: keep cuFFT in-plane
+    for (int d = 0; d < 2; d++) {
+        const int L = g.K[d];
+        if (L == g.K[2]) { p->d_tw12[d] = p->d_tw3; continue; }
+        if (d == 1 && L == g.K[0]) { p->d_tw12[1] = p->d_tw12[0]; continue; }
+        std::vector<T> tw(2 * (size_t)L);
+        for (int t = 0; t < L; t++) {
+            const double a = -2.0 * M_PI * (double)t / (double)L;
+            tw[2 * t] = (T)std::cos(a);
+            tw[2 * t + 1] = (T)std::sin(a);
+        }
+        void* q = nullptr;
+        if (dev_alloc(p, &q, sizeof(T) * 2 * (size_t)L) != B2N_OK) return false;
+        if (cudaMemcpy(q, tw.data(), sizeof(T) * 2 * (size_t)L, cudaMemcpyHostToDevice) != cudaSuccess) return false;
+        p->d_tw12[d] = q;
+        p->tw12_owned[d] = true;
+    }
+    p->inplane_state = 1;
+    return true;
+}
+
+// the two in-plane passes; returns 0 or a cudaError_t
+template <typename T>
+static int run_inplane(b2n_plan* p, bool inverse, const void* image_in, void* image_out, void* grid,
+                       cudaStream_t st) {
+    const Geom& g = p->g;
+    LineArgs<T> rows{};
+    rows.data = (cplx_t<T>*)grid;
+    rows.tw = (const cplx_t<T>*)p->d_tw12[0];
+    rows.image = inverse ? (cplx_t<T>*)image_out : (cplx_t<T>*)const_cast<void*>(image_in);
+    rows.NL2 = g.N[1];
+    rows.K2 = g.K[1];
+    rows.N1 = g.N[0];
+    rows.nlines = (int64_t)g.N[1] * g.N[2];
+    rows.sn1 = p->d_sn[0];
+    rows.sn2 = p->d_sn[1];
+    rows.sn3 = p->d_sn[2];
+    const double sc = inverse ? p->adj_scale : p->fwd_scale;
+    rows.scale = (T)sc;
+    rows.apply_scale = sc != 1.0;
+    LineArgs<T> cols{};
+    cols.data = (cplx_t<T>*)grid;
+    cols.tw = (const cplx_t<T>*)p->d_tw12[1];
+    cols.nz = g.N[1];
+    cols.ntiles = g.N[2];                            // outer blocks: the N3 non-zero planes
+    cols.row_stride = g.K[0];
+    cols.outer_stride = (int64_t)g.K[0] * g.K[1];
+    cols.inner_extent = g.K[0];
+    bool done = false;
+    int rc;
+    if (!inverse) {
+        rc = fft_lines_launch<T, 1>(g.K[0], false, rows, p->sm_count, p->max_smem, st, &done);
+        if (rc != 0 || !done) return rc ? rc : (int)cudaErrorNotSupported;
+        rc = fft_lines_launch<T, 0>(g.K[1], false, cols, p->sm_count, p->max_smem, st, &done);
+        if (rc != 0 || !done) return rc ? rc : (int)cudaErrorNotSupported;
+    } else {
+        rc = fft_lines_launch<T, 0>(g.K[1], true, cols, p->sm_count, p->max_smem, st, &done);
+        if (rc != 0 || !done) return rc ? rc : (int)cudaErrorNotSupported;
+        rc = fft_lines_launch<T, 1>(g.K[0], true, rows, p->sm_count, p->max_smem, st, &done);
+        if (rc != 0 || !done) return rc ? rc : (int)cudaErrorNotSupported;
+    }
+    p->launches += 2;
+    return 0;
 }
 
 template <typename T>
@@ -1522,6 +1621,14 @@ static int grid_fwd_t(b2n_plan* p, const void* image, void* grid, int nbatch, cu
     AxisPtrs ax = axis_ptrs(p);
     C* work = (C*)grid;
     constexpr int VEC = 32 / (int)sizeof(C);   // 32 bytes of grid per thread
+    if (smaps == nullptr && inplane_own<T>(p, nbatch)) {
+        // scale + zero-pad + axis 1, axis 2 on the non-zero rows, axis 3 + phase_before: three own passes
+        rc = run_inplane<T>(p, false, image, nullptr, work, st);
+        if (rc == 0) rc = run_axis3<T>(p, false, p->have_pb ? p->d_pb[0] : nullptr, work, st);
+        if (rc != 0) return fail(B2N_ECUDA, "own FFT pass failed: " + std::string(cudaGetErrorString((cudaError_t)rc)));
+        p->launches += 1;
+        return B2N_OK;
+    }
     if (smaps != nullptr)
         pre_scale_pad_kernel<T, VEC, true><<<grid_for(g.PK * nbatch / VEC + 1, 256, p->sm_count, 32), 256, 0, st>>>(
             g, ax, (T)p->fwd_scale, p->fwd_scale != 1.0, (const C*)image, work, nbatch, (const C*)smaps);
@@ -1550,6 +1657,13 @@ static int grid_adj_t(b2n_plan* p, void* grid, void* image, int nbatch, cudaStre
     int rc;
     AxisPtrs ax = axis_ptrs(p);
     C* work = (C*)grid;
+    if (smaps == nullptr && inplane_own<T>(p, nbatch)) {
+        rc = run_axis3<T>(p, true, p->have_pb ? p->d_pb[0] : nullptr, work, st);
+        if (rc == 0) rc = run_inplane<T>(p, true, nullptr, image, work, st);
+        if (rc != 0) return fail(B2N_ECUDA, "own FFT pass failed: " + std::string(cudaGetErrorString((cudaError_t)rc)));
+        p->launches += 1;
+        return B2N_OK;
+    }
     if (p->have_pb && !axis3_fused<T>(p, nbatch)) {
         constexpr int VEC = 32 / (int)sizeof(C);
         phase_before_kernel<T, VEC><<<grid_for(g.PK * nbatch / VEC + 1, 256, p->sm_count, 32), 256, 0, st>>>(

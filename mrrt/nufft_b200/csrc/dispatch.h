@@ -39,6 +39,33 @@ struct WindowOpts {
     int facew = 0;           // 0 scalar staging records, 1 face-weight staging, 2 ... at 5 CTAs / SM
 };
 
+// run-time radix schedule of the general own axis-3 FFT pass (fft_axis3.cuh)
+struct Axis3Plan {
+    int L;            // transform length K3
+    int npass;
+    int radix[12];
+};
+
+// radices 8.., 4.., 2.., 3.. with one (2, 3) pair merged into a radix-6 pass (384 = 8 * 8 * 6:
+// three passes instead of four); returns false when L has another prime factor
+static inline bool axis3_factor(int L, Axis3Plan* ap) {
+    ap->L = L;
+    ap->npass = 0;
+    if (L < 2) return false;
+    int n2 = 0, n3 = 0;
+    while (L % 8 == 0) { ap->radix[ap->npass++] = 8; L /= 8; }
+    while (L % 4 == 0) { ap->radix[ap->npass++] = 4; L /= 4; }
+    while (L % 2 == 0) { n2++; L /= 2; }
+    while (L % 3 == 0) { n3++; L /= 3; }
+    if (L != 1) return false;
+    const bool six = n2 > 0 && n3 > 0;
+    if (six) { n2--; n3--; }
+    while (n2-- > 0 && ap->npass < 12) ap->radix[ap->npass++] = 2;
+    while (n3-- > 0 && ap->npass < 12) ap->radix[ap->npass++] = 3;
+    if (six && ap->npass < 12) ap->radix[ap->npass++] = 6;
+    return ap->npass <= 11;
+}
+
 // Face of the column-group adjoint kernel (spread_column.cuh: ColumnShape<J>) for window width J
 // in 4..8: FB x FC grid cells shared by the windows of GB x GC neighbouring grid columns.  The
 // plan builds its column sort order from GB, GC and checks that the grid is as large as the face.

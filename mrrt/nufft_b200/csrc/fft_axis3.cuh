@@ -18,34 +18,9 @@
 #pragma once
 #include "aux_kernels.cuh"
 #include "common.cuh"
+#include "dispatch.h"
 
 namespace b2n {
-
-struct Axis3Plan {
-    int L;            // transform length K3
-    int npass;
-    int radix[12];
-};
-
-// radices 8.., 4.., 2.., 3.. with one (2, 3) pair merged into a radix-6 pass (384 = 8 * 8 * 6:
-// three passes instead of four); returns false when L has another prime factor
-static inline bool axis3_factor(int L, Axis3Plan* ap) {
-    ap->L = L;
-    ap->npass = 0;
-    if (L < 2) return false;
-    int n2 = 0, n3 = 0;
-    while (L % 8 == 0) { ap->radix[ap->npass++] = 8; L /= 8; }
-    while (L % 4 == 0) { ap->radix[ap->npass++] = 4; L /= 4; }
-    while (L % 2 == 0) { n2++; L /= 2; }
-    while (L % 3 == 0) { n3++; L /= 3; }
-    if (L != 1) return false;
-    const bool six = n2 > 0 && n3 > 0;
-    if (six) { n2--; n3--; }
-    while (n2-- > 0 && ap->npass < 12) ap->radix[ap->npass++] = 2;
-    while (n3-- > 0 && ap->npass < 12) ap->radix[ap->npass++] = 3;
-    if (six && ap->npass < 12) ap->radix[ap->npass++] = 6;
-    return ap->npass <= 11;
-}
 
 template <typename T>
 __device__ __forceinline__ cplx_t<T> cmulc(cplx_t<T> a, cplx_t<T> b) {      // a * b
@@ -54,6 +29,17 @@ __device__ __forceinline__ cplx_t<T> cmulc(cplx_t<T> a, cplx_t<T> b) {      // a
 
 template <typename T> __device__ __forceinline__ cplx_t<T> cadd(cplx_t<T> a, cplx_t<T> b) { return make_c<T>(a.x + b.x, a.y + b.y); }
 template <typename T> __device__ __forceinline__ cplx_t<T> csub(cplx_t<T> a, cplx_t<T> b) { return make_c<T>(a.x - b.x, a.y - b.y); }
+// float: one packed FADD2 per complex add / subtract (each half an IEEE add: same bits)
+template <> __device__ __forceinline__ float2 cadd<float>(float2 a, float2 b) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b), rd;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    return *reinterpret_cast<float2*>(&rd);
+}
+template <> __device__ __forceinline__ float2 csub<float>(float2 a, float2 b) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b), rd;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    return *reinterpret_cast<float2*>(&rd);
+}
 // (+i) * a for the inverse transform, (-i) * a for the forward one
 template <typename T, bool INV> __device__ __forceinline__ cplx_t<T> rot90(cplx_t<T> a) {
     return INV ? make_c<T>(-a.y, a.x) : make_c<T>(a.y, -a.x);
@@ -299,7 +285,7 @@ __host__ __device__ constexpr int fixed_ns(int L, int p) {          // product o
     return ns;
 }
 
-template <typename T, bool INV, int L, int COLS, int SLOTS, int P>
+template <typename T, bool INV, int L, int PITCH, int SLOTS, int P>
 __device__ __forceinline__ void fixed_pass(const cplx_t<T>* __restrict__ in, cplx_t<T>* __restrict__ out,
                                            const cplx_t<T>* __restrict__ twS, int slot, int c) {
     using C = cplx_t<T>;
@@ -316,14 +302,14 @@ __device__ __forceinline__ void fixed_pass(const cplx_t<T>* __restrict__ in, cpl
         const int j0 = j * R - k * (R - 1);          // (j div Ns) * Ns * R + k
         C v[R];
 #pragma unroll
-        for (int r = 0; r < R; r++) v[r] = in[(j + r * Tn) * COLS + c];
+        for (int r = 0; r < R; r++) v[r] = in[(j + r * Tn) * PITCH + c];
         if (Ns > 1) {
 #pragma unroll
             for (int r = 1; r < R; r++) v[r] = cmulc<T>(v[r], twS[r * k * tstep]);
         }
         butterfly<T, INV, R>(v);
 #pragma unroll
-        for (int r = 0; r < R; r++) out[(j0 + r * Ns) * COLS + c] = v[r];
+        for (int r = 0; r < R; r++) out[(j0 + r * Ns) * PITCH + c] = v[r];
     }
 }
 
@@ -342,29 +328,80 @@ __device__ __forceinline__ cplx_t<T> phase_mul(cplx_t<T> v, T a12, cplx_t<T> e12
     return make_c<T>(v.x * cr - v.y * ci, v.x * ci + v.y * cr);
 }
 
-template <typename T, bool INV, int L, int COLS, int NT>
+// float: the same product with the angle reduced to [-pi, pi] by a two-term Cody-Waite step
+// (exact to ~1e-7 rad for the few-thousand-radian angles of phase_before) and the hardware
+// sine / cosine (2^-21.4 absolute on that interval): ~5e-7 in the phase, 1/20 of the parity
+// budget, for 10 instructions instead of 22.  The angle itself is still the reference's float32 sum.
+template <bool CONJ>
+__device__ __forceinline__ float2 phase_mul(float2 v, float a12, float2, float a3k, float2) {
+    const float s = a12 + a3k;
+    const float n = rintf(s * 0.15915494309189535f);
+    float r = fmaf(n, -6.2831854820251465f, s);
+    r = fmaf(n, 1.7484555e-7f, r);                   // 2 pi = 6.2831854820251465 - 1.7484555e-7
+    const float cr = __cosf(r);
+    const float ci = CONJ ? -__sinf(r) : __sinf(r);
+    return make_float2(v.x * cr - v.y * ci, v.x * ci + v.y * cr);
+}
+template <bool CONJ>
+__device__ __forceinline__ double2 phase_mul(double2 v, double a12, double2 e12, double a3k, double2 e3k) {
+    return phase_mul<double, CONJ>(v, a12, e12, a3k, e3k);
+}
+
+// One kernel for the three passes of the pruned oversampled FFT ("lines" = the 1-D transforms):
+//   MODE 0  lines strided in memory, COLS adjacent lines per tile (axis 3: row stride K1*K2, one
+//           outer block, phase_before fused; axis 2: row stride K1, one outer block per plane)
+//   MODE 1  lines contiguous in memory (axis 1): a tile is COLS consecutive grid rows, loaded and
+//           stored along the row (coalesced) through a transposed shared-memory tile of pitch
+//           COLS + 1; the forward reads the IMAGE rows and applies sn * scale on the way in (the
+//           zero padding is created in shared memory), the adjoint writes the cropped, scaled image
+//           rows: the scale/zero-pad and crop/scale passes of _nufft.py:1325-1331 / :1560-1572 ride
+//           along instead of sweeping the padded planes.
+// nz: forward = leading non-zero entries of a line (the rest is zero padding and is not read),
+// adjoint = leading entries that survive the crop (the rest is not stored).
+template <typename T> struct LineArgs {
+    cplx_t<T>* data;              // oversampled grid
+    const cplx_t<T>* tw;          // L twiddles exp(-2 pi i t / L)
+    int nz;
+    int64_t ntiles;
+    // MODE 0
+    int64_t row_stride, outer_stride, inner_extent, tiles_per_outer;
+    const T *a1, *a2, *a3;        // phase_before angles per axis (axis 3 only), or nullptr
+    int K1;
+    // MODE 1
+    cplx_t<T>* image;             // [..][NL2][N1] image rows (read by the forward, written by the adjoint)
+    int NL2, K2, N1;              // lines per plane (= N2), grid rows per plane, image row length
+    int64_t nlines;
+    const double *sn1, *sn2, *sn3;
+    T scale;
+    int apply_scale;
+};
+
+template <typename T, bool INV, int L, int COLS, int NT, int MODE>
 __global__ void __launch_bounds__(NT)
-fft_axis3_fixed_kernel(int64_t plane, int K1, int NZ, int64_t ntiles, const cplx_t<T>* __restrict__ tw,
-                       const T* __restrict__ a1, const T* __restrict__ a2, const T* __restrict__ a3,
-                       cplx_t<T>* __restrict__ data) {
+fft_lines_kernel(const LineArgs<T> la) {
     using C = cplx_t<T>;
     constexpr int NP = fixed_npass(L);
-    constexpr int SLOTS = NT / COLS;                 // butterflies in flight per pass round = rows per load round
-    constexpr int PF = (L + SLOTS - 1) / SLOTS;      // values per thread and tile
+    constexpr int SLOTS = NT / COLS;                 // butterflies in flight per pass round
+    constexpr int PF = (L * COLS + NT - 1) / NT;     // values per thread and tile
+    constexpr int PITCH = MODE == 1 ? COLS + 1 : COLS;
+    constexpr int LPW = COLS / (NT / 32);            // MODE 1: lines per warp
+    constexpr int VPL = L / 32;                      // MODE 1: values per line and lane
+    static_assert(MODE == 0 || (L % 32 == 0 && COLS % (NT / 32) == 0 && LPW * VPL == PF), "row mode tiling");
     extern __shared__ __align__(16) unsigned char fft3_smem[];
     C* bufA = (C*)fft3_smem;
-    C* bufB = bufA + L * COLS;
-    C* twS = bufB + L * COLS;
+    C* bufB = bufA + L * PITCH;
+    C* twS = bufB + L * PITCH;
     C* e3S = twS + L;
     T* a3S = (T*)(e3S + L);
     const int tid = threadIdx.x;
-    const bool phase = a1 != nullptr;
+    const int lane = tid & 31, wib = tid >> 5;
+    const bool phase = MODE == 0 && la.a1 != nullptr;
     for (int e = tid; e < L; e += NT) {
-        C w = tw[e];
+        C w = la.tw[e];
         if (INV) w.y = -w.y;
         twS[e] = w;
         if (phase) {
-            const T a = a3[e];
+            const T a = la.a3[e];
             T sn, co;
             sincos_t(a, &sn, &co);
             a3S[e] = a;
@@ -372,152 +409,222 @@ fft_axis3_fixed_kernel(int64_t plane, int K1, int NZ, int64_t ntiles, const cplx
         }
     }
     __syncthreads();
-    const int c = tid % COLS;
+    const int c = tid % COLS;                        // pass / MODE 0 load: this thread's line in the tile
     const int r0 = tid / COLS;
-    const int rows_in = INV ? L : NZ;                // forward: only the non-zero planes are read
-    const int rows_out = INV ? NZ : L;               // adjoint: only the planes that survive the crop
+    const int rows_in = INV ? L : la.nz;
+    const int rows_out = INV ? la.nz : L;
+    const int64_t rstride = (int64_t)SLOTS * la.row_stride;
+
+    // ---- loads of one tile into registers (issued one tile ahead)
     C pf[PF];
-    int64_t tile = blockIdx.x;
-    const int64_t rstride = (int64_t)SLOTS * plane;  // elements between the rows of two load rounds
-    if (tile < ntiles) {
-        const int64_t col = tile * COLS + c;
-        const C* src = data + ((int64_t)r0 * plane + col);
+    auto prefetch = [&](int64_t tile) {
+        if constexpr (MODE == 0) {
+            const int64_t o = tile / la.tiles_per_outer;
+            const int64_t col = (tile - o * la.tiles_per_outer) * COLS + c;
+            const C* src = la.data + (o * la.outer_stride + (int64_t)r0 * la.row_stride + col);
 #pragma unroll
-        for (int i = 0; i < PF; i++, src += rstride) {
-            const int k3 = r0 + i * SLOTS;
-            pf[i] = make_c<T>(0, 0);
-            if (k3 < rows_in && col < plane) pf[i] = *src;
+            for (int i = 0; i < PF; i++, src += rstride) {
+                const int k = r0 + i * SLOTS;
+                pf[i] = make_c<T>(0, 0);
+                if (k < rows_in && col < la.inner_extent) pf[i] = *src;
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < LPW; q++) {
+                const int64_t line = tile * COLS + wib * LPW + q;
+                const int64_t z = line / la.NL2;
+                const int k2 = (int)(line - z * la.NL2);
+                const C* src = INV ? la.data + ((z * la.K2 + k2) * (int64_t)L)
+                                   : la.image + ((z * la.NL2 + k2) * (int64_t)la.N1);
+#pragma unroll
+                for (int i = 0; i < VPL; i++) {
+                    const int k = lane + 32 * i;
+                    pf[q * VPL + i] = make_c<T>(0, 0);
+                    if (k < (INV ? L : la.N1) && line < la.nlines) pf[q * VPL + i] = src[k];
+                }
+            }
         }
-    }
-    for (; tile < ntiles; tile += gridDim.x) {
-        const int64_t col = tile * COLS + c;
-        const bool col_ok = col < plane;
+    };
+    int64_t tile = blockIdx.x;
+    if (tile < la.ntiles) prefetch(tile);
+    for (; tile < la.ntiles; tile += gridDim.x) {
+        // ---- registers -> shared memory (the rest of a forward line is zero padding)
+        int64_t col = 0;
+        bool col_ok = true;
         T a12 = (T)0;
         C e12 = make_c<T>(1, 0);
-        if (phase && col_ok) {
-            const int k1 = (int)(col % K1), k2 = (int)(col / K1);
-            a12 = a1[k1] + a2[k2];                   // the reference's summation order
-            T sn, co;
-            sincos_t(a12, &sn, &co);
-            e12 = make_c<T>(co, sn);
-        }
-        // ---- registers -> shared memory (the rest of a forward column is zero padding)
+        if constexpr (MODE == 0) {
+            const int64_t o = tile / la.tiles_per_outer;
+            col = (tile - o * la.tiles_per_outer) * COLS + c;
+            col_ok = col < la.inner_extent;
+            if (phase && col_ok) {
+                const int k1 = (int)(col % la.K1), k2 = (int)(col / la.K1);
+                a12 = la.a1[k1] + la.a2[k2];         // the reference's summation order
+                T sn, co;
+                sincos_t(a12, &sn, &co);
+                e12 = make_c<T>(co, sn);
+            }
 #pragma unroll
-        for (int i = 0; i < PF; i++) {
-            const int k3 = r0 + i * SLOTS;
-            if (L % SLOTS == 0 || k3 < L) {
-                C v = pf[i];
-                if (INV && phase) v = phase_mul<T, true>(v, a12, e12, a3S[k3], e3S[k3]);
-                bufA[k3 * COLS + c] = v;
+            for (int i = 0; i < PF; i++) {
+                const int k = r0 + i * SLOTS;
+                if (L % SLOTS == 0 || k < L) {
+                    C v = pf[i];
+                    if (INV && phase) v = phase_mul<true>(v, a12, e12, a3S[k], e3S[k]);
+                    bufA[k * PITCH + c] = v;
+                }
+            }
+            col += o * la.outer_stride;              // element offset of row 0 of this thread's line
+        } else {
+#pragma unroll
+            for (int q = 0; q < LPW; q++) {
+                const int lc = wib * LPW + q;
+                const int64_t line = tile * COLS + lc;
+                const int64_t z = line / la.NL2;
+                const int k2 = (int)(line - z * la.NL2);
+                double s23 = 1.0;
+                if (!INV && line < la.nlines) s23 = la.sn2[k2] * la.sn3[z];
+#pragma unroll
+                for (int i = 0; i < VPL; i++) {
+                    const int k = lane + 32 * i;
+                    C v = pf[q * VPL + i];
+                    if (!INV && k < la.N1 && line < la.nlines) {
+                        // x * sn (sn = ((s1*s2)*s3) in double, then cast), then the transform scale
+                        const T st = (T)((la.sn1[k] * la.sn2[k2]) * la.sn3[z]);
+                        v = make_c<T>(v.x * st, v.y * st);
+                        if (la.apply_scale) { v.x *= la.scale; v.y *= la.scale; }
+                    }
+                    bufA[k * PITCH + lc] = v;
+                }
+                (void)s23;
             }
         }
         __syncthreads();
         // ---- next tile's loads go out now; they land while this tile is transformed
-        {
-            const int64_t nt = tile + gridDim.x;
-            const int64_t ncol = nt * COLS + c;
-            if (nt < ntiles) {
-                const C* src = data + ((int64_t)r0 * plane + ncol);
-#pragma unroll
-                for (int i = 0; i < PF; i++, src += rstride) {
-                    const int k3 = r0 + i * SLOTS;
-                    pf[i] = make_c<T>(0, 0);
-                    if (k3 < rows_in && ncol < plane) pf[i] = *src;
-                }
-            }
-        }
+        if (tile + gridDim.x < la.ntiles) prefetch(tile + gridDim.x);
         // ---- Stockham passes, schedule known at compile time
-        fixed_pass<T, INV, L, COLS, SLOTS, 0>(bufA, bufB, twS, r0, c);
+        fixed_pass<T, INV, L, PITCH, SLOTS, 0>(bufA, bufB, twS, r0, c);
         __syncthreads();
-        fixed_pass<T, INV, L, COLS, SLOTS, 1>(bufB, bufA, twS, r0, c);
+        fixed_pass<T, INV, L, PITCH, SLOTS, 1>(bufB, bufA, twS, r0, c);
         __syncthreads();
-        fixed_pass<T, INV, L, COLS, SLOTS, 2>(bufA, bufB, twS, r0, c);
+        fixed_pass<T, INV, L, PITCH, SLOTS, 2>(bufA, bufB, twS, r0, c);
         __syncthreads();
         if constexpr (NP == 4) {
-            fixed_pass<T, INV, L, COLS, SLOTS, 3>(bufB, bufA, twS, r0, c);
+            fixed_pass<T, INV, L, PITCH, SLOTS, 3>(bufB, bufA, twS, r0, c);
             __syncthreads();
         }
         const C* res = NP == 4 ? bufA : bufB;
         // ---- store
-        if (col_ok) {
-            C* dst = data + ((int64_t)r0 * plane + col);
+        if constexpr (MODE == 0) {
+            if (col_ok) {
+                C* dst = la.data + ((int64_t)r0 * la.row_stride + col);
 #pragma unroll 4
-            for (int k3 = r0; k3 < rows_out; k3 += SLOTS, dst += rstride) {
-                C v = res[k3 * COLS + c];
-                if (!INV && phase) v = phase_mul<T, false>(v, a12, e12, a3S[k3], e3S[k3]);
-                *dst = v;
+                for (int k = r0; k < rows_out; k += SLOTS, dst += rstride) {
+                    C v = res[k * PITCH + c];
+                    if (!INV && phase) v = phase_mul<false>(v, a12, e12, a3S[k], e3S[k]);
+                    *dst = v;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < LPW; q++) {
+                const int lc = wib * LPW + q;
+                const int64_t line = tile * COLS + lc;
+                if (line >= la.nlines) continue;
+                const int64_t z = line / la.NL2;
+                const int k2 = (int)(line - z * la.NL2);
+                if (INV) {
+                    // image[n] = grid[n] * adj_scale * sn[n]
+                    C* dst = la.image + ((z * la.NL2 + k2) * (int64_t)la.N1);
+                    for (int k = lane; k < la.N1; k += 32) {
+                        C v = res[k * PITCH + lc];
+                        const T st = (T)((la.sn1[k] * la.sn2[k2]) * la.sn3[z]);
+                        if (la.apply_scale) { v.x *= la.scale; v.y *= la.scale; }
+                        dst[k] = make_c<T>(v.x * st, v.y * st);
+                    }
+                } else {
+                    C* dst = la.data + ((z * la.K2 + k2) * (int64_t)L);
+#pragma unroll 4
+                    for (int k = lane; k < L; k += 32) dst[k] = res[k * PITCH + lc];
+                }
             }
         }
         __syncthreads();                             // the buffers are rewritten by the next tile
     }
 }
 
-// Tile width: 128-byte runs per global access (16 float / 8 double columns, 256 threads: measured
-// 0.25 ms per pass on the bench grid against 0.29 ms with 64-byte runs and 0.36 ms with the
-// run-time schedule), 64-byte runs where two 128-byte buffers would not fit in shared memory
-template <typename T, int L> struct Axis3FixedCfg {
+// Tile width: 128-byte runs per global access (16 float / 8 double lines, 256 threads: measured
+// 0.25 ms per axis-3 pass on the bench grid against 0.29 ms with 64-byte runs and 0.36 ms with
+// the run-time schedule), 64-byte runs where two 128-byte buffers would not fit in shared memory
+template <typename T, int L, int MODE> struct LineCfg {
     static constexpr size_t smem_for(int cols) {
-        return (size_t)(2 * L * cols + 2 * L) * 2 * sizeof(T) + (size_t)L * sizeof(T);
+        return (size_t)(2 * L * (cols + (MODE == 1 ? 1 : 0)) + 2 * L) * 2 * sizeof(T) + (size_t)L * sizeof(T);
     }
     static constexpr bool WIDE = smem_for(128 / (2 * (int)sizeof(T))) <= 200 * 1024;
     static constexpr int COLS = (WIDE ? 128 : 64) / (2 * (int)sizeof(T));
-    static constexpr int NT = (L >= 768 ? 256 : 128) * (WIDE ? 2 : 1);   // <= 24 values per thread
+    // MODE 0: <= 24 values per thread.  MODE 1: a warp owns LPW whole lines (LPW a power of two,
+    // about 24 values per thread)
+    static constexpr int lpw() {
+        int l = 24 / (L / 32), q = 1;
+        while (2 * q <= l && 2 * q <= COLS) q *= 2;
+        return q;
+    }
+    static constexpr int NT = MODE == 1 ? 32 * COLS / lpw() : (L >= 768 ? 256 : 128) * (WIDE ? 2 : 1);
     static constexpr size_t smem = smem_for(COLS);
 };
 
-template <typename T, bool INV, int L>
-static int fft_axis3_fixed_launch_L(const Geom& g, const void* tw, const void* a1, const void* a2,
-                                    const void* a3, void* data, int sm_count, int max_smem, cudaStream_t st,
-                                    bool* done) {
-    using C = cplx_t<T>;
-    constexpr int COLS = Axis3FixedCfg<T, L>::COLS;
-    constexpr int NT = Axis3FixedCfg<T, L>::NT;
-    const size_t smem = Axis3FixedCfg<T, L>::smem;
+template <typename T, bool INV, int L, int MODE>
+static int fft_lines_launch_L(const LineArgs<T>& la_in, int sm_count, int max_smem, cudaStream_t st, bool* done) {
+    constexpr int COLS = LineCfg<T, L, MODE>::COLS;
+    constexpr int NT = LineCfg<T, L, MODE>::NT;
+    const size_t smem = LineCfg<T, L, MODE>::smem;
     if (smem > (size_t)max_smem) return 0;
-    const int64_t plane = (int64_t)g.K[0] * g.K[1];
-    const int64_t ntiles = (plane + COLS - 1) / COLS;
-    auto k = fft_axis3_fixed_kernel<T, INV, L, COLS, NT>;
+    LineArgs<T> la = la_in;
+    if (MODE == 0) {
+        la.tiles_per_outer = (la.inner_extent + COLS - 1) / COLS;
+        la.ntiles *= la.tiles_per_outer;             // (ntiles came in as the number of outer blocks)
+    } else {
+        la.ntiles = (la.nlines + COLS - 1) / COLS;
+    }
+    auto k = fft_lines_kernel<T, INV, L, COLS, NT, MODE>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     int per_sm = 1;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, NT, smem);
     if (e != cudaSuccess) return (int)e;
     int64_t nb = (int64_t)sm_count * (per_sm < 1 ? 1 : per_sm);      // persistent: resident CTAs only
-    if (nb > ntiles) nb = ntiles;
-    k<<<(unsigned)nb, NT, smem, st>>>(plane, g.K[0], g.N[2], ntiles, (const C*)tw, (const T*)a1,
-                                      (const T*)a2, (const T*)a3, (C*)data);
+    if (nb > la.ntiles) nb = la.ntiles;
+    if (nb < 1) { *done = true; return 0; }
+    k<<<(unsigned)nb, NT, smem, st>>>(la);
     *done = true;
     return (int)cudaGetLastError();
 }
 
-// returns 0 or a cudaError_t; *done = false when K3 has no fixed schedule (the caller then runs
-// fft_axis3_launch)
-template <typename T>
-static int fft_axis3_fixed_launch(const Geom& g, bool inverse, const void* tw, const void* a1, const void* a2,
-                                  const void* a3, void* data, int sm_count, int max_smem, cudaStream_t st,
-                                  bool* done) {
+// returns 0 or a cudaError_t; *done = false when L has no fixed schedule or the tile does not fit
+template <typename T, int MODE>
+static int fft_lines_launch(int L, bool inverse, const LineArgs<T>& la, int sm_count, int max_smem,
+                            cudaStream_t st, bool* done) {
     *done = false;
-#define B2N_AX3(LL)                                                                                          \
-    case LL:                                                                                                 \
-        return inverse ? fft_axis3_fixed_launch_L<T, true, LL>(g, tw, a1, a2, a3, data, sm_count, max_smem, st, done) \
-                       : fft_axis3_fixed_launch_L<T, false, LL>(g, tw, a1, a2, a3, data, sm_count, max_smem, st, done);
-    switch (g.K[2]) {
-        B2N_AX3(128) B2N_AX3(192) B2N_AX3(256) B2N_AX3(384) B2N_AX3(512) B2N_AX3(768) B2N_AX3(1024)
+#define B2N_FL(LL)                                                                                  \
+    case LL:                                                                                        \
+        return inverse ? fft_lines_launch_L<T, true, LL, MODE>(la, sm_count, max_smem, st, done)    \
+                       : fft_lines_launch_L<T, false, LL, MODE>(la, sm_count, max_smem, st, done);
+    switch (L) {
+        B2N_FL(128) B2N_FL(192) B2N_FL(256) B2N_FL(384) B2N_FL(512) B2N_FL(768) B2N_FL(1024)
         default: return 0;
     }
-#undef B2N_AX3
+#undef B2N_FL
 }
 
-// shared memory the fixed-schedule kernel needs for length L (0: no fixed schedule)
-template <typename T> static size_t fft_axis3_fixed_smem(int L) {
+// shared memory the fixed-schedule kernel needs for length L in mode MODE (0: no fixed schedule)
+template <typename T, int MODE> static size_t fft_lines_smem(int L) {
     switch (L) {
-        case 128: return Axis3FixedCfg<T, 128>::smem;
-        case 192: return Axis3FixedCfg<T, 192>::smem;
-        case 256: return Axis3FixedCfg<T, 256>::smem;
-        case 384: return Axis3FixedCfg<T, 384>::smem;
-        case 512: return Axis3FixedCfg<T, 512>::smem;
-        case 768: return Axis3FixedCfg<T, 768>::smem;
-        case 1024: return Axis3FixedCfg<T, 1024>::smem;
+        case 128: return LineCfg<T, 128, MODE>::smem;
+        case 192: return LineCfg<T, 192, MODE>::smem;
+        case 256: return LineCfg<T, 256, MODE>::smem;
+        case 384: return LineCfg<T, 384, MODE>::smem;
+        case 512: return LineCfg<T, 512, MODE>::smem;
+        case 768: return LineCfg<T, 768, MODE>::smem;
+        case 1024: return LineCfg<T, 1024, MODE>::smem;
         default: return 0;
     }
 }

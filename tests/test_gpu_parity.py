@@ -649,6 +649,39 @@ def test_fixed_schedule_axis3_fft_vs_oracle(K3, N3, precision):
 
 
 @pytest.mark.parametrize("precision", ["single", "double"])
+@pytest.mark.parametrize("Nd,Kd,ortho", [((64, 96, 100), (128, 192, 256), False),
+                                         ((100, 128, 64), (192, 256, 128), True),
+                                         ((256, 20, 70), (384, 128, 192), False),
+                                         ((300, 60, 64), (512, 128, 128), False),
+                                         ((40, 500, 64), (128, 768, 128), True)])
+def test_own_inplane_fft_vs_oracle(Nd, Kd, ortho, precision):
+    """Own in-plane FFT passes (option own_fft12, default on): axis 1 over contiguous rows with
+    the scale / zero-pad and crop / scale fused, axis 2 strided on the non-zero rows only, axis 3
+    with phase_before -- vs the oracle and vs scale/pad + cuFFT + crop/scale (own_fft12 = 0);
+    unequal lengths per axis, image sizes that are not multiples of the tile, ortho scaling."""
+    from oracle import nufft_oracle as orc
+    from mrrt.nufft_b200 import NufftBase
+
+    rs = np.random.RandomState(sum(Kd))
+    rdt = np.float32 if precision == "single" else np.float64
+    om = ((rs.rand(3000, 3) * 2 - 1) * np.pi).astype(rdt)
+    kw = dict(Nd=Nd, omega=om, Jd=4, Kd=Kd, precision=precision, n_shift=(2, 0, 3), ortho=ortho)
+    A = NufftBase(**kw)
+    O = orc.OracleNufft(**kw)
+    x = (rs.standard_normal(Nd) + 1j * rs.standard_normal(Nd)).astype(A._cplx_dtype)
+    tol = TOL[precision]
+    yo, ya = O.fft(x), A.fft(x)
+    assert A.option("inplane_own") == 1
+    assert rel_l2(ya, yo) <= tol
+    xo, xa = O.adj(yo), A.adj(yo)
+    assert rel_l2(xa, xo) <= tol
+    B = NufftBase(options={"own_fft12": 0}, **kw)
+    assert rel_l2(ya, B.fft(x)) <= tol / 4
+    assert rel_l2(xa, B.adj(yo)) <= tol / 4
+    assert B.option("inplane_own") == 0
+
+
+@pytest.mark.parametrize("precision", ["single", "double"])
 @pytest.mark.parametrize("J", [5, 7, 8])
 def test_3d_window_kernels_other_J(J, precision):
     """3-D register-window adjoint / tiled forward at the kernel sizes the golden cases do not
