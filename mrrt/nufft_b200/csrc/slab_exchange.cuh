@@ -18,6 +18,7 @@
 namespace b2n {
 
 constexpr int kMaxPeers = 16;
+constexpr int kExchUnroll = 4;      // 16-byte accesses per lane in flight
 
 struct SlabPeers {
     void* grid[kMaxPeers];     // slab grid of every rank, [K3][nrows][K1] complex, peer-mapped
@@ -54,7 +55,16 @@ slab_scatter_kernel(SlabPeers P, const V* __restrict__ planes, int nz, int z0, i
         if (k2 >= K2) k2 -= K2;
         const V* __restrict__ src = planes + ((int64_t)z * K2 + k2) * vpr;
         V* __restrict__ dst = (V*)P.grid[s] + ((int64_t)(z0 + z) * P.nrows[s] + r) * vpr;
-        for (int e = lane; e < vpr; e += 32) dst[e] = src[e];
+        // four independent 16-byte loads per lane in flight before the peer stores
+        for (int e0 = lane; e0 < vpr; e0 += 32 * kExchUnroll) {
+            V v[kExchUnroll];
+#pragma unroll
+            for (int u = 0; u < kExchUnroll; u++)
+                if (e0 + 32 * u < vpr) v[u] = src[e0 + 32 * u];
+#pragma unroll
+            for (int u = 0; u < kExchUnroll; u++)
+                if (e0 + 32 * u < vpr) dst[e0 + 32 * u] = v[u];
+        }
     }
 }
 
@@ -68,19 +78,29 @@ slab_gather_kernel(SlabPeers P, V* __restrict__ planes, int nz, int z0, int K2, 
         const int z = (int)(it / K2);
         const int k2 = (int)(it - (int64_t)z * K2);
         V* __restrict__ dst = planes + it * vpr;
-        for (int e = lane; e < vpr; e += 32) {
-            V acc;
+        // the slabs holding this row are the same for the whole row: the peer loads of a chunk
+        // (kExchUnroll x 16 bytes per lane) are independent and all in flight together
+        for (int e0 = lane; e0 < vpr; e0 += 32 * kExchUnroll) {
+            V acc[kExchUnroll];
             bool have = false;
             for (int s = 0; s < P.world; s++) {
                 int r = k2 - P.row0[s];
                 if (r < 0) r += K2;
                 if (r < P.nrows[s]) {
-                    const V v = ((const V*)P.grid[s])[((int64_t)(z0 + z) * P.nrows[s] + r) * vpr + e];
-                    acc = have ? vadd<V>(acc, v) : v;
+                    const V* __restrict__ q = (const V*)P.grid[s] + ((int64_t)(z0 + z) * P.nrows[s] + r) * vpr;
+#pragma unroll
+                    for (int u = 0; u < kExchUnroll; u++) {
+                        if (e0 + 32 * u < vpr) {
+                            const V v = q[e0 + 32 * u];
+                            acc[u] = have ? vadd<V>(acc[u], v) : v;      // fixed order: slab index
+                        }
+                    }
                     have = true;
                 }
             }
-            dst[e] = acc;      // every row is owned by exactly one slab: have is true
+#pragma unroll
+            for (int u = 0; u < kExchUnroll; u++)
+                if (e0 + 32 * u < vpr) dst[e0 + 32 * u] = acc[u];      // every row has an owner: have is true
         }
     }
 }
