@@ -70,26 +70,38 @@ int b2n_plan_destroy(b2n_plan *plan);
 /* Integer options.  Layout options must precede b2n_plan_set_points; launch options may
  * change between transforms.  Every non-default value is a tested variant (tests/).
  *   layout:  "tile1","tile2","tile3" bin shape in grid cells; "tileb1".."tileb3" bin shape of
- *            the adjoint sort order; "chunk" max samples per forward work item; "order_b" 1 =
- *            also build the adjoint sort order (3-D); "precomp_weights" 1 = plan-time
- *            interpolation weights (0 = table lookups in the kernels, the table staged in
- *            shared memory); "fwd_pair" 0/1/2 = same-cell sample pairs in the forward kernel
- *            off / automatic / on; "fwd_interleave" column-interleaved slot order.
+ *            the adjoint sort order (ignored by plans in column order); "chunk" max samples per
+ *            forward work item; "order_b" 1 = also build the adjoint-side sort order;
+ *            "adj_column" 1 (default) = 3-D real-table plans build the COLUMN order and the
+ *            column records of csrc/spread_column.cuh (0 = the per-cell register-window kernel
+ *            on the round-1 adjoint order); "win_maxslide" longest window slide in cells before a
+ *            new window is started (0 = J-1; baked into the column records, so it is a layout
+ *            option for those plans); "precomp_weights" 1 = plan-time interpolation weights
+ *            (0 = table lookups in the kernels, the table staged in shared memory);
+ *            "table_order" 1 = linear interpolation between table entries (default, the
+ *            reference's CPU behaviour), 0 = the entry at floor((t-k)*L) (order 0 of the
+ *            reference's GPU templates); "fwd_pair" 0/1/2 = same-cell sample pairs in the forward
+ *            kernel off / automatic / on; "fwd_interleave" column-interleaved slot order;
+ *            "slab_kglobal2", "slab_origin2" (slab plans, below).
  *   launch:  "force_generic" 1 = one-thread-per-sample kernels only; "use_tma" 0 = cooperative
  *            tile loads; "fwd_pitch" shared-memory row pitch of the forward tile (0 = auto);
- *            "slide_pts" samples per warp of the register-window adjoint kernels;
- *            "win_maxslide" longest window slide in cells (0 = J-1); "win_facew" -1 auto / 0
- *            off / 1,2 face-weight staging of the 3-D window adjoint; "pruned_fft" 1 = skip
- *            the all-zero planes of the padded FFT; "own_fft3" 1 (default) = the axis-3 pass of
- *            the pruned FFT by the fused kernel of csrc/fft_axis3.cuh (zero padding,
- *            phase_before and crop inside the pass), 0 = cuFFT strided pass + phase kernel;
- *            "profile" 1 = CUDA events around the interpolation kernels; "sparse_mode" (set
- *            by the host for mode="sparse").
+ *            "slide_pts" samples per warp of the register-window adjoint kernels (0 = automatic:
+ *            256, column kernel 512); "win_facew" -1 auto / 0 off / 1,2 face-weight staging of
+ *            the per-cell 3-D window adjoint; "pruned_fft" 1 = skip the all-zero planes of the
+ *            padded FFT; "own_fft3" 1 (default) = the axis-3 pass of the pruned FFT by the fused
+ *            kernels of csrc/fft_axis3.cuh (zero padding, phase_before and crop inside the pass;
+ *            compile-time radix schedule for K3 in {128,192,256,384,512,768,1024}), 2 = always the
+ *            run-time schedule, 0 = cuFFT strided pass + phase kernel; "own_fft12" 1 (default) =
+ *            also the two in-plane passes by that kernel, with the scale / zero-pad and crop /
+ *            scale fused into the axis-1 pass (single 3-D volume, every Kd in the list above),
+ *            0 = scale/pad kernel + cuFFT 2-D + crop kernel; "profile" 1 = CUDA events around the
+ *            interpolation kernels; "sparse_mode" (set by the host for mode="sparse").
  *   read-only (b2n_plan_get_option): "last_fwd_kernel" (0 one thread per sample, 1 tiled),
- *            "last_adj_kernel" (0 one RED per tap, 3 3-D register window, 4 2-D register
- *            window), "n_items", "n_slots", "lib_calls", "axis3_fused" (1 when the fused
- *            axis-3 kernel serves this plan: b2n_axis3_fwd then ignores the planes >= Nd[2]
- *            of its input instead of requiring them to be zero).
+ *            "last_adj_kernel" (0 one RED per tap, 3 3-D per-cell register window, 4 2-D register
+ *            window, 5 3-D column-group register window), "n_items", "n_slots", "lib_calls",
+ *            "axis3_fused" (1 when a fused axis-3 kernel serves this plan: b2n_axis3_fwd then
+ *            ignores the planes >= Nd[2] of its input instead of requiring them to be zero),
+ *            "inplane_own" (1 once the own in-plane passes have served a transform).
  *
  * Threading / streams: a plan is NOT re-entrant.  It owns one scratch grid and its cuFFT
  * handles are re-pointed at the stream of each call, so transforms on one plan must be issued
