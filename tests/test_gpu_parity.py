@@ -151,8 +151,9 @@ def test_mid_3d_radial_vs_oracle(precision, variant):
     opts = {"generic": {"force_generic": 1}, "no_tma": {"use_tma": 0}, "auto": {},
             "window_a": {"order_b": 0}, "table_in_kernel": {"precomp_weights": 0},
             "window_percell": {"adj_column": 0}, "column_256": {"slide_pts": 256, "win_maxslide": 2},
-            "window_scalar": {"win_facew": 0}, "window_facew": {"win_facew": 1},
-            "window_facew5": {"win_facew": 2}, "pair_on": {"fwd_pair": 2},
+            "window_scalar": {"win_facew": 0, "adj_column": 0},
+            "window_facew": {"win_facew": 1, "adj_column": 0},
+            "window_facew5": {"win_facew": 2, "adj_column": 0}, "pair_on": {"fwd_pair": 2},
             "pair_off": {"fwd_pair": 0}, "pair_sorted": {"fwd_pair": 2, "fwd_interleave": 0},
             "pair_table": {"fwd_pair": 2, "precomp_weights": 0}}[variant]
     A = NufftBase(Nd=Nd, omega=om, Jd=6, Kd=Kd, precision=precision, options=opts)
@@ -166,6 +167,11 @@ def test_mid_3d_radial_vs_oracle(precision, variant):
     g, ys = grid_only_inputs(5, int(np.prod(Kd)), A.M, 2, A._cplx_dtype)
     assert rel_l2(nufft_forward(A, g, grid_only=True).cpu().numpy(), O.fft(g, grid_only=True)) <= tol
     assert rel_l2(nufft_adj(A, ys, grid_only=True).cpu().numpy(), O.adj(ys, grid_only=True)) <= tol
+    # the variant really selected the kernel it is named after (0 one RED per tap, 3 per-cell
+    # register window, 5 column-group register window)
+    assert A.option("last_adj_kernel") == {"generic": 0, "window_percell": 3, "window_scalar": 3,
+                                           "window_facew": 3, "window_facew5": 3, "window_a": 3,
+                                           "table_in_kernel": 3, "pair_table": 3}.get(variant, 5)
     if precision == "double":
         assert rel_l2(A.adj(yo), O.adj(yo)) <= tol
         assert rel_l2(A.norm(x), O.norm(x)) <= tol
