@@ -1506,8 +1506,11 @@ static bool inplane_own(b2n_plan* p, int nbatch) {
 // the two in-plane passes; returns 0 or a cudaError_t
 template <typename T>
 static int run_inplane(b2n_plan* p, bool inverse, const void* image_in, void* image_out, void* grid,
-                       cudaStream_t st) {
+                       cudaStream_t st, int z0 = 0, int nz = -1) {
+    // (z0, nz): the image planes [z0, z0 + nz) only, image and grid pointers at plane z0 (slab
+    // plane stage); default: the whole volume
     const Geom& g = p->g;
+    if (nz < 0) nz = g.N[2];
     LineArgs<T> rows{};
     rows.data = (cplx_t<T>*)grid;
     rows.tw = (const cplx_t<T>*)p->d_tw12[0];
@@ -1515,10 +1518,10 @@ static int run_inplane(b2n_plan* p, bool inverse, const void* image_in, void* im
     rows.NL2 = g.N[1];
     rows.K2 = g.K[1];
     rows.N1 = g.N[0];
-    rows.nlines = (int64_t)g.N[1] * g.N[2];
+    rows.nlines = (int64_t)g.N[1] * nz;
     rows.sn1 = p->d_sn[0];
     rows.sn2 = p->d_sn[1];
-    rows.sn3 = p->d_sn[2];
+    rows.sn3 = p->d_sn[2] + z0;
     const double sc = inverse ? p->adj_scale : p->fwd_scale;
     rows.scale = (T)sc;
     rows.apply_scale = sc != 1.0;
@@ -1526,7 +1529,7 @@ static int run_inplane(b2n_plan* p, bool inverse, const void* image_in, void* im
     cols.data = (cplx_t<T>*)grid;
     cols.tw = (const cplx_t<T>*)p->d_tw12[1];
     cols.nz = g.N[1];
-    cols.ntiles = g.N[2];                            // outer blocks: the N3 non-zero planes
+    cols.ntiles = nz;                                // outer blocks: the non-zero planes
     cols.row_stride = g.K[0];
     cols.outer_stride = (int64_t)g.K[0] * g.K[1];
     cols.inner_extent = g.K[0];
@@ -1855,6 +1858,11 @@ static int planes_fwd_t(b2n_plan* p, const void* image, int z0, int nz, void* pl
     g2.PN = (int64_t)g2.N[0] * g2.N[1] * nz;
     AxisPtrs ax = axis_ptrs(p);
     ax.sn[2] += z0;
+    if (inplane_own<T>(p, 1)) {
+        const int e = run_inplane<T>(p, false, image, nullptr, planes, st, z0, nz);
+        if (e != 0) return fail(B2N_ECUDA, "own FFT pass failed: " + std::string(cudaGetErrorString((cudaError_t)e)));
+        return B2N_OK;
+    }
     constexpr int VEC = 32 / (int)sizeof(C);
     pre_scale_pad_kernel<T, VEC><<<grid_for(g2.PK / VEC + 1, 256, p->sm_count, 32), 256, 0, st>>>(
         g2, ax, (T)p->fwd_scale, p->fwd_scale != 1.0, (const C*)image, (C*)planes, 1);
@@ -1878,6 +1886,11 @@ static int planes_adj_t(b2n_plan* p, void* planes, int z0, int nz, void* image, 
     g2.PN = (int64_t)g2.N[0] * g2.N[1] * nz;
     AxisPtrs ax = axis_ptrs(p);
     ax.sn[2] += z0;
+    if (inplane_own<T>(p, 1)) {
+        const int e = run_inplane<T>(p, true, nullptr, image, planes, st, z0, nz);
+        if (e != 0) return fail(B2N_ECUDA, "own FFT pass failed: " + std::string(cudaGetErrorString((cudaError_t)e)));
+        return B2N_OK;
+    }
     cufftHandle h;
     int rc = get_planes_fft(p, nz, &h);
     if (rc) return rc;
