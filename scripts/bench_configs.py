@@ -81,6 +81,9 @@ if __name__ == "__main__":
         om3.astype(np.float32), 4, "single", "table", 1)
     run("C4 2-D 320^2 radial 503x640, J=6, 32 coils", (320, 320), (480, 480),
         radial2d(503, 640, np.float32), 6, "single", "table", 32)
+    # 1-D (no BASELINE config; the one-thread-per-sample kernels serve it): 2^20-point grid, 8 M samples
+    om1 = ((rs.rand(8 << 20, 1) * 2 - 1) * np.pi).astype(np.float32)
+    run("1-D N=2^19, K=2^20, 8.4 M random samples, J=6", (1 << 19,), (1 << 20,), om1, 6, "single", "table", 1)
     om5 = bench.radial3d(bench.SPOKES, bench.NREAD)
     run("C5 3-D 256^3 radial 102944x512, J=6", bench.ND, bench.KD, om5, 6, "single", "table", 1, n=10)
     run("C5 same, double precision", bench.ND, bench.KD, om5.astype(np.float64), 6, "double", "table", 1, n=5)
