@@ -285,9 +285,14 @@ __host__ __device__ constexpr int fixed_ns(int L, int p) {          // product o
     return ns;
 }
 
-template <typename T, bool INV, int L, int PITCH, int SLOTS, int P>
+// SRC: 0 = inputs from shared memory `in`, 1 = inputs already in registers (`regs`, butterfly
+// order: value i * R + r is input r of butterfly slot + i * SLOTS).  DST: 0 = outputs to shared
+// memory `out`; 1 = handed to `sink(row, value)` (the last pass of the strided mode writes global
+// memory itself).
+template <typename T, bool INV, int L, int PITCH, int SLOTS, int P, int SRC = 0, int DST = 0, typename Sink = int>
 __device__ __forceinline__ void fixed_pass(const cplx_t<T>* __restrict__ in, cplx_t<T>* __restrict__ out,
-                                           const cplx_t<T>* __restrict__ twS, int slot, int c) {
+                                           const cplx_t<T>* __restrict__ twS, int slot, int c,
+                                           const cplx_t<T>* regs = nullptr, Sink sink = Sink()) {
     using C = cplx_t<T>;
     constexpr int R = fixed_radix(L, P);
     constexpr int Ns = fixed_ns(L, P);
@@ -302,14 +307,20 @@ __device__ __forceinline__ void fixed_pass(const cplx_t<T>* __restrict__ in, cpl
         const int j0 = j * R - k * (R - 1);          // (j div Ns) * Ns * R + k
         C v[R];
 #pragma unroll
-        for (int r = 0; r < R; r++) v[r] = in[(j + r * Tn) * PITCH + c];
+        for (int r = 0; r < R; r++) {
+            if constexpr (SRC == 1) v[r] = regs[i * R + r];
+            else v[r] = in[(j + r * Tn) * PITCH + c];
+        }
         if (Ns > 1) {
 #pragma unroll
             for (int r = 1; r < R; r++) v[r] = cmulc<T>(v[r], twS[r * k * tstep]);
         }
         butterfly<T, INV, R>(v);
 #pragma unroll
-        for (int r = 0; r < R; r++) out[(j0 + r * Ns) * PITCH + c] = v[r];
+        for (int r = 0; r < R; r++) {
+            if constexpr (DST == 1) sink(j0 + r * Ns, v[r]);
+            else out[(j0 + r * Ns) * PITCH + c] = v[r];
+        }
     }
 }
 
@@ -382,11 +393,15 @@ fft_lines_kernel(const LineArgs<T> la) {
     using C = cplx_t<T>;
     constexpr int NP = fixed_npass(L);
     constexpr int SLOTS = NT / COLS;                 // butterflies in flight per pass round
-    constexpr int PF = (L * COLS + NT - 1) / NT;     // values per thread and tile
     constexpr int PITCH = MODE == 1 ? COLS + 1 : COLS;
     constexpr int LPW = COLS / (NT / 32);            // MODE 1: lines per warp
     constexpr int VPL = L / 32;                      // MODE 1: values per line and lane
-    static_assert(MODE == 0 || (L % 32 == 0 && COLS % (NT / 32) == 0 && LPW * VPL == PF), "row mode tiling");
+    // first pass (MODE 0: fed from registers): radix, butterflies per line, rounds per thread
+    constexpr int R0 = fixed_radix(L, 0);
+    constexpr int Tn0 = L / R0;
+    constexpr int ROUNDS0 = (Tn0 + SLOTS - 1) / SLOTS;
+    constexpr int PF = MODE == 1 ? LPW * VPL : ROUNDS0 * R0;      // values per thread and tile
+    static_assert(MODE == 0 || (L % 32 == 0 && COLS % (NT / 32) == 0 && LPW >= 1), "row mode tiling");
     extern __shared__ __align__(16) unsigned char fft3_smem[];
     C* bufA = (C*)fft3_smem;
     C* bufB = bufA + L * PITCH;
@@ -409,24 +424,30 @@ fft_lines_kernel(const LineArgs<T> la) {
         }
     }
     __syncthreads();
-    const int c = tid % COLS;                        // pass / MODE 0 load: this thread's line in the tile
-    const int r0 = tid / COLS;
+    const int c = tid % COLS;                        // this thread's line in the tile (passes, MODE 0 I/O)
+    const int r0 = tid / COLS;                       // ... and its butterfly slot
     const int rows_in = INV ? L : la.nz;
     const int rows_out = INV ? la.nz : L;
-    const int64_t rstride = (int64_t)SLOTS * la.row_stride;
 
-    // ---- loads of one tile into registers (issued one tile ahead)
+    // ---- loads of one tile into registers, issued one tile ahead.  MODE 0: exactly the inputs of
+    // this thread's first-pass butterflies (rows j + r * L / R0 of its line: 128-byte runs across
+    // the 16 lanes of a row), so the first pass runs out of registers and the tile never has to be
+    // staged in shared memory first; rows >= rows_in are the zero padding and are not read.
     C pf[PF];
     auto prefetch = [&](int64_t tile) {
         if constexpr (MODE == 0) {
             const int64_t o = tile / la.tiles_per_outer;
             const int64_t col = (tile - o * la.tiles_per_outer) * COLS + c;
-            const C* src = la.data + (o * la.outer_stride + (int64_t)r0 * la.row_stride + col);
+            const C* src = la.data + (o * la.outer_stride + col);
 #pragma unroll
-            for (int i = 0; i < PF; i++, src += rstride) {
-                const int k = r0 + i * SLOTS;
-                pf[i] = make_c<T>(0, 0);
-                if (k < rows_in && col < la.inner_extent) pf[i] = *src;
+            for (int i = 0; i < ROUNDS0; i++) {
+#pragma unroll
+                for (int r = 0; r < R0; r++) {
+                    const int k = r0 + i * SLOTS + r * Tn0;
+                    pf[i * R0 + r] = make_c<T>(0, 0);
+                    if ((Tn0 % SLOTS == 0 || r0 + i * SLOTS < Tn0) && k < rows_in && col < la.inner_extent)
+                        pf[i * R0 + r] = src[(int64_t)k * la.row_stride];
+                }
             }
         } else {
 #pragma unroll
@@ -448,15 +469,12 @@ fft_lines_kernel(const LineArgs<T> la) {
     int64_t tile = blockIdx.x;
     if (tile < la.ntiles) prefetch(tile);
     for (; tile < la.ntiles; tile += gridDim.x) {
-        // ---- registers -> shared memory (the rest of a forward line is zero padding)
-        int64_t col = 0;
-        bool col_ok = true;
-        T a12 = (T)0;
-        C e12 = make_c<T>(1, 0);
         if constexpr (MODE == 0) {
             const int64_t o = tile / la.tiles_per_outer;
-            col = (tile - o * la.tiles_per_outer) * COLS + c;
-            col_ok = col < la.inner_extent;
+            const int64_t col = (tile - o * la.tiles_per_outer) * COLS + c;
+            const bool col_ok = col < la.inner_extent;
+            T a12 = (T)0;
+            C e12 = make_c<T>(1, 0);
             if (phase && col_ok) {
                 const int k1 = (int)(col % la.K1), k2 = (int)(col / la.K1);
                 a12 = la.a1[k1] + la.a2[k2];         // the reference's summation order
@@ -464,25 +482,53 @@ fft_lines_kernel(const LineArgs<T> la) {
                 sincos_t(a12, &sn, &co);
                 e12 = make_c<T>(co, sn);
             }
+            if (INV && phase) {
+                // conj(phase_before) on the way in
 #pragma unroll
-            for (int i = 0; i < PF; i++) {
-                const int k = r0 + i * SLOTS;
-                if (L % SLOTS == 0 || k < L) {
-                    C v = pf[i];
-                    if (INV && phase) v = phase_mul<true>(v, a12, e12, a3S[k], e3S[k]);
-                    bufA[k * PITCH + c] = v;
-                }
+                for (int i = 0; i < ROUNDS0; i++)
+#pragma unroll
+                    for (int r = 0; r < R0; r++) {
+                        const int k = r0 + i * SLOTS + r * Tn0;
+                        if (k < L) pf[i * R0 + r] = phase_mul<true>(pf[i * R0 + r], a12, e12, a3S[k], e3S[k]);
+                    }
             }
-            col += o * la.outer_stride;              // element offset of row 0 of this thread's line
+            // ---- first pass out of the registers
+            fixed_pass<T, INV, L, PITCH, SLOTS, 0, 1, 0>(nullptr, bufA, twS, r0, c, pf);
+            __syncthreads();
+            // ---- next tile's loads go out now; they land while this tile is transformed
+            if (tile + gridDim.x < la.ntiles) prefetch(tile + gridDim.x);
+            // ---- middle passes in shared memory, last pass straight to global memory (rows of the
+            // 16 lines are 128-byte runs; phase_before on the way out; rows >= rows_out are cropped)
+            C* dst = la.data + (o * la.outer_stride + col);
+            auto sink = [&](int k, C v) {
+                if (col_ok && k < rows_out) {
+                    if (!INV && phase) v = phase_mul<false>(v, a12, e12, a3S[k], e3S[k]);
+                    dst[(int64_t)k * la.row_stride] = v;
+                }
+            };
+            if constexpr (NP == 3) {
+                fixed_pass<T, INV, L, PITCH, SLOTS, 1>(bufA, bufB, twS, r0, c);
+                __syncthreads();
+                fixed_pass<T, INV, L, PITCH, SLOTS, 2, 0, 1>(bufB, nullptr, twS, r0, c, nullptr, sink);
+            } else {
+                fixed_pass<T, INV, L, PITCH, SLOTS, 1>(bufA, bufB, twS, r0, c);
+                __syncthreads();
+                fixed_pass<T, INV, L, PITCH, SLOTS, 2>(bufB, bufA, twS, r0, c);
+                __syncthreads();
+                fixed_pass<T, INV, L, PITCH, SLOTS, 3, 0, 1>(bufA, nullptr, twS, r0, c, nullptr, sink);
+            }
+            // (no barrier here: the next tile's first pass writes bufA, last read before the
+            // barrier above; its second pass writes bufB after the next tile's first barrier,
+            // which every thread reaches only after its last-pass reads of bufB / bufA)
+            if constexpr (NP == 4) __syncthreads();  // 4 passes: the last one reads bufA
         } else {
+            // ---- registers -> transposed shared-memory tile (the rest of a forward line is zero padding)
 #pragma unroll
             for (int q = 0; q < LPW; q++) {
                 const int lc = wib * LPW + q;
                 const int64_t line = tile * COLS + lc;
                 const int64_t z = line / la.NL2;
                 const int k2 = (int)(line - z * la.NL2);
-                double s23 = 1.0;
-                if (!INV && line < la.nlines) s23 = la.sn2[k2] * la.sn3[z];
 #pragma unroll
                 for (int i = 0; i < VPL; i++) {
                     const int k = lane + 32 * i;
@@ -495,36 +541,20 @@ fft_lines_kernel(const LineArgs<T> la) {
                     }
                     bufA[k * PITCH + lc] = v;
                 }
-                (void)s23;
             }
-        }
-        __syncthreads();
-        // ---- next tile's loads go out now; they land while this tile is transformed
-        if (tile + gridDim.x < la.ntiles) prefetch(tile + gridDim.x);
-        // ---- Stockham passes, schedule known at compile time
-        fixed_pass<T, INV, L, PITCH, SLOTS, 0>(bufA, bufB, twS, r0, c);
-        __syncthreads();
-        fixed_pass<T, INV, L, PITCH, SLOTS, 1>(bufB, bufA, twS, r0, c);
-        __syncthreads();
-        fixed_pass<T, INV, L, PITCH, SLOTS, 2>(bufA, bufB, twS, r0, c);
-        __syncthreads();
-        if constexpr (NP == 4) {
-            fixed_pass<T, INV, L, PITCH, SLOTS, 3>(bufB, bufA, twS, r0, c);
             __syncthreads();
-        }
-        const C* res = NP == 4 ? bufA : bufB;
-        // ---- store
-        if constexpr (MODE == 0) {
-            if (col_ok) {
-                C* dst = la.data + ((int64_t)r0 * la.row_stride + col);
-#pragma unroll 4
-                for (int k = r0; k < rows_out; k += SLOTS, dst += rstride) {
-                    C v = res[k * PITCH + c];
-                    if (!INV && phase) v = phase_mul<false>(v, a12, e12, a3S[k], e3S[k]);
-                    *dst = v;
-                }
+            if (tile + gridDim.x < la.ntiles) prefetch(tile + gridDim.x);
+            fixed_pass<T, INV, L, PITCH, SLOTS, 0>(bufA, bufB, twS, r0, c);
+            __syncthreads();
+            fixed_pass<T, INV, L, PITCH, SLOTS, 1>(bufB, bufA, twS, r0, c);
+            __syncthreads();
+            fixed_pass<T, INV, L, PITCH, SLOTS, 2>(bufA, bufB, twS, r0, c);
+            __syncthreads();
+            if constexpr (NP == 4) {
+                fixed_pass<T, INV, L, PITCH, SLOTS, 3>(bufB, bufA, twS, r0, c);
+                __syncthreads();
             }
-        } else {
+            const C* res = NP == 4 ? bufA : bufB;
 #pragma unroll
             for (int q = 0; q < LPW; q++) {
                 const int lc = wib * LPW + q;
@@ -547,8 +577,8 @@ fft_lines_kernel(const LineArgs<T> la) {
                     for (int k = lane; k < L; k += 32) dst[k] = res[k * PITCH + lc];
                 }
             }
+            __syncthreads();                         // the buffers are rewritten by the next tile
         }
-        __syncthreads();                             // the buffers are rewritten by the next tile
     }
 }
 
