@@ -314,6 +314,11 @@ def run_gpu_arm(args):
         prof = A
     torch.cuda.synchronize()
     t_plan = time.perf_counter() - t0
+    try:        # device memory owned by the plan(s) of this rank, GB (before the e2e leg builds its sub-plans)
+        plan_gb = (A.device_bytes() if sharding != "slab" else
+                   sum(int(S.k.lib.b2n_plan_device_bytes(q)) for q in (S.k.gplan, S.k.lplan) if q)) / 1e9
+    except Exception:
+        plan_gb = None
 
     # ---- device-resident step
     if sharding == "slab":
@@ -575,7 +580,7 @@ def run_gpu_arm(args):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sharding": shard_txt,
                    "l2": "inputs exceed L2 (grid 453 MB, samples 422 MB > 126 MB L2); no flush needed",
-                   "plan_s": t_plan},
+                   "plan_s": t_plan, "plan_device_gb": plan_gb},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
     }
     if secondary:

@@ -252,7 +252,8 @@ static bool column_mode(const b2n_plan* p, int* GB, int* GC) {
     int FB = 0, FC = 0;
     if (g.ndim != 3 || p->cplx_table || !p->opt_precomp || !p->opt_order_b || !p->opt_adj_column) return false;
     if (!column_shape(p->jk_adj, &FB, &FC, GB, GC)) return false;
-    return g.K[0] >= FB && g.K[1] >= FC && g.K[2] >= p->jk_adj;
+    // (the records pack the origin along axis 3 into 16 bits)
+    return g.K[0] >= FB && g.K[1] >= FC && g.K[2] >= p->jk_adj && g.K[2] < 32768;
 }
 
 static void default_tiles(b2n_plan* p) {
@@ -444,6 +445,8 @@ extern "C" int b2n_plan_set_option(b2n_plan* p, const char* name, long value) {
         p->opt_fwd_interleave = value;
     } else if (n == "win_maxslide") {
         if (value < 0 || value > 15) return fail(B2N_EINVAL, "win_maxslide must be in 0..15");
+        if (p->d_col_rec != nullptr)
+            return fail(B2N_ESTATE, "win_maxslide is baked into the column records: set it before the points and tables");
         p->opt_win_maxslide = value;
     } else if (n == "win_facew") {
         if (value < -1 || value > 2) return fail(B2N_EINVAL, "win_facew must be -1 (auto) or 0..2");

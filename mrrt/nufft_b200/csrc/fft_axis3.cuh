@@ -1,20 +1,25 @@
-// Axis-3 pass of the pruned oversampled 3-D FFT, fused with what surrounds it.
+// Own passes of the pruned oversampled 3-D FFT, fused with what surrounds them.
 //
-// The pruned FFT (b200nufft.cu: run_fft) does the two in-plane passes with a batched 2-D
-// cuFFT plan on the N3 non-zero planes and the pass along axis 3 on all K1*K2 columns.
-// This kernel IS that last pass (first pass of the inverse), written here so that the work
-// the reference does in separate full-grid sweeps rides along:
-//   forward  (_nufft.py:1331-1371): the zero planes k3 >= N3 are never read (the padding is
-//            created in shared memory), and phase_before is multiplied into the output as
-//            it is stored -- one read of N3 planes + one write of K3 planes instead of a
-//            strided FFT pass (r+w K3 planes) and a phase pass (r+w K3 planes);
-//   adjoint  (_nufft.py:1519-1559): conj(phase_before) is applied as the columns are loaded
-//            and only the planes k3 < N3, which survive the crop, are stored.
-// A CTA owns COLS adjacent columns (adjacent along axis 1, so every global access is a run
-// of COLS complex values), keeps them in shared memory and runs a mixed-radix (8, 4, 2, 3)
-// Stockham autosort FFT of length K3 on them: per pass one butterfly per thread, rows of
-// COLS values per shared-memory access (conflict-free), twiddles from a K3-entry table
-// evaluated in double precision on the host.  Unnormalised in both directions, like cuFFT.
+// Two kernels:
+//   fft_lines_kernel  (second half of this file) -- ALL THREE passes of a single-volume 3-D
+//       transform whose lengths have a compile-time radix schedule (128 .. 1024): axis 1 with
+//       x * sn * scale and the zero padding fused (adjoint: crop * scale * sn), axis 2 on the
+//       non-zero rows only, axis 3 with the zero padding, phase_before and the crop fused.
+//   fft_axis3_kernel  (first half) -- the axis-3 pass alone with a RUN-TIME mixed-radix schedule,
+//       for every other K3 = 2^a 3^b; the in-plane passes then stay with cuFFT (b200nufft.cu:
+//       run_fft) on the N3 non-zero planes.
+// What rides along, instead of the reference's separate full-grid sweeps:
+//   forward  (_nufft.py:1325-1371): x * sn is applied as the image rows are loaded; padding rows,
+//            columns and planes are created in shared memory / registers and never read;
+//            phase_before is multiplied into the output of the axis-3 pass as it is stored;
+//   adjoint  (_nufft.py:1519-1572): conj(phase_before) is applied as the axis-3 lines are loaded,
+//            only the planes / rows / columns that survive the crop are stored, and the axis-1
+//            pass writes image[n] = grid[n] * scale * sn[n] directly.
+// A CTA owns COLS adjacent lines (every global access is a run of COLS complex values, or a
+// contiguous row in the axis-1 mode), keeps them in shared memory and runs a Stockham autosort
+// FFT on them: rows of COLS values per shared-memory access (conflict-free), twiddles from an
+// L-entry table evaluated in double precision on the host.  Unnormalised in both directions,
+// like cuFFT.
 #pragma once
 #include "aux_kernels.cuh"
 #include "common.cuh"
