@@ -315,7 +315,7 @@ def run_gpu_arm(args):
     torch.cuda.synchronize()
     t_plan = time.perf_counter() - t0
     try:        # device memory owned by the plan(s) of this rank, GB (before the e2e leg builds its sub-plans)
-        plan_gb = (A.device_bytes() if sharding != "slab" else
+        plan_gb = (A.device_bytes if sharding != "slab" else
                    sum(int(S.k.lib.b2n_plan_device_bytes(q)) for q in (S.k.gplan, S.k.lplan) if q)) / 1e9
     except Exception:
         plan_gb = None
