@@ -659,7 +659,9 @@ def test_fixed_schedule_axis3_fft_vs_oracle(K3, N3, precision):
                                          ((100, 128, 64), (192, 256, 128), True),
                                          ((256, 20, 70), (384, 128, 192), False),
                                          ((300, 60, 64), (512, 128, 128), False),
-                                         ((40, 500, 64), (128, 768, 128), True)])
+                                         ((40, 500, 64), (128, 768, 128), True),
+                                         ((600, 20, 70), (1024, 128, 128), False),
+                                         ((20, 600, 64), (128, 1024, 192), False)])
 def test_own_inplane_fft_vs_oracle(Nd, Kd, ortho, precision):
     """Own in-plane FFT passes (option own_fft12, default on): axis 1 over contiguous rows with
     the scale / zero-pad and crop / scale fused, axis 2 strided on the non-zero rows only, axis 3
