@@ -396,6 +396,8 @@ class SlabShardedNufft(object):
             import torch.distributed._symmetric_memory as symm_mem
 
             K1, K2, K3 = self.Kd
+            if (K1 * np.dtype(self.cdt).itemsize) % 16 != 0 or self.world > 16:
+                raise RuntimeError("the exchange kernels move 16-byte vectors and know at most 16 peers")
             nmax = max(nrows for _, nrows in self.slabs)
             tdt = _TORCH_C[self.cdt]
             rdt = torch.float32 if tdt == torch.complex64 else torch.float64
@@ -407,6 +409,10 @@ class SlabShardedNufft(object):
                 nr = self.slabs[r][1]
                 buf = self._hdl.get_buffer(r, (K3, nr, K1, 2), rdt, 0)
                 self._peer_grids.append(torch.view_as_complex(buf))
+            # argument arrays of the exchange kernels (b2n_slab_scatter / b2n_slab_gather)
+            self._pg_ptrs = (ctypes.c_void_p * self.world)(*[g.data_ptr() for g in self._peer_grids])
+            self._pg_row0 = (ctypes.c_int * self.world)(*[int(r0) for r0, _ in self.slabs])
+            self._pg_nrows = (ctypes.c_int * self.world)(*[int(nr) for _, nr in self.slabs])
         except Exception:
             if strict:
                 raise
@@ -428,12 +434,11 @@ class SlabShardedNufft(object):
         A = self.k.planes_fwd(xp, self.z0)                        # [nz, K2, K1]
         self._mark("fwd_planes")
         self._barrier()                                           # every rank is done with its grid
-        for d in range(self.world):
-            s = (self.rank + d) % self.world                      # spread the traffic over the peers
-            row0, nrows = self.slabs[s]
-            dst = self._peer_grids[s]
-            for glo, llo, n in _pieces(row0, nrows, K2):
-                dst[self.z0:self.z1, llo:llo + n].copy_(A[:, glo:glo + n])
+        # ONE kernel: the rows of this rank's planes stored straight into every slab that holds
+        # them (csrc/slab_exchange.cuh) -- all-to-all, pack and unpack in a single pass
+        _lib.check(self.k.lib.b2n_slab_scatter(self.k.gplan, ctypes.c_void_p(A.data_ptr()), self.z1 - self.z0,
+                                               self.z0, self.world, self._pg_ptrs, self._pg_row0,
+                                               self._pg_nrows, self.k._stream()))
         grid = self._peer_grids[self.rank]
         if not getattr(self.k, "axis3_fused", False):
             grid[N3:].zero_()
@@ -456,17 +461,11 @@ class SlabShardedNufft(object):
         nz = self.z1 - self.z0
         B = self.k.empty((nz, K2, K1))
         self._barrier()                                           # every slab is gridded and transformed
-        order = [(self.rank + d) % self.world for d in range(self.world)]
-        for s in order:                                           # origin rows: plain copies
-            row0, _ = self.slabs[s]
-            own = self.bounds[s + 1] - self.bounds[s]
-            B[:, row0:row0 + own].copy_(self._peer_grids[s][self.z0:self.z1, :own])
-        for s in order:                                           # halo rows of the neighbours add up
-            row0, nrows = self.slabs[s]
-            own = self.bounds[s + 1] - self.bounds[s]
-            if nrows > own:
-                for glo, llo, n in _pieces((row0 + own) % K2, nrows - own, K2):
-                    B[:, glo:glo + n] += self._peer_grids[s][self.z0:self.z1, own + llo:own + llo + n]
+        # ONE kernel: this rank's planes read out of every slab, the rows held by more than one
+        # slab (halos) summed in slab order on the way
+        _lib.check(self.k.lib.b2n_slab_gather(self.k.gplan, ctypes.c_void_p(B.data_ptr()), nz, self.z0,
+                                              self.world, self._pg_ptrs, self._pg_row0, self._pg_nrows,
+                                              self.k._stream()))
         self._barrier()                                           # the grids may be reused
         self._mark("adj_all_to_all")
         out = self.k.planes_adj(B, self.z0)

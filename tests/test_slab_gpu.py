@@ -258,3 +258,49 @@ def test_slab_sharded_peer_memory_exchange():
         for k, v in r.items():
             if k.startswith(("fwd", "adj")):
                 assert v <= 5e-6, (k, r)
+
+
+@pytest.mark.parametrize("precision", ["single", "double"])
+def test_slab_exchange_kernels_one_gpu(precision):
+    """b2n_slab_scatter / b2n_slab_gather (csrc/slab_exchange.cuh) with the "peer" grids of four
+    slabs all on this GPU: the scatter stores every row of the local planes into every slab that
+    holds it (halo rows into two slabs, wrap-around at the seam), the gather returns the sum over
+    the slabs holding each row -- against the same bookkeeping done with torch slices."""
+    import ctypes
+    import torch
+    from mrrt.nufft_b200 import _lib
+    from mrrt.nufft_b200._slab import CudaSlabKernels, _pieces
+
+    Nd, Kd, J = (20, 24, 18), (32, 40, 28), 6
+    K1, K2, K3 = Kd
+    k = CudaSlabKernels(Nd, Kd, (J, J, J), 1024, precision, False, (0.0, 0.0, 0.0), 1.0, None)
+    cdt = torch.complex64 if precision == "single" else torch.complex128
+    bounds = [0, 9, 17, 30, K2]
+    slabs = [(bounds[s], bounds[s + 1] - bounds[s] + J - 1) for s in range(4)]     # (row0, rows + halo)
+    grids = [torch.zeros((K3, nr, K1), dtype=cdt, device="cuda") for _, nr in slabs]
+    ptrs = (ctypes.c_void_p * 4)(*[g.data_ptr() for g in grids])
+    row0 = (ctypes.c_int * 4)(*[r for r, _ in slabs])
+    nrows = (ctypes.c_int * 4)(*[n for _, n in slabs])
+    z0, nz = 3, 7
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    A = torch.randn((nz, K2, K1), dtype=cdt, device="cuda", generator=gen)
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.check(k.lib.b2n_slab_scatter(k.gplan, ctypes.c_void_p(A.data_ptr()), nz, z0, 4, ptrs, row0, nrows, st))
+    torch.cuda.synchronize()
+    for (r0, nr), g in zip(slabs, grids):
+        want = torch.zeros_like(g)
+        for glo, llo, n in _pieces(r0, nr, K2):
+            want[z0:z0 + nz, llo:llo + n] = A[:, glo:glo + n]
+        assert torch.equal(g, want)
+    # adjoint direction: every slab holds its own values; rows in two slabs add up
+    for g in grids:
+        g.copy_(torch.randn(g.shape, dtype=cdt, device="cuda", generator=gen))
+    B = torch.full((nz, K2, K1), float("nan"), dtype=cdt, device="cuda")
+    _lib.check(k.lib.b2n_slab_gather(k.gplan, ctypes.c_void_p(B.data_ptr()), nz, z0, 4, ptrs, row0, nrows, st))
+    torch.cuda.synchronize()
+    want = torch.zeros_like(B)
+    for (r0, nr), g in zip(slabs, grids):
+        for glo, llo, n in _pieces(r0, nr, K2):
+            want[:, glo:glo + n] += g[z0:z0 + nz, llo:llo + n]
+    tol = 1e-6 if precision == "single" else 1e-14
+    assert float((B - want).abs().max() / want.abs().max()) <= tol
