@@ -85,13 +85,13 @@ def row_statistics(omega, Jd, Kd, rdt, device):
     return rows.cpu().numpy(), n.cpu().numpy().astype(np.float64), cells.cpu().numpy().astype(np.float64)
 
 
-# Cost of one origin row in units of "one sample in a dense region", fitted to the per-rank
-# stage times of the 8-GPU bench run (profiles/r02_slab_cost_fit.md): the interpolation
-# kernels cost 9.5e-8 ms per sample plus 1.3e-7 ms per occupied cell (a new cell means a window
-# slide in the adjoint and one forward slot more), the axis-3 pass 1.9e-3 ms per row of
-# K1*K3 = 384^2 cells.
-CELL_COST = 1.38
-ROW_COST_PER_CELL = 19900.0 / (384.0 * 384.0)
+# Cost of one origin row in units of "one sample in a dense region", fitted to the per-slab
+# stage times of the 8-rank bench run (profiles/r02_slab_cost_fit.md, scripts/slab_cost_fit.py):
+# the interpolation kernels cost 8.3e-8 ms per sample plus 5.1e-8 ms per occupied cell (a new
+# cell is a forward slot that cannot be paired and, per group of columns, a window slide in the
+# adjoint), the axis-3 passes 1.5e-3 ms per row of K1*K3 = 384^2 cells.
+CELL_COST = 0.62
+ROW_COST_PER_CELL = 18450.0 / (384.0 * 384.0)
 
 
 def slab_boundaries(cost, world):
