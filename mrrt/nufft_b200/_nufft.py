@@ -216,7 +216,9 @@ class NufftBase(object):
         self._real_dtype, self._cplx_dtype = pm.real_cplx_dtypes(precision)
         rdt, cdt = self._real_dtype, self._cplx_dtype
         self.M = omega_np.shape[0]
-        self._omega_host = omega_np if self.host_chunks > 1 else None
+        # private copy: the sample-range sub-plans are built on the first host call and must see
+        # the coordinates this plan was built from, whatever the caller does to its array
+        self._omega_host = omega_np.copy() if self.host_chunks > 1 else None
         if n_shift is None:
             self.n_shift = (0.0,) * self.ndim
         else:
@@ -472,6 +474,7 @@ class NufftBase(object):
             for k in range(self.host_chunks):
                 lo, hi = shard_range(self.M, self.host_chunks, k)
                 self._children.append((lo, hi, NufftBase(self.Nd, self._omega_host[lo:hi], **kw)))
+            self._omega_host = None              # the sub-plans hold what they need
             # one stream per copy direction: the two DMA directions of the link are
             # independent, so the samples of one call can travel back while the inputs of
             # the next call come in

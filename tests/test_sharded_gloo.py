@@ -39,6 +39,12 @@ def _worker(rank, world, port, q):
         res = {"rank": rank, "lo": S.lo, "hi": S.hi}
         res["fwd"] = rel_l2(S.fft(x), full.fft(x)[S.lo:S.hi])
         res["adj"] = rel_l2(S.adj(y[S.lo:S.hi]), full.adj(y))
+        # sparse mode shards by matrix rows (= samples) with the same reduce
+        fs = orc.OracleNufft(Nd=Nd, omega=om, mode="sparse", **kw)
+        Ss = SampleShardedNufft(Nd, om, op_factory=orc.OracleNufft, mode="sparse", **kw)
+        res["sp_fwd"] = rel_l2(Ss.fft(x), fs.fft(x)[Ss.lo:Ss.hi])
+        res["sp_adj"] = rel_l2(Ss.adj(y[Ss.lo:Ss.hi]), fs.adj(y))
+        res["sp_norm"] = rel_l2(Ss.norm(x), fs.adj(fs.fft(x)))
         xc = rs.standard_normal(Nd + (5,)) + 1j * rs.standard_normal(Nd + (5,))
         Cc = CoilShardedNufft(Nd, om, n_coils=5, op_factory=orc.OracleNufft, **kw)
         loc = Cc.fft(Cc.local_coils(xc))
@@ -78,3 +84,4 @@ def test_sample_and_coil_sharding_world2():
     assert out[0]["coils"] == (0, 3) and out[1]["coils"] == (3, 5)
     for r in out:
         assert r["fwd"] < 1e-13 and r["adj"] < 1e-12 and r["coil"] < 1e-13
+        assert r["sp_fwd"] < 1e-13 and r["sp_adj"] < 1e-12 and r["sp_norm"] < 1e-12
