@@ -23,6 +23,7 @@ interpolators compiled unmodified into oracle/_ref, driven by the NumPy restatem
 its Python pipeline) on bounded spoke subsamples, on the host cores.
 """
 import argparse
+import datetime
 import json
 import os
 import subprocess
@@ -68,9 +69,16 @@ def image(seed=0):
 
 # --------------------------------------------------------------------------- clocks
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region.
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    nvidia-smi needs a few hundred ms to start, more than a short timed region lasts, so it is
+    started before the warm-up steps and `wait_ready` blocks until its first line has arrived;
+    every line carries nvidia-smi's own timestamp and only the samples taken between `mark_begin`
+    and `mark_end` (host wall clock around the timed region) are reported.  If no sample falls
+    inside a very short region, the samples of the 150 ms before / after it are used and
+    `"window"` says so."""
+
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -78,22 +86,51 @@ class ClockSampler(object):
         self.index = index
         self.lines = []
         self.proc = None
+        self.t_begin = self.t_end = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "25"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
 
     def _read(self):
-        for ln in self.proc.stdout:
-            self.lines.append(ln)
+        try:
+            for ln in self.proc.stdout:
+                self.lines.append(ln)
+        except Exception:  # pragma: no cover
+            pass
+
+    def wait_ready(self, timeout=3.0):
+        t0 = time.perf_counter()
+        while self.proc is not None and not self.lines and time.perf_counter() - t0 < timeout:
+            time.sleep(0.01)
+
+    def mark_begin(self):
+        self.t_begin = datetime.datetime.now()
+
+    def mark_end(self):
+        self.t_end = datetime.datetime.now()
+
+    @staticmethod
+    def _stamp(text):
+        try:
+            return datetime.datetime.strptime(text, "%Y/%m/%d %H:%M:%S.%f")
+        except ValueError:
+            return None
 
     def stop(self):
+        try:
+            return self._stop()
+        except Exception as e:  # the clocks line must never cost the bench line
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0,
+                    "reasons": ["clock sampling failed: %s" % type(e).__name__]}
+
+    def _stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -102,23 +139,33 @@ class ClockSampler(object):
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        rows = []
+        for ln in list(self.lines):
             f = [c.strip() for c in ln.split(",")]
-            if len(f) < 8 or f[0] != str(self.index):
+            if len(f) < 9 or f[1] != str(self.index):
                 continue
             try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
+                rows.append((self._stamp(f[0]), float(f[2]), float(f[3]),
+                             [nm for nm, val in zip(names, f[5:9]) if val.lower().startswith("active")]))
             except ValueError:
                 continue
-            for nm, val in zip(names, f[4:8]):
-                if val.lower().startswith("active"):
-                    reasons.add(nm)
+        window = "timed region"
+        pick = rows
+        if self.t_begin is not None and self.t_end is not None and all(r[0] is not None for r in rows):
+            pick = [r for r in rows if self.t_begin <= r[0] <= self.t_end]
+            if not pick:
+                pad = datetime.timedelta(milliseconds=150)
+                pick = [r for r in rows if self.t_begin - pad <= r[0] <= self.t_end + pad]
+                window = "timed region +- 150 ms (no sample inside a region this short)"
+        elif rows:
+            window = "all samples since the warm-up (timestamps not usable)"
+        sm = [r[1] for r in pick]
+        mx = [r[2] for r in pick]
+        reasons = set(nm for r in pick for nm in r[3])
         return {"sm_mhz": float(np.median(sm)) if sm else None,
                 "sm_max_mhz": float(max(mx)) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
 # --------------------------------------------------------------------------- CPU arm
@@ -335,14 +382,15 @@ def run_gpu_arm(args):
                 dist.all_reduce(torch.view_as_real(xa.permute(2, 1, 0)), op=dist.ReduceOp.SUM)
             return xa
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:                       # nvidia-smi is up and sampling before the warm-up ends
+        sampler.start()
+        sampler.wait_ready()
     for _ in range(args.warmup):
         step_dev()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     if S is not None:
         S.k.set_profile(1)
     else:
@@ -352,11 +400,13 @@ def run_gpu_arm(args):
     torch.cuda.synchronize()
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
+    sampler.mark_begin()
     e0.record()
     for _ in range(args.steps):
         step_dev()
     e1.record()
     torch.cuda.synchronize()
+    sampler.mark_end()
     if world > 1:
         dist.barrier()
     ms_total = e0.elapsed_time(e1)
