@@ -9,7 +9,7 @@ the oracle's restatement of the reference pipeline; the restated C when ``_ref``
   C5  3-D 256^3, 3-D radial 102 944 x 512, Kd 384^3, J=6, c64: every 16th spoke
       (M = 3 294 208); the full trajectory is checked through
       size-independent properties in test_gpu_parity.py::test_adjointness_and_linearity_large
-      and tests/test_full_size_properties.py.
+      and tests/test_workload_full_size.py.
 
 Tolerances are north_star's: rel-L2 <= 1e-5 (complex64), <= 1e-12 (complex128); the float32
 ADJOINT uses golden_util.assert_single_parity (1e-5 against the reference, or -- where two
